@@ -1,0 +1,486 @@
+"""ctypes binding of libcellscopes_cuda.so (include/cellscopes_cuda.h).
+
+This is the only way Python reaches the CUDA path, and it is the same C ABI the Julia shim
+(julia/CellScopesCUDA.jl) binds with ``ccall``.  There is no CPU fallback: if the shared library
+is missing or no B200 is visible, calls raise ``CellScopesCudaError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcellscopes_cuda.so")
+
+# enums of the header
+DT_F32, DT_F64, DT_I32, DT_I64 = 0, 1, 2, 3
+NORM_LOGARITHM, NORM_NONE = 0, 1
+METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
+GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
+STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
+          "pca_transform", "knn", "graph", "generate"]
+T_COUNT = len(STAGES)
+
+_NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,
+          np.dtype(np.int32): DT_I32, np.dtype(np.int64): DT_I64}
+_DT_NP = {v: k for k, v in _NP_DT.items()}
+
+
+class CellScopesCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libcellscopes_cuda error {code}: {msg}")
+        self.code = code
+
+
+# every exported symbol: name -> (restype, argtypes).  tests/test_abi.py checks this table against the header.
+_P = C.c_void_p
+_I32, _I64, _F64, _U64, _F32 = C.c_int32, C.c_int64, C.c_double, C.c_uint64, C.c_float
+_PP = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "csc_abi_version": (_I32, []),
+    "csc_create": (_I32, [_I32, _PP]),
+    "csc_destroy": (_I32, [_P]),
+    "csc_last_error": (C.c_char_p, [_P]),
+    "csc_synchronize": (_I32, [_P]),
+    "csc_device_info": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I32)]),
+    "csc_timer_start": (_I32, [_P]),
+    "csc_timer_stop": (_I32, [_P, C.POINTER(_F64)]),
+    "csc_stage_times": (_I32, [_P, C.POINTER(_F64), C.POINTER(_I64), _I32]),
+    "csc_flush_l2": (_I32, [_P]),
+    "csc_vec_alloc": (_I32, [_P, _I64, _I32, _PP]),
+    "csc_vec_wrap": (_I32, [_P, _P, _I64, _I32, _PP]),
+    "csc_vec_free": (_I32, [_P]),
+    "csc_vec_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I32), _PP]),
+    "csc_vec_upload": (_I32, [_P, _P, _I64]),
+    "csc_vec_download": (_I32, [_P, _P, _I64]),
+    "csc_sparse_upload": (_I32, [_P, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _PP]),
+    "csc_sparse_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "csc_sparse_range_nnz": (_I32, [_P, _I64, _I64, C.POINTER(_I64)]),
+    "csc_sparse_download": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32]),
+    "csc_sparse_free": (_I32, [_P]),
+    "csc_generate_counts": (_I32, [_P, _I64, _I64, _I64, _U64, _P, _P, _P, _P, _I32, _I32, _F32, _F32, _F32, _PP]),
+    "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _PP]),
+    "csc_gene_stats_partial": (_I32, [_P, _P, _P]),
+    "csc_hvg_finish": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
+    "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
+    "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
+    "csc_dense_alloc": (_I32, [_P, _I64, _I64, _PP]),
+    "csc_dense_upload": (_I32, [_P, _P, _I32, _I64, _I64, _PP]),
+    "csc_dense_download": (_I32, [_P, _P, _I32, _I64, _I64]),
+    "csc_dense_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), _PP]),
+    "csc_dense_wrap": (_I32, [_P, _P, _I64, _I64, _PP]),
+    "csc_dense_free": (_I32, [_P]),
+    "csc_pca_partial": (_I32, [_P, _P, _P, _P]),
+    "csc_pca_solve": (_I32, [_P, _P, _P, _I64, _I64, _I32, _F64, _I32, _PP, C.POINTER(_I32), C.POINTER(_F64)]),
+    "csc_pca_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I32), _P, C.POINTER(_F64), _P, _P]),
+    "csc_pca_transform": (_I32, [_P, _P, _P, _PP]),
+    "csc_pca_free": (_I32, [_P]),
+    "csc_knn": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _PP, _PP]),
+    "csc_graph_build": (_I32, [_P, _P, _I64, _I32, _I64, _I64, _I32, _F64, _PP]),
+    "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32]),
+    "csc_graph_free": (_I32, [_P]),
+}
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the shared library and declare every signature.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("CELLSCOPES_CUDA_LIB", LIB_PATH)
+    if not os.path.exists(p):
+        raise CellScopesCudaError(
+            -100, f"{p} not found: build it with `python cellscopes.jl_b200/build.py` "
+                  "(the CUDA extension is required; there is no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.csc_abi_version() != 1:
+        raise CellScopesCudaError(-101, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU + stream (csc_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.csc_create(device, C.byref(h))
+        if rc != 0:
+            raise CellScopesCudaError(rc, (self.lib.csc_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise CellScopesCudaError(rc, (self.lib.csc_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.csc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- misc ------------------------------------------------------------------------------
+    def synchronize(self):
+        self.check(self.lib.csc_synchronize(self.h))
+
+    def device_info(self):
+        sm, cmaj, cmin = _I32(), _I32(), _I32()
+        fr, tot = _I64(), _I64()
+        self.check(self.lib.csc_device_info(self.h, C.byref(sm), C.byref(fr), C.byref(tot), C.byref(cmaj), C.byref(cmin)))
+        return {"sm_count": sm.value, "free_bytes": fr.value, "total_bytes": tot.value, "cc": (cmaj.value, cmin.value)}
+
+    def timer_start(self):
+        self.check(self.lib.csc_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = _F64()
+        self.check(self.lib.csc_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def stage_times(self, reset=False):
+        ms = (_F64 * T_COUNT)()
+        n = _I64()
+        self.check(self.lib.csc_stage_times(self.h, ms, C.byref(n), 1 if reset else 0))
+        return {STAGES[i]: ms[i] for i in range(T_COUNT)}, n.value
+
+    def flush_l2(self):
+        self.check(self.lib.csc_flush_l2(self.h))
+
+    # ---- vectors ---------------------------------------------------------------------------
+    def vec(self, n, dtype=np.float64):
+        h = C.c_void_p()
+        self.check(self.lib.csc_vec_alloc(self.h, int(n), _NP_DT[np.dtype(dtype)], C.byref(h)))
+        return Vec(self, h)
+
+    def vec_from(self, arr):
+        arr = np.ascontiguousarray(arr)
+        v = self.vec(arr.size, arr.dtype)
+        v.upload(arr)
+        return v
+
+    def vec_wrap(self, device_ptr, n, dtype, keepalive=None):
+        h = C.c_void_p()
+        self.check(self.lib.csc_vec_wrap(self.h, C.c_void_p(int(device_ptr)), int(n), _NP_DT[np.dtype(dtype)], C.byref(h)))
+        v = Vec(self, h)
+        v._keepalive = keepalive
+        return v
+
+    def vec_wrap_i32(self, tensor):
+        """Non-owning int32 view of a contiguous torch CUDA tensor."""
+        return self.vec_wrap(tensor.data_ptr(), tensor.numel(), np.int32, keepalive=tensor)
+
+    # ---- sparse ----------------------------------------------------------------------------
+    def sparse_upload(self, n_genes, n_cells, colptr, rowval, nzval, index_base=0):
+        colptr = np.ascontiguousarray(colptr)
+        rowval = np.ascontiguousarray(rowval)
+        nzval = np.ascontiguousarray(nzval)
+        if colptr.dtype not in (np.int64, np.int32) or rowval.dtype != colptr.dtype:
+            colptr = colptr.astype(np.int64)
+            rowval = rowval.astype(np.int64)
+        if nzval.dtype not in _NP_DT:
+            nzval = nzval.astype(np.float64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_sparse_upload(self.h, int(n_genes), int(n_cells), _ptr(colptr), _ptr(rowval),
+                                              _NP_DT[colptr.dtype], _ptr(nzval), _NP_DT[nzval.dtype],
+                                              int(index_base), C.byref(h)))
+        return Sparse(self, h)
+
+    def sparse_from_scipy(self, m):
+        import scipy.sparse as sp
+        m = sp.csc_matrix(m)
+        m.sort_indices()
+        return self.sparse_upload(m.shape[0], m.shape[1], m.indptr, m.indices, m.data, 0)
+
+    def generate_counts(self, params, cell_lo, cell_hi):
+        """Device generator; ``params`` is a synth.SynthParams."""
+        h = C.c_void_p()
+        a = np.ascontiguousarray(params.a, dtype=np.float32)
+        mod = np.ascontiguousarray(params.module, dtype=np.int32)
+        load = np.ascontiguousarray(params.loading, dtype=np.float32)
+        tm = np.ascontiguousarray(params.type_mean, dtype=np.float32)
+        self.check(self.lib.csc_generate_counts(self.h, params.n_genes, int(cell_lo), int(cell_hi), params.seed,
+                                                _ptr(a), _ptr(mod), _ptr(load), _ptr(tm), params.n_types,
+                                                params.n_modules, params.lib_sd, params.type_w, params.noise_w,
+                                                C.byref(h)))
+        return Sparse(self, h)
+
+    # ---- stages ----------------------------------------------------------------------------
+    def normalize(self, raw, scale_factor=10000.0, norm_method=NORM_LOGARITHM, pseudocount=1.0, nan_to_zero=False,
+                  gene_stats=None):
+        h = C.c_void_p()
+        self.check(self.lib.csc_normalize(self.h, raw.h, float(scale_factor), int(norm_method), float(pseudocount),
+                                          1 if nan_to_zero else 0, gene_stats.h if gene_stats is not None else None,
+                                          C.byref(h)))
+        return Sparse(self, h)
+
+    def gene_stats_partial(self, raw, gene_stats):
+        self.check(self.lib.csc_gene_stats_partial(self.h, raw.h, gene_stats.h))
+
+    def hvg_finish(self, gene_stats, n_genes, n_cells_total, n_features=2000, span=0.3):
+        g = int(n_genes)
+        out = {k: np.empty(g, dtype=np.float64) for k in
+               ("mean", "variance", "variance_expected", "variance_standardized")}
+        order = np.empty(g, dtype=np.int64)
+        self.check(self.lib.csc_hvg_finish(self.h, gene_stats.h, g, int(n_cells_total), int(n_features), float(span),
+                                           _ptr(out["mean"]), _ptr(out["variance"]), _ptr(out["variance_expected"]),
+                                           _ptr(out["variance_standardized"]), _ptr(order)))
+        out["order"] = order
+        out["features"] = order[:min(int(n_features), g)].copy()
+        return out
+
+    def scale_stats_partial(self, norm, features, partial):
+        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        self.check(self.lib.csc_scale_stats_partial(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h))
+
+    def scale_fill(self, norm, features, partial, n_cells_total, scale_max=10.0, do_scale=True, do_center=True):
+        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_scale_fill(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h,
+                                           int(n_cells_total), float(scale_max), 1 if do_scale else 0,
+                                           1 if do_center else 0, C.byref(h)))
+        return Dense(self, h)
+
+    def dense_upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_dense_upload(self.h, _ptr(arr), _NP_DT[arr.dtype], arr.shape[0], arr.shape[1], C.byref(h)))
+        return Dense(self, h)
+
+    def dense_alloc(self, n_rows, n_cols):
+        h = C.c_void_p()
+        self.check(self.lib.csc_dense_alloc(self.h, int(n_rows), int(n_cols), C.byref(h)))
+        return Dense(self, h)
+
+    def dense_wrap(self, device_ptr, n_rows, n_cols, keepalive=None):
+        h = C.c_void_p()
+        self.check(self.lib.csc_dense_wrap(self.h, C.c_void_p(int(device_ptr)), int(n_rows), int(n_cols), C.byref(h)))
+        d = Dense(self, h)
+        d._keepalive = keepalive
+        return d
+
+    def pca_partial(self, scaled, colsum, gram):
+        self.check(self.lib.csc_pca_partial(self.h, scaled.h, colsum.h, gram.h))
+
+    def pca_solve(self, colsum, gram, n_feat, n_cells_total, maxoutdim, tol=1e-9, max_iter=500):
+        h = C.c_void_p()
+        it, res = _I32(), _F64()
+        self.check(self.lib.csc_pca_solve(self.h, colsum.h, gram.h, int(n_feat), int(n_cells_total), int(maxoutdim),
+                                          float(tol), int(max_iter), C.byref(h), C.byref(it), C.byref(res)))
+        p = Pca(self, h)
+        p.iters, p.resid = it.value, res.value
+        return p
+
+    def pca_transform(self, scaled, pca):
+        h = C.c_void_p()
+        self.check(self.lib.csc_pca_transform(self.h, scaled.h, pca.h, C.byref(h)))
+        return Dense(self, h)
+
+    def knn(self, queries, keys, k, query_offset=0, dim_lo=0, dim_hi=None, metric=METRIC_COSINE):
+        hi, hd = C.c_void_p(), C.c_void_p()
+        if dim_hi is None:
+            dim_hi = keys.shape[1]
+        self.check(self.lib.csc_knn(self.h, queries.h, keys.h, int(query_offset), int(dim_lo), int(dim_hi), int(k),
+                                    int(metric), C.byref(hi), C.byref(hd)))
+        return Vec(self, hi), Vec(self, hd)
+
+    def graph_build(self, knn_idx, n_cells_total, k, cell_lo=0, cell_hi=None, mode=GRAPH_SUM, snn_prune=0.0):
+        h = C.c_void_p()
+        cell_hi = n_cells_total if cell_hi is None else cell_hi
+        self.check(self.lib.csc_graph_build(self.h, knn_idx.h, int(n_cells_total), int(k), int(cell_lo), int(cell_hi),
+                                            int(mode), float(snn_prune), C.byref(h)))
+        return Graph(self, h)
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self, ctx: Context, h):
+        self.ctx = ctx
+        self.h = h
+
+    def free(self):
+        if getattr(self, "h", None):
+            getattr(self.ctx.lib, self._free)(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Vec(_Handle):
+    _free = "csc_vec_free"
+
+    def info(self):
+        n, dt, p = _I64(), _I32(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.csc_vec_info(self.h, C.byref(n), C.byref(dt), C.byref(p)))
+        return n.value, _DT_NP[dt.value], p.value
+
+    @property
+    def n(self):
+        return self.info()[0]
+
+    @property
+    def dtype(self):
+        return self.info()[1]
+
+    @property
+    def device_ptr(self):
+        return self.info()[2]
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        self.ctx.check(self.ctx.lib.csc_vec_upload(self.h, _ptr(arr), arr.size))
+
+    def download(self, n=None):
+        total, dt, _ = self.info()
+        n = total if n is None else n
+        out = np.empty(n, dtype=dt)
+        self.ctx.check(self.ctx.lib.csc_vec_download(self.h, _ptr(out), n))
+        return out
+
+    @property
+    def __cuda_array_interface__(self):
+        n, dt, p = self.info()
+        return {"shape": (n,), "typestr": np.dtype(dt).str, "data": (p or 0, False), "version": 3, "strides": None}
+
+
+class Sparse(_Handle):
+    _free = "csc_sparse_free"
+
+    @property
+    def shape(self):
+        g, n, _ = self.info()
+        return g, n
+
+    def info(self):
+        g, n, z = _I64(), _I64(), _I64()
+        self.ctx.check(self.ctx.lib.csc_sparse_info(self.h, C.byref(g), C.byref(n), C.byref(z)))
+        return g.value, n.value, z.value
+
+    @property
+    def nnz(self):
+        return self.info()[2]
+
+    def range_nnz(self, lo, hi):
+        z = _I64()
+        self.ctx.check(self.ctx.lib.csc_sparse_range_nnz(self.h, int(lo), int(hi), C.byref(z)))
+        return z.value
+
+    def download(self, cell_lo=0, cell_hi=None, index_base=0, values_only=False):
+        g, n, _ = self.info()
+        cell_hi = n if cell_hi is None else cell_hi
+        nnz = self.range_nnz(cell_lo, cell_hi)
+        val = np.empty(nnz, dtype=np.float64)
+        if values_only:
+            self.ctx.check(self.ctx.lib.csc_sparse_download(self.h, int(cell_lo), int(cell_hi), None, None, _ptr(val),
+                                                            int(index_base)))
+            return val
+        colptr = np.empty(cell_hi - cell_lo + 1, dtype=np.int64)
+        rowval = np.empty(nnz, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.csc_sparse_download(self.h, int(cell_lo), int(cell_hi), _ptr(colptr), _ptr(rowval),
+                                                        _ptr(val), int(index_base)))
+        return colptr, rowval, val
+
+    def to_scipy(self, cell_lo=0, cell_hi=None):
+        import scipy.sparse as sp
+        g, n, _ = self.info()
+        cell_hi = n if cell_hi is None else cell_hi
+        colptr, rowval, val = self.download(cell_lo, cell_hi, 0)
+        return sp.csc_matrix((val, rowval, colptr), shape=(g, cell_hi - cell_lo))
+
+
+class Dense(_Handle):
+    _free = "csc_dense_free"
+
+    def info(self):
+        r, c, p = _I64(), _I64(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.csc_dense_info(self.h, C.byref(r), C.byref(c), C.byref(p)))
+        return r.value, c.value, p.value
+
+    @property
+    def shape(self):
+        r, c, _ = self.info()
+        return r, c
+
+    @property
+    def device_ptr(self):
+        return self.info()[2]
+
+    def download(self, dtype=np.float64, row_lo=0, row_hi=None):
+        r, c, _ = self.info()
+        row_hi = r if row_hi is None else row_hi
+        out = np.empty((row_hi - row_lo, c), dtype=dtype)
+        self.ctx.check(self.ctx.lib.csc_dense_download(self.h, _ptr(out), _NP_DT[np.dtype(dtype)], int(row_lo), int(row_hi)))
+        return out
+
+    @property
+    def __cuda_array_interface__(self):
+        r, c, p = self.info()
+        return {"shape": (r, c), "typestr": "<f4", "data": (p or 0, False), "version": 3, "strides": None}
+
+
+class Pca(_Handle):
+    _free = "csc_pca_free"
+    iters = 0
+    resid = 0.0
+
+    def info(self):
+        nf, k = _I64(), _I32()
+        self.ctx.check(self.ctx.lib.csc_pca_info(self.h, C.byref(nf), C.byref(k), None, None, None, None))
+        pv = np.empty(k.value, dtype=np.float64)
+        load = np.empty((k.value, nf.value), dtype=np.float64)   # column-major H x k == row-major k x H
+        mean = np.empty(nf.value, dtype=np.float64)
+        tv = _F64()
+        self.ctx.check(self.ctx.lib.csc_pca_info(self.h, None, None, _ptr(pv), C.byref(tv), _ptr(load), _ptr(mean)))
+        return {"n_feat": nf.value, "k": k.value, "principalvars": pv, "tvar": tv.value, "loadings": load.T.copy(),
+                "mean": mean}
+
+
+class Graph(_Handle):
+    _free = "csc_graph_free"
+
+    def info(self):
+        r, c, z = _I64(), _I64(), _I64()
+        self.ctx.check(self.ctx.lib.csc_graph_info(self.h, C.byref(r), C.byref(c), C.byref(z)))
+        return r.value, c.value, z.value
+
+    def download(self, index_base=0):
+        r, c, z = self.info()
+        colptr = np.empty(c + 1, dtype=np.int64)
+        rowval = np.empty(z, dtype=np.int64)
+        val = np.empty(z, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.csc_graph_download(self.h, _ptr(colptr), _ptr(rowval), _ptr(val), int(index_base)))
+        return colptr, rowval, val
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        r, c, _ = self.info()
+        colptr, rowval, val = self.download(0)
+        return sp.csc_matrix((val, rowval, colptr), shape=(r, c))

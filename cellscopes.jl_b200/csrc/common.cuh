@@ -1,0 +1,184 @@
+// Internal definitions shared by the translation units of libcellscopes_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cellscopes_cuda.h"
+
+// ------------------------------------------------------------------------------------------
+// context and handles
+// ------------------------------------------------------------------------------------------
+struct csc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  cudaEvent_t ev_timer0 = nullptr, ev_timer1 = nullptr;
+  cudaEvent_t ev_stage0 = nullptr, ev_stage1 = nullptr;
+  double stage_ms[CSC_T_COUNT] = {0};
+  int64_t launches = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+};
+
+// device allocation with shared ownership (a normalised matrix shares colptr/rowval with the raw one)
+struct DevMem {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = 0;
+  bool owned = true;
+  ~DevMem() {
+    if (p && owned) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      if (cur != device) cudaSetDevice(device);
+      cudaFree(p);
+      if (cur != device) cudaSetDevice(cur);
+    }
+  }
+};
+typedef std::shared_ptr<DevMem> DevPtr;
+
+struct csc_sparse {
+  csc_ctx* ctx;
+  int64_t n_genes, n_cells, nnz;
+  DevPtr colptr;  // int64 [n_cells+1], 0-based
+  DevPtr rowval;  // int32 [nnz], 0-based
+  DevPtr val;     // float [nnz]
+  const int64_t* cp() const { return (const int64_t*)colptr->p; }
+  const int32_t* rv() const { return (const int32_t*)rowval->p; }
+  float* v() const { return (float*)val->p; }
+};
+
+struct csc_dense {
+  csc_ctx* ctx;
+  int64_t n_rows, n_cols;  // row-major, rows = cells
+  DevPtr mem;
+  float* p() const { return (float*)mem->p; }
+};
+
+struct csc_vec {
+  csc_ctx* ctx;
+  int64_t n;
+  int32_t dtype;
+  DevPtr mem;
+  template <typename T>
+  T* as() const { return (T*)mem->p; }
+};
+
+struct csc_pca {
+  csc_ctx* ctx;
+  int64_t n_feat;
+  int32_t k;
+  std::vector<double> principalvars, loadings, mean;  // loadings column-major H x k
+  double tvar;
+  DevPtr d_loadings_f32;  // [n_feat x kpad] row-major fp32 (kpad = k rounded up to 16)
+  DevPtr d_proj_mean;     // fp32 [kpad]: m' U
+  int32_t kpad;
+};
+
+struct csc_graph {
+  csc_ctx* ctx;
+  int64_t n_rows, n_cols, nnz;
+  int64_t col_lo;
+  DevPtr colptr;  // int64 [n_cols+1]
+  DevPtr rowval;  // int32 [nnz]
+  DevPtr val;     // float [nnz]
+};
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: no exception or abort ever crosses the C ABI
+// ------------------------------------------------------------------------------------------
+csc_status csc_fail(csc_ctx* ctx, csc_status code, const char* fmt, ...);
+
+#define CSC_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return csc_fail((ctx), e__ == cudaErrorMemoryAllocation ? CSC_ERR_OOM : CSC_ERR_CUDA,      \
+                      "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+  } while (0)
+
+#define CSC_TRY(expr)                 \
+  do {                                \
+    csc_status s__ = (expr);          \
+    if (s__ != CSC_OK) return s__;    \
+  } while (0)
+
+#define CSC_REQUIRE(ctx, cond, ...) \
+  do {                              \
+    if (!(cond)) return csc_fail((ctx), CSC_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+// after a kernel launch: count it and surface launch errors
+#define CSC_LAUNCHED(ctx)                     \
+  do {                                        \
+    (ctx)->launches++;                        \
+    CSC_CUDA((ctx), cudaGetLastError());      \
+  } while (0)
+
+csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero = false);
+
+// Wrap a C-ABI body so that C++ exceptions (std::bad_alloc from the host containers) become codes.
+#define CSC_GUARD_BEGIN try {
+#define CSC_GUARD_END(ctx)                                                    \
+  }                                                                           \
+  catch (const std::bad_alloc&) {                                             \
+    return csc_fail((ctx), CSC_ERR_OOM, "host allocation failed");            \
+  }                                                                           \
+  catch (const std::exception& ex) {                                          \
+    return csc_fail((ctx), CSC_ERR_INTERNAL, "exception: %s", ex.what());     \
+  }                                                                           \
+  catch (...) {                                                               \
+    return csc_fail((ctx), CSC_ERR_INTERNAL, "unknown exception");            \
+  }
+
+// stage timing: CUDA events on the launching stream, accumulated per stage slot
+struct StageTimer {
+  csc_ctx* ctx;
+  int slot;
+  StageTimer(csc_ctx* c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev_stage0, ctx->stream); }
+  ~StageTimer() {
+    cudaEventRecord(ctx->ev_stage1, ctx->stream);
+    if (cudaEventSynchronize(ctx->ev_stage1) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev_stage0, ctx->ev_stage1) == cudaSuccess) ctx->stage_ms[slot] += ms;
+    }
+  }
+};
+
+__host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// streaming (read-once) loads: keep them out of L1
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+#endif
+
+// stage launchers implemented in the other translation units ------------------------------------
+csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, int64_t n_cells_total,
+                           int64_t n_features, double span, double* mean, double* variance, double* var_exp,
+                           double* var_std, int64_t* order);

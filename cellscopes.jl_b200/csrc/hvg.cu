@@ -1,0 +1,210 @@
+// find_variable_genes (src/scrna/processing.jl:133-155), the part after the per-gene moments:
+// loess of log10(variance) on log10(mean), variance_expected, variance_standardized and the
+// stable descending rank.  G <= a few 10^4 points and ~33 local fits: host code, a few ms.
+// The local regression restates Loess.jl 0.6.3 (kd-tree vertices + cubic Hermite blending);
+// the operation order follows oracle/cellscopes_oracle.py::loess_fit so both agree to rounding.
+#include <cmath>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace {
+
+// Householder QR with column pivoting on a q x 3 system (Julia: qr(us, ColumnNorm()) \ vs)
+void pivoted_qr_solve3(std::vector<double>& a /* q x 3 column-major */, std::vector<double>& b, int64_t q,
+                       double coef[3]) {
+  const int ncol = 3;
+  int perm[3] = {0, 1, 2};
+  auto col = [&](int j) { return a.data() + (size_t)j * q; };
+  for (int k = 0; k < ncol; ++k) {
+    int p = k;
+    double best = -1.0;
+    for (int j = k; j < ncol; ++j) {
+      double s = 0.0;
+      const double* c = col(j);
+      for (int64_t i = k; i < q; ++i) s += c[i] * c[i];
+      if (s > best) {
+        best = s;
+        p = j;
+      }
+    }
+    if (p != k) {
+      double* ck = col(k);
+      double* cp = col(p);
+      for (int64_t i = 0; i < q; ++i) std::swap(ck[i], cp[i]);
+      std::swap(perm[k], perm[p]);
+    }
+    double* x = col(k);
+    double nrm2 = 0.0;
+    for (int64_t i = k; i < q; ++i) nrm2 += x[i] * x[i];
+    double alpha = std::sqrt(nrm2);
+    if (alpha == 0.0) continue;
+    if (x[k] > 0) alpha = -alpha;
+    // v = x - alpha e1 (stored in place of x below the diagonal after use)
+    std::vector<double> v((size_t)(q - k));
+    for (int64_t i = k; i < q; ++i) v[i - k] = x[i];
+    v[0] -= alpha;
+    double vnorm2 = 0.0;
+    for (double t : v) vnorm2 += t * t;
+    if (vnorm2 == 0.0) continue;
+    for (int j = k; j < ncol; ++j) {
+      double* c = col(j);
+      double s = 0.0;
+      for (int64_t i = k; i < q; ++i) s += v[i - k] * c[i];
+      s = 2.0 * s / vnorm2;
+      for (int64_t i = k; i < q; ++i) c[i] -= s * v[i - k];
+    }
+    double s = 0.0;
+    for (int64_t i = k; i < q; ++i) s += v[i - k] * b[i];
+    s = 2.0 * s / vnorm2;
+    for (int64_t i = k; i < q; ++i) b[i] -= s * v[i - k];
+  }
+  double cp[3] = {0, 0, 0};
+  for (int k = ncol - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int j = k + 1; j < ncol; ++j) s -= col(j)[k] * cp[j];
+    double d = col(k)[k];
+    cp[k] = d != 0.0 ? s / d : 0.0;
+  }
+  for (int k = 0; k < ncol; ++k) coef[perm[k]] = cp[k];
+}
+
+void kd_vertices(const std::vector<double>& xs_sorted, int64_t cutoff, std::vector<double>& verts) {
+  verts.clear();
+  verts.push_back(xs_sorted.front());
+  verts.push_back(xs_sorted.back());
+  std::vector<std::pair<int64_t, int64_t>> stack;
+  stack.emplace_back(0, (int64_t)xs_sorted.size());
+  while (!stack.empty()) {
+    auto [lo, hi] = stack.back();
+    stack.pop_back();
+    int64_t n = hi - lo;
+    if (n <= cutoff || xs_sorted[hi - 1] - xs_sorted[lo] <= 0.0) continue;
+    int64_t mid = n / 2;
+    double med = (n % 2 == 1) ? xs_sorted[lo + mid] : (xs_sorted[lo + mid - 1] + xs_sorted[lo + mid]) / 2;
+    verts.push_back(med);
+    stack.emplace_back(lo, lo + mid);
+    stack.emplace_back(lo + mid, hi);
+  }
+  std::sort(verts.begin(), verts.end());
+  verts.erase(std::unique(verts.begin(), verts.end()), verts.end());
+}
+
+}  // namespace
+
+// x, y: the points (genes with variance > 0).  out[i] = loess prediction at x[i].
+static void loess_fit_predict(const std::vector<double>& x, const std::vector<double>& y, double span,
+                              std::vector<double>& out) {
+  const int64_t n = (int64_t)x.size();
+  const double cell = 0.2;
+  const int64_t q = std::max<int64_t>(1, (int64_t)std::floor(span * (double)n));
+  const int64_t cutoff = (int64_t)std::ceil(cell * span * (double)n);
+  std::vector<double> xs(x);
+  std::stable_sort(xs.begin(), xs.end());
+  std::vector<double> verts;
+  kd_vertices(xs, cutoff, verts);
+  const size_t nv = verts.size();
+  std::vector<double> val(nv), slope(nv);
+  std::vector<int64_t> order((size_t)n);
+  std::vector<double> d((size_t)n), a((size_t)q * 3), b((size_t)q);
+  for (size_t vi = 0; vi < nv; ++vi) {
+    const double v = verts[vi];
+    for (int64_t i = 0; i < n; ++i) d[i] = std::fabs(x[i] - v);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    // the q nearest, ties by lower index (stable)
+    auto cmp = [&](int64_t i, int64_t j) { return d[i] < d[j] || (d[i] == d[j] && i < j); };
+    if (q < n) std::nth_element(order.begin(), order.begin() + q, order.end(), cmp);
+    std::sort(order.begin(), order.begin() + q, cmp);
+    double dmax = 0.0;
+    for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[order[i]]);
+    if (dmax == 0.0) dmax = 1.0;
+    for (int64_t i = 0; i < q; ++i) {
+      const int64_t p = order[i];
+      const double u = d[p] / dmax;
+      const double u3 = u * u * u;
+      const double t = 1.0 - u3;
+      const double w = std::sqrt(t * t * t);
+      const double xc = x[p] - v;
+      a[i] = w;
+      a[(size_t)q + i] = w * xc;
+      a[(size_t)2 * q + i] = w * xc * xc;
+      b[i] = y[p] * w;
+    }
+    double coef[3];
+    pivoted_qr_solve3(a, b, q, coef);
+    val[vi] = coef[0];
+    slope[vi] = coef[1];
+  }
+  out.resize((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    const double z = x[i];
+    size_t hi = (size_t)(std::lower_bound(verts.begin(), verts.end(), z) - verts.begin());
+    if (hi < 1) hi = 1;
+    if (hi > nv - 1) hi = nv - 1;
+    if (nv == 1) {
+      out[i] = val[0];
+      continue;
+    }
+    const size_t lo = hi - 1;
+    const double v1 = verts[lo], v2 = verts[hi];
+    if (z == v1) {
+      out[i] = val[lo];
+      continue;
+    }
+    if (z == v2) {
+      out[i] = val[hi];
+      continue;
+    }
+    const double h = v2 - v1;
+    const double t = (z - v1) / h;
+    const double omt = 1.0 - t;
+    const double h00 = (1 + 2 * t) * omt * omt;
+    const double h10 = t * omt * omt;
+    const double h01 = t * t * (3 - 2 * t);
+    const double h11 = t * t * (t - 1);
+    out[i] = h00 * val[lo] + h10 * h * slope[lo] + h01 * val[hi] + h11 * h * slope[hi];
+  }
+}
+
+csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, int64_t n_cells_total,
+                           int64_t n_features, double span, double* mean, double* variance, double* var_exp,
+                           double* var_std, int64_t* order) {
+  (void)n_features;  // the caller takes order[0:n_features]; clamping is :134-137
+  const double N = (double)n_cells_total;
+  std::vector<double> mu((size_t)n_genes), var((size_t)n_genes), ve((size_t)n_genes, 0.0), vs((size_t)n_genes, 0.0);
+  std::vector<double> lx, ly;
+  std::vector<int64_t> kept;
+  for (int64_t g = 0; g < n_genes; ++g) {
+    const double s1 = s1s2[g], s2 = s1s2[n_genes + g];
+    mu[g] = s1 / N;                            // exact-moment rule, SURVEY A.3-7
+    var[g] = (s2 - s1 * s1 / N) / (N - 1.0);
+    if (var[g] > 0.0) {  // filter(:variance => >(0.0)) processing.jl:143
+      kept.push_back(g);
+      lx.push_back(std::log10(mu[g]));
+      ly.push_back(std::log10(var[g]));
+    }
+  }
+  // The reference requires every gene to have variance > 0 (:143,:151 would mis-assign names otherwise);
+  // here such genes are kept out of the fit and rank last with variance_standardized = 0.
+  if (!kept.empty()) {
+    std::vector<double> pred;
+    loess_fit_predict(lx, ly, span, pred);
+    for (size_t i = 0; i < kept.size(); ++i) {
+      const int64_t g = kept[i];
+      ve[g] = std::pow(10.0, pred[i]);
+      vs[g] = var[g] / ve[g];
+    }
+  }
+  if (mean) std::copy(mu.begin(), mu.end(), mean);
+  if (variance) std::copy(var.begin(), var.end(), variance);
+  if (var_exp) std::copy(ve.begin(), ve.end(), var_exp);
+  if (var_std) std::copy(vs.begin(), vs.end(), var_std);
+  if (order) {
+    std::vector<int64_t> ord((size_t)n_genes);
+    std::iota(ord.begin(), ord.end(), (int64_t)0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t i, int64_t j) { return vs[i] > vs[j]; });
+    std::copy(ord.begin(), ord.end(), order);
+  }
+  (void)ctx;
+  return CSC_OK;
+}

@@ -1,0 +1,565 @@
+// Sparse stages: ingest (narrowing), normalize_object, raw gene moments, scale_object.
+// All kernels stream the cell-major CSC once, a warp per cell (column), coalesced along the
+// non-zeros of the column, with warp-shuffle reductions for the per-cell sums.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// ingest: Int64/Float64 host arrays -> int64 colptr (0-based) / int32 rowval / fp32 values
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_colptr_rebase(const T* __restrict__ in, int64_t* __restrict__ out, int64_t n, int64_t base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (int64_t)in[i] - base;
+}
+template <typename T>
+__global__ void k_narrow_idx(const T* __restrict__ in, int32_t* __restrict__ out, int64_t n, int64_t base,
+                             int64_t n_rows, int* __restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int64_t r = (int64_t)in[i] - base;
+    if (r < 0 || r >= n_rows) *bad = 1;
+    out[i] = (int32_t)r;
+  }
+}
+template <typename T>
+__global__ void k_narrow_val(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)in[i];
+}
+__global__ void k_widen_idx(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n, int64_t base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (int64_t)in[i] + base;
+}
+__global__ void k_widen_val(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (double)in[i];
+}
+
+static inline unsigned grid_for(int64_t n, int sm) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256), (int64_t)sm * 16));
+}
+
+static size_t dt_size(int32_t dt) { return (dt == CSC_DT_F32 || dt == CSC_DT_I32) ? 4 : 8; }
+
+// stage `n` host elements through a bounded device buffer and run `conv(dev_src, offset, count)` on each chunk
+template <typename F>
+static csc_status staged_upload(csc_ctx* ctx, const void* host, size_t elem, int64_t n, F conv) {
+  const int64_t chunk = (int64_t)64 << 20;  // elements per chunk
+  if (n == 0) return CSC_OK;
+  DevPtr stage[2];
+  int64_t cap = std::min(n, chunk);
+  CSC_TRY(dev_alloc(ctx, (size_t)cap * elem, &stage[0]));
+  if (n > chunk) CSC_TRY(dev_alloc(ctx, (size_t)cap * elem, &stage[1]));
+  int b = 0;
+  for (int64_t o = 0; o < n; o += chunk, b ^= 1) {
+    int64_t m = std::min(chunk, n - o);
+    // same stream: the copy into stage[b] is ordered after the kernel that last read it
+    CSC_CUDA(ctx, cudaMemcpyAsync(stage[b]->p, (const char*)host + (size_t)o * elem, (size_t)m * elem,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    CSC_TRY(conv(stage[b]->p, o, m));
+  }
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CSC_OK;
+}
+
+extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n_cells, const void* colptr,
+                                        const void* rowval, int32_t idx_dtype, const void* nzval, int32_t val_dtype,
+                                        int32_t index_base, csc_sparse** out) {
+  if (!ctx || !out) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, colptr != nullptr, "csc_sparse_upload: colptr is NULL");
+  CSC_REQUIRE(ctx, n_genes > 0 && n_cells >= 0, "csc_sparse_upload: bad shape %lld x %lld", (long long)n_genes,
+              (long long)n_cells);
+  CSC_REQUIRE(ctx, n_genes < ((int64_t)1 << 31), "csc_sparse_upload: n_genes must fit int32");
+  CSC_REQUIRE(ctx, idx_dtype == CSC_DT_I64 || idx_dtype == CSC_DT_I32, "csc_sparse_upload: idx_dtype must be I64 or I32");
+  CSC_REQUIRE(ctx, val_dtype >= CSC_DT_F32 && val_dtype <= CSC_DT_I64, "csc_sparse_upload: bad val_dtype");
+  CSC_REQUIRE(ctx, index_base == 0 || index_base == 1, "csc_sparse_upload: index_base must be 0 or 1");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_UPLOAD);
+  int64_t first, last;
+  if (idx_dtype == CSC_DT_I64) {
+    first = ((const int64_t*)colptr)[0];
+    last = ((const int64_t*)colptr)[n_cells];
+  } else {
+    first = ((const int32_t*)colptr)[0];
+    last = ((const int32_t*)colptr)[n_cells];
+  }
+  CSC_REQUIRE(ctx, first == index_base, "csc_sparse_upload: colptr[0]=%lld != index_base=%d", (long long)first, index_base);
+  int64_t nnz = last - first;
+  CSC_REQUIRE(ctx, nnz >= 0, "csc_sparse_upload: negative nnz");
+  CSC_REQUIRE(ctx, nnz == 0 || (rowval && nzval), "csc_sparse_upload: rowval/nzval NULL with nnz>0");
+  std::unique_ptr<csc_sparse> m(new csc_sparse());
+  m->ctx = ctx;
+  m->n_genes = n_genes;
+  m->n_cells = n_cells;
+  m->nnz = nnz;
+  CSC_TRY(dev_alloc(ctx, (size_t)(n_cells + 1) * 8, &m->colptr));
+  CSC_TRY(dev_alloc(ctx, (size_t)nnz * 4, &m->rowval));
+  CSC_TRY(dev_alloc(ctx, (size_t)nnz * 4, &m->val));
+  DevPtr bad;
+  CSC_TRY(dev_alloc(ctx, 4, &bad, true));
+  int sm = ctx->sm_count;
+  int64_t* d_cp = (int64_t*)m->colptr->p;
+  int32_t* d_rv = (int32_t*)m->rowval->p;
+  float* d_v = (float*)m->val->p;
+  int* d_bad = (int*)bad->p;
+  CSC_TRY(staged_upload(ctx, colptr, dt_size(idx_dtype), n_cells + 1, [&](void* src, int64_t o, int64_t cnt) {
+    if (idx_dtype == CSC_DT_I64)
+      k_colptr_rebase<int64_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)src, d_cp + o, cnt, index_base);
+    else
+      k_colptr_rebase<int32_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int32_t*)src, d_cp + o, cnt, index_base);
+    CSC_LAUNCHED(ctx);
+    return (csc_status)CSC_OK;
+  }));
+  CSC_TRY(staged_upload(ctx, rowval, dt_size(idx_dtype), nnz, [&](void* src, int64_t o, int64_t cnt) {
+    if (idx_dtype == CSC_DT_I64)
+      k_narrow_idx<int64_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)src, d_rv + o, cnt, index_base, n_genes, d_bad);
+    else
+      k_narrow_idx<int32_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int32_t*)src, d_rv + o, cnt, index_base, n_genes, d_bad);
+    CSC_LAUNCHED(ctx);
+    return (csc_status)CSC_OK;
+  }));
+  CSC_TRY(staged_upload(ctx, nzval, dt_size(val_dtype), nnz, [&](void* src, int64_t o, int64_t cnt) {
+    switch (val_dtype) {
+      case CSC_DT_F32: k_narrow_val<float><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const float*)src, d_v + o, cnt); break;
+      case CSC_DT_F64: k_narrow_val<double><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const double*)src, d_v + o, cnt); break;
+      case CSC_DT_I32: k_narrow_val<int32_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int32_t*)src, d_v + o, cnt); break;
+      default: k_narrow_val<int64_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)src, d_v + o, cnt); break;
+    }
+    CSC_LAUNCHED(ctx);
+    return (csc_status)CSC_OK;
+  }));
+  int h_bad = 0;
+  CSC_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CSC_REQUIRE(ctx, h_bad == 0, "csc_sparse_upload: a row index is outside [0, n_genes)");
+  *out = m.release();
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_sparse_info(const csc_sparse* m, int64_t* n_genes, int64_t* n_cells, int64_t* nnz) {
+  if (!m) return CSC_ERR_ARG;
+  if (n_genes) *n_genes = m->n_genes;
+  if (n_cells) *n_cells = m->n_cells;
+  if (nnz) *nnz = m->nnz;
+  return CSC_OK;
+}
+
+extern "C" csc_status csc_sparse_free(csc_sparse* m) {
+  delete m;
+  return CSC_OK;
+}
+
+static csc_status range_ptrs(const csc_sparse* m, int64_t lo, int64_t hi, int64_t* b, int64_t* e) {
+  csc_ctx* ctx = m->ctx;
+  CSC_REQUIRE(ctx, 0 <= lo && lo <= hi && hi <= m->n_cells, "cell range [%lld,%lld) outside [0,%lld)", (long long)lo,
+              (long long)hi, (long long)m->n_cells);
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  CSC_CUDA(ctx, cudaMemcpyAsync(b, m->cp() + lo, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaMemcpyAsync(e, m->cp() + hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CSC_OK;
+}
+
+extern "C" csc_status csc_sparse_range_nnz(const csc_sparse* m, int64_t cell_lo, int64_t cell_hi, int64_t* nnz) {
+  if (!m || !nnz) return CSC_ERR_ARG;
+  int64_t b, e;
+  CSC_TRY(range_ptrs(m, cell_lo, cell_hi, &b, &e));
+  *nnz = e - b;
+  return CSC_OK;
+}
+
+extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, int64_t cell_hi, int64_t* colptr_out,
+                                          int64_t* rowval_out, double* nzval_out, int32_t index_base) {
+  if (!m) return CSC_ERR_ARG;
+  csc_ctx* ctx = m->ctx;
+  CSC_GUARD_BEGIN
+  int64_t b, e;
+  CSC_TRY(range_ptrs(m, cell_lo, cell_hi, &b, &e));
+  int64_t nc = cell_hi - cell_lo, nnz = e - b;
+  int sm = ctx->sm_count;
+  if (colptr_out) {
+    DevPtr tmp;
+    CSC_TRY(dev_alloc(ctx, (size_t)(nc + 1) * 8, &tmp));
+    k_colptr_rebase<int64_t><<<grid_for(nc + 1, sm), 256, 0, ctx->stream>>>(m->cp() + cell_lo, (int64_t*)tmp->p, nc + 1,
+                                                                             b - index_base);
+    CSC_LAUNCHED(ctx);
+    CSC_CUDA(ctx, cudaMemcpyAsync(colptr_out, tmp->p, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  const int64_t chunk = (int64_t)32 << 20;
+  if ((rowval_out || nzval_out) && nnz > 0) {
+    DevPtr tmp;
+    CSC_TRY(dev_alloc(ctx, (size_t)std::min(nnz, chunk) * 8, &tmp));
+    for (int64_t o = 0; o < nnz && rowval_out; o += chunk) {
+      int64_t cnt = std::min(chunk, nnz - o);
+      k_widen_idx<<<grid_for(cnt, sm), 256, 0, ctx->stream>>>(m->rv() + b + o, (int64_t*)tmp->p, cnt, index_base);
+      CSC_LAUNCHED(ctx);
+      CSC_CUDA(ctx, cudaMemcpyAsync(rowval_out + o, tmp->p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int64_t o = 0; o < nnz && nzval_out; o += chunk) {
+      int64_t cnt = std::min(chunk, nnz - o);
+      k_widen_val<<<grid_for(cnt, sm), 256, 0, ctx->stream>>>(m->v() + b + o, (double*)tmp->p, cnt);
+      CSC_LAUNCHED(ctx);
+      CSC_CUDA(ctx, cudaMemcpyAsync(nzval_out + o, tmp->p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+// ------------------------------------------------------------------------------------------
+// K1/K2  normalize_object (processing.jl:15-31) fused with the raw per-gene moments that
+// find_variable_genes needs (processing.jl:138-139).
+//
+// A CTA owns a contiguous range of cells; a warp owns one cell at a time.  Pass 1 over the
+// column: fp64 column sum (warp-shuffle reduction).  Pass 2 (the column is still in L1/L2):
+// y = log((x * inv) * sf + pc), written with the same pattern.  Gene moments: sum x goes to a
+// CTA-private u32 table in shared memory (flushed once per CTA with fp64 atomics), the
+// excess sum(x^2 - x) of the rare entries with x >= 2 goes straight to the fp64 table in L2.
+// All partial sums are integers below 2^53, so the result is exact and order-independent.
+// HBM traffic: 4 B read + 4 B written per non-zero (+ 4 B row index when moments are fused).
+// ------------------------------------------------------------------------------------------
+template <bool WRITE_NORM, bool STATS, bool SMEM_TABLE>
+__global__ void __launch_bounds__(512)
+k_normalize(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ raw,
+            float* __restrict__ out, int64_t n_cells, int32_t n_genes, double sf, double pc, int method,
+            int nan_to_zero, double* __restrict__ gstats, int64_t cells_per_cta) {
+  extern __shared__ unsigned int s1tab[];
+  if (STATS && SMEM_TABLE) {
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) s1tab[g] = 0u;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * cells_per_cta;
+  const int64_t c1 = min(c0 + cells_per_cta, n_cells);
+  const bool pc_is_one = (pc == 1.0);
+  const float pcf = (float)pc;
+  for (int64_t c = c0 + warp; c < c1; c += nwarp) {
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    double inv = 0.0;
+    if (WRITE_NORM) {
+      double s = 0.0;
+#pragma unroll 4
+      for (int64_t i = b + lane; i < e; i += 32) s += (double)raw[i];
+      s = warp_sum(s);
+      inv = 1.0 / s;  // 1/0 = Inf: the reference's NaN column (processing.jl:18)
+    }
+#pragma unroll 4
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const float x = raw[i];
+      if (WRITE_NORM) {
+        const double t = ((double)x * inv) * sf;  // association order of processing.jl:24
+        float y;
+        if (method == CSC_NORM_LOGARITHM) {
+          const float tf = (float)t;
+          y = pc_is_one ? log1pf(tf) : logf(tf + pcf);
+        } else {
+          y = (float)t;
+        }
+        if (nan_to_zero && y != y) y = 0.f;
+        __stcs(out + i, y);
+      }
+      if (STATS) {
+        const int g = __ldcs(rowval + i);
+        const float xr = rintf(x);
+        if (SMEM_TABLE && xr == x && x >= 0.f && x <= 65535.f) {
+          atomicAdd(&s1tab[g], (unsigned int)x);
+          if (x >= 2.f) {
+            const double xd = (double)x;
+            atomicAdd(&gstats[(int64_t)n_genes + g], xd * xd - xd);
+          }
+        } else {
+          const double xd = (double)x;
+          atomicAdd(&gstats[g], xd);
+          atomicAdd(&gstats[(int64_t)n_genes + g], xd * xd);
+        }
+      }
+    }
+  }
+  if (STATS && SMEM_TABLE) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
+      const unsigned int v = s1tab[g];
+      if (v) {
+        atomicAdd(&gstats[g], (double)v);
+        atomicAdd(&gstats[(int64_t)n_genes + g], (double)v);  // sum x^2 = sum x + sum (x^2 - x)
+      }
+    }
+  }
+}
+
+template <bool WRITE_NORM, bool STATS>
+static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* out, double sf, double pc, int method,
+                                   int nan_to_zero, double* gstats) {
+  if (raw->n_cells == 0) return CSC_OK;
+  const int threads = 512;
+  size_t smem = STATS ? (size_t)raw->n_genes * 4 : 0;
+  const bool smem_table = STATS && smem <= (size_t)200 * 1024;
+  if (!smem_table) smem = 0;
+  int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)220 * 1024) / (smem + 1024))) : 4;
+  int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
+  // a CTA's u32 table must not overflow: <= 65535 per entry * 65536 cells
+  int64_t cells_per_cta = std::max<int64_t>(16, ceil_div64(raw->n_cells, grid));
+  cells_per_cta = std::min<int64_t>(cells_per_cta, 65536);
+  grid = ceil_div64(raw->n_cells, cells_per_cta);
+  auto launch = [&](auto kern) -> csc_status {
+    if (smem > 48 * 1024)
+      CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(raw->cp(), raw->rv(), raw->v(), out, raw->n_cells,
+                                                         (int32_t)raw->n_genes, sf, pc, method, nan_to_zero, gstats,
+                                                         cells_per_cta);
+    CSC_LAUNCHED(ctx);
+    return CSC_OK;
+  };
+  if (smem_table) return launch(k_normalize<WRITE_NORM, STATS, true>);
+  return launch(k_normalize<WRITE_NORM, STATS, false>);
+}
+
+extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
+                                    double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out) {
+  if (!ctx || !raw || !out) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  // processing.jl:28: throw(ArgumentError("Unknown normalization method"))
+  CSC_REQUIRE(ctx, norm_method == CSC_NORM_LOGARITHM || norm_method == CSC_NORM_NONE,
+              "Unknown normalization method: %d", norm_method);
+  CSC_REQUIRE(ctx, !gene_stats || (gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * raw->n_genes),
+              "csc_normalize: gene_stats must be fp64[2*n_genes]");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_NORMALIZE);
+  std::unique_ptr<csc_sparse> m(new csc_sparse());
+  m->ctx = ctx;
+  m->n_genes = raw->n_genes;
+  m->n_cells = raw->n_cells;
+  m->nnz = raw->nnz;
+  m->colptr = raw->colptr;  // shared pattern: the output keeps the stored structure (processing.jl:24)
+  m->rowval = raw->rowval;
+  CSC_TRY(dev_alloc(ctx, (size_t)raw->nnz * 4, &m->val));
+  if (gene_stats)
+    CSC_TRY((launch_normalize<true, true>(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
+                                          gene_stats->as<double>())));
+  else
+    CSC_TRY((launch_normalize<true, false>(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
+                                           nullptr)));
+  *out = m.release();
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw, csc_vec* gene_stats) {
+  if (!ctx || !raw || !gene_stats) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * raw->n_genes,
+              "csc_gene_stats_partial: gene_stats must be fp64[2*n_genes]");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_GENE_STATS);
+  CSC_TRY((launch_normalize<false, true>(ctx, raw, nullptr, 1.0, 1.0, 0, 0, gene_stats->as<double>())));
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
+                                     int64_t n_features, double span, double* mean, double* variance,
+                                     double* variance_expected, double* variance_standardized, int64_t* order) {
+  if (!ctx || !gene_stats) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * n_genes && n_genes > 0,
+              "csc_hvg_finish: gene_stats must be fp64[2*n_genes]");
+  CSC_REQUIRE(ctx, n_cells_total >= 2, "csc_hvg_finish: need at least 2 cells");
+  CSC_REQUIRE(ctx, span > 0.0 && span <= 1.0, "span must be in the range (0, 1].");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_HVG);
+  std::vector<double> h((size_t)2 * n_genes);
+  CSC_CUDA(ctx, cudaMemcpyAsync(h.data(), gene_stats->mem->p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return launch_hvg_host(ctx, h.data(), n_genes, n_cells_total, n_features, span, mean, variance, variance_expected,
+                         variance_standardized, order);
+  CSC_GUARD_END(ctx)
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  scale_object (processing.jl:65-93)
+// ------------------------------------------------------------------------------------------
+// per-gene sum y / sum y^2 of the normalised values of the selected rows
+__global__ void __launch_bounds__(256)
+k_scale_stats(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+              const int32_t* __restrict__ gene2h, int64_t n_cells, int32_t n_feat, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    const int64_t b = colptr[c], e = colptr[c + 1];
+#pragma unroll 4
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const int h = __ldg(gene2h + __ldcs(rowval + i));
+      if (h >= 0) {
+        const double y = (double)__ldcs(val + i);
+        atomicAdd(&part[h], y);
+        atomicAdd(&part[n_feat + h], y * y);
+      }
+    }
+  }
+}
+
+// mean / 1/sd / fill value per selected gene from the (already all-reduced) sums
+__global__ void k_scale_params(const double* __restrict__ part, int32_t n_feat, double n_cells_total, float scale_max,
+                               int do_scale, int do_center, float* __restrict__ mu, float* __restrict__ inv_sd,
+                               float* __restrict__ z0) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_feat) return;
+  const double s1 = part[h], s2 = part[n_feat + h];
+  const double mean = s1 / n_cells_total;
+  const double var = (s2 - s1 * s1 / n_cells_total) / (n_cells_total - 1.0);
+  const double sd = sqrt(var);  // sd == 0 -> division by zero below, NaN/Inf like the reference
+  const float m = do_center ? (float)mean : 0.f;
+  const float is = do_scale ? (float)(1.0 / sd) : 1.f;
+  float z = (0.f - m) * is;
+  z = (z != z) ? z : fminf(z, scale_max);
+  mu[h] = m;
+  inv_sd[h] = is;
+  z0[h] = z;
+}
+
+// a warp builds one cell's dense row in shared memory (fill value, then scatter of the non-zeros)
+// and writes it out with coalesced 16-byte stores: 4*H bytes written per cell, each once.
+__global__ void __launch_bounds__(256)
+k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+             const int32_t* __restrict__ gene2h, const float* __restrict__ mu, const float* __restrict__ inv_sd,
+             const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, float scale_max, float* __restrict__ out) {
+  extern __shared__ float srow[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float* row = srow + (size_t)wib * n_feat;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    for (int h = lane; h < n_feat; h += 32) row[h] = __ldg(z0 + h);
+    __syncwarp();
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const int h = __ldg(gene2h + __ldcs(rowval + i));
+      if (h >= 0) {
+        float z = (__ldcs(val + i) - __ldg(mu + h)) * __ldg(inv_sd + h);
+        z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
+        row[h] = z;
+      }
+    }
+    __syncwarp();
+    float* dst = out + c * (int64_t)n_feat;
+    if ((n_feat & 3) == 0) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int h = lane; h < (n_feat >> 2); h += 32) __stcs(d4 + h, r4[h]);
+    } else {
+      for (int h = lane; h < n_feat; h += 32) __stcs(dst + h, row[h]);
+    }
+    __syncwarp();
+  }
+}
+
+// features (any order, 0-based) -> gene2h lookup in ORIGINAL gene order (utils.jl:72-76)
+static csc_status build_gene2h(csc_ctx* ctx, int64_t n_genes, const int64_t* features, int64_t n_feat, DevPtr* d_map,
+                               int64_t* n_rows_out) {
+  std::vector<int32_t> map((size_t)n_genes, -1);
+  int64_t H = 0;
+  if (!features) {
+    for (int64_t g = 0; g < n_genes; ++g) map[g] = (int32_t)g;
+    H = n_genes;
+  } else {
+    std::vector<char> mask((size_t)n_genes, 0);
+    for (int64_t i = 0; i < n_feat; ++i) {
+      CSC_REQUIRE(ctx, features[i] >= 0 && features[i] < n_genes, "feature id %lld outside [0,%lld)",
+                  (long long)features[i], (long long)n_genes);
+      mask[features[i]] = 1;
+    }
+    for (int64_t g = 0; g < n_genes; ++g)
+      if (mask[g]) map[g] = (int32_t)H++;
+  }
+  CSC_REQUIRE(ctx, H > 0, "no features selected");
+  CSC_TRY(dev_alloc(ctx, (size_t)n_genes * 4, d_map));
+  CSC_CUDA(ctx, cudaMemcpyAsync((*d_map)->p, map.data(), (size_t)n_genes * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_rows_out = H;
+  return CSC_OK;
+}
+
+extern "C" csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features,
+                                              int64_t n_feat, csc_vec* partial) {
+  if (!ctx || !norm || !partial) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_SCALE_STATS);
+  DevPtr map;
+  int64_t H = 0;
+  CSC_TRY(build_gene2h(ctx, norm->n_genes, features, n_feat, &map, &H));
+  CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_partial: partial must be fp64[2*H], H=%lld",
+              (long long)H);
+  if (norm->n_cells > 0) {
+    k_scale_stats<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p,
+                                                               norm->n_cells, (int32_t)H, partial->as<double>());
+    CSC_LAUNCHED(ctx);
+  }
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                                     const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
+                                     int32_t do_center, csc_dense** out) {
+  if (!ctx || !norm || !partial || !out) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_SCALE_FILL);
+  DevPtr map;
+  int64_t H = 0;
+  CSC_TRY(build_gene2h(ctx, norm->n_genes, features, n_feat, &map, &H));
+  CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_fill: partial must be fp64[2*H]");
+  CSC_REQUIRE(ctx, n_cells_total >= 2, "csc_scale_fill: need at least 2 cells");
+  CSC_REQUIRE(ctx, H <= 56000, "csc_scale_fill: more than 56000 selected genes is not supported");
+  DevPtr params;
+  CSC_TRY(dev_alloc(ctx, (size_t)H * 4 * 3, &params));
+  float* mu = (float*)params->p;
+  float* inv_sd = mu + H;
+  float* z0 = inv_sd + H;
+  k_scale_params<<<(unsigned)ceil_div64(H, 256), 256, 0, ctx->stream>>>(partial->as<double>(), (int32_t)H,
+                                                                        (double)n_cells_total, (float)scale_max, do_scale,
+                                                                        do_center, mu, inv_sd, z0);
+  CSC_LAUNCHED(ctx);
+  csc_dense* d = nullptr;
+  CSC_TRY(csc_dense_alloc(ctx, norm->n_cells, H, &d));
+  if (norm->n_cells > 0) {
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * H * 4 > (size_t)200 * 1024) warps >>= 1;
+    size_t smem = (size_t)warps * H * 4;
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_scale_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
+      int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells, warps));
+      k_scale_fill<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(),
+                                                                      (const int32_t*)map->p, mu, inv_sd, z0, norm->n_cells,
+                                                                      (int32_t)H, (float)scale_max, d->p());
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      csc_dense_free(d);
+      return csc_fail(ctx, CSC_ERR_CUDA, "csc_scale_fill: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = d;
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}

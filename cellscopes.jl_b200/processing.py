@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's operator interface for the hot path
+(src/scrna/processing.jl): same function names, keyword names, defaults, mutation-and-return
+behaviour and error cases, with the arithmetic done by libcellscopes_cuda.so through the C ABI.
+
+    obj = scRNAObject(RawCountObject(counts, cells, genes))
+    obj = normalize_object(obj)                       # processing.jl:40
+    obj = find_variable_genes(obj)                    # processing.jl:157
+    obj = scale_object(obj, features=obj.varGene.var_gene)   # processing.jl:88
+    obj = run_pca(obj, maxoutdim=50)                  # processing.jl:164
+    obj = run_clustering(obj, n_neighbors=20)         # processing.jl:309 (graph part; Leiden is out of scope)
+
+A session (one ``Context`` = one GPU + the uploaded raw counts and the intermediate device
+handles) is attached to the object on first use, so consecutive stages reuse device-resident data.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+from . import _capi
+from .objects import (ClusteringObject, LazyDeviceMatrix, NormCountObject, PCAObject, RawCountObject,
+                      ReductionObject, ScaleCountObject, VariableGeneObject, scRNAObject)
+from .pipeline import metric_code, norm_code
+
+_default_ctx = None
+
+
+def default_context(device: int = 0) -> _capi.Context:
+    global _default_ctx
+    if _default_ctx is None or _default_ctx.h is None or _default_ctx.device != device:
+        _default_ctx = _capi.Context(device)
+    return _default_ctx
+
+
+class _Session:
+    """Device-resident state of one object."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.raw = None          # Sparse
+        self.raw_key = None
+        self.gene_stats = None   # Vec fp64[2G]
+        self.norm = None         # Sparse
+        self.scaled = None       # Dense
+        self.scaled_rows = None  # gene ids (original order) of the scaled matrix
+        self.pca = None
+        self.emb = None
+        self.knn = None
+
+
+def _session(sc_obj, ctx=None) -> _Session:
+    s = getattr(sc_obj, "_session", None)
+    if s is None or (ctx is not None and s.ctx is not ctx):
+        s = _Session(ctx or default_context())
+        sc_obj._session = s
+    return s
+
+
+def _ensure_raw(sc_obj, s: _Session):
+    m = sc_obj.rawCount._mtx
+    key = id(m)
+    if s.raw is None or s.raw_key != key:
+        if isinstance(m, LazyDeviceMatrix):
+            s.raw = m.handle
+        else:
+            if not sp.issparse(m):
+                m = sp.csc_matrix(np.asarray(m))      # dense input is legal (atac_processing.jl:87-89)
+            s.raw = s.ctx.sparse_from_scipy(m)
+        s.raw_key = key
+        s.gene_stats = None
+    return s.raw
+
+
+# ---------------------------------------------------------------------------------------------
+# normalize_object  (processing.jl:15-48)
+# ---------------------------------------------------------------------------------------------
+def normalize_object(x, scale_factor=10000, norm_method="logarithm", pseudocount=1, ctx=None):
+    code = norm_code(norm_method)
+    if isinstance(x, scRNAObject):
+        s = _session(x, ctx)
+        raw = _ensure_raw(x, s)
+        g = raw.shape[0]
+        s.gene_stats = s.ctx.vec(2 * g, np.float64)
+        # processing.jl:44-46: imaging objects replace NaN by 0
+        s.norm = s.ctx.normalize(raw, scale_factor, code, pseudocount, bool(getattr(x, "imaging", False)), s.gene_stats)
+        pattern = x.rawCount._mtx if sp.issparse(x.rawCount._mtx) else None
+        lazy = LazyDeviceMatrix(s.norm, "sparse", raw.shape, pattern)
+        x.normCount = NormCountObject(lazy, x.rawCount.cell_name, x.rawCount.gene_name, scale_factor, norm_method,
+                                      pseudocount)
+        return x
+    if isinstance(x, RawCountObject):
+        mtx = normalize_object(x.count_mtx, scale_factor, norm_method, pseudocount, ctx)
+        return NormCountObject(mtx, x.cell_name, x.gene_name, scale_factor, norm_method, pseudocount)
+    # matrix method (processing.jl:15-31): returns a matrix with the same stored pattern
+    c = ctx or default_context()
+    m = sp.csc_matrix(x) if not sp.issparse(x) else x.tocsc()
+    m.sort_indices()
+    raw = c.sparse_from_scipy(m)
+    norm = c.normalize(raw, scale_factor, code, pseudocount, False, None)
+    val = norm.download(values_only=True)
+    return sp.csc_matrix((val, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# find_variable_genes  (processing.jl:133-162)
+# ---------------------------------------------------------------------------------------------
+def _vst_frame(res, gene_name):
+    order = res["order"]
+    df = pd.DataFrame({
+        "mean": res["mean"][order], "variance": res["variance"][order],
+        "variance_expected": res["variance_expected"][order],
+        "variance_standardized": res["variance_standardized"][order],
+        "gene": [gene_name[i] for i in order],
+    })
+    return df
+
+
+def find_variable_genes(x, nFeatures: int = 2000, span: float = 0.3, ctx=None):
+    if isinstance(x, scRNAObject):
+        s = _session(x, ctx)
+        raw = _ensure_raw(x, s)
+        g, n = raw.shape
+        if s.gene_stats is None:
+            s.gene_stats = s.ctx.vec(2 * g, np.float64)
+            s.ctx.gene_stats_partial(raw, s.gene_stats)
+        res = s.ctx.hvg_finish(s.gene_stats, g, n, nFeatures, span)
+        genes = x.rawCount.gene_name
+        vst = _vst_frame(res, genes)
+        feats = [genes[i] for i in res["features"]]
+        x.varGene = VariableGeneObject(feats, vst)
+        x.varGene.feature_idx = res["features"]
+        return x
+    if isinstance(x, RawCountObject):
+        c = ctx or default_context()
+        m = x.count_mtx
+        raw = c.sparse_from_scipy(m if sp.issparse(m) else sp.csc_matrix(np.asarray(m)))
+        g, n = raw.shape
+        st = c.vec(2 * g, np.float64)
+        c.gene_stats_partial(raw, st)
+        res = c.hvg_finish(st, g, n, nFeatures, span)
+        return _vst_frame(res, x.gene_name), [x.gene_name[i] for i in res["features"]]
+    raise TypeError("find_variable_genes expects an scRNAObject or a RawCountObject")
+
+
+# ---------------------------------------------------------------------------------------------
+# scale_object  (processing.jl:65-93)
+# ---------------------------------------------------------------------------------------------
+def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, do_center):
+    g = norm_dev.shape[0]
+    rows = np.arange(g, dtype=np.int64) if feature_idx is None else np.unique(np.asarray(feature_idx, dtype=np.int64))
+    part = c.vec(2 * rows.size, np.float64)
+    c.scale_stats_partial(norm_dev, feature_idx, part)
+    dense = c.scale_fill(norm_dev, feature_idx, part, n_cells_total, scale_max, do_scale, do_center)
+    return dense, rows
+
+
+def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_center: bool = True, ctx=None, **kwargs):
+    if isinstance(x, scRNAObject):
+        if x.normCount is None:
+            raise ValueError("scale_object: normCount is missing; run normalize_object first")
+        s = _session(x, ctx)
+        if s.norm is None:
+            s.norm = s.ctx.sparse_from_scipy(x.normCount.count_mtx)
+        genes = x.normCount.gene_name
+        fidx = None
+        if features is not None:
+            pos = {g: i for i, g in enumerate(genes)}
+            fidx = np.array([pos[f] for f in features if f in pos], dtype=np.int64)
+        # processing.jl:78-83 forwards only kwargs... to the matrix method, so the effective values are
+        # always the defaults (10.0, true, true) while the user's values are recorded in the object.
+        eff_max = kwargs.get("scale_max", 10.0)
+        eff_scale = kwargs.get("do_scale", True)
+        eff_center = kwargs.get("do_center", True)
+        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center)
+        s.scaled, s.scaled_rows = dense, rows
+        lazy = LazyDeviceMatrix(dense, "dense_t", (rows.size, s.norm.shape[1]))
+        x.scaleCount = ScaleCountObject(lazy, x.normCount.cell_name, [genes[i] for i in rows], do_scale, do_center,
+                                        scale_max)
+        return x
+    # matrix method (processing.jl:65-76): genes x cells in, same shape out (dense)
+    c = ctx or default_context()
+    m = x.count_mtx if isinstance(x, NormCountObject) else x
+    m = sp.csc_matrix(m) if not sp.issparse(m) else m.tocsc()
+    dev = c.sparse_from_scipy(m)
+    dense, _ = _scale_device(c, dev, None, m.shape[1], scale_max, do_scale, do_center)
+    out = dense.download(np.float64).T
+    if isinstance(x, NormCountObject):
+        return ScaleCountObject(out, x.cell_name, x.gene_name, do_scale, do_center, scale_max)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# run_pca  (processing.jl:164-193)
+# ---------------------------------------------------------------------------------------------
+def _pca_device(c, dense, n_cells_total, maxoutdim, tol=1e-9, max_iter=500):
+    h = dense.shape[1]
+    colsum = c.vec(h, np.float64)
+    gram = c.vec(h * h, np.float64)
+    c.pca_partial(dense, colsum, gram)
+    model = c.pca_solve(colsum, gram, h, n_cells_total, maxoutdim, tol, max_iter)
+    emb = c.pca_transform(dense, model)
+    return model, emb
+
+
+def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=None):
+    if method not in ("svd", "auto", "cov"):
+        raise ValueError(f"unsupported PCA method {method!r}")
+    if sc_obj.scaleCount is None or sc_obj.varGene is None:
+        raise ValueError("run_pca: scaleCount / varGene missing; run scale_object and find_variable_genes first")
+    s = _session(sc_obj, ctx)
+    features = sc_obj.varGene.var_gene
+    sgenes = sc_obj.scaleCount.gene_name
+    if len(sgenes) == len(sc_obj.rawCount.gene_name) and len(features) != len(sgenes):
+        # processing.jl:166-167: scaleCount still holds all genes -> subset to the variable genes.
+        # Re-scaling the subset from normCount gives the same rows (scaling is per gene).
+        if s.norm is None:
+            s.norm = s.ctx.sparse_from_scipy(sc_obj.normCount.count_mtx)
+        pos = {g: i for i, g in enumerate(sc_obj.normCount.gene_name)}
+        fidx = np.array([pos[f] for f in features], dtype=np.int64)
+        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True)
+    elif s.scaled is not None:
+        dense = s.scaled
+    else:
+        dense = s.ctx.dense_upload(np.ascontiguousarray(np.asarray(sc_obj.scaleCount.count_mtx).T))
+    n = dense.shape[0]
+    model, emb = _pca_device(s.ctx, dense, n, maxoutdim)
+    s.pca, s.emb = model, emb
+    info = model.info()
+    proj = emb.download(np.float64)                     # N x k Float64 (utils.jl:108-117, int_objects.jl:153)
+    # default "MLJ" branch stores no model and no explained variance (processing.jl:180-181); the other branch
+    # stores percent_var (:186).  Its loadings-as-embedding quirk (:185) is NOT replicated.
+    percent_var = None if package == "MLJ" else info["principalvars"] / info["tvar"] * 100
+    pca_obj = PCAObject(proj, None, percent_var, "PC", method, pratio, maxoutdim)
+    pca_obj.device = emb
+    pca_obj.principalvars = info["principalvars"]
+    pca_obj.tvar = info["tvar"]
+    pca_obj.loadings = info["loadings"]
+    pca_obj.solver = {"iters": model.iters, "resid": model.resid}
+    sc_obj.dimReduction = ReductionObject(pca_obj, None, None)
+    return sc_obj
+
+
+# ---------------------------------------------------------------------------------------------
+# run_clustering  (processing.jl:195-318): kNN + adjacency.  Leiden (:233-234, :279-280) is out of scope.
+# ---------------------------------------------------------------------------------------------
+def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1234, graph=None, snn_prune=0.0,
+                   partition_fn=None, ctx=None):
+    """Builds the graph the reference hands to Leiden.
+
+    n < 10000 cells -> the "small" binary union adjacency (:268-278); otherwise the "atlas" COO-summed
+    adjacency where mutual pairs carry 2 (:218-232).  ``graph="snn"`` gives the Jaccard-weighted SNN graph.
+    The kNN is exact (the reference's NN-descent is approximate and unseeded).  ``partition_fn(adj, res,
+    seed)`` may supply a community-detection step; without it ``clustData.clustering`` stays None.
+    """
+    if sc_obj.dimReduction is None or sc_obj.dimReduction.pca is None:
+        raise ValueError("run_clustering: run_pca first")
+    s = _session(sc_obj, ctx)
+    pca = sc_obj.dimReduction.pca
+    emb = pca.device if pca.device is not None else s.ctx.dense_upload(np.asarray(pca.cell_embedding))
+    n = emb.shape[0]
+    if n != sc_obj.rawCount.shape[1]:
+        raise ValueError("embedding and count matrix disagree on the number of cells")
+    idx, dist = s.ctx.knn(emb, emb, n_neighbors, 0, 0, emb.shape[1], metric_code(metric))
+    if graph is None:
+        graph = "binary" if n < 10000 else "sum"       # processing.jl:310-317
+    mode = {"binary": _capi.GRAPH_BINARY, "sum": _capi.GRAPH_SUM, "snn": _capi.GRAPH_SNN_JACCARD}[graph]
+    gdev = s.ctx.graph_build(idx, n, n_neighbors, 0, n, mode, snn_prune)
+    adj = gdev.to_scipy()
+    if graph != "snn":
+        adj = adj.astype(np.int64)
+    s.knn = (idx, dist)
+    clustering = None
+    result = None
+    if partition_fn is not None:
+        result = partition_fn(adj, res, seed_use)
+        labels = np.empty(n, dtype=object)
+        for i, members in enumerate(result["partition"]):
+            labels[np.asarray(members)] = str(i + 1)
+        clustering = pd.DataFrame({"cluster": labels, "cell_id": sc_obj.rawCount.cell_name})
+        sc_obj.metaData["cluster"] = labels
+    cl = ClusteringObject(clustering, str(metric), adj, result, res)
+    cl.knn_indices = idx.download().reshape(n, n_neighbors).T + 1        # k x n, 1-based
+    cl.knn_distances = dist.download().reshape(n, n_neighbors).T.astype(np.float64)
+    cl.device_graph = gdev
+    sc_obj.clustData = cl
+    return sc_obj

@@ -1,0 +1,183 @@
+"""Synthetic sparse count matrices for tests and benchmarks.
+
+There is no network and the reference ships no data, so every workload is
+synthetic.  The model is a module-structured Poisson model,
+
+    log lambda_gc = a_g + l_c + s_g * h_{c, m(g)} - s_g^2 / 2
+    x_gc ~ Poisson(lambda_gc)
+
+with a_g a per-gene base level (log-normal expression spectrum), l_c a per-cell
+library-size factor, m(g) the gene module of gene g (or none), s_g a signed
+loading and h_{c,m} the cell's score for module m: a cell-type mean plus
+cell-level noise.  Module strengths decay geometrically, which plants a
+spectrum of well-separated principal components; the cell types give the kNN
+graph real structure.
+
+Everything that depends on one gene or one (type, module) pair is drawn on the
+host with NumPy (``make_params``) and is tiny.  Everything that depends on a
+cell is derived from a counter-based hash of (seed, cell[, gene|module]) so any
+cell range can be generated anywhere: on the device by the library's generator
+(``csc_generate_counts``), or on the CPU by ``sample_counts`` below, which is
+the same formula in NumPy.  The two are statistically identical but not
+bit-identical (libm vs CUDA exp/log differ in the last bit), so parity tests
+always move the same matrix between the two sides instead of regenerating it.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+@dataclasses.dataclass
+class SynthParams:
+    n_genes: int
+    n_cells_total: int
+    density: float
+    seed: int
+    n_modules: int
+    n_types: int
+    a: np.ndarray          # [G] float32 base log-rate
+    module: np.ndarray     # [G] int32 module id or -1
+    loading: np.ndarray    # [G] float32 signed loading s_g
+    type_mean: np.ndarray  # [T, M] float32 cell-type module means
+    lib_sd: float = 0.4
+    type_w: float = 0.75
+    noise_w: float = 0.65
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _hash3(seed, a, b) -> np.ndarray:
+    """64-bit hash of (seed, a, b); identical to ``synth_hash3`` in csrc/synth.cuh."""
+    with np.errstate(over="ignore"):
+        h = _splitmix64(np.uint64(seed) ^ np.uint64(0xD1B54A32D192ED03))
+        h = _splitmix64(h ^ np.asarray(a, dtype=np.uint64))
+        h = _splitmix64(h ^ (np.asarray(b, dtype=np.uint64) * np.uint64(0x2545F4914F6CDD1D) & _M64))
+    return h
+
+
+def _u01(h: np.ndarray) -> np.ndarray:
+    return ((h >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def _gauss(h: np.ndarray) -> np.ndarray:
+    """Box-Muller from one 64-bit hash (two 32-bit halves)."""
+    u1 = ((h >> np.uint64(32)).astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+    u2 = ((h & np.uint64(0xFFFFFFFF)).astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * math.pi * u2)
+
+
+def make_params(n_genes, n_cells_total, density=0.05, seed=1234, n_modules=64, n_types=40,
+                module_frac=None, min_gene_total=40.0) -> SynthParams:
+    """Draw the per-gene and per-type parameters and tune the base level so that the
+    mean P(x > 0) matches ``density``."""
+    rng = np.random.default_rng(seed)
+    g = int(n_genes)
+    a0 = rng.normal(0.0, 1.6, size=g)
+    if module_frac is None:
+        module_frac = 0.6 if g <= 8000 else 0.16
+    n_mod_genes = int(min(module_frac * g, 80 * n_modules))
+    n_mod_genes = max(n_mod_genes, min(g, 4 * n_modules))
+    mod_genes = rng.choice(g, size=n_mod_genes, replace=False)
+    module = np.full(g, -1, dtype=np.int32)
+    module[mod_genes] = rng.integers(0, n_modules, size=n_mod_genes).astype(np.int32)
+    strength = 1.3 * 0.98 ** np.arange(n_modules)
+    sign = rng.choice([-1.0, 1.0], size=g)
+    wmag = rng.uniform(0.7, 1.3, size=g)
+    loading = np.where(module >= 0, strength[np.maximum(module, 0)] * wmag * sign, 0.0)
+    a0 = a0 + np.where(module >= 0, 1.5, 0.0)           # module genes are well expressed
+    type_mean = rng.normal(0.0, 1.0, size=(n_types, n_modules))
+    # tune the offset mu so that mean_g P(x>0) == density, using the lognormal mixing
+    # of l_c and the module term approximated by its variance
+    floor = math.log(min_gene_total / max(n_cells_total, 1))
+    sd_cell = np.sqrt(0.4 ** 2 + loading ** 2 * (0.75 ** 2 + 0.65 ** 2))
+    zs = np.linspace(-4, 4, 81)
+    wz = np.exp(-0.5 * zs * zs)
+    wz /= wz.sum()
+
+    def mean_density(mu):
+        a = np.maximum(a0 + mu, floor)
+        lam = np.exp(a[:, None] - 0.5 * loading[:, None] ** 2 + sd_cell[:, None] * zs[None, :])
+        return float(((1.0 - np.exp(-lam)) * wz[None, :]).sum(axis=1).mean())
+
+    lo, hi = -20.0, 10.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if mean_density(mid) < density:
+            lo = mid
+        else:
+            hi = mid
+    mu = 0.5 * (lo + hi)
+    a = np.maximum(a0 + mu, floor)
+    return SynthParams(n_genes=g, n_cells_total=int(n_cells_total), density=float(density),
+                       seed=int(seed), n_modules=int(n_modules), n_types=int(n_types),
+                       a=a.astype(np.float32), module=module,
+                       loading=loading.astype(np.float32),
+                       type_mean=type_mean.astype(np.float32))
+
+
+def cell_scores(p: SynthParams, cells: np.ndarray):
+    """(l_c [n], h_cm [n, M]) for global cell ids ``cells``."""
+    cells = np.asarray(cells, dtype=np.uint64)
+    lib = p.lib_sd * _gauss(_hash3(p.seed, cells, np.uint64(0xFFFFFFF1)))
+    typ = (_hash3(p.seed, cells, np.uint64(0xFFFFFFF2)) % np.uint64(p.n_types)).astype(np.int64)
+    m = np.arange(p.n_modules, dtype=np.uint64)
+    eps = _gauss(_hash3(p.seed, cells[:, None], m[None, :] + np.uint64(0x40000000)))
+    h = p.type_w * p.type_mean.astype(np.float64)[typ] + p.noise_w * eps
+    return lib, h, typ
+
+
+def sample_counts(p: SynthParams, cell_lo=0, cell_hi=None, chunk=2048):
+    """CPU sampler: scipy CSC (genes x cells) int64 counts for cells [cell_lo, cell_hi)."""
+    import scipy.sparse as sp
+    cell_hi = p.n_cells_total if cell_hi is None else cell_hi
+    g = p.n_genes
+    a = p.a.astype(np.float64)
+    s = p.loading.astype(np.float64)
+    mod = np.maximum(p.module, 0)
+    has = p.module >= 0
+    genes = np.arange(g, dtype=np.uint64)
+    blocks = []
+    for lo in range(cell_lo, cell_hi, chunk):
+        cells = np.arange(lo, min(lo + chunk, cell_hi), dtype=np.uint64)
+        lib, h, _ = cell_scores(p, cells)
+        hm = np.where(has[None, :], h[:, mod], 0.0)                  # [n, G]
+        loglam = a[None, :] + lib[:, None] + s[None, :] * hm - 0.5 * (s * s)[None, :]
+        lam = np.exp(loglam)
+        u = _u01(_hash3(p.seed, genes[None, :], cells[:, None]))
+        # Poisson by CDF inversion: x = #{k : u > CDF(k)}; only the still-active entries
+        # are revisited, so the cost follows the number of non-zeros
+        x = np.zeros(lam.shape, dtype=np.int64)
+        pk0 = np.exp(-lam)
+        act = np.flatnonzero((u > pk0).ravel())
+        lam_a = lam.ravel()[act]
+        u_a = u.ravel()[act]
+        pk = pk0.ravel()[act]
+        cdf = pk.copy()
+        xf = x.ravel()
+        k = 0
+        while act.size and k < 100000:
+            k += 1
+            xf[act] += 1
+            pk = pk * lam_a / k
+            cdf = cdf + pk
+            keep = (u_a > cdf) & (pk > 0)
+            act, lam_a, u_a, pk, cdf = act[keep], lam_a[keep], u_a[keep], pk[keep], cdf[keep]
+        empty = x.sum(axis=1) == 0
+        if empty.any():
+            rows = np.flatnonzero(empty)
+            x[rows, (cells[rows] % np.uint64(g)).astype(np.int64)] = 1
+        blocks.append(sp.csr_matrix(x))
+    m = sp.vstack(blocks).T.tocsc()
+    m.sort_indices()
+    return m

@@ -1,0 +1,198 @@
+/*
+ * libcellscopes_cuda.so -- C ABI of the B200 (sm_100a) implementation of the
+ * CellScopes.jl preprocessing-to-graph path:
+ *
+ *   normalize_object -> find_variable_genes -> scale_object -> run_pca -> run_clustering(kNN/adjacency)
+ *
+ * The reference (HaojiaWu/CellScopes.jl) is pure Julia and has no FFI of its own
+ * (SURVEY.md section 0.1): the boundary it offers is Julia multiple dispatch on the
+ * function names in src/scrna/processing.jl.  Every entry point below therefore cites
+ * the reference FUNCTION it replaces (file:line under /root/reference); the Julia
+ * `ccall` shim that binds them is julia/CellScopesCUDA.jl and is described in
+ * INTEGRATION.md.  The same symbols are bound from Python by ctypes
+ * (cellscopes.jl_b200/_capi.py), which is how every test and benchmark reaches them.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  No exceptions, abort() or signals cross
+ *     the boundary.  Every function returns csc_status (0 = OK, < 0 = error class);
+ *     csc_last_error() gives the message.
+ *   - Host buffers are caller-allocated and caller-owned; the library never keeps a
+ *     host pointer after the call returns.  Device objects are opaque handles owned by
+ *     the library and released with the matching *_free or with csc_destroy.
+ *   - A context owns one GPU, one stream.  It is not thread-safe; distinct contexts are
+ *     independent.  Multi-GPU = one context per process per GPU (cells sharded in
+ *     contiguous column ranges); the few exchange steps are exposed as device-resident
+ *     "partials" that the host all-reduces / all-gathers (torch.distributed / NCCL)
+ *     between the *_partial and the *_finish call.  With one GPU the host simply skips
+ *     the collective.
+ *   - Matrices are genes x cells, compressed sparse COLUMN: a column is a cell
+ *     (src/scrna/objects.jl:10-24).  Indices at the ABI are int64 with an explicit
+ *     index_base (1 for Julia, 0 for C/Python).  On the device they are narrowed to
+ *     int64 colptr / int32 rowval / fp32 values.
+ */
+#ifndef CELLSCOPES_CUDA_H
+#define CELLSCOPES_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSC_ABI_VERSION 1
+
+typedef int32_t csc_status;
+enum {
+  CSC_OK = 0,
+  CSC_ERR_ARG = -1,         /* bad argument (the reference throws ArgumentError / DimensionMismatch) */
+  CSC_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  CSC_ERR_OOM = -3,         /* device or host allocation failed */
+  CSC_ERR_UNSUPPORTED = -4, /* valid in the reference, not built here */
+  CSC_ERR_NUMERIC = -5,     /* e.g. eigensolver did not converge */
+  CSC_ERR_INTERNAL = -6
+};
+
+typedef struct csc_ctx csc_ctx;       /* one GPU + stream */
+typedef struct csc_sparse csc_sparse; /* device CSC shard: genes x local cells */
+typedef struct csc_dense csc_dense;   /* device dense fp32, cell-major: rows = cells */
+typedef struct csc_vec csc_vec;       /* device buffer of fp64/fp32/int32 (partials, tables) */
+typedef struct csc_pca csc_pca;       /* PCA model: loadings, variances */
+typedef struct csc_graph csc_graph;   /* device CSC graph: cells x local cells */
+
+enum { CSC_DT_F32 = 0, CSC_DT_F64 = 1, CSC_DT_I32 = 2, CSC_DT_I64 = 3 };
+enum { CSC_NORM_LOGARITHM = 0, CSC_NORM_NONE = 1 };       /* processing.jl:23-29 */
+enum { CSC_METRIC_COSINE = 0, CSC_METRIC_EUCLIDEAN = 1 }; /* Distances.jl CosineDist / Euclidean */
+enum {
+  CSC_GRAPH_BINARY = 0,     /* run_clustering_small, processing.jl:268-278: union, value 1 */
+  CSC_GRAPH_SUM = 1,        /* run_clustering_atlas, processing.jl:218-232: mutual pairs carry 2 */
+  CSC_GRAPH_SNN_JACCARD = 2 /* extension: Jaccard weight of the shared neighbourhoods */
+};
+/* stage slots of csc_stage_times */
+enum {
+  CSC_T_UPLOAD = 0, CSC_T_NORMALIZE, CSC_T_GENE_STATS, CSC_T_HVG, CSC_T_SCALE_STATS, CSC_T_SCALE_FILL,
+  CSC_T_PCA_GRAM, CSC_T_PCA_SOLVE, CSC_T_PCA_TRANSFORM, CSC_T_KNN, CSC_T_GRAPH, CSC_T_GENERATE,
+  CSC_T_COUNT
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int32_t csc_abi_version(void);
+csc_status csc_create(int32_t device, csc_ctx** ctx);
+csc_status csc_destroy(csc_ctx* ctx);
+/* message of the last failure on ctx (ctx == NULL: last failure of csc_create on this thread) */
+const char* csc_last_error(const csc_ctx* ctx);
+csc_status csc_synchronize(csc_ctx* ctx);
+csc_status csc_device_info(csc_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes,
+                           int32_t* cc_major, int32_t* cc_minor);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel is launched on) */
+csc_status csc_timer_start(csc_ctx* ctx);
+csc_status csc_timer_stop(csc_ctx* ctx, double* elapsed_ms);
+/* device milliseconds spent in each stage since the last reset, and kernels launched */
+csc_status csc_stage_times(csc_ctx* ctx, double* ms /*[CSC_T_COUNT]*/, int64_t* kernel_launches, int32_t reset);
+/* scratch-flush: overwrite a buffer larger than L2 (bench hygiene between timed iterations) */
+csc_status csc_flush_l2(csc_ctx* ctx);
+
+/* ---- device buffers (partials that the host reduces/gathers between ranks) ------------- */
+csc_status csc_vec_alloc(csc_ctx* ctx, int64_t n, int32_t dtype, csc_vec** out); /* zero-filled */
+/* non-owning view of caller-managed device memory (e.g. an all-gathered table held by torch) */
+csc_status csc_vec_wrap(csc_ctx* ctx, void* device_ptr, int64_t n, int32_t dtype, csc_vec** out);
+csc_status csc_vec_free(csc_vec* v);
+csc_status csc_vec_info(const csc_vec* v, int64_t* n, int32_t* dtype, void** device_ptr);
+csc_status csc_vec_upload(csc_vec* v, const void* host, int64_t n);
+csc_status csc_vec_download(const csc_vec* v, void* host, int64_t n);
+
+/* ---- sparse count matrix: rawCount.count_mtx (src/scrna/objects.jl:10-24) --------------- */
+/* colptr[n_cells+1], rowval[nnz], nzval[nnz] of a SparseMatrixCSC; idx_dtype I64|I32,
+ * val_dtype I64|F64|F32|I32 (readers yield Int64, merge_matrices Float64: SURVEY A.1). */
+csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n_cells, const void* colptr,
+                             const void* rowval, int32_t idx_dtype, const void* nzval, int32_t val_dtype,
+                             int32_t index_base, csc_sparse** out);
+csc_status csc_sparse_info(const csc_sparse* m, int64_t* n_genes, int64_t* n_cells, int64_t* nnz);
+/* columns [cell_lo, cell_hi): colptr_out[cell_hi-cell_lo+1] rebased to index_base; rowval/nzval sized by
+ * csc_sparse_range_nnz.  Any output pointer may be NULL. */
+csc_status csc_sparse_range_nnz(const csc_sparse* m, int64_t cell_lo, int64_t cell_hi, int64_t* nnz);
+csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, int64_t cell_hi, int64_t* colptr_out,
+                               int64_t* rowval_out, double* nzval_out, int32_t index_base);
+csc_status csc_sparse_free(csc_sparse* m);
+/* synthetic module-structured Poisson counts for global cells [cell_lo, cell_hi) (the
+ * per-gene tables come from cellscopes.jl_b200/synth.py::make_params) */
+csc_status csc_generate_counts(csc_ctx* ctx, int64_t n_genes, int64_t cell_lo, int64_t cell_hi, uint64_t seed,
+                               const float* gene_base, const int32_t* gene_module, const float* gene_loading,
+                               const float* type_mean, int32_t n_types, int32_t n_modules, float lib_sd,
+                               float type_w, float noise_w, csc_sparse** out);
+
+/* ---- a1: normalize_object(mtx) src/scrna/processing.jl:15-31 ---------------------------- */
+/* out shares the sparsity pattern of raw.  nan_to_zero = the replace!(NaN=>0) of :44-46.
+ * gene_stats (optional, fp64[2*n_genes]) receives += per-gene (sum x, sum x^2) of the RAW counts of this
+ * shard, fused into the same pass (find_variable_genes :138-139 needs them). */
+csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
+                         double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out);
+
+/* ---- a2: find_variable_genes src/scrna/processing.jl:133-155 ---------------------------- */
+/* per-gene (sum x, sum x^2) of this shard, += into gene_stats fp64[2*n_genes] (standalone K2) */
+csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw, csc_vec* gene_stats);
+/* gene_stats already summed over ranks.  Outputs (host, any may be NULL): mean/variance/
+ * variance_expected/variance_standardized [n_genes] = the vst_data columns of :141; order[n_genes] =
+ * gene ids (0-based) sorted by variance_standardized descending, stable (:152); the first n_features of
+ * it are Features (:153).  n_features is clamped to n_genes (:134-137). */
+csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
+                          int64_t n_features, double span, double* mean, double* variance,
+                          double* variance_expected, double* variance_standardized, int64_t* order);
+
+/* ---- a3: scale_object src/scrna/processing.jl:65-93 ------------------------------------- */
+/* features[n_feat]: 0-based gene ids in any order; rows are taken in ORIGINAL gene order like
+ * subset_count (src/scrna/utils.jl:72-76).  features == NULL -> all genes.
+ * partial: fp64[2*H] += (sum y, sum y^2) of the normalised values of this shard. */
+csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                                   csc_vec* partial);
+/* partial already summed over ranks; out = dense fp32 [n_cells_local x H], cell-major, which is the
+ * memory layout of Julia's genes x cells column-major Matrix: min((y-mean)/sd, scale_max) (:69-74). */
+csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                          const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
+                          int32_t do_center, csc_dense** out);
+
+/* ---- dense cell-major matrices: scaleCount.count_mtx', pca.cell_embedding ---------------- */
+csc_status csc_dense_alloc(csc_ctx* ctx, int64_t n_rows, int64_t n_cols, csc_dense** out);
+/* host is row-major [n_rows x n_cols] (== Julia column-major [n_cols x n_rows]) */
+csc_status csc_dense_upload(csc_ctx* ctx, const void* host, int32_t dtype, int64_t n_rows, int64_t n_cols,
+                            csc_dense** out);
+csc_status csc_dense_download(const csc_dense* d, void* host, int32_t dtype, int64_t row_lo, int64_t row_hi);
+csc_status csc_dense_info(const csc_dense* d, int64_t* n_rows, int64_t* n_cols, void** device_ptr);
+/* non-owning view of caller-managed device memory (e.g. an all-gathered embedding held by torch) */
+csc_status csc_dense_wrap(csc_ctx* ctx, void* device_ptr, int64_t n_rows, int64_t n_cols, csc_dense** out);
+csc_status csc_dense_free(csc_dense* d);
+
+/* ---- a4: run_pca src/scrna/processing.jl:164-193 (MultivariateStats PCA, method=:svd) ---- */
+/* colsum fp64[H] += sum over local cells of z; gram fp64[H*H] += Z'Z of this shard (symmetric, full) */
+csc_status csc_pca_partial(csc_ctx* ctx, const csc_dense* scaled, csc_vec* colsum, csc_vec* gram);
+/* colsum/gram already summed over ranks.  Top-k eigenpairs of (Z-m)'(Z-m); principalvars = lambda/(N-1),
+ * tvar = trace/(N-1).  iters_out/resid_out report the eigensolver (may be NULL). */
+csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const csc_vec* gram, int64_t n_feat,
+                         int64_t n_cells_total, int32_t maxoutdim, double tol, int32_t max_iter, csc_pca** out,
+                         int32_t* iters_out, double* resid_out);
+csc_status csc_pca_info(const csc_pca* p, int64_t* n_feat, int32_t* k, double* principalvars /*[k]*/, double* tvar,
+                        double* loadings /*[n_feat*k], column-major H x k*/, double* mean /*[n_feat]*/);
+/* embedding of the local cells: (Z - 1 m') U_k, dense fp32 [n_cells_local x k] */
+csc_status csc_pca_transform(csc_ctx* ctx, const csc_dense* scaled, const csc_pca* p, csc_dense** out);
+csc_status csc_pca_free(csc_pca* p);
+
+/* ---- a5/a6: kNN inside run_clustering src/scrna/processing.jl:195-201, 263-266 ----------- */
+/* Exact brute force (the reference's nndescent is approximate and unseeded).  queries: local cells
+ * [n_q x d]; keys: all cells [n_keys x d] (the same object with one GPU); query_offset = global id of
+ * query row 0 (its own key, excluded).  Columns [dim_lo, dim_hi) are used (run_umap dims_use, :335).
+ * idx int32 [n_q x k] 0-based global ids, ascending distance, ties by lower id; dist fp32 [n_q x k]. */
+csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_dense* keys, int64_t query_offset,
+                   int32_t dim_lo, int32_t dim_hi, int32_t k, int32_t metric, csc_vec** idx, csc_vec** dist);
+
+/* ---- adjacency fed to Leiden src/scrna/processing.jl:218-232, 268-278 ------------------- */
+/* knn_idx: int32 [n_cells_total x k] of ALL cells (all-gathered); builds columns [cell_lo, cell_hi). */
+csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int64_t n_cells_total, int32_t k,
+                           int64_t cell_lo, int64_t cell_hi, int32_t mode, double snn_prune, csc_graph** out);
+csc_status csc_graph_info(const csc_graph* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
+csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, double* nzval,
+                              int32_t index_base);
+csc_status csc_graph_free(csc_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLSCOPES_CUDA_H */

@@ -1,0 +1,469 @@
+"""CPU oracle for the counts -> normalise -> HVG -> scale -> PCA -> kNN/SNN path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a float64 NumPy/SciPy restatement of
+the reference's Julia algorithm for the hot path.  It is the checker for the
+CUDA library; it is never the thing shipped or measured.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.
+
+PARITY UNPINNED.  The reference ships no tests, fixtures or golden vectors
+ and Julia is not installed in the build image, so this
+restatement could not be run against the reference itself.  Where the arithmetic
+lives in a third-party Julia package that is not under /root/reference the
+published algorithm of the pinned version is restated and marked [3P]:
+
+  SparseArrays / Statistics stdlib 1.10.0   (sum, mean, var, sparse broadcast)
+  Loess.jl 0.6.3                            (kd-tree vertices + cubic Hermite blending)
+  MultivariateStats.jl 0.10.3               (PCA: centre, SVD, principalvars, tvar)
+  Distances.jl 0.10.11                      (CosineDist)
+  NearestNeighborDescent.jl 0.3.6           (replaced by EXACT kNN, see knn_exact)
+
+All citations ``processing.jl:N`` are /root/reference/src/scrna/processing.jl,
+``utils.jl:N`` are /root/reference/src/scrna/utils.jl.
+
+Conventions: count matrices are genes x cells (``objects.jl:15-20``), held as
+``scipy.sparse.csc_matrix`` so that a column is a cell, like Julia's
+SparseMatrixCSC.  Indices returned by this module are 0-based.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse as sp
+
+__all__ = [
+    "subset_matrix", "subset_count_rows", "normalize_object", "gene_moments",
+    "loess_fit", "loess_predict", "find_variable_genes", "scale_object",
+    "run_pca", "cosine_dist", "knn_exact", "adjacency_small", "adjacency_atlas",
+    "snn_jaccard", "run_pipeline",
+]
+
+
+# ----------------------------------------------------------------------------
+# helpers the path relies on (utils.jl)
+# ----------------------------------------------------------------------------
+def subset_matrix(count_mat, min_gene=0, min_cell=0):
+    """utils.jl:313-320: keep genes with row sum > min_cell and cells with column
+    sum > min_gene (STRICT >).  Returns (matrix, gene_kept, cell_kept)."""
+    count_mat = sp.csc_matrix(count_mat)
+    row_sum = np.asarray(count_mat.sum(axis=1)).ravel()
+    col_sum = np.asarray(count_mat.sum(axis=0)).ravel()
+    gene_kept = np.flatnonzero(row_sum > min_cell)
+    cell_kept = np.flatnonzero(col_sum > min_gene)
+    return count_mat[gene_kept][:, cell_kept].tocsc(), gene_kept, cell_kept
+
+
+def subset_count_rows(n_genes, feature_idx):
+    """utils.jl:59-76: subsetting by a boolean mask keeps the ORIGINAL gene order,
+    whatever order ``genes`` was given in.  Returns the sorted unique row ids."""
+    mask = np.zeros(n_genes, dtype=bool)
+    mask[np.asarray(feature_idx, dtype=np.int64)] = True
+    return np.flatnonzero(mask)
+
+
+# ----------------------------------------------------------------------------
+# a1  normalize_object (processing.jl:15-31)
+# ----------------------------------------------------------------------------
+def normalize_object(mtx, scale_factor=10000, norm_method="logarithm", pseudocount=1,
+                     nan_to_zero=False):
+    """processing.jl:15-31.
+
+    ``inv = 1.0 ./ sum(mtx, dims=1)`` (:17-18), then
+    ``log((mtx .* inv') * scale_factor + pseudocount)`` (:24) or, for "none",
+    ``(mtx .* inv') * scale_factor`` (:26); anything else throws (:28).
+    The result keeps the stored pattern.  A zero-sum column gives inv = Inf and
+    0*Inf = NaN; the sparse broadcast then stores NaN for the WHOLE column [3P].
+    ``nan_to_zero`` is the ``replace!(NaN=>0)`` of :44-46 (imaging objects).
+    The NaN-column rule is only representable here on the stored pattern; a
+    fully empty column has nothing stored so it stays empty (documented deviation:
+    Julia would densify that column to NaN).
+    """
+    if norm_method not in ("logarithm", "none"):
+        raise ValueError(f"Unknown normalization method: {norm_method}")
+    m = sp.csc_matrix(mtx).astype(np.float64)        # :16 convert to Float64
+    m.sort_indices()
+    sum_val = np.asarray(m.sum(axis=0)).ravel()      # :17
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / sum_val                           # :18
+        per_nz_inv = np.repeat(inv, np.diff(m.indptr))
+        v = (m.data * per_nz_inv) * float(scale_factor)   # association order of :24
+        if norm_method == "logarithm":
+            v = np.log(v + float(pseudocount))
+    if nan_to_zero:
+        v = np.where(np.isnan(v), 0.0, v)
+    return sp.csc_matrix((v, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+
+
+# ----------------------------------------------------------------------------
+# a2  find_variable_genes (processing.jl:133-155) + Loess.jl 0.6.3 [3P]
+# ----------------------------------------------------------------------------
+def gene_moments(mtx):
+    """Exact integer moments per gene, SURVEY A.3-7: S1 = sum x, S2 = sum x^2
+    over all N cells (zeros included), then
+        mean = S1/N ;  var = (S2 - S1*S1/N)/(N-1)          (corrected, n-1)
+    in float64 with exactly this operation order (processing.jl:138-139 computes
+    the same quantities with Statistics.mean/var)."""
+    m = sp.csc_matrix(mtx)
+    n = m.shape[1]
+    d = m.data.astype(np.float64)
+    s1 = np.bincount(m.indices, weights=d, minlength=m.shape[0])
+    s2 = np.bincount(m.indices, weights=d * d, minlength=m.shape[0])
+    mean = s1 / n
+    var = (s2 - s1 * s1 / n) / (n - 1)
+    return s1, s2, mean, var
+
+
+def _kd_vertices(x, leaf_size_cutoff):
+    """Loess.jl 0.6.3 src/kd.jl [3P]: 1-D kd-tree.  Vertices = {min, max} plus every
+    split median.  A node with <= leaf_size_cutoff points is a leaf.  Split at the
+    median: even length -> mean of the two middle order statistics, left/right get
+    n/2 each; odd length -> the middle order statistic, left gets floor(n/2) points
+    and right the rest (median included).  (The odd-length convention is recalled,
+    not verified: see SURVEY A.3.)"""
+    xs = np.sort(np.asarray(x, dtype=np.float64), kind="stable")
+    verts = {float(xs[0]), float(xs[-1])}
+    stack = [(0, xs.size)]
+    while stack:
+        lo, hi = stack.pop()
+        n = hi - lo
+        if n <= leaf_size_cutoff or xs[hi - 1] - xs[lo] <= 0.0:
+            continue
+        mid = n // 2
+        if n % 2 == 1:
+            med = float(xs[lo + mid])
+        else:
+            med = float((xs[lo + mid - 1] + xs[lo + mid]) / 2)
+        verts.add(med)
+        stack.append((lo, lo + mid))
+        stack.append((lo + mid, hi))
+    return np.array(sorted(verts), dtype=np.float64)
+
+
+def _pivoted_qr_solve3(us, vs):
+    """Least squares ``us \\ vs`` through Householder QR with column pivoting
+    (Julia: ``qr(us, ColumnNorm()) \\ vs``), written out so the C++ host code in
+    the library can follow the identical operation order."""
+    a = np.array(us, dtype=np.float64, copy=True)
+    b = np.array(vs, dtype=np.float64, copy=True)
+    q, ncol = a.shape
+    perm = list(range(ncol))
+    for k in range(ncol):
+        norms = [float(np.dot(a[k:, j], a[k:, j])) for j in range(k, ncol)]
+        p = k + int(np.argmax(norms))
+        if p != k:
+            a[:, [k, p]] = a[:, [p, k]]
+            perm[k], perm[p] = perm[p], perm[k]
+        x = a[k:, k]
+        alpha = math.sqrt(float(np.dot(x, x)))
+        if alpha == 0.0:
+            continue
+        if x[0] > 0:
+            alpha = -alpha
+        v = x.copy()
+        v[0] -= alpha
+        vnorm2 = float(np.dot(v, v))
+        if vnorm2 == 0.0:
+            continue
+        for j in range(k, ncol):
+            s = 2.0 * float(np.dot(v, a[k:, j])) / vnorm2
+            a[k:, j] -= s * v
+        s = 2.0 * float(np.dot(v, b[k:])) / vnorm2
+        b[k:] -= s * v
+    coef_p = np.zeros(ncol)
+    for k in range(ncol - 1, -1, -1):
+        s = b[k]
+        for j in range(k + 1, ncol):
+            s -= a[k, j] * coef_p[j]
+        coef_p[k] = s / a[k, k] if a[k, k] != 0.0 else 0.0
+    coef = np.zeros(ncol)
+    for k in range(ncol):
+        coef[perm[k]] = coef_p[k]
+    return coef
+
+
+def loess_fit(x, y, span=0.75, degree=2, cell=0.2):
+    """Loess.jl 0.6.3 ``loess(xs, ys; span, degree=2, cell=0.2)`` for one predictor [3P].
+
+    q = max(1, floor(span*n)); kd-tree leaf cutoff = ceil(cell*span*n).  At every
+    vertex v: the q nearest points by |x-v| (ties: lower index first), dmax = largest
+    of those distances (1 if 0), weights tricube (1-(d/dmax)^3)^3, weighted least
+    squares of y on [1, (x-v), (x-v)^2] with rows scaled by sqrt(w), solved by
+    column-pivoted QR; the intercept is the fitted value at v, the linear
+    coefficient its derivative.  Returns (verts, value_at_vert, slope_at_vert)."""
+    if degree != 2:
+        raise ValueError("oracle restates degree=2 only (the reference never changes it)")
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.size
+    if n == 0:
+        raise ValueError("input arrays are empty")
+    if not (0 < span <= 1):
+        raise ValueError("span must be in the range (0, 1].")
+    q = max(1, int(math.floor(span * n)))
+    cutoff = int(math.ceil(cell * span * n))
+    verts = _kd_vertices(x, cutoff)
+    val = np.empty(verts.size)
+    slope = np.empty(verts.size)
+    for vi, v in enumerate(verts):
+        d = np.abs(x - v)
+        order = np.argsort(d, kind="stable")[:q]
+        dq = d[order]
+        dmax = float(dq.max())
+        if dmax == 0.0:
+            dmax = 1.0
+        u = dq / dmax
+        w = np.sqrt((1.0 - u ** 3) ** 3)
+        xc = x[order] - v
+        us = np.stack([w, w * xc, w * xc * xc], axis=1)
+        vs = y[order] * w
+        coef = _pivoted_qr_solve3(us, vs)
+        val[vi] = coef[0]
+        slope[vi] = coef[1]
+    return verts, val, slope
+
+
+def loess_predict(model, z):
+    """Loess.jl ``predict`` [3P]: at a vertex return its fitted value; otherwise the
+    cubic Hermite interpolant through the two enclosing vertices."""
+    verts, val, slope = model
+    z = np.asarray(z, dtype=np.float64)
+    out = np.empty(z.shape, dtype=np.float64)
+    hi = np.searchsorted(verts, z, side="left")      # verts[hi-1] < z <= verts[hi]
+    if np.any(z < verts[0]) or np.any(z > verts[-1]):
+        raise ValueError("Loess cannot extrapolate outside the fitted range")
+    hi = np.clip(hi, 1, verts.size - 1)
+    lo = hi - 1
+    v1, v2 = verts[lo], verts[hi]
+    y1, y2 = val[lo], val[hi]
+    d1, d2 = slope[lo], slope[hi]
+    h = v2 - v1
+    t = (z - v1) / h
+    h00 = (1 + 2 * t) * (1 - t) ** 2
+    h10 = t * (1 - t) ** 2
+    h01 = t * t * (3 - 2 * t)
+    h11 = t * t * (t - 1)
+    out = h00 * y1 + h10 * h * d1 + h01 * y2 + h11 * h * d2
+    exact_lo = z == v1
+    exact_hi = z == v2
+    out = np.where(exact_lo, y1, out)
+    out = np.where(exact_hi, y2, out)
+    return out
+
+
+def find_variable_genes(mtx, nFeatures=2000, span=0.3):
+    """processing.jl:133-155.
+
+    mean/var of RAW counts per gene over all cells (:138-139, exact-moment rule of
+    SURVEY A.3-7), loess of log10(var) on log10(mean) with span (:144),
+    variance_expected = 10^predict (:145), variance_standardized =
+    var((x - mean)/sqrt(variance_expected)) (:146-150) = var/variance_expected,
+    stable descending sort (:152), first nFeatures (:153).
+    The reference requires every gene to have variance > 0 (:143,:151)."""
+    m = sp.csc_matrix(mtx)
+    n_genes = m.shape[0]
+    nFeatures = min(int(nFeatures), n_genes)               # :134-137
+    s1, s2, mean, var = gene_moments(m)
+    if np.any(~(var > 0.0)):
+        raise ValueError("find_variable_genes: a gene has variance <= 0 "
+                         "(reference precondition, processing.jl:143,151)")
+    lx = np.log10(mean)
+    ly = np.log10(var)
+    model = loess_fit(lx, ly, span=span)
+    var_exp = 10.0 ** loess_predict(model, lx)
+    var_std = var / var_exp
+    # sort(..., rev=true) is stable: ties keep ascending gene order (:152)
+    order = np.lexsort((np.arange(n_genes), -var_std))
+    return {
+        "mean": mean, "variance": var, "variance_expected": var_exp,
+        "variance_standardized": var_std, "order": order,
+        "features": order[:nFeatures].copy(), "S1": s1, "S2": s2,
+        "loess": model,
+    }
+
+
+# ----------------------------------------------------------------------------
+# a3  scale_object (processing.jl:65-76)
+# ----------------------------------------------------------------------------
+def scale_object(count_mtx, scale_max=10.0, do_scale=True, do_center=True):
+    """processing.jl:65-76 on a genes x cells matrix of NORMALISED values.
+
+    rmean = mean(dims=2) (:66); rsd = sqrt.(var(dims=2)) corrected (:67);
+    ``.-= rmean`` (:69); ``./ rsd`` (:72); ``min.(x, scale_max)`` (:74), an UPPER
+    clip only.  Returns a dense float64 genes x cells array."""
+    if sp.issparse(count_mtx):
+        x = np.asarray(count_mtx.todense(), dtype=np.float64)
+    else:
+        x = np.array(count_mtx, dtype=np.float64, copy=True)
+    rmean = x.mean(axis=1, keepdims=True)
+    rsd = np.sqrt(x.var(axis=1, ddof=1, keepdims=True))
+    if do_center:
+        x = x - rmean
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if do_scale:
+            x = x / rsd
+        x = np.where(np.isnan(x), x, np.minimum(x, scale_max))
+    return x
+
+
+# ----------------------------------------------------------------------------
+# a4  run_pca (processing.jl:164-193; MultivariateStats 0.10.3 [3P])
+# ----------------------------------------------------------------------------
+def run_pca(scaled, maxoutdim=10, method="svd"):
+    """processing.jl:164-193 with the MultivariateStats ``fit(PCA, X; method=:svd,
+    pratio=1, maxoutdim)`` semantics [3P].  ``scaled`` is genes(H) x cells(N).
+
+    m = mean over cells; Zc = Z - m; thin SVD Zc = U S V'; principalvars = s^2/(N-1);
+    tvar = sum over ALL components; keep the first maxoutdim; embedding = Zc' * U_k
+    (N x k).  ``method="gram"`` diagonalises Zc*Zc' instead (same result, used on
+    the wide matrices where a full SVD would take minutes)."""
+    z = np.asarray(scaled, dtype=np.float64)
+    h, n = z.shape
+    mean = z.mean(axis=1, keepdims=True)
+    zc = z - mean
+    k = min(int(maxoutdim), min(h, n))
+    if method == "svd":
+        u, s, _ = np.linalg.svd(zc, full_matrices=False)
+        lam = s * s
+    else:
+        g = zc @ zc.T
+        lam, u = scipy.linalg.eigh(g)
+        lam = np.maximum(lam[::-1], 0.0)
+        u = u[:, ::-1]
+    principalvars = lam / (n - 1)
+    tvar = float(principalvars.sum())
+    uk = u[:, :k]
+    emb = zc.T @ uk
+    return {
+        "embedding": emb, "principalvars": principalvars[:k].copy(), "tvar": tvar,
+        "loadings": uk, "mean": mean.ravel(), "all_vars": principalvars,
+    }
+
+
+# ----------------------------------------------------------------------------
+# a5/a6  kNN and graphs (processing.jl:195-232, 263-278)
+# ----------------------------------------------------------------------------
+def cosine_dist(a, b):
+    """Distances.jl 0.10.11 CosineDist [3P]: max(1 - <a,b>/(|a||b|), 0)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return max(1.0 - float(a @ b) / (math.sqrt(float(a @ a)) * math.sqrt(float(b @ b))), 0.0)
+
+
+def knn_exact(emb, k, metric="cosine", block=2048, queries=None):
+    """EXACT brute-force kNN in float64 (the reference uses the approximate, unseeded
+    NN-descent at processing.jl:200,265; exact kNN is what the build computes, SURVEY
+    finding 5).  Self excluded by index; ascending distance; ties by lower index.
+    Returns (idx [n,k] int64 0-based, dist [n,k] float64).  ``queries`` restricts the
+    query rows (for spot checks on large inputs)."""
+    x = np.asarray(emb, dtype=np.float64)
+    n = x.shape[0]
+    k = int(k)
+    if k > n - 1:
+        raise ValueError("k must be < number of cells")
+    if metric == "cosine":
+        nrm = np.sqrt((x * x).sum(axis=1))
+        xn = x / nrm[:, None]
+    elif metric == "euclidean":
+        xn = x
+        sq = (x * x).sum(axis=1)
+    else:
+        raise ValueError(f"unknown metric {metric}")
+    qrows = np.arange(n) if queries is None else np.asarray(queries, dtype=np.int64)
+    idx = np.empty((qrows.size, k), dtype=np.int64)
+    dist = np.empty((qrows.size, k), dtype=np.float64)
+    for s in range(0, qrows.size, block):
+        rows = qrows[s:s + block]
+        if metric == "cosine":
+            d = np.maximum(1.0 - xn[rows] @ xn.T, 0.0)
+        else:
+            d = np.sqrt(np.maximum(sq[rows, None] + sq[None, :] - 2.0 * (xn[rows] @ xn.T), 0.0))
+        d[np.arange(rows.size), rows] = np.inf
+        # exact ordering incl. ties by index: take every candidate <= the k-th smallest
+        kth = np.partition(d, k - 1, axis=1)[:, k - 1]
+        for r in range(rows.size):
+            cand = np.flatnonzero(d[r] <= kth[r])
+            o = np.lexsort((cand, d[r, cand]))[:k]
+            idx[s + r] = cand[o]
+            dist[s + r] = d[r, cand[o]]
+    return idx, dist
+
+
+def adjacency_small(idx, n=None):
+    """processing.jl:268-278: ``adj[idx[j,i], i] = 1; adj[i, idx[j,i]] = 1``: the
+    binary union-symmetrised kNN adjacency (Int64).  Returned sparse (CSC); the
+    reference holds it dense (n < 10000 only)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    n = idx.shape[0] if n is None else n
+    k = idx.shape[1]
+    cols = np.repeat(np.arange(idx.shape[0]), k)
+    rows = idx.ravel()
+    a = sp.coo_matrix((np.ones(rows.size * 2, dtype=np.int64),
+                       (np.concatenate([rows, cols]), np.concatenate([cols, rows]))),
+                      shape=(n, n)).tocsc()
+    a.data[:] = 1
+    a.sort_indices()
+    return a
+
+
+def adjacency_atlas(idx, n=None):
+    """processing.jl:218-232: COO push of (idx,i,1) and (i,idx,1); ``sparse`` SUMS
+    duplicates, so a mutual pair carries 2 and a one-directional pair 1."""
+    idx = np.asarray(idx, dtype=np.int64)
+    n = idx.shape[0] if n is None else n
+    k = idx.shape[1]
+    cols = np.repeat(np.arange(idx.shape[0]), k)
+    rows = idx.ravel()
+    a = sp.coo_matrix((np.ones(rows.size * 2, dtype=np.int64),
+                       (np.concatenate([rows, cols]), np.concatenate([cols, rows]))),
+                      shape=(n, n)).tocsc()          # duplicates are summed
+    a.sort_indices()
+    return a
+
+
+def snn_jaccard(idx, prune=0.0):
+    """SNN extension (not in the reference).  N+(i) = {i} U kNN(i).  For
+    every edge (i,j) of the union-symmetrised kNN graph
+        w_ij = |N+(i) & N+(j)| / |N+(i) U N+(j)| ;
+    edges with w < prune are dropped.  Symmetric CSC with float64 weights."""
+    idx = np.asarray(idx, dtype=np.int64)
+    n, k = idx.shape
+    pattern = adjacency_small(idx)
+    plus = np.concatenate([np.arange(n)[:, None], idx], axis=1)
+    coo = pattern.tocoo()
+    inter = _intersections(plus, coo.row, coo.col)
+    union = 2 * (k + 1) - inter          # kNN lists hold k distinct cells, none of them i
+    w = inter.astype(np.float64) / union.astype(np.float64)
+    keep = w >= prune
+    out = sp.coo_matrix((w[keep], (coo.row[keep], coo.col[keep])), shape=(n, n)).tocsc()
+    out.sort_indices()
+    return out
+
+
+def _intersections(plus, rows, cols, chunk=20000):
+    out = np.empty(rows.size, dtype=np.int64)
+    for s in range(0, rows.size, chunk):
+        a = plus[rows[s:s + chunk]]
+        b = plus[cols[s:s + chunk]]
+        out[s:s + chunk] = (a[:, :, None] == b[:, None, :]).sum(axis=(1, 2))
+    return out
+
+
+# ----------------------------------------------------------------------------
+# the whole path, in the atlas order of docs/scRNA_tutorial/README.md:260-280
+# ----------------------------------------------------------------------------
+def run_pipeline(counts, nFeatures=2000, span=0.3, scale_max=10.0, n_pcs=50, k=20,
+                 scale_factor=10000, pca_method="svd", metric="cosine", graph="atlas"):
+    """normalize_object -> find_variable_genes -> scale_object(features=HVG) ->
+    run_pca(maxoutdim=n_pcs) -> exact kNN -> adjacency (+ SNN)."""
+    counts = sp.csc_matrix(counts)
+    norm = normalize_object(counts, scale_factor=scale_factor)
+    hvg = find_variable_genes(counts, nFeatures=nFeatures, span=span)
+    rows = subset_count_rows(counts.shape[0], hvg["features"])
+    scaled = scale_object(norm.tocsr()[rows].tocsc(), scale_max=scale_max)
+    pca = run_pca(scaled, maxoutdim=n_pcs, method=pca_method)
+    idx, dist = knn_exact(pca["embedding"], k, metric=metric)
+    adj = adjacency_atlas(idx) if graph == "atlas" else adjacency_small(idx)
+    return {"norm": norm, "hvg": hvg, "rows": rows, "scaled": scaled, "pca": pca,
+            "knn_idx": idx, "knn_dist": dist, "adj": adj}

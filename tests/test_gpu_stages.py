@@ -1,0 +1,412 @@
+"""Stage-isolated parity of the CUDA path (through the C ABI) against the CPU oracle, each stage on
+the SAME input.  Tolerances are the ones BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_close(a, b, rtol, atol=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+# ---- a1 normalize ---------------------------------------------------------------------------
+@pytest.mark.parametrize("method,pc,sf", [("logarithm", 1, 10000), ("logarithm", 0.5, 1e4), ("none", 1, 1e6)])
+def test_normalize_matches_oracle(cs, oracle, ctx, small_counts, method, pc, sf):
+    raw = ctx.sparse_from_scipy(small_counts)
+    norm = ctx.normalize(raw, sf, cs.pipeline.norm_code(method), pc)
+    got = norm.to_scipy()
+    want = oracle.normalize_object(small_counts, sf, method, pc)
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    # north_star: normalised matrix within 1e-5 relative (fp32 storage gives ~1e-7)
+    assert rel_close(got.data, want.data, 1e-5)
+    assert np.max(np.abs(got.data - want.data) / np.abs(want.data)) < 2e-6
+
+
+def test_normalize_round_trip_property(cs, ctx, medium_counts):
+    """expm1(norm)/sf * colsum recovers the counts (size-independent property)."""
+    raw = ctx.sparse_from_scipy(medium_counts)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0).to_scipy()
+    colsum = np.asarray(medium_counts.sum(axis=0)).ravel()
+    rec = np.expm1(norm.data) / 1e4 * np.repeat(colsum, np.diff(norm.indptr))
+    assert np.allclose(rec, medium_counts.data, rtol=2e-5)
+
+
+def test_normalize_unknown_method_errors(cs, ctx, small_counts):
+    raw = ctx.sparse_from_scipy(small_counts)
+    with pytest.raises(cs.CellScopesCudaError) as e:
+        ctx.normalize(raw, 1e4, 7, 1.0)
+    assert "Unknown normalization method" in str(e.value)
+    with pytest.raises(ValueError):
+        cs.normalize_object(small_counts, norm_method="bogus")
+
+
+def test_normalize_zero_sum_column_is_nan_then_zero(cs, oracle, ctx):
+    """A column whose stored values sum to zero becomes NaN; imaging objects replace by 0."""
+    m = sp.csc_matrix(np.array([[1, 0, 0], [2, 0, 3], [0, 0, 1]], dtype=np.int64))
+    m = sp.csc_matrix((np.array([1, 2, 0, 0, 3, 1], dtype=np.int64), np.array([0, 1, 0, 2, 1, 2]),
+                       np.array([0, 2, 4, 6])), shape=(3, 3))       # column 1 stores explicit zeros
+    raw = ctx.sparse_from_scipy(m)
+    got = ctx.normalize(raw, 1e4, 0, 1.0).to_scipy()
+    want = oracle.normalize_object(m)
+    assert np.isnan(got.data[2:4]).all() and np.isnan(want.data[2:4]).all()
+    assert rel_close(got.data[[0, 1, 4, 5]], want.data[[0, 1, 4, 5]], 1e-6)
+    got0 = ctx.normalize(raw, 1e4, 0, 1.0, nan_to_zero=True).to_scipy()
+    assert np.all(got0.data[2:4] == 0.0)
+
+
+def test_upload_int64_one_based_and_float_values(cs, ctx, small_counts):
+    m = small_counts
+    a = ctx.sparse_upload(m.shape[0], m.shape[1], m.indptr.astype(np.int64) + 1, m.indices.astype(np.int64) + 1,
+                          m.data.astype(np.int64), index_base=1)
+    b = ctx.sparse_upload(m.shape[0], m.shape[1], m.indptr.astype(np.int32), m.indices.astype(np.int32),
+                          m.data.astype(np.float64), index_base=0)
+    for h in (a, b):
+        back = h.to_scipy()
+        assert (back != m).nnz == 0
+    cp, rv, v = a.download(10, 50, index_base=1)
+    assert cp[0] == 1 and rv.min() >= 1
+    sub = m[:, 10:50]
+    assert np.array_equal(cp - 1, sub.indptr) and np.array_equal(rv - 1, sub.indices)
+
+
+def test_upload_rejects_bad_rows(cs, ctx):
+    with pytest.raises(cs.CellScopesCudaError):
+        ctx.sparse_upload(3, 2, np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0]))
+
+
+def test_empty_and_ragged_columns(cs, oracle, ctx):
+    """Empty columns, a single-entry column and a full column."""
+    rng = np.random.default_rng(0)
+    d = np.zeros((40, 7), dtype=np.int64)
+    d[:, 1] = rng.integers(1, 5, 40)      # full
+    d[3, 2] = 9                           # single
+    d[:17, 4] = rng.integers(0, 3, 17)
+    d[5:, 6] = rng.integers(0, 2, 35)
+    m = sp.csc_matrix(d)
+    raw = ctx.sparse_from_scipy(m)
+    got = ctx.normalize(raw, 1e4, 0, 1.0).to_scipy()
+    want = oracle.normalize_object(m)
+    assert np.array_equal(got.indptr, want.indptr)
+    assert rel_close(got.data, want.data, 1e-5)
+
+
+# ---- a2 HVG ---------------------------------------------------------------------------------
+def test_gene_moments_exact(cs, oracle, ctx, medium_counts):
+    raw = ctx.sparse_from_scipy(medium_counts)
+    g = medium_counts.shape[0]
+    st = ctx.vec(2 * g)
+    ctx.gene_stats_partial(raw, st)
+    got = st.download()
+    s1, s2, _, _ = oracle.gene_moments(medium_counts)
+    assert np.array_equal(got[:g], s1) and np.array_equal(got[g:], s2)      # integers: bit-exact
+    # fused into normalize: same table
+    st2 = ctx.vec(2 * g)
+    ctx.normalize(raw, 1e4, 0, 1.0, False, st2)
+    assert np.array_equal(st2.download(), got)
+
+
+def test_gene_moments_large_counts(cs, oracle, ctx):
+    """Counts above the shared-memory fast path (>65535) and non-integer values take the direct path."""
+    rng = np.random.default_rng(1)
+    d = rng.integers(0, 4, size=(50, 300)).astype(np.float64)
+    d[7, 5] = 100000.0
+    d[9, 6] = 70000.0
+    d[11, :] *= 1.5
+    m = sp.csc_matrix(d)
+    raw = ctx.sparse_from_scipy(m)
+    st = ctx.vec(100)
+    ctx.gene_stats_partial(raw, st)
+    s1, s2, _, _ = oracle.gene_moments(m)
+    got = st.download()
+    assert np.allclose(got[:50], s1, rtol=1e-12) and np.allclose(got[50:], s2, rtol=1e-12)
+
+
+@pytest.mark.parametrize("nfeat", [200, 2000])
+def test_hvg_set_bit_exact(cs, oracle, ctx, medium_counts, nfeat):
+    raw = ctx.sparse_from_scipy(medium_counts)
+    g, n = medium_counts.shape
+    st = ctx.vec(2 * g)
+    ctx.gene_stats_partial(raw, st)
+    got = ctx.hvg_finish(st, g, n, nfeat, 0.3)
+    want = oracle.find_variable_genes(medium_counts, nfeat, 0.3)
+    assert np.array_equal(got["mean"], want["mean"])
+    assert np.array_equal(got["variance"], want["variance"])
+    assert np.allclose(got["variance_expected"], want["variance_expected"], rtol=1e-10)
+    assert np.allclose(got["variance_standardized"], want["variance_standardized"], rtol=1e-10)
+    # north_star: HVG set bit-exact (rank order included)
+    assert np.array_equal(got["features"], want["features"])
+    margin = want["variance_standardized"][want["order"][nfeat - 1]] - want["variance_standardized"][want["order"][nfeat]]
+    print(f"HVG boundary margin at rank {nfeat}: {margin:.3e}")
+
+
+def test_hvg_nfeatures_clamped(cs, ctx, small_counts):
+    raw = ctx.sparse_from_scipy(small_counts)
+    g, n = small_counts.shape
+    st = ctx.vec(2 * g)
+    ctx.gene_stats_partial(raw, st)
+    got = ctx.hvg_finish(st, g, n, 10 * g, 0.3)       # processing.jl:134-137
+    assert got["features"].size == g
+    assert np.array_equal(np.sort(got["features"]), np.arange(g))
+
+
+# ---- a3 scale -------------------------------------------------------------------------------
+def _scaled_pair(cs, oracle, ctx, counts, nfeat, **kw):
+    norm_o = oracle.normalize_object(counts)
+    hv = oracle.find_variable_genes(counts, nfeat)
+    rows = oracle.subset_count_rows(counts.shape[0], hv["features"])
+    want = oracle.scale_object(norm_o.tocsr()[rows].tocsc(), **kw)
+    raw = ctx.sparse_from_scipy(counts)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0)
+    part = ctx.vec(2 * rows.size)
+    ctx.scale_stats_partial(norm, hv["features"], part)
+    dense = ctx.scale_fill(norm, hv["features"], part, counts.shape[1], kw.get("scale_max", 10.0),
+                           kw.get("do_scale", True), kw.get("do_center", True))
+    return dense, want, rows
+
+
+@pytest.mark.parametrize("kw", [{}, {"scale_max": 3.0}, {"do_center": False}, {"do_scale": False}])
+def test_scale_matches_oracle(cs, oracle, ctx, medium_counts, kw):
+    dense, want, rows = _scaled_pair(cs, oracle, ctx, medium_counts, 800, **kw)
+    got = dense.download(np.float64).T          # genes x cells
+    assert got.shape == want.shape
+    # north_star: scaled matrix within 1e-5 relative; z-scores near 0 need an absolute component
+    assert rel_close(got, want, 1e-5, atol=2e-6)
+    assert got.max() <= kw.get("scale_max", 10.0) + 1e-6
+    if not kw:
+        assert (want >= 10.0).any(), "the clip must actually be exercised"
+
+
+def test_scale_rows_in_original_gene_order(cs, oracle, ctx, small_counts):
+    """features given in rank order; rows come out in original gene order (utils.jl:72-76)."""
+    dense, want, rows = _scaled_pair(cs, oracle, ctx, small_counts, 100)
+    assert np.all(np.diff(rows) > 0)
+    assert dense.shape == (small_counts.shape[1], 100)
+
+
+def test_scale_zero_variance_gene_gives_nan(cs, oracle, ctx):
+    d = np.zeros((4, 6))
+    d[0] = [1, 2, 3, 4, 5, 6]
+    d[1] = [2, 2, 2, 2, 2, 2]     # constant -> sd 0 -> NaN (0/0)
+    d[2] = [0, 1, 0, 1, 0, 7]
+    d[3] = [5, 0, 0, 0, 0, 1]
+    m = sp.csc_matrix(d)
+    dev = ctx.sparse_from_scipy(m)
+    part = ctx.vec(8)
+    ctx.scale_stats_partial(dev, None, part)
+    got = ctx.scale_fill(dev, None, part, 6).download(np.float64).T
+    want = oracle.scale_object(m)
+    assert np.isnan(got[1]).all() and np.isnan(want[1]).all()
+    assert rel_close(got[[0, 2, 3]], want[[0, 2, 3]], 1e-5, atol=1e-6)
+
+
+# ---- a4 PCA ---------------------------------------------------------------------------------
+def _align(got, want):
+    sign = np.sign(np.sum(got * want, axis=0))
+    sign[sign == 0] = 1
+    return got * sign
+
+
+def _check_pca(got_emb, info, want, k):
+    lam_w = want["principalvars"]
+    assert np.allclose(info["principalvars"], lam_w, rtol=1e-4), "explained variance"
+    assert abs(info["tvar"] - want["tvar"]) <= 1e-5 * want["tvar"]
+    allv = want["all_vars"]
+    gaps = np.minimum(np.abs(np.diff(allv[:k + 1])), np.r_[np.inf, np.abs(np.diff(allv[:k]))]) / allv[:k]
+    emb_w = want["embedding"]
+    got = _align(got_emb, emb_w)
+    scale = np.sqrt((emb_w ** 2).mean(axis=0))
+    err = np.abs(got - emb_w).max(axis=0) / scale
+    well = gaps >= 1e-2          # gap-aware check
+    assert well.sum() >= 1
+    # north_star: PCA embeddings within 1e-4 after per-component sign alignment
+    assert np.all(err[well] < 1e-4 / np.minimum(1.0, gaps[well] * 10)), (err, gaps)
+    # ill-separated components: compare the subspace instead
+    qg, _ = np.linalg.qr(got_emb)
+    qw, _ = np.linalg.qr(emb_w)
+    s = np.linalg.svd(qg.T @ qw, compute_uv=False)
+    if gaps.min() >= 1e-3:
+        assert s.min() > 1 - 1e-6
+    return err, gaps
+
+
+def test_pca_direct_small_h(cs, oracle, ctx):
+    """H <= 160: full Jacobi eigendecomposition."""
+    rng = np.random.default_rng(3)
+    n, h, k = 3000, 96, 20
+    lat = rng.normal(size=(n, 25)) * np.linspace(6, 1.5, 25)
+    z = lat @ rng.normal(size=(25, h)) + rng.normal(size=(n, h))
+    z = np.minimum((z - z.mean(0)) / z.std(0, ddof=1), 10.0)
+    dense = ctx.dense_upload(z.astype(np.float32))
+    z32 = dense.download(np.float64)
+    want = oracle.run_pca(z32.T, k)
+    model, emb = cs.processing._pca_device(ctx, dense, n, k)
+    _check_pca(emb.download(np.float64), model.info(), want, k)
+
+
+def test_pca_block_solver(cs, oracle, ctx):
+    """H > 160: Gram + block subspace iteration with Rayleigh-Ritz."""
+    rng = np.random.default_rng(4)
+    n, h, k = 6000, 600, 30
+    lat = rng.normal(size=(n, 40)) * (8.0 * 0.9 ** np.arange(40))
+    z = lat @ rng.normal(size=(40, h)) / np.sqrt(h) * 6 + rng.normal(size=(n, h))
+    z = np.minimum((z - z.mean(0)) / z.std(0, ddof=1), 10.0)
+    dense = ctx.dense_upload(z.astype(np.float32))
+    z32 = dense.download(np.float64)
+    want = oracle.run_pca(z32.T, k)
+    model, emb = cs.processing._pca_device(ctx, dense, n, k)
+    print("eigensolver iters", model.iters, "resid", model.resid)
+    assert model.resid < 1e-7
+    _check_pca(emb.download(np.float64), model.info(), want, k)
+
+
+def test_pca_on_pipeline_data(cs, oracle, ctx, medium_counts):
+    dense, want_scaled, rows = _scaled_pair(cs, oracle, ctx, medium_counts, 1000)
+    n = medium_counts.shape[1]
+    z32 = dense.download(np.float64)
+    want = oracle.run_pca(z32.T, 30, method="gram")
+    model, emb = cs.processing._pca_device(ctx, dense, n, 30)
+    err, gaps = _check_pca(emb.download(np.float64), model.info(), want, 30)
+    print("pipeline-data PCA: max err", err.max(), "min gap", gaps.min(), "iters", model.iters)
+
+
+def test_gram_partials_add_up(cs, ctx):
+    """Sharding invariance: partials of two cell ranges sum to the partial of the whole (multi-GPU allreduce)."""
+    rng = np.random.default_rng(5)
+    z = rng.normal(size=(5000, 300)).astype(np.float32)
+    full, a, b = ctx.dense_upload(z), ctx.dense_upload(z[:1777]), ctx.dense_upload(z[1777:])
+    outs = []
+    for parts in ([full], [a, b]):
+        cs_, g = ctx.vec(300), ctx.vec(300 * 300)
+        for d in parts:
+            ctx.pca_partial(d, cs_, g)
+        outs.append((cs_.download(), g.download()))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-12, atol=1e-9)
+    assert np.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
+    ref = z.astype(np.float64).T @ z.astype(np.float64)
+    assert np.allclose(outs[0][1].reshape(300, 300), ref, rtol=1e-5, atol=2e-3)
+
+
+# ---- a5/a6 kNN ------------------------------------------------------------------------------
+def _knn_check(idx, dist, widx, wdist, tie=1e-6):
+    """Bit-exact neighbour sets except at distance ties within `tie` (north_star)."""
+    n, k = idx.shape
+    assert np.allclose(dist, wdist, atol=2e-6)
+    same = idx == widx
+    bad_rows = np.flatnonzero(~same.all(axis=1))
+    for r in bad_rows:
+        for j in np.flatnonzero(~same[r]):
+            # a mismatch is only allowed inside a tie band: the two candidates' distances differ by <= tie
+            assert abs(wdist[r, j] - dist[r, j]) <= tie, (r, j)
+            lo = wdist[r, j] - tie
+            hi = wdist[r, j] + tie
+            assert lo <= dist[r, j] <= hi
+        # as sets, everything strictly inside the k-th distance must agree
+        kth = wdist[r, -1]
+        strict_w = set(widx[r][wdist[r] < kth - tie])
+        assert strict_w <= set(idx[r])
+    return bad_rows.size
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+@pytest.mark.parametrize("n,d,k", [(3000, 50, 20), (1111, 10, 30), (700, 33, 5)])
+def test_knn_exact_vs_oracle(cs, oracle, ctx, metric, n, d, k):
+    rng = np.random.default_rng(n + d)
+    centers = rng.normal(size=(12, d)) * 3
+    x = (centers[rng.integers(0, 12, n)] + rng.normal(size=(n, d))).astype(np.float32)
+    dense = ctx.dense_upload(x)
+    idx, dist = ctx.knn(dense, dense, k, metric=cs.pipeline.metric_code(metric))
+    idx = idx.download().reshape(n, k)
+    dist = dist.download().reshape(n, k).astype(np.float64)
+    widx, wdist = oracle.knn_exact(x.astype(np.float64), k, metric)
+    nbad = _knn_check(idx, dist, widx, wdist, tie=1e-6 if metric == "cosine" else 1e-5)
+    assert nbad <= max(2, n // 200)
+    assert np.all(idx != np.arange(n)[:, None]), "self excluded"
+    assert np.all(np.diff(dist, axis=1) >= -1e-7), "ascending distance"
+
+
+def test_knn_ties_broken_by_lower_index(cs, ctx):
+    """Duplicated points: equal distances must come out in ascending id order."""
+    rng = np.random.default_rng(9)
+    base = rng.normal(size=(40, 8)).astype(np.float32)
+    x = np.concatenate([base, base, base], axis=0)      # every point has two exact duplicates
+    dense = ctx.dense_upload(x)
+    idx, dist = ctx.knn(dense, dense, 4)
+    idx = idx.download().reshape(-1, 4)
+    dist = dist.download().reshape(-1, 4)
+    for i in range(x.shape[0]):
+        dup = sorted(j for j in (i % 40, i % 40 + 40, i % 40 + 80) if j != i)
+        assert list(idx[i, :2]) == dup
+        assert np.all(dist[i, :2] <= 1e-6)
+
+
+def test_knn_dims_subset_and_query_shard(cs, oracle, ctx):
+    """dims_use (run_umap dims 1:10) and a query shard against all keys (multi-GPU layout)."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(2000, 30)).astype(np.float32)
+    keys = ctx.dense_upload(x)
+    widx, wdist = oracle.knn_exact(x[:, :10].astype(np.float64), 15, "cosine")
+    q = ctx.dense_upload(x[500:1300])
+    idx, dist = ctx.knn(q, keys, 15, query_offset=500, dim_lo=0, dim_hi=10)
+    idx = idx.download().reshape(800, 15)
+    dist = dist.download().reshape(800, 15).astype(np.float64)
+    _knn_check(idx, dist, widx[500:1300], wdist[500:1300])
+
+
+def test_knn_bad_k(cs, ctx):
+    x = ctx.dense_upload(np.random.default_rng(0).normal(size=(10, 4)).astype(np.float32))
+    with pytest.raises(cs.CellScopesCudaError):
+        ctx.knn(x, x, 10)
+
+
+# ---- adjacency / SNN ------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(500, 10), (3000, 20)])
+def test_graphs_identical_to_oracle(cs, oracle, ctx, n, k):
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(n, 16))
+    widx, _ = oracle.knn_exact(x, k, "cosine")
+    tab = ctx.vec_from(widx.astype(np.int32).ravel())
+    for mode, want in ((cs._capi.GRAPH_BINARY, oracle.adjacency_small(widx)),
+                       (cs._capi.GRAPH_SUM, oracle.adjacency_atlas(widx)),
+                       (cs._capi.GRAPH_SNN_JACCARD, oracle.snn_jaccard(widx))):
+        got = ctx.graph_build(tab, n, k, mode=mode).to_scipy()
+        got.sort_indices()
+        assert np.array_equal(got.indptr, want.indptr)
+        assert np.array_equal(got.indices, want.indices)          # SNN graph edges identical
+        assert np.array_equal(got.data, want.data.astype(np.float64))
+        assert (got != got.T).nnz == 0                            # symmetric
+    pruned = ctx.graph_build(tab, n, k, mode=cs._capi.GRAPH_SNN_JACCARD, snn_prune=1 / 15).to_scipy()
+    wantp = oracle.snn_jaccard(widx, prune=1 / 15)
+    assert np.array_equal(pruned.indices, wantp.indices) and np.array_equal(pruned.data, wantp.data)
+
+
+def test_graph_column_shards_concatenate(cs, oracle, ctx):
+    n, k = 1200, 12
+    widx, _ = oracle.knn_exact(np.random.default_rng(2).normal(size=(n, 8)), k)
+    tab = ctx.vec_from(widx.astype(np.int32).ravel())
+    full = ctx.graph_build(tab, n, k, mode=cs._capi.GRAPH_SUM).to_scipy()
+    parts = [ctx.graph_build(tab, n, k, lo, hi, cs._capi.GRAPH_SUM).to_scipy() for lo, hi in ((0, 400), (400, 1200))]
+    cat = sp.hstack(parts).tocsc()
+    assert (cat != full).nnz == 0
+
+
+# ---- device generator -----------------------------------------------------------------------
+def test_device_generator_density_and_determinism(cs, ctx):
+    p = cs.synth.make_params(3000, 50000, density=0.05, seed=1234)
+    a = ctx.generate_counts(p, 1000, 3000)
+    b = ctx.generate_counts(p, 1000, 3000)
+    ma, mb = a.to_scipy(), b.to_scipy()
+    assert (ma != mb).nnz == 0
+    dens = ma.nnz / (ma.shape[0] * ma.shape[1])
+    assert 0.03 < dens < 0.08, dens
+    assert np.all(ma.data >= 1) and np.all(ma.data == np.round(ma.data))
+    assert np.all(np.diff(ma.indptr) > 0)
+    # a shard is a slice of the whole: cells 1000..3000 of [0,4000) equal the direct generation
+    whole = ctx.generate_counts(p, 0, 4000).to_scipy()
+    assert (whole[:, 1000:3000] != ma).nnz == 0
+    # statistically the same model as the NumPy twin
+    twin = cs.synth.sample_counts(p, 1000, 3000)
+    assert abs(twin.nnz - ma.nnz) / ma.nnz < 0.02
