@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the counts -> normalise -> HVG -> scale -> PCA -> kNN -> graph path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
+
+One "step" = one pass of the whole hot path over one synthetic count matrix.
+  value   cells/s with the sharded CSC counts already resident in HBM when the timed region starts
+          (CUDA events on the library's stream, max over ranks).
+  e2e     the same metric through the reference-facing host API with HOST buffers: H2D of the Int64/Float64
+          CSC arrays and D2H of the embedding, the kNN table and the adjacency inside the timed region.
+  roofline  the dominant kernel (the all-pairs kNN scan): algorithmic flops 2*N_q*N_keys*n_pcs per launch
+          over its CUDA-event time, against the measured tensor peak.
+  cpu_baseline  the oracle (restated reference algorithm, exact kNN) on a bounded cell sample of the same
+          workload on the host cores.
+`--impl reference` times that CPU restatement alone (Julia is not installed: see DESIGN.md).
+Rendezvous for N > 1: launched by torchrun (one rank per GPU), NCCL for the data-path collectives.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_genes, n_cells, density, n_features, n_pcs, k)  -- BASELINE.json configs
+    "C1": (33000, 10000, 0.05, 2000, 50, 20),
+    "C2": (5000, 500000, 0.05, 2000, 50, 20),
+    "C3": (33000, 1000000, 0.05, 2000, 50, 20),
+    "C4": (18000, 2000000, 0.005, 2000, 50, 20),
+    "tiny": (2000, 20000, 0.05, 500, 20, 10),
+}
+WORKLOAD_DESC = {
+    "C1": "scRNA-seq tutorial scale 10k cells x 33k genes d=5% (configs[0])",
+    "C2": "Xenium-scale 500k cells x 5k-gene panel d=5% (configs[1])",
+    "C3": "1M cells x 33k genes d=5% atlas (configs[2])",
+    "C4": "VisiumHD 2M spots x 18k genes d=0.5% (configs[3])",
+    "tiny": "20k cells x 2k genes (debug)",
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_pipeline(counts, n_features, n_pcs, k):
+    """The oracle restatement, end to end, on the host cores (checker / baseline only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cellscopes_oracle as oracle
+    # the reference's object constructor drops all-zero genes/cells first (utils.jl:313-320)
+    counts, _, _ = oracle.subset_matrix(counts)
+    t0 = time.perf_counter()
+    oracle.run_pipeline(counts, nFeatures=min(n_features, counts.shape[0]), n_pcs=n_pcs, k=k, pca_method="svd")
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU algorithm (restated; Julia absent) on a bounded sample per step."""
+    import csb200 as cs
+    n_genes, n_cells, density, n_features, n_pcs, k = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(n_cells, args.ref_sample)
+    p = cs.synth.make_params(n_genes, n_cells, density=density, seed=1234)
+    counts = cs.synth.sample_counts(p, 0, sample)
+    cores = os.cpu_count()
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_pipeline(counts, n_features, n_pcs, k)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    v = sample / t
+    line = {
+        "impl": "reference", "metric": "cells/sec counts->PCA->kNN/SNN", "value": v, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "n_features": n_features, "n_pcs": n_pcs, "k": k},
+        "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": f"first {sample} cells of the workload, full path incl. exact LAPACK SVD and "
+                                   f"exact brute-force kNN; restated reference algorithm (NumPy/SciPy/OpenBLAS), "
+                                   f"JULIA_NUM_THREADS n/a (Julia absent)"},
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="cells in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-sample", type=int, default=8000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", default="sum", choices=["sum", "binary", "snn"])
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import csb200 as cs
+    n_genes, n_cells, density, n_features, n_pcs, k = wl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = cs.TorchComm(device=torch.device("cuda", local_rank))
+    else:
+        comm = cs.LocalComm()
+    ctx = cs.Context(local_rank)
+    offsets = cs.partition_cells(n_cells, world)
+    lo, hi = int(offsets[rank]), int(offsets[rank + 1])
+    params = cs.PathParams(n_features=n_features, n_pcs=n_pcs, k=k, graph_mode=args.graph)
+
+    # ---- synthetic input, generated on the device --------------------------------
+    sp_params = cs.synth.make_params(n_genes, n_cells, density=density, seed=1234)
+    raw = ctx.generate_counts(sp_params, lo, hi)
+    nnz_local = raw.nnz
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def one_step():
+        return cs.run_path(ctx, comm, raw, n_cells, lo, params, offsets)
+
+    # ---- device-resident metric ------------------------------------------------------------
+    for _ in range(args.warmup):
+        out = one_step()
+        del out
+    ctx.stage_times(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        barrier()
+        ctx.timer_start()
+        out = one_step()
+        ms = ctx.timer_stop()
+        barrier()
+        step_ms.append(ms)
+        last = out
+    sampler.stop_flag.set()
+    sampler.join()
+    stage_ms, launches = ctx.stage_times()
+    total_ms = float(np.sum(step_ms))
+    if rank == 0:
+        print("[bench] step ms", [round(x, 2) for x in step_ms], "stage ms/step",
+              {kk: round(v / args.steps, 3) for kk, v in stage_ms.items() if v > 0}, file=sys.stderr, flush=True)
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_cells / (ms_per_step * 1e-3)
+
+    # solver / data diagnostics of the last step
+    info = last["pca"].info()
+    diag = {"pca_iters": last["pca"].iters, "pca_resid": last["pca"].resid,
+            "lambda_1": float(info["principalvars"][0]), "lambda_k": float(info["principalvars"][-1]),
+            "min_rel_gap": float(np.min(-np.diff(info["principalvars"]) / info["principalvars"][:-1])),
+            "nnz_local": int(nnz_local)}
+    del last, out
+
+    # ---- roofline of the dominant kernel (kNN scan) -------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    scan_ms = stage_ms["knn_scan"] / args.steps
+    flops = 2.0 * (hi - lo) * n_cells * n_pcs
+    achieved = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
+    # TF32 tensor rate is half the bf16 rate on this part; the kernel runs inside a long step -> sustained figure
+    peak_tf32 = 0.5 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    roofline = {"bound": "tensor", "kernel": "k_knn_scan", "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf32, "traffic": None, "peak_kind": f"{peak_kind} bf16 sustained / 2 (tf32)",
+                "ms_per_launch": scan_ms, "share_of_step": scan_ms / ms_per_step,
+                "candidates_per_s": (hi - lo) * n_cells / (scan_ms * 1e-3) if scan_ms > 0 else 0.0}
+    # sparse stages against the HBM roofline (context for the dominant-kernel figure)
+    hbm = {}
+    per_step = {kk: v / args.steps for kk, v in stage_ms.items()}
+    if per_step["normalize"] > 0:
+        hbm["normalize_fused_stats"] = {"bytes_per_nnz": 12, "GB/s": 12.0 * nnz_local / (per_step["normalize"] * 1e-3) / 1e9}
+        hbm["normalize_fused_stats"]["frac"] = hbm["normalize_fused_stats"]["GB/s"] / peaks["hbm_gbs"]
+
+    # ---- e2e: host buffers through the reference-facing API -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(cs, ctx, comm, dist, raw, n_genes, n_cells, lo, hi, params, offsets, args, world, local_rank)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        sample = min(hi - lo, args.cpu_sample)
+        counts = raw.to_scipy(0, sample)
+        dt = cpu_pipeline(counts, n_features, n_pcs, k)
+        cpu = {"value": sample / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {sample} cells of the workload through the whole path (exact SVD + exact kNN), "
+                         f"{dt:.1f} s; restated reference algorithm, JULIA_NUM_THREADS n/a (Julia absent)"}
+
+    if rank == 0:
+        line = {
+            "metric": "cells/sec counts->PCA->kNN/SNN", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "n_genes": n_genes, "n_cells": n_cells,
+                       "density": density, "n_features": n_features, "n_pcs": n_pcs, "k": k, "graph": args.graph,
+                       "parallelism": f"cells sharded over {world} GPU(s)",
+                       "l2": "inputs larger than L2 (CSC shard >= 1 GB) and a 256 MiB flush between iterations"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms": {kk: round(v, 3) for kk, v in per_step.items() if v > 0}, "hbm_stages": hbm, "diag": diag,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(cs, ctx, comm, dist, raw, n_genes, n_cells, lo, hi, params, offsets, args, world, local_rank):
+    """Host CSC (Int64 indices, Float64 values, pinned) -> results on the host, every copy inside the timed region."""
+    import torch
+    import scipy.sparse as sp
+    colptr, rowval, nzval = raw.download(0, hi - lo, 0)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        v = t.numpy()
+        v[...] = a
+        return t, v
+    keep = [pinned(colptr), pinned(rowval), pinned(nzval)]
+    colptr, rowval, nzval = (kp[1] for kp in keep)
+    h2d = colptr.nbytes + rowval.nbytes + nzval.nbytes
+    n_loc = hi - lo
+    times = []
+    d2h = 0
+    launches0 = ctx.stage_times()[1]
+    for it in range(max(1, min(args.steps, 3)) + 1):
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            # the reference-facing calls, in the atlas order of docs/scRNA_tutorial/README.md:260-280
+            m = sp.csc_matrix((nzval, rowval, colptr), shape=(n_genes, n_loc), copy=False)
+            m.has_sorted_indices = True
+            obj = cs.scRNAObject.__new__(cs.scRNAObject)
+            obj.rawCount = cs.RawCountObject(m, np.arange(n_loc), np.arange(n_genes))
+            obj.normCount = obj.scaleCount = obj.varGene = obj.dimReduction = obj.clustData = None
+            obj.metaData, obj.imaging, obj._session = None, False, None
+            obj = cs.normalize_object(obj, ctx=ctx)
+            obj = cs.find_variable_genes(obj, nFeatures=params.n_features, span=params.span, ctx=ctx)
+            obj = cs.scale_object(obj, features=obj.varGene.var_gene, ctx=ctx)
+            obj = cs.run_pca(obj, maxoutdim=params.n_pcs, ctx=ctx)
+            obj = cs.run_clustering(obj, n_neighbors=params.k, graph=params.graph_mode, ctx=ctx)
+            emb = obj.dimReduction.pca.cell_embedding
+            adj = obj.clustData.adj_mat
+            d2h = emb.nbytes + obj.clustData.knn_indices.size * 4 + obj.clustData.knn_distances.size * 4 + \
+                adj.indptr.size * 8 + adj.nnz * 16
+            del obj
+        else:
+            shard = ctx.sparse_upload(n_genes, n_loc, colptr, rowval, nzval, 0)
+            out = cs.run_path(ctx, comm, shard, n_cells, lo, params, offsets)
+            emb = out["embedding"].download(np.float64)
+            idx = out["knn_idx"].download()
+            dd = out["knn_dist"].download()
+            gcp, grv, gv = out["graph"].download(0)
+            d2h = emb.nbytes + idx.nbytes + dd.nbytes + gcp.nbytes + grv.nbytes + gv.nbytes
+            del out, shard
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    t = float(np.mean(times))
+    if dist is not None:
+        tt = torch.tensor([t], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    return {"value": n_cells / t, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": t * 1e3, "api": "normalize_object/find_variable_genes/scale_object/run_pca/run_clustering"
+            if world == 1 else "csc_sparse_upload + run_path + downloads per rank",
+            "timer": "host wall clock around synchronised calls (includes H2D, D2H and host marshalling)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,14 @@ csc_status csc_fail(csc_ctx* ctx, csc_status code, const char* fmt, ...) {
   return code;
 }
 
+#include <chrono>
+void csc_trace(csc_ctx* ctx, const char* label) {
+  cudaStreamSynchronize(ctx->stream);
+  const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  fprintf(stderr, "[csc trace] %-28s +%9.3f ms\n", label, ctx->trace_t0 > 0 ? now - ctx->trace_t0 : 0.0);
+  ctx->trace_t0 = now;
+}
+
 csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero) {
   DevPtr m;
   try {
@@ -27,11 +35,13 @@ csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero) {
   m->device = ctx->device;
   m->bytes = bytes;
   size_t req = bytes ? bytes : 16;
-  cudaError_t e = cudaMalloc(&m->p, req);
+  m->stream = ctx->stream;
+  m->ctx_alive = ctx->alive;
+  cudaError_t e = cudaMallocAsync(&m->p, req, ctx->stream);
   if (e != cudaSuccess) {
     m->p = nullptr;
     cudaGetLastError();
-    return csc_fail(ctx, CSC_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", req, cudaGetErrorString(e));
+    return csc_fail(ctx, CSC_ERR_OOM, "cudaMallocAsync(%zu bytes) failed: %s", req, cudaGetErrorString(e));
   }
   if (zero) CSC_CUDA(ctx, cudaMemsetAsync(m->p, 0, req, ctx->stream));
   *out = m;
@@ -78,10 +88,21 @@ csc_status csc_create(int32_t device, csc_ctx** out) {
     return CSC_ERR_UNSUPPORTED;
   }
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool;
+    CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    CREATE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  ctx->alive = std::make_shared<bool>(true);
+  if (const char* lv = getenv("CSC_LOG_LEVEL")) ctx->trace = atoi(lv) >= 2;
   CREATE_CUDA(cudaEventCreate(&ctx->ev_timer0));
   CREATE_CUDA(cudaEventCreate(&ctx->ev_timer1));
   CREATE_CUDA(cudaEventCreate(&ctx->ev_stage0));
   CREATE_CUDA(cudaEventCreate(&ctx->ev_stage1));
+  CREATE_CUDA(cudaEventCreate(&ctx->ev_k0));
+  CREATE_CUDA(cudaEventCreate(&ctx->ev_k1));
 #undef CREATE_CUDA
   *out = ctx;
   return CSC_OK;
@@ -90,12 +111,15 @@ csc_status csc_create(int32_t device, csc_ctx** out) {
 csc_status csc_destroy(csc_ctx* ctx) {
   if (!ctx) return CSC_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->alive) *ctx->alive = false;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->ev_timer0) cudaEventDestroy(ctx->ev_timer0);
   if (ctx->ev_timer1) cudaEventDestroy(ctx->ev_timer1);
   if (ctx->ev_stage0) cudaEventDestroy(ctx->ev_stage0);
   if (ctx->ev_stage1) cudaEventDestroy(ctx->ev_stage1);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CSC_OK;

@@ -25,24 +25,38 @@ struct csc_ctx {
   std::string err;
   cudaEvent_t ev_timer0 = nullptr, ev_timer1 = nullptr;
   cudaEvent_t ev_stage0 = nullptr, ev_stage1 = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around one kernel of interest inside a stage
   double stage_ms[CSC_T_COUNT] = {0};
   int64_t launches = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  std::shared_ptr<bool> alive;  // cleared by csc_destroy: late frees then fall back to cudaFree
+  int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
+  double trace_t0 = 0.0;
 };
+void csc_trace(csc_ctx* ctx, const char* label);
+#define CSC_TRACE(ctx, label)                 \
+  do {                                        \
+    if ((ctx)->trace) csc_trace((ctx), label); \
+  } while (0)
 
 // device allocation with shared ownership (a normalised matrix shares colptr/rowval with the raw one)
+// Allocations come from the stream-ordered pool (cudaMallocAsync) so that the many short-lived work
+// buffers of a stage cost microseconds, not a device synchronisation each.
 struct DevMem {
   void* p = nullptr;
   size_t bytes = 0;
   int device = 0;
   bool owned = true;
+  cudaStream_t stream = nullptr;
+  std::shared_ptr<bool> ctx_alive;
   ~DevMem() {
     if (p && owned) {
       int cur = 0;
       cudaGetDevice(&cur);
       if (cur != device) cudaSetDevice(device);
-      cudaFree(p);
+      if (ctx_alive && *ctx_alive) cudaFreeAsync(p, stream);
+      else cudaFree(p);
       if (cur != device) cudaSetDevice(cur);
     }
   }
@@ -93,7 +107,7 @@ struct csc_graph {
   int64_t col_lo;
   DevPtr colptr;  // int64 [n_cols+1]
   DevPtr rowval;  // int32 [nnz]
-  DevPtr val;     // float [nnz]
+  DevPtr val;     // double [nnz]
 };
 
 // ------------------------------------------------------------------------------------------

@@ -154,6 +154,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   const int64_t n_loc = cell_hi - cell_lo;
   const int64_t n_all = n_loc * k + n_cells_total * k;
   const int32_t* idx = knn_idx->as<int32_t>();
+  CSC_TRACE(ctx, "graph: begin");
 
   std::unique_ptr<csc_graph> g(new csc_graph());
   g->ctx = ctx;
@@ -172,6 +173,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   CSC_TRY(dev_alloc(ctx, (size_t)n_all * 8, &keys_a));
   CSC_TRY(dev_alloc(ctx, (size_t)n_all * 8, &keys_b));
   CSC_TRY(dev_alloc(ctx, 8, &counter, true));
+  CSC_TRACE(ctx, "graph: alloc keys");
   k_graph_keys<<<nblk(n_all), 256, 0, ctx->stream>>>(idx, n_cells_total, k, cell_lo, cell_hi, (unsigned long long*)keys_a->p,
                                                       (unsigned long long*)counter->p);
   CSC_LAUNCHED(ctx);
@@ -189,6 +191,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
     ctx->launches += 8;
     (void)col_bits;
   }
+  CSC_TRACE(ctx, "graph: keys+sort");
   unsigned long long n_valid = 0;
   CSC_CUDA(ctx, cudaMemcpyAsync(&n_valid, counter->p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -201,6 +204,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   k_graph_heads<<<nblk(nv), 256, 0, ctx->stream>>>(skeys, nv, (int64_t*)head->p);
   CSC_LAUNCHED(ctx);
   CSC_TRY(exclusive_scan(ctx, (const int64_t*)head->p, (int64_t*)pos->p, nv + 1));
+  CSC_TRACE(ctx, "graph: heads+scan");
   int64_t n_unique = 0;
   CSC_CUDA(ctx, cudaMemcpyAsync(&n_unique, (int64_t*)pos->p + nv, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -225,6 +229,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
                                                            (int64_t*)keep->p);
   CSC_LAUNCHED(ctx);
   CSC_TRY(exclusive_scan(ctx, (const int64_t*)keep->p, (int64_t*)kpos->p, n_unique + 1));
+  CSC_TRACE(ctx, "graph: compact+values+scan");
   int64_t nnz = 0;
   CSC_CUDA(ctx, cudaMemcpyAsync(&nnz, (int64_t*)kpos->p + n_unique, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -240,6 +245,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   k_graph_colptr<<<nblk(n_loc + 1), 256, 0, ctx->stream>>>((const int32_t*)cols->p, nnz, n_loc, (int64_t*)g->colptr->p);
   CSC_LAUNCHED(ctx);
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CSC_TRACE(ctx, "graph: emit+colptr");
   *out = g.release();
   return CSC_OK;
   CSC_GUARD_END(ctx)

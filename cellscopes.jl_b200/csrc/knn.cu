@@ -220,11 +220,13 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
   if (queries->n_rows > 0) {
     const float* qd = (const float*)qp->p;
     const float* kd = (const float*)kp->p;
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
     switch (DP) {
       case 16: s = launch_scan<16>(ctx, qd, queries->n_rows, kd, keys->n_rows, query_offset, k, vd->as<float>(), vi->as<int32_t>()); break;
       case 32: s = launch_scan<32>(ctx, qd, queries->n_rows, kd, keys->n_rows, query_offset, k, vd->as<float>(), vi->as<int32_t>()); break;
       default: s = launch_scan<64>(ctx, qd, queries->n_rows, kd, keys->n_rows, query_offset, k, vd->as<float>(), vi->as<int32_t>()); break;
     }
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
     if (s == CSC_OK) {
       k_knn_finish<<<(unsigned)ceil_div64(queries->n_rows * k, 256), 256, 0, ctx->stream>>>(
           vd->as<float>(), qsq ? (const float*)qsq->p : nullptr, queries->n_rows, k, metric);
@@ -232,6 +234,9 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
       cudaError_t e = cudaGetLastError();
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       if (e != cudaSuccess) s = csc_fail(ctx, CSC_ERR_CUDA, "csc_knn: %s", cudaGetErrorString(e));
+      float ms = 0.f;
+      if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess)
+        ctx->stage_ms[CSC_T_KNN_SCAN] += ms;
     }
     if (s != CSC_OK) {
       csc_vec_free(vi);
