@@ -1,0 +1,87 @@
+"""Host-side logic that needs no GPU: partitioning, container semantics, synthetic generator, argument errors."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+
+def test_partition_cells_by_count(cs):
+    off = cs.partition_cells(10, 3)
+    assert list(off) == [0, 4, 7, 10]
+    assert list(cs.partition_cells(5, 1)) == [0, 5]
+    off = cs.partition_cells(2, 4)
+    assert off[0] == 0 and off[-1] == 2 and np.all(np.diff(off) >= 0)
+    with pytest.raises(ValueError):
+        cs.partition_cells(5, 0)
+
+
+def test_partition_cells_by_nnz(cs):
+    colptr = np.array([0, 100, 100, 110, 120, 200, 200, 300])      # 7 cells, ragged incl. empty columns
+    off = cs.partition_cells(7, 2, colptr)
+    assert off[0] == 0 and off[-1] == 7
+    left = colptr[off[1]] - colptr[0]
+    assert abs(left - 150) <= 80
+    off8 = cs.partition_cells(7, 8, colptr)
+    assert off8.size == 9 and np.all(np.diff(off8) >= 0) and off8[-1] == 7
+
+
+def test_objects_dimension_checks(cs):
+    m = sp.csc_matrix(np.ones((3, 2)))
+    with pytest.raises(ValueError, match="cell ID do not match"):
+        cs.RawCountObject(m, ["a"], ["g1", "g2", "g3"])
+    with pytest.raises(ValueError, match="gene name do not match"):
+        cs.RawCountObject(m, ["a", "b"], ["g1"])
+    r = cs.RawCountObject(m, ["a", "b"], ["g1", "g2", "g3"])
+    assert r.shape == (3, 2) and r.device is None
+
+
+def test_screate_filters_like_subset_matrix(cs):
+    d = np.array([[0, 0, 0, 0], [1, 0, 2, 0], [0, 0, 3, 1], [2, 0, 0, 0]])
+    raw = cs.RawCountObject(sp.csc_matrix(d), ["c1", "c2", "c3", "c4"], ["A", "B", "C", "B"])
+    obj = cs.scRNAObject(raw)
+    # zero gene A and zero cell c2 dropped (strict >), duplicated gene name B keeps its first occurrence
+    assert obj.rawCount.gene_name == ["B", "C"] and obj.rawCount.cell_name == ["c1", "c3", "c4"]
+    assert list(obj.metaData["nFeatures"]) == [1, 5, 1]           # total counts per cell (objects.jl:148)
+    assert list(obj.metaData["nGenes"]) == [1, 2, 1]
+    obj2 = cs.scRNAObject(raw, min_gene=1, prefix="s1")
+    assert obj2.rawCount.cell_name == ["s1_c1", "s1_c3"]
+
+
+def test_subset_count_keeps_original_order(cs):
+    m = sp.csc_matrix(np.arange(12).reshape(4, 3))
+    n = cs.NormCountObject(m, ["a", "b", "c"], ["g1", "g2", "g3", "g4"], 1e4, "logarithm", 1)
+    s = cs.subset_count(n, genes=["g4", "g1"], cells=["c", "a"])
+    assert s.gene_name == ["g1", "g4"] and s.cell_name == ["a", "c"]
+    assert np.array_equal(s.count_mtx.toarray(), np.array([[0, 2], [9, 11]]))
+    assert isinstance(s, cs.NormCountObject) and s.scale_factor == 1e4
+
+
+def test_enum_mapping_and_errors(cs):
+    assert cs.pipeline.norm_code("logarithm") == 0 and cs.pipeline.norm_code("none") == 1
+    with pytest.raises(ValueError, match="Unknown normalization method"):
+        cs.pipeline.norm_code("clr")
+    assert cs.pipeline.metric_code("CosineDist()") == 0 and cs.pipeline.metric_code("euclidean") == 1
+    with pytest.raises(ValueError):
+        cs.pipeline.metric_code("manhattan")
+
+
+def test_synth_params_and_sampler(cs):
+    p = cs.synth.make_params(800, 5000, density=0.05, seed=1)
+    q = cs.synth.make_params(800, 5000, density=0.05, seed=1)
+    assert np.array_equal(p.a, q.a) and np.array_equal(p.module, q.module)
+    m = cs.synth.sample_counts(p, 100, 400)
+    assert m.shape == (800, 300)
+    dens = m.nnz / (800 * 300)
+    assert 0.03 < dens < 0.08
+    assert np.all(np.diff(m.indptr) > 0), "no empty cells"
+    # any cell range is reproducible anywhere
+    sub = cs.synth.sample_counts(p, 150, 200)
+    assert (m[:, 50:100] != sub).nnz == 0
+
+
+def test_lazy_matrix_is_not_touched_by_shape(cs):
+    class Boom:
+        def download(self, *a, **k):
+            raise AssertionError("must not download")
+    lz = cs.objects.LazyDeviceMatrix(Boom(), "dense_t", (5, 7))
+    n = cs.ScaleCountObject(lz, list("abcdefg"), list("vwxyz"), True, True, 10.0)
+    assert n.shape == (5, 7) and n.device is lz.handle

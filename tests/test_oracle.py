@@ -1,0 +1,186 @@
+"""The oracle against hand-computed known answers and the committed golden vectors.
+
+The reference ships no tests or fixtures, so these known answers are worked out by
+hand from the reference's formulas (cited per test) and the golden file pins the oracle's own output."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_small.json")
+
+COUNTS = np.array([[1, 0, 2, 0],
+                   [0, 3, 0, 1],
+                   [4, 0, 0, 1],
+                   [0, 1, 1, 0],
+                   [5, 0, 2, 2]], dtype=np.int64)          # 5 genes x 4 cells
+
+
+def test_normalize_hand_computed(oracle):
+    # processing.jl:17-24: log((x * (1/colsum)) * 10000 + 1)
+    out = oracle.normalize_object(sp.csc_matrix(COUNTS)).toarray()
+    colsum = COUNTS.sum(axis=0)                      # [10, 4, 5, 4]
+    assert list(colsum) == [10, 4, 5, 4]
+    for g in range(5):
+        for c in range(4):
+            if COUNTS[g, c]:
+                assert out[g, c] == pytest.approx(math.log(COUNTS[g, c] / colsum[c] * 10000 + 1), rel=1e-14)
+            else:
+                assert out[g, c] == 0.0
+    assert out[0, 0] == pytest.approx(math.log(1001.0))
+    none = oracle.normalize_object(sp.csc_matrix(COUNTS), 100, "none").toarray()
+    assert none[4, 0] == pytest.approx(50.0)         # 5/10*100
+    with pytest.raises(ValueError):
+        oracle.normalize_object(sp.csc_matrix(COUNTS), norm_method="clr")
+
+
+def test_normalize_keeps_pattern_and_nan_rule(oracle):
+    m = sp.csc_matrix((np.array([1., 2., 0., 0.]), np.array([0, 1, 0, 2]), np.array([0, 2, 4])), shape=(3, 2))
+    out = oracle.normalize_object(m)
+    assert np.array_equal(out.indptr, m.indptr) and np.array_equal(out.indices, m.indices)
+    assert np.isnan(out.data[2:]).all()              # zero-sum column -> stored NaN
+    assert np.all(oracle.normalize_object(m, nan_to_zero=True).data[2:] == 0)
+
+
+def test_gene_moments_hand_computed(oracle):
+    s1, s2, mean, var = oracle.gene_moments(sp.csc_matrix(COUNTS))
+    assert list(s1) == [3, 4, 5, 2, 9] and list(s2) == [5, 10, 17, 2, 33]
+    assert np.allclose(mean, COUNTS.mean(axis=1))
+    assert np.allclose(var, COUNTS.var(axis=1, ddof=1))          # Statistics.var is corrected (n-1)
+
+
+def test_scale_hand_computed(oracle):
+    # processing.jl:66-74: (x - mean)/sd with sd corrected, then min(x, scale_max): upper clip only
+    x = np.array([[0., 0., 0., 10.], [1., 2., 3., 4.]])
+    z = oracle.scale_object(x, scale_max=1.0)
+    sd0 = np.std(x[0], ddof=1)
+    assert z[0, 3] == 1.0                            # (10-2.5)/5 = 1.5 clipped to 1
+    assert z[0, 0] == pytest.approx(-2.5 / sd0)      # no lower clip
+    assert np.allclose(z[1], np.minimum((x[1] - 2.5) / np.std(x[1], ddof=1), 1.0))
+    z2 = oracle.scale_object(x, do_center=False, do_scale=False)
+    assert np.array_equal(z2, np.minimum(x, 10.0))
+
+
+def test_loess_reproduces_a_quadratic(oracle):
+    # local quadratic regression + cubic Hermite blending is exact on a global quadratic at the vertices
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.uniform(-2, 3, 400))
+    y = 0.5 + 1.5 * x - 0.7 * x * x
+    model = oracle.loess_fit(x, y, span=0.3)
+    verts, val, slope = model
+    assert np.allclose(val, 0.5 + 1.5 * verts - 0.7 * verts ** 2, atol=1e-9)
+    assert np.allclose(slope, 1.5 - 1.4 * verts, atol=1e-8)
+    pred = oracle.loess_predict(model, x)
+    assert np.allclose(pred, y, atol=1e-3)           # cubic blending of a quadratic between vertices
+    # kd-tree vertex count: leaves hold <= ceil(0.2*0.3*n) = 24 points -> 400/32 -> 32 leaves, 33 vertices
+    assert verts.size == 33 and verts[0] == x[0] and verts[-1] == x[-1]
+    with pytest.raises(ValueError):
+        oracle.loess_predict(model, [x[-1] + 1.0])
+
+
+def test_loess_kd_median_rules(oracle):
+    from cellscopes_oracle import _kd_vertices
+    v = _kd_vertices(np.arange(8.0), 2)              # even splits: median = mean of the two middle values
+    assert list(v) == [0.0, 1.5, 3.5, 5.5, 7.0]
+    v = _kd_vertices(np.arange(5.0), 2)              # odd: middle order statistic, right half keeps it
+    assert list(v) == [0.0, 2.0, 3.0, 4.0]
+
+
+def test_hvg_rank_is_stable_and_clamped(oracle):
+    rng = np.random.default_rng(1)
+    m = sp.csc_matrix(rng.poisson(0.3, size=(300, 500)) * (rng.random((300, 1)) < 0.9))
+    m, _, _ = oracle.subset_matrix(m)
+    dup = sp.vstack([m, m[:5]]).tocsc()              # exact duplicates tie: ascending gene order wins
+    res = oracle.find_variable_genes(dup, nFeatures=10 ** 6)
+    g = dup.shape[0]
+    assert res["features"].size == g
+    pos = {int(gg): i for i, gg in enumerate(res["order"])}
+    for j in range(5):
+        assert pos[j] < pos[m.shape[0] + j]
+    vs = res["variance_standardized"]
+    assert np.allclose(vs, res["variance"] / res["variance_expected"])
+    # var((x-mean)/sqrt(var_exp)) == var/var_exp (processing.jl:149, SURVEY finding 9)
+    d = np.asarray(dup[7].todense(), dtype=np.float64).ravel()
+    direct = np.var((d - res["mean"][7]) / math.sqrt(res["variance_expected"][7]), ddof=1)
+    assert direct == pytest.approx(vs[7], rel=1e-12)
+
+
+def test_hvg_rejects_zero_variance_gene(oracle):
+    m = sp.csc_matrix(np.array([[1, 1, 1], [0, 2, 1]]))
+    with pytest.raises(ValueError):
+        oracle.find_variable_genes(m)
+
+
+def test_pca_matches_definition(oracle):
+    rng = np.random.default_rng(2)
+    z = rng.normal(size=(30, 200)) * np.linspace(3, 0.5, 30)[:, None]
+    a = oracle.run_pca(z, 5)
+    b = oracle.run_pca(z, 5, method="gram")
+    zc = z - z.mean(axis=1, keepdims=True)
+    assert a["tvar"] == pytest.approx((zc ** 2).sum() / 199)
+    assert np.allclose(a["principalvars"], b["principalvars"], rtol=1e-10)
+    assert np.allclose(np.abs(a["embedding"]), np.abs(b["embedding"]), atol=1e-8)
+    # scores are uncorrelated with variance = principalvars
+    cov = a["embedding"].T @ a["embedding"] / 199
+    assert np.allclose(cov, np.diag(a["principalvars"]), atol=1e-9)
+
+
+def test_knn_hand_case_and_ties(oracle):
+    x = np.array([[1, 0], [1, 0.1], [0, 1], [1, 0], [-1, 0]], dtype=np.float64)
+    idx, dist = oracle.knn_exact(x, 2, "cosine")
+    assert list(idx[0]) == [3, 1]                    # exact duplicate first (distance 0), self excluded
+    assert dist[0, 0] == 0.0
+    assert list(idx[3]) == [0, 1]
+    assert oracle.cosine_dist(x[0], x[4]) == 2.0 and oracle.cosine_dist(x[0], x[3]) == 0.0
+    idx_e, dist_e = oracle.knn_exact(x, 1, "euclidean")
+    assert idx_e[1, 0] == 0 and dist_e[1, 0] == pytest.approx(0.1)   # tie between 0 and 3 -> lower index
+    with pytest.raises(ValueError):
+        oracle.knn_exact(x, 5)
+
+
+def test_adjacency_formats(oracle):
+    idx = np.array([[1, 2], [0, 2], [3, 0], [2, 1]])     # 4 cells, k=2
+    small = oracle.adjacency_small(idx).toarray()
+    atlas = oracle.adjacency_atlas(idx).toarray()
+    # reference loops (processing.jl:268-278 and :218-232) written out literally
+    want_s = np.zeros((4, 4), dtype=np.int64)
+    want_a = np.zeros((4, 4), dtype=np.int64)
+    for i in range(4):
+        for j in range(2):
+            want_s[idx[i, j], i] = 1
+            want_s[i, idx[i, j]] = 1
+            want_a[idx[i, j], i] += 1
+            want_a[i, idx[i, j]] += 1
+    assert np.array_equal(small, want_s) and np.array_equal(atlas, want_a)
+    assert atlas[0, 1] == 2 and atlas[1, 3] == 1         # mutual pair carries 2
+    snn = oracle.snn_jaccard(idx).toarray()
+    # N+(0)={0,1,2}, N+(1)={0,1,2}: |I|=3,|U|=3 -> 1.0 ; N+(2)={0,2,3}: with N+(0) |I|=2,|U|=4 -> 0.5
+    assert snn[0, 1] == 1.0 and snn[0, 2] == 0.5
+    assert np.array_equal(snn != 0, want_s != 0)
+    assert oracle.snn_jaccard(idx, prune=0.6).nnz < oracle.snn_jaccard(idx).nnz
+
+
+def test_subset_helpers(oracle):
+    m = sp.csc_matrix(np.array([[0, 0, 0], [1, 0, 2], [0, 0, 3]]))
+    out, gk, ck = oracle.subset_matrix(m)                # strict >: zero gene 0 and zero cell 1 dropped
+    assert list(gk) == [1, 2] and list(ck) == [0, 2] and out.shape == (2, 2)
+    assert list(oracle.subset_count_rows(6, [4, 1, 3])) == [1, 3, 4]
+
+
+def test_golden_vectors(oracle):
+    """Pinned outputs of the oracle on a fixed tiny input (tests/golden/make_golden.py wrote them)."""
+    with open(GOLDEN) as f:
+        g = json.load(f)
+    counts = sp.csc_matrix(np.array(g["counts"], dtype=np.int64))
+    res = oracle.run_pipeline(counts, nFeatures=g["nFeatures"], n_pcs=g["n_pcs"], k=g["k"])
+    assert np.allclose(res["norm"].toarray(), np.array(g["norm"]), rtol=1e-13)
+    assert list(res["hvg"]["features"]) == g["features"]
+    assert np.allclose(res["hvg"]["variance_standardized"], g["variance_standardized"], rtol=1e-10)
+    assert np.allclose(res["scaled"], np.array(g["scaled"]), rtol=1e-10, atol=1e-12)
+    assert np.allclose(res["pca"]["principalvars"], g["principalvars"], rtol=1e-9)
+    assert np.allclose(np.abs(res["pca"]["embedding"]), np.abs(np.array(g["embedding"])), rtol=1e-7, atol=1e-9)
+    assert res["knn_idx"].tolist() == g["knn_idx"]
+    assert res["adj"].toarray().tolist() == g["adj"]
