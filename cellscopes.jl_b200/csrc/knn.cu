@@ -151,6 +151,9 @@ __global__ void k_knn_finish(float* __restrict__ score, const float* __restrict_
   score[i] = d;
 }
 
+csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                       int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx);
+
 static int pad_dim(int d) {
   if (d <= 16) return 16;
   if (d <= 32) return 32;
@@ -198,7 +201,10 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
               "csc_knn: queries [%lld,+%lld) are not a row range of the keys", (long long)query_offset,
               (long long)queries->n_rows);
   const int d = dim_hi - dim_lo + (metric == CSC_METRIC_EUCLIDEAN ? 1 : 0);
-  const int DP = pad_dim(d);
+  // v2 (tcgen05 + TMA + TMEM) serves k <= 32 and up to 64 dimensions; the CUDA-core kernel the rest
+  const char* impl = getenv("CSC_KNN_IMPL");
+  const bool use_tc = d <= 64 && k <= 32 && !(impl && strcmp(impl, "simt") == 0);
+  const int DP = use_tc ? 64 : pad_dim(d);
   CSC_REQUIRE(ctx, DP > 0, "csc_knn: %d dimensions not supported (max 64, 63 for euclidean)", dim_hi - dim_lo);
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_KNN);
@@ -220,6 +226,9 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
   if (queries->n_rows > 0) {
     const float* qd = (const float*)qp->p;
     const float* kd = (const float*)kp->p;
+    if (use_tc) {
+      s = knn_scan_tc(ctx, qd, queries->n_rows, kd, keys->n_rows, same, query_offset, k, d, vd->as<float>(), vi->as<int32_t>());
+    } else {
     cudaEventRecord(ctx->ev_k0, ctx->stream);
     switch (DP) {
       case 16: s = launch_scan<16>(ctx, qd, queries->n_rows, kd, keys->n_rows, query_offset, k, vd->as<float>(), vi->as<int32_t>()); break;
@@ -227,6 +236,7 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
       default: s = launch_scan<64>(ctx, qd, queries->n_rows, kd, keys->n_rows, query_offset, k, vd->as<float>(), vi->as<int32_t>()); break;
     }
     cudaEventRecord(ctx->ev_k1, ctx->stream);
+    }
     if (s == CSC_OK) {
       k_knn_finish<<<(unsigned)ceil_div64(queries->n_rows * k, 256), 256, 0, ctx->stream>>>(
           vd->as<float>(), qsq ? (const float*)qsq->p : nullptr, queries->n_rows, k, metric);
@@ -235,7 +245,7 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       if (e != cudaSuccess) s = csc_fail(ctx, CSC_ERR_CUDA, "csc_knn: %s", cudaGetErrorString(e));
       float ms = 0.f;
-      if (e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess)
+      if (!use_tc && e == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess)
         ctx->stage_ms[CSC_T_KNN_SCAN] += ms;
     }
     if (s != CSC_OK) {
