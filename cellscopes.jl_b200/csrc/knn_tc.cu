@@ -29,11 +29,13 @@ namespace {
 constexpr int TC_TQ = 128;      // query rows per CTA = UMMA M
 constexpr int TC_BN = 128;      // keys per tile     = UMMA N
 constexpr int TC_DP = 64;       // padded feature dimension (floats): two 128-byte swizzle rows
-constexpr int TC_STAGES = 2;    // shared-memory stages of key tiles
+constexpr int TC_STAGES = 3;    // shared-memory stages of key tiles
 constexpr int TC_ACC = 2;       // TMEM accumulator stages
 constexpr int TC_CHUNK_BYTES = TC_BN * 128;          // one [128 rows x 32 floats] swizzled block = 16 KB
 constexpr int TC_TILE_BYTES = 4 * TC_CHUNK_BYTES;    // hi c0, hi c1, lo c0, lo c1 = 64 KB
 constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;                    // 2 x 128 accumulator columns + 64 (Q hi) + 64 (Q lo)
+constexpr int TC_TMEM_A = TC_ACC * TC_BN;            // first column of the query operand
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -53,10 +55,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !ok; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware instead of polling
+        : "r"(bar), "r"(parity)
         : "memory");
     if (!ok && (spin & 1023u) == 1023u) {
       const long long now = clock64();
@@ -71,19 +73,38 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// one lane of a converged warp; unlike `lane == 0` the compiler keeps the surrounding values in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]', kind::tf32, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]', kind::tf32, fp32 accumulate.  The query operand lives in TMEM (one row per
+// lane, K along the columns): with both operands in shared memory a 128x128x8 tf32 MMA has to read 8 KB per
+// 64-cycle instruction, which is the whole shared-memory bandwidth of the SM (measured: ~100 cycles per MMA).
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 // K-major, 128-byte swizzle: 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
@@ -110,25 +131,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 struct __align__(64) TcMaps {
-  CUtensorMap q_hi, q_lo, k_hi, k_lo;
+  CUtensorMap k_hi, k_lo;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, int64_t query_offset, int32_t kl,
-              int32_t ksteps, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+k_knn_scan_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ q_hi, const float* __restrict__ q_lo,
+              int64_t n_q, int64_t n_keys, int64_t query_offset, int32_t kl,
+              int32_t ksteps, float* __restrict__ out_score, int32_t* __restrict__ out_idx, long long* __restrict__ trace, int64_t trace_t0) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled operand blocks
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                                   // [hi c0 | hi c1 | lo c0 | lo c1]  64 KB
-  unsigned char* sB = base + TC_TILE_BYTES;                   // TC_STAGES x 64 KB
+  unsigned char* sB = base;                                   // TC_STAGES x [hi c0 | hi c1 | lo c0 | lo c1] 64 KB
   uint2* lists = reinterpret_cast<uint2*>(sB + TC_STAGES * TC_TILE_BYTES);   // [128 rows][32] (score, id)
   uint64_t* bars = reinterpret_cast<uint64_t*>(lists + TC_TQ * 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar_full = smem_u32(bars + 0);        // [TC_STAGES]
-  const uint32_t bar_empty = smem_u32(bars + 2);       // [TC_STAGES]
-  const uint32_t bar_tfull = smem_u32(bars + 4);       // [TC_ACC]
-  const uint32_t bar_tempty = smem_u32(bars + 6);      // [TC_ACC]
-  const uint32_t bar_a = smem_u32(bars + 8);
+  const uint32_t bar_empty = smem_u32(bars + 4);       // [TC_STAGES]
+  const uint32_t bar_tfull = smem_u32(bars + 8);       // [TC_ACC]
+  const uint32_t bar_tempty = smem_u32(bars + 10);     // [TC_ACC]
+  const uint32_t bar_a = smem_u32(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * TC_TQ;
@@ -143,12 +164,12 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, 128);
     }
-    mbar_init(bar_a, 1);
+    mbar_init(bar_a, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(TC_ACC * TC_BN))
+                 "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -159,18 +180,16 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.k_hi)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.k_lo)) : "memory");
-      mbar_expect_tx(bar_a, TC_TILE_BYTES);
-      tma_load_2d(smem_u32(sA + 0 * TC_CHUNK_BYTES), &maps.q_hi, bar_a, 0, (int)q0);
-      tma_load_2d(smem_u32(sA + 1 * TC_CHUNK_BYTES), &maps.q_hi, bar_a, 32, (int)q0);
-      tma_load_2d(smem_u32(sA + 2 * TC_CHUNK_BYTES), &maps.q_lo, bar_a, 0, (int)q0);
-      tma_load_2d(smem_u32(sA + 3 * TC_CHUNK_BYTES), &maps.q_lo, bar_a, 32, (int)q0);
-      for (int64_t t = 0; t < n_tiles; ++t) {
-        const int s = (int)(t % TC_STAGES);
-        const uint32_t par = (uint32_t)((t / TC_STAGES) & 1);
-        mbar_wait(bar_empty + 8 * s, par ^ 1);
+    }
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      const int s = (int)(t % TC_STAGES);
+      const uint32_t par = (uint32_t)((t / TC_STAGES) & 1);
+      mbar_wait(bar_empty + 8 * s, par ^ 1);
+      if (elect_one()) {
+        if (trace && blockIdx.x == 0 && lane == 0 && t >= trace_t0 && t < trace_t0 + 64) trace[(t - trace_t0) * 8 + 0] = clock64();
         mbar_expect_tx(bar_full + 8 * s, TC_TILE_BYTES);
         unsigned char* dst = sB + (size_t)s * TC_TILE_BYTES;
         const int row = (int)(t * TC_BN);
@@ -179,40 +198,51 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
         tma_load_2d(smem_u32(dst + 2 * TC_CHUNK_BYTES), &maps.k_lo, bar_full + 8 * s, 0, row);
         tma_load_2d(smem_u32(dst + 3 * TC_CHUNK_BYTES), &maps.k_lo, bar_full + 8 * s, 32, row);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=128, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_TQ >> 4) << 24);
-      const uint32_t a_addr = smem_u32(sA);
+      // high word of the shared-memory descriptor: SBO = 1024 B, version 1, SWIZZLE_128B
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       mbar_wait(bar_a, 0);
       tc_fence_after();
       for (int64_t t = 0; t < n_tiles; ++t) {
         const int s = (int)(t % TC_STAGES);
         const int a = (int)(t % TC_ACC);
         mbar_wait(bar_tempty + 8 * a, (uint32_t)(((t / TC_ACC) & 1) ^ 1));
+        if (trace && blockIdx.x == 0 && lane == 0 && t >= trace_t0 && t < trace_t0 + 64) trace[(t - trace_t0) * 8 + 1] = clock64();
         mbar_wait(bar_full + 8 * s, (uint32_t)((t / TC_STAGES) & 1));
+        if (trace && blockIdx.x == 0 && lane == 0 && t >= trace_t0 && t < trace_t0 + 64) trace[(t - trace_t0) * 8 + 2] = clock64();
         tc_fence_after();
         const uint32_t b_addr = smem_u32(sB + (size_t)s * TC_TILE_BYTES);
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN);
+        // descriptors differ only in their low word: (address >> 4) | LBO; all offsets are compile-time
+        const uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (1u << 16);
+        if (elect_one()) {
         uint32_t acc = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
           // pass 0: Qhi Khi'   pass 1: Qhi Klo'   pass 2: Qlo Khi'
-          const uint32_t a_off = (pass == 2) ? 2 * TC_CHUNK_BYTES : 0;
+          const uint32_t a_col = tmem_base + TC_TMEM_A + ((pass == 2) ? 64u : 0u);
           const uint32_t b_off = (pass == 1) ? 2 * TC_CHUNK_BYTES : 0;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t chunk = (uint32_t)(ks >> 2) * TC_CHUNK_BYTES;
-            const uint32_t koff = (uint32_t)(ks & 3) * 32;      // 8 tf32 = 32 bytes inside the 128-byte row
-            const uint64_t da = make_desc_sw128(a_addr + a_off + chunk + koff);
-            const uint64_t db = make_desc_sw128(b_addr + b_off + chunk + koff);
-            tc_mma_tf32(d_tmem, da, db, idesc, acc);
-            acc = 1;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < ksteps) {
+              const uint32_t off = (uint32_t)(ks >> 2) * TC_CHUNK_BYTES + (uint32_t)(ks & 3) * 32;   // 8 tf32 = 32 bytes
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + ((b_off + off) >> 4));
+              tc_mma_tf32_ts(d_tmem, a_col + (uint32_t)ks * 8u, db, idesc, acc);
+              acc = 1;
+            }
           }
         }
         tc_commit(bar_empty + 8 * s);     // key stage reusable once these MMAs have read it
         tc_commit(bar_tfull + 8 * a);     // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (trace && blockIdx.x == 0 && lane == 0 && t >= trace_t0 && t < trace_t0 + 64) trace[(t - trace_t0) * 8 + 3] = clock64();
       }
     }
   } else {
@@ -225,7 +255,28 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
     const int row = quarter * 32 + lane;
     const int64_t qrow = q0 + row;
     const bool qvalid = qrow < n_q;
-    const int64_t self = query_offset + qrow;
+    const int self_i = (int)(query_offset + qrow);
+    {
+      // stage this thread's query row (hi and lo parts) into the TMEM operand block: lane = row, column = feature
+      const uint32_t a_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + TC_TMEM_A;
+#pragma unroll 1
+      for (int part = 0; part < 4; ++part) {           // hi[0:32], hi[32:64], lo[0:32], lo[32:64]
+        const float* src = (part < 2 ? q_hi : q_lo) + (qvalid ? qrow : 0) * TC_DP + (part & 1) * 32;
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 f = qvalid ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * i] = __float_as_uint(f.x);
+          v[4 * i + 1] = __float_as_uint(f.y);
+          v[4 * i + 2] = __float_as_uint(f.z);
+          v[4 * i + 3] = __float_as_uint(f.w);
+        }
+        tmem_st32(a_base + (uint32_t)part * 32u, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
     uint2* wl = lists + (size_t)quarter * 32 * 32;      // this warp's 32 rows
     for (int r = 0; r < 32; ++r) wl[r * 32 + lane] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
     __syncwarp();
@@ -250,35 +301,48 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
         }
         const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
         if (__any_sync(FULL, m > tau)) {
+          // Slow path, warp-uniform.  Candidates are detected against a snapshot of the thresholds so that the
+          // votes of a group are independent instructions (pipelined); the insertion re-checks against the list.
+          const float tsnap = tau;
+          const bool h0 = __any_sync(FULL, g[0] > tsnap), h1 = __any_sync(FULL, g[1] > tsnap);
+          const bool h2 = __any_sync(FULL, g[2] > tsnap), h3 = __any_sync(FULL, g[3] > tsnap);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (__any_sync(FULL, g[q] > tau)) {
+            const bool hq = q == 0 ? h0 : q == 1 ? h1 : q == 2 ? h2 : h3;
+            if (hq) {
+              unsigned bm[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float v = __uint_as_float(r[q * 8 + j]);
-                const int64_t id = key0 + c * 32 + q * 8 + j;          // the same key for every lane
-                unsigned bm = __ballot_sync(FULL, v > tau && id != self && id < n_keys);
-                while (bm) {
-                  const int src = __ffs(bm) - 1;
-                  bm &= bm - 1;
-                  const float cv = __shfl_sync(FULL, v, src);
+                const int id = (int)key0 + c * 32 + q * 8 + j;          // the same key for every lane
+                bm[j] = __ballot_sync(FULL, __uint_as_float(r[q * 8 + j]) > tsnap && id != self_i && id < (int)n_keys);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                unsigned b = bm[j];
+                const int id = (int)key0 + c * 32 + q * 8 + j;
+                while (b) {
+                  const int src = __ffs(b) - 1;
+                  b &= b - 1;
+                  const float cv = __shfl_sync(FULL, __uint_as_float(r[q * 8 + j]), src);
                   const uint2 e = wl[src * 32 + lane];
                   float es = __uint_as_float(e.x);
                   int ei = (int)e.y;
                   // entries that rank before the candidate form a prefix of the sorted list
-                  const int pos = __popc(__ballot_sync(FULL, es > cv || (es == cv && ei < (int)id)));
-                  const float ps = __shfl_up_sync(FULL, es, 1);
-                  const int pi = __shfl_up_sync(FULL, ei, 1);
-                  if (lane == pos) {
-                    es = cv;
-                    ei = (int)id;
-                  } else if (lane > pos) {
-                    es = ps;
-                    ei = pi;
+                  const int pos = __popc(__ballot_sync(FULL, es > cv || (es == cv && ei < id)));
+                  if (pos < kl) {
+                    const float ps = __shfl_up_sync(FULL, es, 1);
+                    const int pi = __shfl_up_sync(FULL, ei, 1);
+                    if (lane == pos) {
+                      es = cv;
+                      ei = id;
+                    } else if (lane > pos) {
+                      es = ps;
+                      ei = pi;
+                    }
+                    wl[src * 32 + lane] = make_uint2(__float_as_uint(es), (unsigned)ei);
+                    const float nt = __shfl_sync(FULL, es, kl - 1);
+                    if (lane == src) tau = nt;
                   }
-                  wl[src * 32 + lane] = make_uint2(__float_as_uint(es), (unsigned)ei);
-                  const float nt = __shfl_sync(FULL, es, kl - 1);
-                  if (lane == src) tau = nt;
                 }
               }
             }
@@ -287,6 +351,7 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * a);
+      if (trace && blockIdx.x == 0 && t >= trace_t0 && t < trace_t0 + 64 && lane == 0) trace[(t - trace_t0) * 8 + 4 + (warp & 3)] = clock64();
     }
     __syncwarp();
     for (int r = 0; r < 32; ++r) {
@@ -302,7 +367,7 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, int64_t n_q, int64_t n_keys, 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_ACC * TC_BN))
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
   }
 }
@@ -413,15 +478,17 @@ csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const flo
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * kl * 4, &cs));
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * kl * 4, &ci));
   TcMaps maps;
-  CSC_TRY(make_map(ctx, encode, &maps.q_hi, (const float*)qhi->p, n_q));
-  CSC_TRY(make_map(ctx, encode, &maps.q_lo, (const float*)qlo->p, n_q));
   CSC_TRY(make_map(ctx, encode, &maps.k_hi, (const float*)khi->p, n_keys));
   CSC_TRY(make_map(ctx, encode, &maps.k_lo, (const float*)klo->p, n_keys));
-  const size_t smem = 1024 + (size_t)TC_TILE_BYTES * (1 + TC_STAGES) + (size_t)TC_TQ * 32 * 8 + 256;
+  const size_t smem = 1024 + (size_t)TC_TILE_BYTES * TC_STAGES + (size_t)TC_TQ * 32 * 8 + 256;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DevPtr trace;
+  const bool want_trace = getenv("CSC_KNN_TRACE") != nullptr;
+  if (want_trace) CSC_TRY(dev_alloc(ctx, 64 * 8 * 8, &trace, true));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
-  k_knn_scan_tc<<<(unsigned)ceil_div64(n_q, TC_TQ), TC_THREADS, smem, ctx->stream>>>(maps, n_q, n_keys, query_offset, kl, ksteps,
-                                                                                      (float*)cs->p, (int32_t*)ci->p);
+  k_knn_scan_tc<<<(unsigned)ceil_div64(n_q, TC_TQ), TC_THREADS, smem, ctx->stream>>>(maps, (const float*)qhi->p, (const float*)qlo->p, n_q, n_keys, query_offset, kl, ksteps,
+                                                                                      (float*)cs->p, (int32_t*)ci->p,
+                                                                                      want_trace ? (long long*)trace->p : nullptr, want_trace ? atoll(getenv("CSC_KNN_TRACE")) : 0);
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_knn_refine<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(q_prep, k_prep, n_q, kl, k, d_eff, (const float*)cs->p,
@@ -430,5 +497,14 @@ csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const flo
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->stage_ms[CSC_T_KNN_SCAN] += ms;
+  if (want_trace) {
+    std::vector<long long> h(64 * 8);
+    CSC_CUDA(ctx, cudaMemcpy(h.data(), trace->p, h.size() * 8, cudaMemcpyDeviceToHost));
+    const long long t0 = h[0];
+    fprintf(stderr, "[knn trace] tile: producer_empty_ok  mma_tempty_ok  mma_full_ok  mma_issued | epilogue done q0..q3 (cycles since first)\n");
+    for (int t = 0; t < 40; ++t)
+      fprintf(stderr, "[knn trace] %2d: %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld\n", t, h[t * 8 + 0] - t0, h[t * 8 + 1] - t0,
+              h[t * 8 + 2] - t0, h[t * 8 + 3] - t0, h[t * 8 + 4] - t0, h[t * 8 + 5] - t0, h[t * 8 + 6] - t0, h[t * 8 + 7] - t0);
+  }
   return CSC_OK;
 }
