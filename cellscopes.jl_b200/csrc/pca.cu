@@ -10,6 +10,7 @@
 //                                                    small dense eigenproblems by parallel Jacobi)
 //   principalvars = lambda / (N-1), tvar = trace(Gc)/(N-1), embedding = (Z - 1 m') U_k
 #include <cmath>
+#include <cuda_pipeline.h>
 
 #include "common.cuh"
 
@@ -187,69 +188,242 @@ __global__ void k_center_gram(const double* __restrict__ g, const double* __rest
   gc[idx] = 0.5 * (g[idx] + g[(int64_t)b * H + a]) - s[a] * s[b] * inv_n;
 }
 
-// C[M x N] = op(A) * B, row-major.  TA = false: A is [M x K]; TA = true: A is [K x M] (C = A' B).
-// 64x64 tile, 256 threads, 4x4 per thread.
-template <bool TA>
+// C[M x N] = (alpha * op(A) * B + g1 * X1 + g2 * X2) * colscale, row-major, fp64.
+//   TA = false: A is [M x K]; TA = true: A is [K x M] (C = A' B).  X1 / X2 / colscale are optional ([M x N],
+//   leading dimension ldc; X2 may alias C: every element is read and written by the same thread).
+//   blockIdx.z batches over K-chunks of `kchunk` rows (A, B advance by kchunk rows, C by M*ldc): the small
+//   Gram products of the block solver are split this way and summed by k_reduce_parts, which keeps them
+//   deterministic and fills the machine (a b x b output alone is 4 CTAs).
+//   BM x 64 tile, 256 threads, (BM/16) x 4 per thread.
+template <bool TA, int BM>
 __global__ void __launch_bounds__(256)
-k_dgemm(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N, int K, int lda,
-        int ldb, int ldc) {
-  __shared__ double As[16][64 + 1];
+k_dgemm(const double* __restrict__ A, const double* __restrict__ B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
+        double alpha, double g1, const double* __restrict__ X1, double g2, const double* X2,
+        const double* __restrict__ colscale, int kchunk) {
+  constexpr int TM = BM / 16;
+  __shared__ double As[16][BM + 1];
   __shared__ double Bs[16][64 + 1];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  double acc[4][4] = {{0}};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = t; i < 16 * 64; i += 256) {
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * 64;
+  int kbeg = 0, kend = K;
+  if (kchunk > 0) {
+    kbeg = blockIdx.z * kchunk;
+    kend = min(K, kbeg + kchunk);
+    C += (int64_t)blockIdx.z * M * ldc;
+  }
+  double acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    for (int i = t; i < 16 * BM; i += 256) {
       int kk, mm;
       if (TA) {
-        kk = i / 64;
-        mm = i % 64;  // A[k][m] contiguous in m
-        const int gk = k0 + kk, gm = m0 + mm;
-        As[kk][mm] = (gk < K && gm < M) ? A[(int64_t)gk * lda + gm] : 0.0;
+        kk = i / BM;
+        mm = i % BM;  // A[k][m] contiguous in m
       } else {
         mm = i / 16;
         kk = i % 16;  // A[m][k] contiguous in k
-        const int gk = k0 + kk, gm = m0 + mm;
-        As[kk][mm] = (gk < K && gm < M) ? A[(int64_t)gm * lda + gk] : 0.0;
       }
+      const int gk = k0 + kk, gm = m0 + mm;
+      double v = 0.0;
+      if (gk < kend && gm < M) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      As[kk][mm] = v;
+    }
+    for (int i = t; i < 16 * 64; i += 256) {
       const int bk = i / 64, bn = i % 64;
-      const int gk2 = k0 + bk, gn = n0 + bn;
-      Bs[bk][bn] = (gk2 < K && gn < N) ? B[(int64_t)gk2 * ldb + gn] : 0.0;
+      const int gk = k0 + bk, gn = n0 + bn;
+      Bs[bk][bn] = (gk < kend && gn < N) ? B[(int64_t)gk * ldb + gn] : 0.0;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      double a[4], b[4];
+      double a[TM], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty + 16 * i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty + 16 * i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx + 16 * j;
-      if (n < N) C[(int64_t)m * ldc + n] = acc[i][j];
+      if (n >= N) continue;
+      const int64_t o = (int64_t)m * ldc + n;
+      double v = alpha * acc[i][j];
+      if (X1) v = fma(g1, X1[o], v);
+      if (X2) v = fma(g2, X2[o], v);
+      if (colscale) v *= colscale[n];
+      C[o] = v;
     }
   }
 }
 
+// C[M x N] = alpha * A[M x K] * B[K x N] + g1 * X1 + g2 * X2 for the tall products of the block solver
+// (Gc Q, Y R^-1): 32 x 64 tile, 128 threads, 4 x 4 per thread, 16-byte global and shared accesses, the next
+// K-tile prefetched into registers while the current one is multiplied out of double-buffered shared memory
+// (one barrier per K-step).  Needs even lda/ldb/ldc/K/N and 16-byte aligned bases; dgemm() checks.
+__global__ void __launch_bounds__(128)
+k_dgemm_nn(const double* __restrict__ A, const double* __restrict__ B, double* C, int M, int N, int K, int lda, int ldb,
+           int ldc, double alpha, double g1, const double* __restrict__ X1, double g2, const double* X2) {
+  __shared__ __align__(16) double As[2][16][32 + 2];   // [kk][m]
+  __shared__ __align__(16) double Bs[2][16][64 + 2];   // [kk][n]
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 64;
+  double2 ra[2], rb[4];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = t + 128 * u, row = idx >> 3, kc = (idx & 7) * 2;
+      const int gm = m0 + row, gk = k0 + kc;
+      ra[u] = (gm < M && gk < K) ? __ldg(reinterpret_cast<const double2*>(A + (int64_t)gm * lda + gk)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + 128 * u, kk = idx >> 5, nc = (idx & 31) * 2;
+      const int gk = k0 + kk, gn = n0 + nc;
+      rb[u] = (gk < K && gn < N) ? *reinterpret_cast<const double2*>(B + (int64_t)gk * ldb + gn) : make_double2(0.0, 0.0);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = t + 128 * u, row = idx >> 3, kc = (idx & 7) * 2;
+      As[buf][kc][row] = ra[u].x;
+      As[buf][kc + 1][row] = ra[u].y;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + 128 * u, kk = idx >> 5, nc = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(&Bs[buf][kk][nc]) = rb[u];
+    }
+  };
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) load_tiles(k0 + 16);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4 + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const int64_t o = (int64_t)m * ldc + n;
+      double2 v = make_double2(alpha * acc[i][j], alpha * acc[i][j + 1]);
+      if (X1) {
+        const double2 x = *reinterpret_cast<const double2*>(X1 + o);
+        v.x = fma(g1, x.x, v.x);
+        v.y = fma(g1, x.y, v.y);
+      }
+      if (X2) {
+        const double2 x = *reinterpret_cast<const double2*>(X2 + o);
+        v.x = fma(g2, x.x, v.x);
+        v.y = fma(g2, x.y, v.y);
+      }
+      *reinterpret_cast<double2*>(C + o) = v;
+    }
+  }
+}
+
+struct GemmEpi {
+  double alpha = 1.0;
+  double g1 = 0.0;
+  const double* X1 = nullptr;
+  double g2 = 0.0;
+  const double* X2 = nullptr;
+  const double* colscale = nullptr;
+};
+
 static csc_status dgemm(csc_ctx* ctx, bool ta, const double* A, const double* B, double* C, int M, int N, int K, int lda,
-                        int ldb, int ldc) {
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-  if (ta) k_dgemm<true><<<grid, 256, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc);
-  else k_dgemm<false><<<grid, 256, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc);
+                        int ldb, int ldc, const GemmEpi& e = GemmEpi(), int kchunk = 0) {
+  const int nz = kchunk > 0 ? (K + kchunk - 1) / kchunk : 1;
+  auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  if (!ta && kchunk == 0 && !e.colscale && ((lda | ldb | ldc | K | N) & 1) == 0 && al16(A) && al16(B) && al16(C) &&
+      al16(e.X1) && al16(e.X2)) {
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 31) / 32));
+    k_dgemm_nn<<<grid, 128, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2);
+    CSC_LAUNCHED(ctx);
+    return CSC_OK;
+  }
+  // tall outputs with few column tiles: halve the row tile so that the grid covers the SMs
+  const bool small_tile = !ta && ((N + 63) / 64) * ((M + 63) / 64) < ctx->sm_count;
+  if (small_tile) {
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 31) / 32), (unsigned)nz);
+    k_dgemm<false, 32><<<grid, 256, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2,
+                                                       e.colscale, kchunk);
+  } else {
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)nz);
+    if (ta)
+      k_dgemm<true, 64><<<grid, 256, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2,
+                                                        e.colscale, kchunk);
+    else
+      k_dgemm<false, 64><<<grid, 256, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2,
+                                                         e.colscale, kchunk);
+  }
   CSC_LAUNCHED(ctx);
   return CSC_OK;
+}
+
+// S[i][j] = sum_z parts[z][i][j]  (fixed order: deterministic); sym: S = (S + S')/2
+__global__ void k_reduce_parts(const double* __restrict__ parts, int nz, int b, int sym, double* __restrict__ S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= b * b) return;
+  const int i = idx / b, j = idx % b;
+  double s = 0.0, st = 0.0;
+  for (int z = 0; z < nz; ++z) {
+    s += parts[(int64_t)z * b * b + idx];
+    if (sym) st += parts[(int64_t)z * b * b + (int64_t)j * b + i];
+  }
+  S[idx] = sym ? 0.5 * (s + st) : s;
+}
+
+// out = (a * X + c * Y) * colscale
+__global__ void k_axpby_cols(const double* X, const double* Y, double a, double c,
+                             const double* __restrict__ colscale, int64_t n, int b, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = a * X[i] + c * Y[i];
+  if (colscale) v *= colscale[i % b];
+  out[i] = v;
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -268,96 +442,134 @@ __global__ void k_init_block(double* __restrict__ q, int64_t n, uint64_t seed) {
   q[i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
-// upper Cholesky S = R'R of a b x b matrix (single CTA), in place; rinv_diag[j] = 1/R_jj (0 if the pivot
-// vanished: that direction is dropped instead of poisoning the block)
-__global__ void __launch_bounds__(256)
-k_cholesky(double* __restrict__ S, int b, double* __restrict__ rinv_diag) {
-  __shared__ double s_piv;
-  __shared__ double s_scale;
-  const int t = threadIdx.x;
-  if (t == 0) {
-    double mx = 0.0;
-    for (int i = 0; i < b; ++i) mx = fmax(mx, fabs(S[(int64_t)i * b + i]));
-    s_scale = mx;
-  }
-  __syncthreads();
-  const double tiny = s_scale * 1e-14;
-  for (int j = 0; j < b; ++j) {
-    if (t == 0) {
-      const double d = S[(int64_t)j * b + j];
-      if (d > tiny) {
-        const double r = sqrt(d);
-        S[(int64_t)j * b + j] = r;
-        s_piv = 1.0 / r;
-      } else {
-        S[(int64_t)j * b + j] = 0.0;
-        s_piv = 0.0;
-      }
-      rinv_diag[j] = s_piv;
-    }
-    __syncthreads();
-    const double inv = s_piv;
-    for (int c = j + 1 + t; c < b; c += blockDim.x) S[(int64_t)j * b + c] *= inv;  // row j of R
-    __syncthreads();
-    // trailing update: S[r][c] -= R[j][r] R[j][c] for r,c > j (upper part)
-    const int m = b - j - 1;
-    for (int idx = t; idx < m * m; idx += blockDim.x) {
-      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
-      if (c >= r) S[(int64_t)r * b + c] -= S[(int64_t)j * b + r] * S[(int64_t)j * b + c];
-    }
-    __syncthreads();
-  }
-}
-
-// Q = Y R^{-1}: one thread per row of Y (forward substitution over the columns), R upper b x b
-__global__ void __launch_bounds__(128)
-k_trsm_right(const double* __restrict__ Y, const double* __restrict__ R, const double* __restrict__ rinv_diag, int H, int b,
-             double* __restrict__ Q) {
-  extern __shared__ double sR[];  // b*b
-  for (int i = threadIdx.x; i < b * b; i += blockDim.x) sR[i] = R[i];
-  __syncthreads();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= H) return;
-  const double* y = Y + (int64_t)row * b;
-  double* q = Q + (int64_t)row * b;
-  for (int j = 0; j < b; ++j) {
-    double s = y[j];
-    for (int i = 0; i < j; ++i) s -= q[i] * sR[i * b + j];
-    q[j] = s * rinv_diag[j];
-  }
-}
-
-// Parallel cyclic Jacobi for a symmetric n x n matrix (single CTA): A -> diag, V = eigenvectors (columns).
-// Round-robin ordering: n/2 disjoint rotations per round applied simultaneously.
-// On exit eval[i] (descending) and Vs = V with columns permuted accordingly.
+// Upper Cholesky S = R'R of a b x b matrix followed by the in-place inverse of R, all in shared memory
+// (single CTA, b <= 160).  Rinv (upper triangular, zeros below) is written to global memory, so that
+// Q = Y R^{-1} becomes a plain matrix product.  A pivot that has lost all its digits against the column's
+// own norm (S_jj) drops that direction (row/column of zeros) instead of poisoning the block.
 __global__ void __launch_bounds__(1024)
-k_jacobi(double* __restrict__ A, double* __restrict__ V, int n, double* __restrict__ eval, double* __restrict__ Vs,
-         int max_sweeps, int* __restrict__ sweeps_out) {
-  extern __shared__ double sh[];
-  const int m = (n + 1) & ~1;
-  double* cs = sh;            // [m/2] cos
-  double* sn = sh + m / 2;    // [m/2] sin
-  int* pp = (int*)(sh + m);   // [m/2]
-  int* qq = pp + m / 2;       // [m/2]
-  __shared__ double s_off, s_diag;
-  __shared__ int s_done;
+k_chol_inv(const double* __restrict__ S, int b, double* __restrict__ Rinv) {
+  extern __shared__ double sm[];
+  const int ld = b + 1;
+  double* A = sm;             // [b][ld]
+  double* rs = sm + b * ld;   // [b] 1/sqrt(pivot)
+  double* d0 = rs + b;        // [b] original diagonal
   const int t = threadIdx.x, nt = blockDim.x;
-  for (int i = t; i < n * n; i += nt) V[i] = ((i / n) == (i % n)) ? 1.0 : 0.0;
+  const int lane = t & 31, warp = t >> 5, nwarp = nt >> 5;
+  for (int i = t; i < b * b; i += nt) A[(i / b) * ld + (i % b)] = S[i];
+  __syncthreads();
+  for (int i = t; i < b; i += nt) d0[i] = fabs(A[i * ld + i]);
+  __syncthreads();
+  const double rel = 4.0 * (double)b * 1.1e-16;
+  // right-looking Cholesky on the unscaled rows: S[r][c] -= S[j][r] S[j][c] / d_j; rows are scaled at the end
+  for (int j = 0; j < b; ++j) {
+    const double d = A[j * ld + j];
+    const bool ok = d > rel * d0[j] && d > 0.0;
+    const double invd = ok ? 1.0 / d : 0.0;
+    if (t == 0) rs[j] = ok ? rsqrt(d) : 0.0;
+    for (int r = j + 1 + warp; r < b; r += nwarp) {
+      const double f = A[j * ld + r] * invd;
+      for (int c = r + lane; c < b; c += 32) A[r * ld + c] -= f * A[j * ld + c];
+    }
+    __syncthreads();
+  }
+  for (int r = warp; r < b; r += nwarp) {
+    const double f = rs[r];
+    for (int c = r + lane; c < b; c += 32) A[r * ld + c] *= f;   // R (diagonal: d * rsqrt(d) = sqrt(d))
+  }
+  __syncthreads();
+  // inverse of the upper triangle by back substitution, R X = I, one column per group of 8 lanes (columns are
+  // independent: no block barrier).  X' is stored in the unused lower triangle, X[l][c] at A[c][l]; the
+  // diagonal of R is read from a copy.
+  double* rd = d0 + b;
+  for (int i = t; i < b; i += nt) rd[i] = A[i * ld + i];
+  __syncthreads();
+  {
+    const int grp = t >> 3, gl = t & 7;
+    const unsigned gmask = 0xFFu << ((t & 31) & ~7);
+    for (int c = grp; c < b; c += nt >> 3) {
+      for (int i = c; i >= 0; --i) {
+        double acc = 0.0;
+        for (int l = i + 1 + gl; l <= c; l += 8) acc = fma(A[i * ld + l], A[c * ld + l], acc);
+        acc += __shfl_xor_sync(gmask, acc, 1);
+        acc += __shfl_xor_sync(gmask, acc, 2);
+        acc += __shfl_xor_sync(gmask, acc, 4);
+        __syncwarp(gmask);
+        if (gl == 0) {
+          const double rii = rd[i];
+          A[c * ld + i] = rii != 0.0 ? ((i == c ? 1.0 : 0.0) - acc) / rii : 0.0;
+        }
+        __syncwarp(gmask);
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = t; idx < b * b; idx += nt) {
+    const int r = idx / b, c = idx % b;
+    Rinv[idx] = c >= r ? A[c * ld + r] : 0.0;
+  }
+}
+
+// round-robin pair (p < q) number i of round r for m (even) players; q == m - 1 may be the dummy index
+__device__ __forceinline__ void jacobi_pair(int m, int r, int i, int& p, int& q) {
+  if (i == 0) {
+    p = m - 1;
+    q = r;
+  } else {
+    p = (r + i) % (m - 1);
+    q = (r - i + (m - 1)) % (m - 1);
+  }
+  if (p > q) {
+    const int tmp = p;
+    p = q;
+    q = tmp;
+  }
+}
+
+// Parallel cyclic Jacobi for a symmetric n x n matrix (single CTA, matrix resident in shared memory, n <= 160).
+// Round-robin ordering: n/2 disjoint rotations per round; the two-sided update J' A J is applied as independent
+// 2x2 blocks (pair i, pair j), so a round needs two barriers and touches shared memory only.  The eigenvectors
+// are NOT accumulated here: every rotation (c, s) is appended to `rot` and k_apply_rot replays the list on
+// whatever tall matrix needs X <- X V (the Ritz step applies it to [Q; Gc Q] directly, thousands of rows in
+// parallel).  On exit eval[] is descending and rank[i] = position of original column i in that order.
+__global__ void __launch_bounds__(1024)
+k_jacobi(const double* __restrict__ Ain, int n, double2* __restrict__ rot, uchar2* __restrict__ rot_pq,
+         double* __restrict__ eval, int* __restrict__ rank_out, int max_sweeps, double off_tol2, int* __restrict__ sweeps_out) {
+  extern __shared__ double sm[];
+  const int ld = n;                // a warp works along one row with scattered columns: no padding needed
+  const int m = (n + 1) & ~1;
+  const int hp = m / 2;
+  double* A = sm;                  // [n][ld]
+  double* cs = sm + n * ld;        // [hp]
+  double* sn = cs + hp;            // [hp]
+  int* pp = (int*)(sn + hp);       // [hp]
+  int* qq = pp + hp;               // [hp]
+  __shared__ double s_off, s_diag;
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (int i = t; i < n * n; i += nt) {
+    const int r = i / n, c = i % n;
+    A[r * ld + c] = 0.5 * (Ain[i] + Ain[c * n + r]);
+  }
+  // the pair schedule of one sweep (the same for every sweep), for k_apply_rot
+  for (int idx = t; idx < (m - 1) * hp; idx += nt) {
+    int p, q;
+    jacobi_pair(m, idx / hp, idx % hp, p, q);
+    rot_pq[idx] = make_uchar2((unsigned char)p, (unsigned char)q);
+  }
   __syncthreads();
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
-    // convergence: off-diagonal Frobenius norm against the diagonal
     if (t == 0) {
       s_off = 0.0;
       s_diag = 0.0;
     }
     __syncthreads();
     double off = 0.0, dg = 0.0;
-    for (int i = t; i < n * n; i += nt) {
-      const double v = A[i];
-      if ((i / n) == (i % n)) dg += v * v;
-      else off += v * v;
-    }
+    for (int r = t >> 5; r < n; r += nt >> 5)
+      for (int c = t & 31; c < n; c += 32) {
+        const double v = A[r * ld + c];
+        if (r == c) dg += v * v;
+        else off += v * v;
+      }
     off = warp_sum(off);
     dg = warp_sum(dg);
     if ((t & 31) == 0) {
@@ -365,80 +577,153 @@ k_jacobi(double* __restrict__ A, double* __restrict__ V, int n, double* __restri
       atomicAdd(&s_diag, dg);
     }
     __syncthreads();
-    if (t == 0) s_done = (s_off <= 1e-26 * (s_diag + s_off)) || (s_off == 0.0);
+    const bool done = (s_off <= off_tol2 * (s_diag + s_off)) || (s_off == 0.0);
     __syncthreads();
-    if (s_done) break;
+    if (done) break;
     for (int r = 0; r < m - 1; ++r) {
-      // pairs of this round
-      for (int i = t; i < m / 2; i += nt) {
+      // rotation of every pair of this round, from the current matrix
+      if (t < hp) {
         int p, q;
-        if (i == 0) {
-          p = m - 1;
-          q = r;
-        } else {
-          p = (r + i) % (m - 1);
-          q = (r - i + (m - 1)) % (m - 1);
-        }
-        if (p > q) {
-          const int tmp = p;
-          p = q;
-          q = tmp;
-        }
+        jacobi_pair(m, r, t, p, q);
         double c = 1.0, s = 0.0;
         if (q < n) {
-          const double apq = A[(int64_t)p * n + q];
+          const double apq = A[p * ld + q];
           if (apq != 0.0) {
-            const double app = A[(int64_t)p * n + p], aqq = A[(int64_t)q * n + q];
+            const double app = A[p * ld + p], aqq = A[q * ld + q];
             const double theta = (aqq - app) / (2.0 * apq);
             const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(tt * tt + 1.0);
+            c = rsqrt(tt * tt + 1.0);
             s = tt * c;
           }
         }
-        cs[i] = c;
-        sn[i] = s;
-        pp[i] = p;
-        qq[i] = q;
+        cs[t] = c;
+        sn[t] = s;
+        pp[t] = p;
+        qq[t] = q;
+        rot[((int64_t)sweep * (m - 1) + r) * hp + t] = make_double2(c, s);
       }
       __syncthreads();
-      // rows: A <- J' A
-      for (int idx = t; idx < (m / 2) * n; idx += nt) {
-        const int i = idx / n, j = idx % n;
-        const int p = pp[i], q = qq[i];
-        if (q >= n) continue;
-        const double c = cs[i], s = sn[i];
-        const double apj = A[(int64_t)p * n + j], aqj = A[(int64_t)q * n + j];
-        A[(int64_t)p * n + j] = c * apj - s * aqj;
-        A[(int64_t)q * n + j] = s * apj + c * aqj;
-      }
-      __syncthreads();
-      // columns: A <- A J, V <- V J
-      for (int idx = t; idx < (m / 2) * n; idx += nt) {
-        const int i = idx % (m / 2), row = idx / (m / 2);
-        const int p = pp[i], q = qq[i];
-        if (q >= n) continue;
-        const double c = cs[i], s = sn[i];
-        const double aip = A[(int64_t)row * n + p], aiq = A[(int64_t)row * n + q];
-        A[(int64_t)row * n + p] = c * aip - s * aiq;
-        A[(int64_t)row * n + q] = s * aip + c * aiq;
-        const double vip = V[(int64_t)row * n + p], viq = V[(int64_t)row * n + q];
-        V[(int64_t)row * n + p] = c * vip - s * viq;
-        V[(int64_t)row * n + q] = s * vip + c * viq;
+      // A <- J' A J, one independent 2x2 block per (pair i, pair j); 16 lanes share a pair i
+      for (int i = t >> 4; i < hp; i += nt >> 4) {
+        const int pi = pp[i], qi = qq[i];
+        const double ci = cs[i], si = sn[i];
+        for (int j = t & 15; j < hp; j += 16) {
+          const int pj = pp[j], qj = qq[j];
+          if (qi >= n || qj >= n) {
+            // odd n: the pair that holds the dummy index does not rotate (c = 1, s = 0); its real row/column
+            // still takes the other pair's rotation
+            if (qi >= n && qj >= n) continue;
+            if (qi >= n) {
+              const double c = cs[j], s = sn[j];
+              const double a0 = A[pi * ld + pj], a1 = A[pi * ld + qj];
+              A[pi * ld + pj] = c * a0 - s * a1;
+              A[pi * ld + qj] = s * a0 + c * a1;
+            } else {
+              const double a0 = A[pi * ld + pj], a1 = A[qi * ld + pj];
+              A[pi * ld + pj] = ci * a0 - si * a1;
+              A[qi * ld + pj] = si * a0 + ci * a1;
+            }
+            continue;
+          }
+          const double cj = cs[j], sj = sn[j];
+          const double b00 = A[pi * ld + pj], b01 = A[pi * ld + qj], b10 = A[qi * ld + pj], b11 = A[qi * ld + qj];
+          const double r00 = ci * b00 - si * b10, r01 = ci * b01 - si * b11;
+          const double r10 = si * b00 + ci * b10, r11 = si * b01 + ci * b11;
+          double o00 = cj * r00 - sj * r01, o01 = sj * r00 + cj * r01;
+          double o10 = cj * r10 - sj * r11, o11 = sj * r10 + cj * r11;
+          if (i == j) {
+            o01 = 0.0;   // annihilated by construction
+            o10 = 0.0;
+          }
+          A[pi * ld + pj] = o00;
+          A[pi * ld + qj] = o01;
+          A[qi * ld + pj] = o10;
+          A[qi * ld + qj] = o11;
+        }
       }
       __syncthreads();
     }
   }
   if (t == 0 && sweeps_out) *sweeps_out = sweep;
-  // sort eigenvalues descending (rank by counting; ties by index), permute the columns of V
+  __syncthreads();
+  // eigenvalues descending (rank by counting; ties by index)
   for (int i = t; i < n; i += nt) {
-    const double di = A[(int64_t)i * n + i];
+    const double di = A[i * ld + i];
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const double dj = A[(int64_t)j * n + j];
+      const double dj = A[j * ld + j];
       rank += (dj > di) || (dj == di && j < i);
     }
     eval[rank] = di;
-    for (int row = 0; row < n; ++row) Vs[(int64_t)row * n + rank] = V[(int64_t)row * n + i];
+    rank_out[i] = rank;
+  }
+}
+
+// Xout[:, rank[c]] = (X V)[:, c] where V is the product of the recorded rotations: a CTA keeps APPLY_ROWS rows
+// of X in shared memory and replays the list; rows are independent, so the grid is n_rows / APPLY_ROWS CTAs.
+// blockIdx.y selects one of two matrices (the Ritz step rotates Q and Gc Q with the same list).
+constexpr int APPLY_ROWS = 8;
+constexpr int APPLY_CHUNK = 8;    // rounds of rotations staged in shared memory at a time (double-buffered cp.async)
+__global__ void __launch_bounds__(APPLY_ROWS * 80)
+k_apply_rot(const double* __restrict__ X0, double* __restrict__ O0, const double* __restrict__ X1, double* __restrict__ O1,
+            int n_rows, int n, const double2* __restrict__ rot, const uchar2* __restrict__ rot_pq,
+            const int* __restrict__ sweeps_ptr, const int* __restrict__ rank) {
+  extern __shared__ __align__(16) double sm[];
+  const int ld = n + 1;
+  const int m = (n + 1) & ~1;
+  const int hp = m / 2;
+  double2* stage = reinterpret_cast<double2*>(sm);                  // [2][APPLY_CHUNK * hp]
+  double* xs = sm + 2 * 2 * APPLY_CHUNK * hp;                       // [APPLY_ROWS][ld]
+  uchar2* pq = reinterpret_cast<uchar2*>(xs + APPLY_ROWS * ld);     // [(m-1) * hp] pair schedule of a sweep
+  const double* X = blockIdx.y ? X1 : X0;
+  double* O = blockIdx.y ? O1 : O0;
+  const int row0 = blockIdx.x * APPLY_ROWS;
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int rounds = *sweeps_ptr * (m - 1);
+  const int n_chunks = (rounds + APPLY_CHUNK - 1) / APPLY_CHUNK;
+  auto fetch = [&](int chunk, int buf) {
+    const int64_t base = (int64_t)chunk * APPLY_CHUNK * hp;
+    const int cnt = min(APPLY_CHUNK, rounds - chunk * APPLY_CHUNK) * hp;
+    for (int i = t; i < cnt; i += nt) __pipeline_memcpy_async(stage + buf * APPLY_CHUNK * hp + i, rot + base + i, 16);
+    __pipeline_commit();
+  };
+  if (n_chunks > 0) fetch(0, 0);
+  for (int i = t; i < (m - 1) * hp; i += nt) pq[i] = rot_pq[i];
+  for (int i = t; i < APPLY_ROWS * n; i += nt) {
+    const int rr = i / n, c = i - rr * n;
+    xs[rr * ld + c] = (row0 + rr < n_rows) ? X[(int64_t)(row0 + rr) * n + c] : 0.0;
+  }
+  const int rr = t / hp, i = t - rr * hp;     // blockDim.x == APPLY_ROWS * hp
+  double* xr = xs + rr * ld;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < n_chunks) {
+      fetch(ch + 1, buf ^ 1);
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    const int g0 = ch * APPLY_CHUNK;
+    const int cnt = min(APPLY_CHUNK, rounds - g0);
+    int r = g0 % (m - 1);
+    const double2* st = stage + buf * APPLY_CHUNK * hp + i;
+    for (int g = 0; g < cnt; ++g) {
+      const double2 cs = st[g * hp];
+      const uchar2 pr = pq[r * hp + i];
+      if (pr.y < n) {
+        const double xp = xr[pr.x], xq = xr[pr.y];
+        xr[pr.x] = cs.x * xp - cs.y * xq;
+        xr[pr.y] = cs.y * xp + cs.x * xq;
+      }
+      if (++r == m - 1) r = 0;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int idx = t; idx < APPLY_ROWS * n; idx += nt) {
+    const int r2 = idx / n, c = idx - r2 * n;
+    if (row0 + r2 < n_rows) O[(int64_t)(row0 + r2) * n + rank[c]] = xs[r2 * ld + c];
   }
 }
 
@@ -463,23 +748,73 @@ __global__ void k_resid(const double* __restrict__ Yn, const double* __restrict_
   }
 }
 
-static csc_status jacobi(csc_ctx* ctx, double* A, double* V, int n, double* eval, double* Vs, int* d_sweeps) {
+// diagonal of ones into a zero-filled n x n matrix
+__global__ void k_set_identity(double* __restrict__ a, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[(int64_t)i * n + i] = 1.0;
+}
+
+constexpr int PCA_SMALL_MAX = 160;   // largest matrix the single-CTA shared-memory kernels hold
+
+constexpr int JACOBI_MAX_SWEEPS = 40;
+// rotation list of a Jacobi run: (c, s) per pair per round, followed by the pair schedule of one sweep
+struct RotList {
+  DevPtr mem;
+  double2* cs = nullptr;
+  uchar2* pq = nullptr;
+};
+static csc_status rot_alloc(csc_ctx* ctx, int n, RotList* r) {
   const int m = (n + 1) & ~1;
-  size_t smem = (size_t)m * 8 + (size_t)m * 4 + 64;
-  k_jacobi<<<1, 1024, smem, ctx->stream>>>(A, V, n, eval, Vs, 60, d_sweeps);
+  const size_t cs_bytes = (size_t)JACOBI_MAX_SWEEPS * (m - 1) * (m / 2) * sizeof(double2);
+  CSC_TRY(dev_alloc(ctx, cs_bytes + (size_t)(m - 1) * (m / 2) * sizeof(uchar2), &r->mem));
+  r->cs = (double2*)r->mem->p;
+  r->pq = (uchar2*)((char*)r->mem->p + cs_bytes);
+  return CSC_OK;
+}
+// off_tol: stop when ||offdiag||_F <= off_tol * ||A||_F
+static csc_status jacobi(csc_ctx* ctx, const double* A, int n, const RotList& rot, double* eval, int* rank, int* d_sweeps,
+                         double off_tol = 1e-13) {
+  const int hp = ((n + 1) & ~1) / 2;
+  const size_t smem = (size_t)n * n * 8 + (size_t)hp * 24 + 64;
+  CSC_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_jacobi<<<1, 1024, smem, ctx->stream>>>(A, n, rot.cs, rot.pq, eval, rank, JACOBI_MAX_SWEEPS, off_tol * off_tol, d_sweeps);
+  CSC_LAUNCHED(ctx);
+  return CSC_OK;
+}
+// O0 = X0 V (columns in eigenvalue order), optionally O1 = X1 V
+static csc_status apply_rot(csc_ctx* ctx, const double* X0, double* O0, const double* X1, double* O1, int n_rows, int n,
+                            const RotList& rot, const int* d_sweeps, const int* rank) {
+  const int m = (n + 1) & ~1, hp = m / 2;
+  const size_t smem = (size_t)APPLY_ROWS * (n + 1) * 8 + (size_t)2 * APPLY_CHUNK * hp * 16 + (size_t)(m - 1) * hp * 2 + 16;
+  CSC_CUDA(ctx, cudaFuncSetAttribute(k_apply_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n_rows + APPLY_ROWS - 1) / APPLY_ROWS), X1 ? 2u : 1u);
+  k_apply_rot<<<grid, APPLY_ROWS * hp, smem, ctx->stream>>>(X0, O0, X1, O1, n_rows, n, rot.cs, rot.pq, d_sweeps, rank);
   CSC_LAUNCHED(ctx);
   return CSC_OK;
 }
 
-static csc_status chol_qr(csc_ctx* ctx, const double* Y, double* Q, double* S, double* rinv, int H, int b) {
-  CSC_TRY(dgemm(ctx, true, Y, Y, S, b, b, H, b, b, b));  // S = Y'Y
-  k_cholesky<<<1, 256, 0, ctx->stream>>>(S, b, rinv);
-  CSC_LAUNCHED(ctx);
-  size_t smem = (size_t)b * b * 8;
-  if (smem > 48 * 1024) CSC_CUDA(ctx, cudaFuncSetAttribute(k_trsm_right, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_trsm_right<<<(unsigned)((H + 127) / 128), 128, smem, ctx->stream>>>(Y, S, rinv, H, b, Q);
+// workspace of the block solver
+struct BlockWs {
+  int H, b, nz, kchunk;
+  double *parts, *S, *Rinv;
+};
+
+// out[b x b] = X' Y for two H x b blocks (K split over the grid, deterministic reduction)
+static csc_status small_gram(csc_ctx* ctx, const BlockWs& w, const double* X, const double* Y, int sym, double* out) {
+  CSC_TRY(dgemm(ctx, true, X, Y, w.parts, w.b, w.b, w.H, w.b, w.b, w.b, GemmEpi(), w.kchunk));
+  k_reduce_parts<<<(unsigned)((w.b * w.b + 255) / 256), 256, 0, ctx->stream>>>(w.parts, w.nz, w.b, sym, out);
   CSC_LAUNCHED(ctx);
   return CSC_OK;
+}
+
+// Q = Y R^{-1} with R'R = Y'Y
+static csc_status chol_qr(csc_ctx* ctx, const BlockWs& w, const double* Y, double* Q) {
+  CSC_TRY(small_gram(ctx, w, Y, Y, 1, w.S));
+  const size_t smem = (size_t)w.b * (w.b + 1) * 8 + (size_t)w.b * 24;
+  CSC_CUDA(ctx, cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chol_inv<<<1, 1024, smem, ctx->stream>>>(w.S, w.b, w.Rinv);
+  CSC_LAUNCHED(ctx);
+  return dgemm(ctx, false, Y, w.Rinv, Q, w.H, w.b, w.b, w.b, w.b, w.b);
 }
 
 extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const csc_vec* gram, int64_t n_feat,
@@ -517,15 +852,21 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
   std::vector<double> evals((size_t)k), U((size_t)H * k);
   int iters = 0;
   double resid = 0.0;
-  const int direct_max = 160;
-  if (H <= direct_max) {
-    // small problem: full Jacobi eigendecomposition of Gc
-    DevPtr v, vs, ev, sw;
-    CSC_TRY(dev_alloc(ctx, (size_t)H * H * 8, &v));
+  if (H <= PCA_SMALL_MAX) {
+    // small problem: full Jacobi eigendecomposition of Gc; V = I * (rotations)
+    DevPtr eye, vs, ev, sw, rk;
+    RotList rot;
+    CSC_TRY(dev_alloc(ctx, (size_t)H * H * 8, &eye, true));
     CSC_TRY(dev_alloc(ctx, (size_t)H * H * 8, &vs));
     CSC_TRY(dev_alloc(ctx, (size_t)H * 8, &ev));
     CSC_TRY(dev_alloc(ctx, 4, &sw));
-    CSC_TRY(jacobi(ctx, Gc, (double*)v->p, H, (double*)ev->p, (double*)vs->p, (int*)sw->p));
+    CSC_TRY(dev_alloc(ctx, (size_t)H * 4, &rk));
+    CSC_TRY(rot_alloc(ctx, H, &rot));
+    k_set_identity<<<(unsigned)((H + 255) / 256), 256, 0, ctx->stream>>>((double*)eye->p, H);
+    CSC_LAUNCHED(ctx);
+    CSC_TRY(jacobi(ctx, Gc, H, rot, (double*)ev->p, (int*)rk->p, (int*)sw->p));
+    CSC_TRY(apply_rot(ctx, (const double*)eye->p, (double*)vs->p, nullptr, nullptr, H, H, rot, (const int*)sw->p,
+                      (const int*)rk->p));
     std::vector<double> hv((size_t)H * H), he((size_t)H);
     CSC_CUDA(ctx, cudaMemcpyAsync(hv.data(), vs->p, hv.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CSC_CUDA(ctx, cudaMemcpyAsync(he.data(), ev->p, he.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -535,57 +876,137 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
       for (int r = 0; r < H; ++r) U[(size_t)j * H + r] = hv[(size_t)r * H + j];
     }
   } else {
+    // Chebyshev-filtered block subspace iteration with Rayleigh-Ritz:
+    //   block of b >= 2k+28 vectors; two plain power cycles and a first Rayleigh-Ritz step give Ritz values
+    //   theta_1 >= ... >= theta_b.  Every following cycle applies the degree-m Chebyshev polynomial that is
+    //   bounded by 1 on [0, theta_b] (three-term recurrence, one Gc product per degree, fused epilogue) and
+    //   re-orthonormalises by CholeskyQR2.  m is chosen so that the growth T_m(x_1) of the leading direction,
+    //   which is what contaminates the guard columns, stays inside the range CholeskyQR2 resolves.  A
+    //   Rayleigh-Ritz step (Jacobi on the b x b projection, rotations replayed on [Q; Gc Q]) follows every
+    //   second cycle and yields the residuals that stop the iteration.  All arithmetic fp64 on the device;
+    //   the host sees only the b Ritz values and k residual norms per Ritz step.
     int b = std::min(H, std::max(64, ((2 * k + 28 + 31) / 32) * 32));
-    b = std::min(b, direct_max);
+    b = std::min(b, PCA_SMALL_MAX);
     CSC_REQUIRE(ctx, k <= b, "csc_pca_solve: maxoutdim=%d too large for the block solver (max %d)", k, b);
-    DevPtr q, y, qn, yn, s, w, ws, bb, th, rinv, res, sw;
-    CSC_TRY(dev_alloc(ctx, (size_t)H * b * 8, &q));
-    CSC_TRY(dev_alloc(ctx, (size_t)H * b * 8, &y));
-    CSC_TRY(dev_alloc(ctx, (size_t)H * b * 8, &qn));
-    CSC_TRY(dev_alloc(ctx, (size_t)H * b * 8, &yn));
+    BlockWs w;
+    w.H = H;
+    w.b = b;
+    w.kchunk = 64;
+    w.nz = (H + w.kchunk - 1) / w.kchunk;
+    DevPtr buf[4], parts, s, rinv, bm, rk, th, res, sw;
+    RotList rot;
+    for (int i = 0; i < 4; ++i) CSC_TRY(dev_alloc(ctx, (size_t)H * b * 8, &buf[i]));
+    CSC_TRY(dev_alloc(ctx, (size_t)w.nz * b * b * 8, &parts));
     CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &s));
-    CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &w));
-    CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &ws));
-    CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &bb));
+    CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &rinv));
+    CSC_TRY(dev_alloc(ctx, (size_t)b * b * 8, &bm));
+    CSC_TRY(rot_alloc(ctx, b, &rot));
+    CSC_TRY(dev_alloc(ctx, (size_t)b * 4, &rk));
     CSC_TRY(dev_alloc(ctx, (size_t)b * 8, &th));
-    CSC_TRY(dev_alloc(ctx, (size_t)b * 8, &rinv));
     CSC_TRY(dev_alloc(ctx, (size_t)b * 8, &res));
     CSC_TRY(dev_alloc(ctx, 4, &sw));
-    double *Q = (double*)q->p, *Y = (double*)y->p, *Qn = (double*)qn->p, *Yn = (double*)yn->p;
-    k_init_block<<<(unsigned)ceil_div64((int64_t)H * b, 256), 256, 0, ctx->stream>>>(Y, (int64_t)H * b, 42);
-    CSC_LAUNCHED(ctx);
-    CSC_TRY(chol_qr(ctx, Y, Q, (double*)s->p, (double*)rinv->p, H, b));
+    w.parts = (double*)parts->p;
+    w.S = (double*)s->p;
+    w.Rinv = (double*)rinv->p;
+    double *Q = (double*)buf[0]->p, *T1 = (double*)buf[1]->p, *T2 = (double*)buf[2]->p, *T3 = (double*)buf[3]->p;
+    const int64_t nel = (int64_t)H * b;
     std::vector<double> hres((size_t)k), hth((size_t)b);
-    int next_check = 8;
-    bool converged = false;
-    for (iters = 1; iters <= max_iter; ++iters) {
-      CSC_TRY(dgemm(ctx, false, Gc, Q, Y, H, b, H, H, b, b));  // Y = Gc Q
-      if (iters == next_check || iters == max_iter) {
-        CSC_TRY(dgemm(ctx, true, Q, Y, (double*)bb->p, b, b, H, b, b, b));  // B = Q'Y
-        CSC_TRY(jacobi(ctx, (double*)bb->p, (double*)w->p, b, (double*)th->p, (double*)ws->p, (int*)sw->p));
-        CSC_TRY(dgemm(ctx, false, Q, (double*)ws->p, Qn, H, b, b, b, b, b));  // Qn = Q W
-        CSC_TRY(dgemm(ctx, false, Y, (double*)ws->p, Yn, H, b, b, b, b, b));  // Yn = Y W = Gc Qn
-        k_resid<<<k, 256, 0, ctx->stream>>>(Yn, Qn, (double*)th->p, H, b, k, (double*)res->p);
-        CSC_LAUNCHED(ctx);
-        CSC_CUDA(ctx, cudaMemcpyAsync(hres.data(), res->p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CSC_CUDA(ctx, cudaMemcpyAsync(hth.data(), th->p, (size_t)b * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        resid = 0.0;
-        for (int i = 0; i < k; ++i) resid = std::max(resid, hres[i]);
-        resid /= std::max(hth[0], 1e-300);
-        std::swap(Q, Qn);
-        std::swap(Y, Yn);
-        if (resid <= tol || iters == max_iter) {
-          converged = resid <= tol;
-          break;
-        }
-        next_check = iters + std::max(8, iters / 4);
-      }
-      // re-orthonormalise the block: CholeskyQR2
-      CSC_TRY(chol_qr(ctx, Y, Qn, (double*)s->p, (double*)rinv->p, H, b));
-      CSC_TRY(chol_qr(ctx, Qn, Q, (double*)s->p, (double*)rinv->p, H, b));
+    bool have_gq = false;   // T3 == Gc Q
+
+    // Q <- Ritz vectors of span(Q) (Q orthonormal on entry), T3 <- Gc Q; Ritz values and residual to the host
+    auto rayleigh_ritz = [&]() -> csc_status {
+      CSC_TRY(dgemm(ctx, false, Gc, Q, T1, H, b, H, H, b, b));   // Y = Gc Q
+      ++iters;
+      CSC_TRY(small_gram(ctx, w, Q, T1, 1, (double*)bm->p));     // B = Q'Y
+      // the projected problem is solved two digits beyond the residual tolerance
+      CSC_TRY(jacobi(ctx, (double*)bm->p, b, rot, (double*)th->p, (int*)rk->p, (int*)sw->p, std::max(1e-13, 0.01 * tol)));
+      // Qn = Q W, Yn = Y W = Gc Qn
+      CSC_TRY(apply_rot(ctx, Q, T2, T1, T3, H, b, rot, (const int*)sw->p, (const int*)rk->p));
+      k_resid<<<k, 256, 0, ctx->stream>>>(T3, T2, (double*)th->p, H, b, k, (double*)res->p);
+      CSC_LAUNCHED(ctx);
+      CSC_CUDA(ctx, cudaMemcpyAsync(hres.data(), res->p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CSC_CUDA(ctx, cudaMemcpyAsync(hth.data(), th->p, (size_t)b * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      resid = 0.0;
+      for (int i = 0; i < k; ++i) resid = std::max(resid, hres[i]);
+      resid /= std::max(std::fabs(hth[0]), 1e-300);
+      std::swap(Q, T2);
+      have_gq = true;
+      return CSC_OK;
+    };
+
+    k_init_block<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(T1, nel, 42);
+    CSC_LAUNCHED(ctx);
+    CSC_TRY(chol_qr(ctx, w, T1, T2));
+    CSC_TRY(chol_qr(ctx, w, T2, Q));
+    for (int c = 0; c < 2; ++c) {
+      // three plain products per cycle: growth (lambda_1/lambda_b)^3 stays far inside CholeskyQR2's range
+      CSC_TRY(dgemm(ctx, false, Gc, Q, T1, H, b, H, H, b, b));
+      CSC_TRY(dgemm(ctx, false, Gc, T1, T2, H, b, H, H, b, b));
+      CSC_TRY(dgemm(ctx, false, Gc, T2, T1, H, b, H, H, b, b));
+      iters += 3;
+      CSC_TRY(chol_qr(ctx, w, T1, T2));
+      CSC_TRY(chol_qr(ctx, w, T2, Q));
     }
-    (void)converged;
+    CSC_TRY(rayleigh_ritz());
+    int n_rr = 1;
+    double rate_per_degree = 0.0;   // d log(resid) / d (filter degree), measured between Ritz steps
+    while (resid > tol && iters < max_iter) {
+      const double th1 = hth[0];
+      const double resid_before = resid;
+      const double beta = std::max(hth[b - 1], 1e-10 * std::fabs(th1));
+      const double c = 0.5 * beta, e = 0.5 * beta;
+      const double x1 = std::max((th1 - c) / e, 1.0 + 1e-12);
+      // A filtered guard column (error O(1)) is contaminated by the leading eigenvectors in proportion to
+      // T_m(x1)/T_m(1): keep that growth where the Cholesky pivots still have digits (growth^2 * b * eps << 1).
+      int m = (int)std::floor(std::log(4e5) / std::acosh(x1));
+      m = std::max(1, std::min(m, 24));
+      // Ritz steps are the expensive part of a cycle: once two of them have measured the convergence rate per
+      // filter degree, run as many cycles as the tolerance is predicted to need (at most 6) before the next one
+      int cycles = 1;
+      if (rate_per_degree < -1e-3) {
+        const double need = std::log(0.3 * tol / resid) / rate_per_degree;
+        cycles = (int)std::max(1.0, std::min(6.0, std::ceil(need / m)));
+      }
+      int degrees = 0;
+      for (int cyc = 0; cyc < cycles && iters < max_iter; ++cyc) {
+        // Y0 = Q, Y1 = (Gc Q - c Q)/e
+        double *Y0 = Q, *Y1 = T3;
+        if (have_gq) {
+          k_axpby_cols<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(T3, Q, 1.0 / e, -c / e, nullptr, nel, b, T3);
+          CSC_LAUNCHED(ctx);
+          have_gq = false;
+        } else {
+          GemmEpi ep;
+          ep.alpha = 1.0 / e;
+          ep.g1 = -c / e;
+          ep.X1 = Q;
+          CSC_TRY(dgemm(ctx, false, Gc, Q, T3, H, b, H, H, b, b, ep));
+          ++iters;
+        }
+        for (int j = 1; j < m; ++j) {
+          // Y2 = (2/e) Gc Y1 - (2c/e) Y1 - Y0, written over Y0
+          GemmEpi ep;
+          ep.alpha = 2.0 / e;
+          ep.g1 = -2.0 * c / e;
+          ep.X1 = Y1;
+          ep.g2 = -1.0;
+          ep.X2 = Y0;
+          CSC_TRY(dgemm(ctx, false, Gc, Y1, Y0, H, b, H, H, b, b, ep));
+          ++iters;
+          std::swap(Y0, Y1);
+        }
+        degrees += m;
+        // Y1 holds the filtered block; orthonormalise into the other one of {Q, T3}
+        double* dst = (Y1 == T3) ? Q : T3;
+        CSC_TRY(chol_qr(ctx, w, Y1, T1));
+        CSC_TRY(chol_qr(ctx, w, T1, dst));
+        if (dst != Q) std::swap(Q, T3);      // Q now names the orthonormal block
+      }
+      CSC_TRY(rayleigh_ritz());
+      ++n_rr;
+      rate_per_degree = (resid > 0.0 && degrees > 0) ? std::log(resid / resid_before) / (double)degrees : -1e9;
+    }
     std::vector<double> hq((size_t)H * b);
     CSC_CUDA(ctx, cudaMemcpyAsync(hq.data(), Q, hq.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
