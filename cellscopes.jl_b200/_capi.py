@@ -20,7 +20,7 @@ NORM_LOGARITHM, NORM_NONE = 0, 1
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
 STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
-          "pca_transform", "knn", "graph", "generate", "knn_scan"]
+          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma"]
 T_COUNT = len(STAGES)
 
 _NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,

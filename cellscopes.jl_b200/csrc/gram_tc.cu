@@ -1,0 +1,353 @@
+// PCA Gram matrix G += Z'Z on the 5th-generation tensor cores (run_pca, src/scrna/processing.jl:164-193: the
+// reference hands the centred H x N matrix to a LAPACK SVD; here the same decomposition goes through the
+// H x H Gram matrix).
+//
+//   Z is the cell-major scaled matrix [N cells][H genes] fp32.  G[a][b] = sum_c Z[c][a] Z[c][b]: the contraction
+//   runs over cells, i.e. over the SLOW index of Z, so both MMA operands are "MN-major" (the 128-byte rows that
+//   TMA lays down in shared memory run along the gene axis).  tcgen05 kind::tf32 takes MN-major operands
+//   directly (in the 128-byte swizzle with 32-byte atomicity), so no transpose is ever materialised.
+//
+//   3xTF32: Z = hi + lo with hi = tf32(Z), lo = Z - hi (k_split_colsum, fused with the fp64 column sums that
+//   the centring needs);  Z'Z ~= hi'hi + hi'lo + lo'hi, three MMA passes into one fp32 TMEM accumulator.
+//
+//   Accumulation.  The tensor core adds into its fp32 accumulator with truncation, so a long same-sign sum (a
+//   diagonal entry, a pair of correlated genes) picks up a relative bias proportional to the number of MMAs it
+//   went through: 3e-5 after 4096 cells (measured), far too much for eigenvectors that must hold 1e-4.  The
+//   kernel therefore lets the tensor core accumulate only 32 cells (12 MMAs, bias < 1e-6), then the flush warps
+//   pull the tile out of TMEM and add it, round-to-nearest, into fp32 REGISTER accumulators (128 x 256 tile =
+//   128 registers in each of 256 threads); TMEM is double-buffered so the tensor pipe never waits for that.
+//   Every 4096 cells the registers are added into the CTA's private fp64 tile in global memory (plain
+//   load-add-store, no atomics); k_gram_reduce sums the splits in a fixed order and mirrors the tiles into the
+//   full symmetric fp64 matrix.
+//
+//   One CTA = one 128 x 256 tile (genes a in [128 ti, +128), b in [256 tj, +256), ti <= 2 tj + 1) over one
+//   contiguous range of cells ("split"): 72 tiles x 2 splits = 144 CTAs for H = 2000.
+//
+// Warp roles (320 threads, 1 CTA per SM):
+//   warp 0      TMA producer: [16 cells x 32 genes] boxes (SWIZZLE_128B_ATOM_32B) of hi and lo into a 4-stage ring
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-9   flush: tcgen05.ld -> register accumulators -> fp64 tile
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int GT_BM = 128;                            // tile rows  = UMMA M
+constexpr int GT_BN = 256;                            // tile cols  = UMMA N
+constexpr int GT_BK = 16;                             // cells per pipeline stage
+constexpr int GT_STAGES = 4;
+constexpr int GT_ATOM_BYTES = GT_BK * 128;            // [16 cells][32 genes] fp32, one 128-byte row per cell
+constexpr int GT_PART_BYTES = 12 * GT_ATOM_BYTES;     // A: atoms 0-3 (128 genes), B: atoms 4-11 (256 genes)
+constexpr int GT_STAGE_BYTES = 2 * GT_PART_BYTES;     // hi | lo  = 48 KB
+constexpr int GT_THREADS = 64 + 256;
+constexpr int GT_TC_STAGES = 2;                       // stages (32 cells) accumulated inside the tensor core
+constexpr int GT_FLUSH_CHUNKS = 128;                  // chunks (4096 cells) accumulated in fp32 registers
+constexpr int GT_TILE_ELEMS = GT_BM * GT_BN;
+
+struct __align__(64) GramMaps {
+  CUtensorMap hi, lo;
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs, int n_pairs, int64_t n_cells,
+          int64_t cells_per_split, double* __restrict__ part) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* stages = base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)GT_STAGES * GT_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_full = smem_u32(bars + 0);      // [GT_STAGES]
+  const uint32_t bar_empty = smem_u32(bars + 4);     // [GT_STAGES]
+  const uint32_t bar_tfull = smem_u32(bars + 8);     // [2] TMEM buffer holds a finished chunk
+  const uint32_t bar_tempty = smem_u32(bars + 10);   // [2] TMEM buffer drained
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int2 pr = pairs[blockIdx.x];
+  // the A genes are a sub-range of the B genes (the tile straddles the diagonal): load B only
+  const bool diag = (pr.x >> 1) == pr.y;
+  const int64_t c_begin = (int64_t)blockIdx.y * cells_per_split;
+  const int64_t c_end = min(n_cells, c_begin + cells_per_split);
+  const int64_t n_stages = c_end > c_begin ? (c_end - c_begin + GT_BK - 1) / GT_BK : 0;
+  const int64_t n_chunks = (n_stages + GT_TC_STAGES - 1) / GT_TC_STAGES;
+  double* out = part + ((size_t)blockIdx.y * n_pairs + blockIdx.x) * (size_t)GT_TILE_ELEMS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GT_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.lo)) : "memory");
+    }
+    const uint32_t tx_bytes = diag ? 2u * 8u * GT_ATOM_BYTES : 2u * 12u * GT_ATOM_BYTES;
+    for (int64_t st = 0; st < n_stages; ++st) {
+      const int s = (int)(st % GT_STAGES);
+      mbar_wait(bar_empty + 8 * s, (uint32_t)(((st / GT_STAGES) & 1) ^ 1));
+      if (elect_one()) {
+        mbar_expect_tx(bar_full + 8 * s, tx_bytes);
+        const uint32_t dst = smem_u32(stages + (size_t)s * GT_STAGE_BYTES);
+        const int cell = (int)(c_begin + st * GT_BK);
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+          const CUtensorMap* map = p ? &maps.lo : &maps.hi;
+          const uint32_t pd = dst + (uint32_t)p * GT_PART_BYTES;
+          if (!diag) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) tma_load_2d(pd + (uint32_t)a * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.x * GT_BM + a * 32, cell);
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+            tma_load_2d(pd + (uint32_t)(4 + a) * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.y * GT_BN + a * 32, cell);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D = F32, A = B = TF32, both MN-major (bits 15, 16), N = 256, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GT_BN >> 3) << 17) |
+                           ((uint32_t)(GT_BM >> 4) << 24);
+    // shared-memory descriptor: MN-major tf32 operands exist only in the "128-byte swizzle with 32-byte
+    // atomicity" layout (type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose K-atom is 4 rows of 128 bytes:
+    // LBO = distance between 32-gene atoms, SBO = distance between 4-cell groups (512 bytes), version 1
+    const uint32_t desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (1u << 29);
+    const uint32_t lbo = (uint32_t)(GT_ATOM_BYTES >> 4) << 16;
+    const uint32_t a_atom = diag ? 4u + (uint32_t)(pr.x & 1) * 4u : 0u;
+    for (int64_t st = 0; st < n_stages; ++st) {
+      const int s = (int)(st % GT_STAGES);
+      const int64_t chunk = st / GT_TC_STAGES;
+      const int buf = (int)(chunk & 1);
+      const bool chunk_first = (st % GT_TC_STAGES) == 0;
+      const bool chunk_last = ((st + 1) % GT_TC_STAGES) == 0 || st + 1 == n_stages;
+      if (chunk_first) {
+        mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((chunk >> 1) & 1) ^ 1));
+        tc_fence_after();
+      }
+      mbar_wait(bar_full + 8 * s, (uint32_t)((st / GT_STAGES) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sb = smem_u32(stages + (size_t)s * GT_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * GT_BN;
+#pragma unroll
+        for (int kg = 0; kg < GT_BK / 8; ++kg) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            // pass 0: hi'hi   pass 1: hi'lo   pass 2: lo'hi
+            const uint32_t a_addr = sb + (pass == 2 ? GT_PART_BYTES : 0) + a_atom * GT_ATOM_BYTES + (uint32_t)kg * 1024u;
+            const uint32_t b_addr = sb + (pass == 1 ? GT_PART_BYTES : 0) + 4u * GT_ATOM_BYTES + (uint32_t)kg * 1024u;
+            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFF) | lbo);
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFF) | lbo);
+            tc_mma_tf32_ss(d_tmem, da, db, idesc, (chunk_first && kg == 0 && pass == 0) ? 0u : 1u);
+          }
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (chunk_last) tc_commit(bar_tfull + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= flush warps: TMEM -> fp32 registers -> private fp64 tile =================
+    const int ew = warp - 2;                     // 0..7
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                    // which 128 of the 256 columns
+    const int row = quarter * 32 + lane;
+    double* orow = out + (size_t)row * GT_BN + half * 128;
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+    bool first_flush = true;
+    for (int64_t ch = 0; ch < n_chunks; ++ch) {
+      const int buf = (int)(ch & 1);
+      mbar_wait(bar_tfull + 8 * buf, (uint32_t)((ch >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * GT_BN + half * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c * 32u, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+      if (((ch + 1) % GT_FLUSH_CHUNKS) == 0 || ch + 1 == n_chunks) {
+        double2* dst = reinterpret_cast<double2*>(orow);
+        if (first_flush) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) dst[j] = make_double2((double)acc[2 * j], (double)acc[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            double2 v = dst[j];
+            v.x += (double)acc[2 * j];
+            v.y += (double)acc[2 * j + 1];
+            dst[j] = v;
+          }
+        }
+        first_flush = false;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      }
+    }
+    if (n_chunks == 0) {
+      // an empty cell range still owns a tile: it must read as zero
+      for (int i = threadIdx.x - 64; i < GT_TILE_ELEMS; i += 256) out[i] = 0.0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// gram[a][b] (+)= sum over splits of the tile entries; tiles that do not straddle the diagonal are mirrored
+__global__ void __launch_bounds__(256)
+k_gram_reduce(const double* __restrict__ part, const int2* __restrict__ pairs, int n_pairs, int n_splits, int H,
+              double* __restrict__ gram) {
+  const int2 pr = pairs[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // entry of the 128 x 256 tile
+  const int r = idx / GT_BN, c = idx % GT_BN;
+  const int a = pr.x * GT_BM + r, b = pr.y * GT_BN + c;
+  if (a >= H || b >= H) return;
+  double s = 0.0;
+  for (int z = 0; z < n_splits; ++z) s += part[((size_t)z * n_pairs + blockIdx.y) * (size_t)GT_TILE_ELEMS + idx];
+  gram[(int64_t)a * H + b] += s;
+  if ((pr.x >> 1) != pr.y) gram[(int64_t)b * H + a] += s;
+}
+
+// hi = tf32(z) (round to nearest, low 13 bits zero), lo = z - hi (exact), written with row pitch Hp;
+// colsum[h] += sum over rows of z (fp64).  One thread = 4 consecutive columns of a block of rows.
+__global__ void __launch_bounds__(256)
+k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64_t rows_per_cta, float* __restrict__ hi,
+               float* __restrict__ lo, double* __restrict__ colsum) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= Hp) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, n_rows);
+  const bool vec = (H & 3) == 0;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t r = r0; r < r1; ++r) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = z + r * (int64_t)H + c0;
+    if (vec) {
+      const float4 f = __ldcs(reinterpret_cast<const float4*>(src));
+      v[0] = f.x;
+      v[1] = f.y;
+      v[2] = f.z;
+      v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < H) v[j] = __ldcs(src + j);
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+      h[j] = __uint_as_float(u);
+      l[j] = v[j] - h[j];
+      s[j] += (double)v[j];
+    }
+    *reinterpret_cast<float4*>(hi + r * (int64_t)Hp + c0) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + r * (int64_t)Hp + c0) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (c0 + j < H) atomicAdd(colsum + c0 + j, s[j]);
+}
+
+csc_status gram_make_map(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const float* ptr, int64_t n_rows, int H, int Hp) {
+  cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Hp * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)GT_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled (gram) failed with %d", (int)r);
+  return CSC_OK;
+}
+
+}  // namespace
+
+// colsum[H] += column sums of z; gram[H*H] += z'z (full symmetric), both fp64.
+csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* colsum, double* gram) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CSC_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeTiledFn)fn;
+  }
+  const int Hp = (H + 3) & ~3;
+  DevPtr hi, lo, d_pairs, part;
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 4, &hi));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 4, &lo));
+  {
+    const int64_t rows_per_cta = 256;
+    dim3 grid((unsigned)((Hp / 4 + 255) / 256), (unsigned)ceil_div64(n_rows, rows_per_cta));
+    k_split_colsum<<<grid, 256, 0, ctx->stream>>>(z, n_rows, H, Hp, rows_per_cta, (float*)hi->p, (float*)lo->p, colsum);
+    CSC_LAUNCHED(ctx);
+  }
+  const int ntm = (H + GT_BM - 1) / GT_BM, ntn = (H + GT_BN - 1) / GT_BN;
+  std::vector<int2> pairs;
+  for (int tj = 0; tj < ntn; ++tj)
+    for (int ti = 0; ti < ntm && ti <= 2 * tj + 1; ++ti) pairs.push_back(make_int2(ti, tj));
+  const int n_pairs = (int)pairs.size();
+  // splits: fill the SMs, but keep at least one register-flush period of cells per split
+  const int64_t flush_cells = (int64_t)GT_FLUSH_CHUNKS * GT_TC_STAGES * GT_BK;
+  int n_splits = std::max(1, ctx->sm_count / n_pairs);
+  n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, ceil_div64(n_rows, flush_cells)));
+  const int64_t align = (int64_t)GT_TC_STAGES * GT_BK;
+  int64_t cells_per_split = ceil_div64(ceil_div64(n_rows, n_splits), align) * align;
+  n_splits = (int)ceil_div64(n_rows, cells_per_split);
+  CSC_TRY(dev_alloc(ctx, pairs.size() * sizeof(int2), &d_pairs));
+  CSC_CUDA(ctx, cudaMemcpyAsync(d_pairs->p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_pairs * n_splits * GT_TILE_ELEMS * 8, &part));
+  GramMaps maps;
+  CSC_TRY(gram_make_map(ctx, encode, &maps.hi, (const float*)hi->p, n_rows, H, Hp));
+  CSC_TRY(gram_make_map(ctx, encode, &maps.lo, (const float*)lo->p, n_rows, H, Hp));
+  const size_t smem = 1024 + (size_t)GT_STAGES * GT_STAGE_BYTES + 256;
+  CSC_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEventRecord(ctx->ev_k0, ctx->stream);
+  k_gram_tc<<<dim3((unsigned)n_pairs, (unsigned)n_splits), GT_THREADS, smem, ctx->stream>>>(
+      maps, (const int2*)d_pairs->p, n_pairs, n_rows, cells_per_split, (double*)part->p);
+  CSC_LAUNCHED(ctx);
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
+  k_gram_reduce<<<dim3(GT_TILE_ELEMS / 256, (unsigned)n_pairs), 256, 0, ctx->stream>>>(
+      (const double*)part->p, (const int2*)d_pairs->p, n_pairs, n_splits, H, gram);
+  CSC_LAUNCHED(ctx);
+  // the pageable pair table must outlive the async copy
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->stage_ms[CSC_T_GRAM_MMA] += ms;
+  return CSC_OK;
+}

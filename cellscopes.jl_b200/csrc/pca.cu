@@ -141,6 +141,8 @@ k_gram_simt(const float* __restrict__ z, int64_t n_rows, int32_t H, int64_t rows
   }
 }
 
+csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* colsum, double* gram);
+
 extern "C" csc_status csc_pca_partial(csc_ctx* ctx, const csc_dense* scaled, csc_vec* colsum, csc_vec* gram) {
   if (!ctx || !scaled || !colsum || !gram) return CSC_ERR_ARG;
   CSC_GUARD_BEGIN
@@ -151,6 +153,10 @@ extern "C" csc_status csc_pca_partial(csc_ctx* ctx, const csc_dense* scaled, csc
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_PCA_GRAM);
   if (N == 0) return CSC_OK;
+  // v2: tcgen05 3xTF32 (gram_tc.cu).  CSC_GRAM_IMPL=simt selects the CUDA-core kernel (kept for A/B runs).
+  const char* impl = getenv("CSC_GRAM_IMPL");
+  if (!(impl && strcmp(impl, "simt") == 0))
+    return gram_tc(ctx, scaled->p(), N, (int)H, colsum->as<double>(), gram->as<double>());
   {
     const int64_t rows_per_cta = 2048;
     dim3 grid((unsigned)ceil_div64(H, 256), (unsigned)ceil_div64(N, rows_per_cta));

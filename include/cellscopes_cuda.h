@@ -72,6 +72,7 @@ enum {
   CSC_T_UPLOAD = 0, CSC_T_NORMALIZE, CSC_T_GENE_STATS, CSC_T_HVG, CSC_T_SCALE_STATS, CSC_T_SCALE_FILL,
   CSC_T_PCA_GRAM, CSC_T_PCA_SOLVE, CSC_T_PCA_TRANSFORM, CSC_T_KNN, CSC_T_GRAPH, CSC_T_GENERATE,
   CSC_T_KNN_SCAN, /* the all-pairs scan kernel alone (inside CSC_T_KNN): the dominant kernel of the path */
+  CSC_T_GRAM_MMA, /* the tcgen05 Gram kernel alone (inside CSC_T_PCA_GRAM) */
   CSC_T_COUNT
 };
 
