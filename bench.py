@@ -204,7 +204,9 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     step_ms = []
+    out = last = None
     for _ in range(args.steps):
+        out = last = None          # the previous step's device results are released before the next one starts
         ctx.flush_l2()
         barrier()
         ctx.timer_start()
@@ -280,7 +282,8 @@ def main():
                        "l2": "inputs larger than L2 (CSC shard >= 1 GB) and a 256 MiB flush between iterations"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "stage_ms": {kk: round(v, 3) for kk, v in per_step.items() if v > 0}, "hbm_stages": hbm, "diag": diag,
+            "stage_ms": {kk: round(v, 3) for kk, v in per_step.items() if v > 0}, "step_ms": [round(x, 2) for x in step_ms],
+            "hbm_stages": hbm, "diag": diag,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -20,7 +20,7 @@ NORM_LOGARITHM, NORM_NONE = 0, 1
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
 STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
-          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma"]
+          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host"]
 T_COUNT = len(STAGES)
 
 _NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,
@@ -61,10 +61,11 @@ SIGNATURES = {
     "csc_sparse_download": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32]),
     "csc_sparse_free": (_I32, [_P]),
     "csc_generate_counts": (_I32, [_P, _I64, _I64, _I64, _U64, _P, _P, _P, _P, _I32, _I32, _F32, _F32, _F32, _PP]),
-    "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _PP]),
+    "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _P, _PP]),
     "csc_gene_stats_partial": (_I32, [_P, _P, _P]),
     "csc_hvg_finish": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
+    "csc_scale_stats_select": (_I32, [_P, _P, _I64, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
     "csc_dense_alloc": (_I32, [_P, _I64, _I64, _PP]),
     "csc_dense_upload": (_I32, [_P, _P, _I32, _I64, _I64, _PP]),
@@ -228,11 +229,11 @@ class Context:
 
     # ---- stages ----------------------------------------------------------------------------
     def normalize(self, raw, scale_factor=10000.0, norm_method=NORM_LOGARITHM, pseudocount=1.0, nan_to_zero=False,
-                  gene_stats=None):
+                  gene_stats=None, norm_stats=None):
         h = C.c_void_p()
         self.check(self.lib.csc_normalize(self.h, raw.h, float(scale_factor), int(norm_method), float(pseudocount),
                                           1 if nan_to_zero else 0, gene_stats.h if gene_stats is not None else None,
-                                          C.byref(h)))
+                                          norm_stats.h if norm_stats is not None else None, C.byref(h)))
         return Sparse(self, h)
 
     def gene_stats_partial(self, raw, gene_stats):
@@ -253,6 +254,12 @@ class Context:
     def scale_stats_partial(self, norm, features, partial):
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
         self.check(self.lib.csc_scale_stats_partial(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h))
+
+    def scale_stats_select(self, norm_stats, n_genes, features, partial):
+        """partial += the rows of the all-gene (sum y, sum y^2) table that csc_normalize filled"""
+        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        self.check(self.lib.csc_scale_stats_select(self.h, norm_stats.h, int(n_genes), _ptr(f), 0 if f is None else f.size,
+                                                   partial.h))
 
     def scale_fill(self, norm, features, partial, n_cells_total, scale_max=10.0, do_scale=True, do_center=True):
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)

@@ -1,6 +1,8 @@
 // Lifecycle, buffers, upload/download: the plumbing half of the C ABI (include/cellscopes_cuda.h).
 #include "common.cuh"
 
+#include <chrono>
+
 static thread_local std::string g_create_err;
 
 csc_status csc_fail(csc_ctx* ctx, csc_status code, const char* fmt, ...) {
@@ -17,7 +19,6 @@ csc_status csc_fail(csc_ctx* ctx, csc_status code, const char* fmt, ...) {
   return code;
 }
 
-#include <chrono>
 void csc_trace(csc_ctx* ctx, const char* label) {
   cudaStreamSynchronize(ctx->stream);
   const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -34,14 +35,30 @@ csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero) {
   }
   m->device = ctx->device;
   m->bytes = bytes;
-  size_t req = bytes ? bytes : 16;
-  m->stream = ctx->stream;
+  m->ctx = ctx;
   m->ctx_alive = ctx->alive;
-  cudaError_t e = cudaMallocAsync(&m->p, req, ctx->stream);
+  // block sizes: 512-byte granules below 1 MiB, 2 MiB granules above (so that near-equal requests share blocks)
+  size_t req = bytes ? bytes : 16;
+  req = req < ((size_t)1 << 20) ? (req + 511) & ~(size_t)511 : (req + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  const auto t0 = std::chrono::steady_clock::now();
+  m->p = ctx->cache.take(req, &m->block_bytes);   // a cached block may be larger than the request
+  cudaError_t e = cudaSuccess;
+  if (!m->p) {
+    e = cudaMalloc(&m->p, req);
+    if (e == cudaErrorMemoryAllocation) {
+      // give the cached blocks back to the driver and retry once
+      cudaGetLastError();
+      cudaStreamSynchronize(ctx->stream);
+      ctx->cache.release_all();
+      e = cudaMalloc(&m->p, req);
+    }
+    m->block_bytes = req;
+  }
+  ctx->stage_ms[CSC_T_ALLOC_HOST] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (e != cudaSuccess) {
     m->p = nullptr;
     cudaGetLastError();
-    return csc_fail(ctx, CSC_ERR_OOM, "cudaMallocAsync(%zu bytes) failed: %s", req, cudaGetErrorString(e));
+    return csc_fail(ctx, CSC_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", req, cudaGetErrorString(e));
   }
   if (zero) CSC_CUDA(ctx, cudaMemsetAsync(m->p, 0, req, ctx->stream));
   *out = m;
@@ -113,6 +130,7 @@ csc_status csc_destroy(csc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->alive) *ctx->alive = false;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->cache.release_all();
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->ev_timer0) cudaEventDestroy(ctx->ev_timer0);
   if (ctx->ev_timer1) cudaEventDestroy(ctx->ev_timer1);

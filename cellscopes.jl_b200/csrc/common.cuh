@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,36 @@
 // ------------------------------------------------------------------------------------------
 // context and handles
 // ------------------------------------------------------------------------------------------
+// Caching block allocator of a context.  Every stage allocates work buffers of the same sizes on every call
+// (a step of the path allocates ~60 buffers, some of them gigabytes); handing those to the driver each time,
+// even through the stream-ordered pool, cost tens of milliseconds of host time per step (measured).  Freed
+// blocks are kept in a size-ordered free list instead and reused when a request fits within 25 %; they go back
+// to the driver at csc_destroy or when an allocation fails.  Reuse is safe without events because a context
+// issues all of its work on one stream: a block is freed by the host after the last kernel that uses it was
+// enqueued, and whoever gets it next enqueues later on the same stream.
+struct BlockCache {
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached_bytes = 0;
+  void* take(size_t bytes, size_t* block_bytes) {
+    auto it = free_blocks.lower_bound(bytes);
+    if (it == free_blocks.end() || it->first > bytes + bytes / 4 + (1u << 20)) return nullptr;
+    void* p = it->second;
+    *block_bytes = it->first;
+    cached_bytes -= it->first;
+    free_blocks.erase(it);
+    return p;
+  }
+  void give(size_t bytes, void* p) {
+    free_blocks.emplace(bytes, p);
+    cached_bytes += bytes;
+  }
+  void release_all() {
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+
 struct csc_ctx {
   int device = 0;
   int sm_count = 0;
@@ -31,6 +62,7 @@ struct csc_ctx {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   std::shared_ptr<bool> alive;  // cleared by csc_destroy: late frees then fall back to cudaFree
+  BlockCache cache;
   int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
   double trace_t0 = 0.0;
 };
@@ -41,23 +73,25 @@ void csc_trace(csc_ctx* ctx, const char* label);
   } while (0)
 
 // device allocation with shared ownership (a normalised matrix shares colptr/rowval with the raw one)
-// Allocations come from the stream-ordered pool (cudaMallocAsync) so that the many short-lived work
-// buffers of a stage cost microseconds, not a device synchronisation each.
 struct DevMem {
   void* p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;       // requested size
+  size_t block_bytes = 0; // size of the underlying block (the cache key)
   int device = 0;
   bool owned = true;
-  cudaStream_t stream = nullptr;
+  csc_ctx* ctx = nullptr;
   std::shared_ptr<bool> ctx_alive;
   ~DevMem() {
     if (p && owned) {
-      int cur = 0;
-      cudaGetDevice(&cur);
-      if (cur != device) cudaSetDevice(device);
-      if (ctx_alive && *ctx_alive) cudaFreeAsync(p, stream);
-      else cudaFree(p);
-      if (cur != device) cudaSetDevice(cur);
+      if (ctx_alive && *ctx_alive) {
+        ctx->cache.give(block_bytes, p);
+      } else {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        cudaFree(p);
+        if (cur != device) cudaSetDevice(cur);
+      }
     }
   }
 };

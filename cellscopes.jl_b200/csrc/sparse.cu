@@ -1,6 +1,8 @@
 // Sparse stages: ingest (narrowing), normalize_object, raw gene moments, scale_object.
 // All kernels stream the cell-major CSC once, a warp per cell (column), coalesced along the
 // non-zeros of the column, with warp-shuffle reductions for the per-cell sums.
+#include <cmath>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -217,117 +219,229 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K1/K2  normalize_object (processing.jl:15-31) fused with the raw per-gene moments that
-// find_variable_genes needs (processing.jl:138-139).
+// K1/K2  normalize_object (processing.jl:15-31) fused with the per-gene moments the next two stages need:
+//   raw counts   (sum x, sum x^2)  -> find_variable_genes (processing.jl:138-139)
+//   normalised   (sum y, sum y^2)  -> scale_object        (processing.jl:66-67)
 //
-// A CTA owns a contiguous range of cells; a warp owns one cell at a time.  Pass 1 over the
-// column: fp64 column sum (warp-shuffle reduction).  Pass 2 (the column is still in L1/L2):
-// y = log((x * inv) * sf + pc), written with the same pattern.  Gene moments: sum x goes to a
-// CTA-private u32 table in shared memory (flushed once per CTA with fp64 atomics), the
-// excess sum(x^2 - x) of the rare entries with x >= 2 goes straight to the fp64 table in L2.
-// All partial sums are integers below 2^53, so the result is exact and order-independent.
-// HBM traffic: 4 B read + 4 B written per non-zero (+ 4 B row index when moments are fused).
+// A CTA owns a contiguous range of cells; a warp owns one cell at a time.  Pass 1 over the column: fp64 column
+// sum (warp-shuffle reduction).  Pass 2 (the column is still in L1): y = log((x * inv) * sf + pc), written with
+// the same pattern, and the moment updates.  All moment tables live in shared memory as 32-bit integers, the
+// only type shared memory adds natively (ATOMS.ADD; 64-bit and float adds are CAS loops), and are flushed to the
+// fp64 tables in global memory once per CTA:
+//   S1 = sum x            u32, exact (x integer <= 65535; anything else goes straight to the fp64 table)
+//   E  = sum (x^2 - x)    u32, exact (x <= 255)            -> sum x^2 = S1 + E
+//   Y1 = sum round(y s1)  i32, fixed point; s1 = 2^31 / (cells_per_cta * ymax): resolution ~ 4e-6 per entry
+//   Y2 = sum round(y^2 s2) u32, fixed point
+// Integer sums are order-independent, so the result is deterministic; the raw moments are exact.
+// HBM traffic: 4 B value read + 4 B value written + 4 B row index per non-zero.
 // ------------------------------------------------------------------------------------------
-template <bool WRITE_NORM, bool STATS, bool SMEM_TABLE>
+struct NormArgs {
+  const int64_t* colptr;
+  const int32_t* rowval;
+  const float* raw;
+  float* out;
+  int64_t n_cells;
+  int32_t n_genes;
+  double sf, pc;
+  int method, nan_to_zero;
+  double* gstats;     // fp64 [2G] raw moments (or null)
+  double* nstats;     // fp64 [2G] normalised moments (or null)
+  int64_t cells_per_cta;
+  float ymax, s1, s2; // fixed-point range and scales of the normalised moments
+  double inv_s1, inv_s2;
+};
+
+// RAW: 0 = no raw moments, 1 = S1 table only (E goes to global memory), 2 = S1 and E tables,
+//      3 = no table fits: every update goes to the fp64 table in global memory
+template <bool WRITE_NORM, int RAW, bool NSTATS>
 __global__ void __launch_bounds__(512)
-k_normalize(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ raw,
-            float* __restrict__ out, int64_t n_cells, int32_t n_genes, double sf, double pc, int method,
-            int nan_to_zero, double* __restrict__ gstats, int64_t cells_per_cta) {
-  extern __shared__ unsigned int s1tab[];
-  if (STATS && SMEM_TABLE) {
-    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) s1tab[g] = 0u;
+k_normalize(const NormArgs a) {
+  extern __shared__ unsigned int stab[];
+  const int G = a.n_genes;
+  unsigned int* s1tab = stab;
+  constexpr int NRAW = RAW == 2 ? 2 : RAW == 1 ? 1 : 0;
+  unsigned int* etab = stab + (NRAW >= 1 ? G : 0);
+  int* y1tab = reinterpret_cast<int*>(stab + NRAW * G);
+  unsigned int* y2tab = reinterpret_cast<unsigned int*>(y1tab) + G;
+  constexpr int NTAB = NRAW + (NSTATS ? 2 : 0);
+  if (NTAB > 0) {
+    for (int g = threadIdx.x; g < NTAB * G; g += blockDim.x) stab[g] = 0u;
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
-  const int64_t c0 = (int64_t)blockIdx.x * cells_per_cta;
-  const int64_t c1 = min(c0 + cells_per_cta, n_cells);
-  const bool pc_is_one = (pc == 1.0);
-  const float pcf = (float)pc;
+  const int64_t c0 = (int64_t)blockIdx.x * a.cells_per_cta;
+  const int64_t c1 = min(c0 + a.cells_per_cta, a.n_cells);
+  const bool pc_is_one = (a.pc == 1.0);
+  const float pcf = (float)a.pc;
   for (int64_t c = c0 + warp; c < c1; c += nwarp) {
-    const int64_t b = colptr[c], e = colptr[c + 1];
+    const int64_t b = a.colptr[c], e = a.colptr[c + 1];
     double inv = 0.0;
-    if (WRITE_NORM) {
+    if (WRITE_NORM || NSTATS) {
       double s = 0.0;
 #pragma unroll 4
-      for (int64_t i = b + lane; i < e; i += 32) s += (double)raw[i];
+      for (int64_t i = b + lane; i < e; i += 32) s += (double)a.raw[i];
       s = warp_sum(s);
       inv = 1.0 / s;  // 1/0 = Inf: the reference's NaN column (processing.jl:18)
     }
 #pragma unroll 4
     for (int64_t i = b + lane; i < e; i += 32) {
-      const float x = raw[i];
-      if (WRITE_NORM) {
-        const double t = ((double)x * inv) * sf;  // association order of processing.jl:24
-        float y;
-        if (method == CSC_NORM_LOGARITHM) {
+      const float x = a.raw[i];
+      float y = 0.f;
+      if (WRITE_NORM || NSTATS) {
+        const double t = ((double)x * inv) * a.sf;  // association order of processing.jl:24
+        if (a.method == CSC_NORM_LOGARITHM) {
           const float tf = (float)t;
           y = pc_is_one ? log1pf(tf) : logf(tf + pcf);
         } else {
           y = (float)t;
         }
-        if (nan_to_zero && y != y) y = 0.f;
-        __stcs(out + i, y);
+        if (a.nan_to_zero && y != y) y = 0.f;
+        if (WRITE_NORM) __stcs(a.out + i, y);
       }
-      if (STATS) {
-        const int g = __ldcs(rowval + i);
-        const float xr = rintf(x);
-        if (SMEM_TABLE && xr == x && x >= 0.f && x <= 65535.f) {
-          atomicAdd(&s1tab[g], (unsigned int)x);
-          if (x >= 2.f) {
+      if (RAW > 0 || NSTATS) {
+        const int g = __ldcs(a.rowval + i);
+        if (RAW > 0) {
+          const float xr = rintf(x);
+          if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
+            const unsigned int xi = (unsigned int)x;
+            atomicAdd(&s1tab[g], xi);
+            if (RAW == 2 && xi <= 255u) {
+              if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
+            } else if (xi >= 2u) {
+              const double xd = (double)x;
+              atomicAdd(&a.gstats[(int64_t)G + g], xd * xd - xd);
+            }
+          } else {
             const double xd = (double)x;
-            atomicAdd(&gstats[(int64_t)n_genes + g], xd * xd - xd);
+            atomicAdd(&a.gstats[g], xd);
+            atomicAdd(&a.gstats[(int64_t)G + g], xd * xd);
           }
-        } else {
-          const double xd = (double)x;
-          atomicAdd(&gstats[g], xd);
-          atomicAdd(&gstats[(int64_t)n_genes + g], xd * xd);
+        }
+        if (NSTATS) {
+          if (fabsf(y) <= a.ymax) {   // false for NaN / Inf / out-of-range values
+            atomicAdd(&y1tab[g], __float2int_rn(y * a.s1));
+            atomicAdd(&y2tab[g], __float2uint_rn(y * y * a.s2));
+          } else {
+            const double yd = (double)y;
+            atomicAdd(&a.nstats[g], yd);
+            atomicAdd(&a.nstats[(int64_t)G + g], yd * yd);
+          }
         }
       }
     }
   }
-  if (STATS && SMEM_TABLE) {
+  if (NTAB > 0) {
     __syncthreads();
-    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
-      const unsigned int v = s1tab[g];
-      if (v) {
-        atomicAdd(&gstats[g], (double)v);
-        atomicAdd(&gstats[(int64_t)n_genes + g], (double)v);  // sum x^2 = sum x + sum (x^2 - x)
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      if (NRAW > 0) {
+        const unsigned int v = s1tab[g];
+        const unsigned int ex = RAW == 2 ? etab[g] : 0u;
+        if (v) atomicAdd(&a.gstats[g], (double)v);
+        if (v || ex) atomicAdd(&a.gstats[(int64_t)G + g], (double)v + (double)ex);  // sum x^2 = sum x + sum (x^2 - x)
+      }
+      if (NSTATS) {
+        const int v1 = y1tab[g];
+        const unsigned int v2 = y2tab[g];
+        if (v1) atomicAdd(&a.nstats[g], (double)v1 * a.inv_s1);
+        if (v2) atomicAdd(&a.nstats[(int64_t)G + g], (double)v2 * a.inv_s2);
       }
     }
   }
 }
 
-template <bool WRITE_NORM, bool STATS>
+// norm_stats fallback (tables do not fit): per-gene sum y / sum y^2 over all genes straight from the normalised values
+__global__ void __launch_bounds__(256)
+k_norm_moments_global(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+                      int64_t n_cells, int32_t n_genes, double* __restrict__ nstats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    const int64_t b = colptr[c], e = colptr[c + 1];
+#pragma unroll 4
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const int g = __ldcs(rowval + i);
+      const double y = (double)__ldcs(val + i);
+      atomicAdd(&nstats[g], y);
+      atomicAdd(&nstats[(int64_t)n_genes + g], y * y);
+    }
+  }
+}
+
 static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* out, double sf, double pc, int method,
-                                   int nan_to_zero, double* gstats) {
+                                   int nan_to_zero, double* gstats, double* nstats) {
   if (raw->n_cells == 0) return CSC_OK;
   const int threads = 512;
-  size_t smem = STATS ? (size_t)raw->n_genes * 4 : 0;
-  const bool smem_table = STATS && smem <= (size_t)200 * 1024;
-  if (!smem_table) smem = 0;
-  int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)220 * 1024) / (smem + 1024))) : 4;
+  const size_t G = (size_t)raw->n_genes;
+  const size_t budget = (size_t)200 * 1024;
+  // which tables fit: raw S1 (+E), normalised Y1/Y2
+  int raw_mode = 0;
+  bool nst = false;
+  if (gstats) raw_mode = (2 * G * 4 <= budget) ? 2 : (G * 4 <= budget ? 1 : 3);
+  const int nraw = raw_mode == 2 ? 2 : raw_mode == 1 ? 1 : 0;
+  if (nstats && out && (size_t)(nraw + 2) * G * 4 <= budget) nst = true;
+  const int ntab = nraw + (nst ? 2 : 0);
+  const size_t smem = (size_t)ntab * G * 4;
+  const int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)220 * 1024) / (smem + 1024))) : 4;
   int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
-  // a CTA's u32 table must not overflow: <= 65535 per entry * 65536 cells
+  // a CTA's u32 tables must not overflow: <= 65535 (S1) and <= 65025 (E) per entry * 65536 cells
   int64_t cells_per_cta = std::max<int64_t>(16, ceil_div64(raw->n_cells, grid));
   cells_per_cta = std::min<int64_t>(cells_per_cta, 65536);
   grid = ceil_div64(raw->n_cells, cells_per_cta);
+  NormArgs a;
+  a.colptr = raw->cp();
+  a.rowval = raw->rv();
+  a.raw = raw->v();
+  a.out = out;
+  a.n_cells = raw->n_cells;
+  a.n_genes = (int32_t)raw->n_genes;
+  a.sf = sf;
+  a.pc = pc;
+  a.method = method;
+  a.nan_to_zero = nan_to_zero;
+  a.gstats = gstats;
+  a.nstats = nstats;
+  a.cells_per_cta = cells_per_cta;
+  // range of y for non-negative counts: t = x/colsum*sf in [0, sf]
+  double ymax = method == CSC_NORM_LOGARITHM ? std::max(std::fabs(std::log(pc > 0 ? pc : 1e-300)), std::fabs(std::log(sf + pc)))
+                                              : std::fabs(sf);
+  if (!(ymax > 0.0) || !std::isfinite(ymax)) ymax = 1.0;
+  a.ymax = (float)(ymax * 1.0001);
+  const double s1 = 0.98 * 2147483648.0 / ((double)cells_per_cta * a.ymax);
+  const double s2 = 0.98 * 4294967296.0 / ((double)cells_per_cta * (double)a.ymax * a.ymax);
+  a.s1 = (float)s1;
+  a.s2 = (float)s2;
+  a.inv_s1 = 1.0 / (double)a.s1;
+  a.inv_s2 = 1.0 / (double)a.s2;
   auto launch = [&](auto kern) -> csc_status {
     if (smem > 48 * 1024)
       CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(raw->cp(), raw->rv(), raw->v(), out, raw->n_cells,
-                                                         (int32_t)raw->n_genes, sf, pc, method, nan_to_zero, gstats,
-                                                         cells_per_cta);
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     CSC_LAUNCHED(ctx);
     return CSC_OK;
   };
-  if (smem_table) return launch(k_normalize<WRITE_NORM, STATS, true>);
-  return launch(k_normalize<WRITE_NORM, STATS, false>);
+  const bool wn = out != nullptr;
+  csc_status st = CSC_OK;
+#define NORM_CASE(W, R, N) if (wn == W && raw_mode == R && nst == N) st = launch(k_normalize<W, R, N>);
+  NORM_CASE(true, 0, false) NORM_CASE(true, 1, false) NORM_CASE(true, 2, false) NORM_CASE(true, 3, false)
+  NORM_CASE(true, 0, true) NORM_CASE(true, 1, true) NORM_CASE(true, 2, true) NORM_CASE(true, 3, true)
+  NORM_CASE(false, 1, false) NORM_CASE(false, 2, false) NORM_CASE(false, 3, false)
+#undef NORM_CASE
+  CSC_TRY(st);
+  if (nstats && !nst && out) {
+    // tables did not fit: one more pass over the normalised values
+    k_norm_moments_global<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(raw->cp(), raw->rv(), out, raw->n_cells,
+                                                                       (int32_t)raw->n_genes, nstats);
+    CSC_LAUNCHED(ctx);
+  }
+  return CSC_OK;
 }
 
 extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
-                                    double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out) {
+                                    double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
+                                    csc_sparse** out) {
   if (!ctx || !raw || !out) return CSC_ERR_ARG;
   CSC_GUARD_BEGIN
   // processing.jl:28: throw(ArgumentError("Unknown normalization method"))
@@ -335,6 +449,8 @@ extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double 
               "Unknown normalization method: %d", norm_method);
   CSC_REQUIRE(ctx, !gene_stats || (gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * raw->n_genes),
               "csc_normalize: gene_stats must be fp64[2*n_genes]");
+  CSC_REQUIRE(ctx, !norm_stats || (norm_stats->dtype == CSC_DT_F64 && norm_stats->n >= 2 * raw->n_genes),
+              "csc_normalize: norm_stats must be fp64[2*n_genes]");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_NORMALIZE);
   std::unique_ptr<csc_sparse> m(new csc_sparse());
@@ -345,12 +461,8 @@ extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double 
   m->colptr = raw->colptr;  // shared pattern: the output keeps the stored structure (processing.jl:24)
   m->rowval = raw->rowval;
   CSC_TRY(dev_alloc(ctx, (size_t)raw->nnz * 4, &m->val));
-  if (gene_stats)
-    CSC_TRY((launch_normalize<true, true>(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
-                                          gene_stats->as<double>())));
-  else
-    CSC_TRY((launch_normalize<true, false>(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
-                                           nullptr)));
+  CSC_TRY(launch_normalize(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
+                           gene_stats ? gene_stats->as<double>() : nullptr, norm_stats ? norm_stats->as<double>() : nullptr));
   *out = m.release();
   return CSC_OK;
   CSC_GUARD_END(ctx)
@@ -363,9 +475,21 @@ extern "C" csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw
               "csc_gene_stats_partial: gene_stats must be fp64[2*n_genes]");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_GENE_STATS);
-  CSC_TRY((launch_normalize<false, true>(ctx, raw, nullptr, 1.0, 1.0, 0, 0, gene_stats->as<double>())));
+  CSC_TRY(launch_normalize(ctx, raw, nullptr, 1.0, 1.0, 0, 0, gene_stats->as<double>(), nullptr));
   return CSC_OK;
   CSC_GUARD_END(ctx)
+}
+
+// partial[0:H] = all_stats[rows], partial[H:2H] = all_stats[G + rows] for the selected rows in original gene order
+__global__ void k_stats_select(const double* __restrict__ all, int32_t n_genes, const int32_t* __restrict__ gene2h,
+                               int32_t n_feat, double* __restrict__ part) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genes) return;
+  const int h = gene2h[g];
+  if (h >= 0) {
+    part[h] += all[g];
+    part[n_feat + h] += all[(int64_t)n_genes + g];
+  }
 }
 
 extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
@@ -560,6 +684,28 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
     }
   }
   *out = d;
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_stats, int64_t n_genes, const int64_t* features,
+                                             int64_t n_feat, csc_vec* partial) {
+  if (!ctx || !norm_stats || !partial) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, norm_stats->dtype == CSC_DT_F64 && norm_stats->n >= 2 * n_genes && n_genes > 0,
+              "csc_scale_stats_select: norm_stats must be fp64[2*n_genes]");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_SCALE_STATS);
+  DevPtr map;
+  int64_t H = 0;
+  CSC_TRY(build_gene2h(ctx, n_genes, features, n_feat, &map, &H));
+  CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_select: partial must be fp64[2*H], H=%lld",
+              (long long)H);
+  k_stats_select<<<(unsigned)ceil_div64(n_genes, 256), 256, 0, ctx->stream>>>(norm_stats->as<double>(), (int32_t)n_genes,
+                                                                              (const int32_t*)map->p, (int32_t)H,
+                                                                              partial->as<double>());
+  CSC_LAUNCHED(ctx);
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CSC_OK;
   CSC_GUARD_END(ctx)
 }

@@ -6,7 +6,8 @@ point) and to a *communicator* (``LocalComm`` for one GPU, ``TorchComm`` for one
 ``torch.distributed``).  The collectives are exactly the natural ones:
 
   all-reduce  fp64 [2G]      per-gene sum x, sum x^2            (find_variable_genes)
-  all-reduce  fp64 [2H]      per-HVG sum y, sum y^2             (scale_object)
+  all-reduce  fp64 [2H]      per-HVG sum y, sum y^2             (scale_object; selected from the all-gene
+                             table that the normalise pass filled)
   all-reduce  fp64 [H], [H*H] column sums and Gram of Z         (run_pca)
   all-gather  fp32 [N x k_pc] embedding                          (kNN keys)
   all-gather  int32 [N x k]   neighbour table                    (adjacency / SNN)
@@ -161,9 +162,10 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     G, n_loc = raw.shape
     if offsets is None:
         offsets = np.array([0, n_cells_total], dtype=np.int64)
-    # a1 + the raw moments of a2, one pass
+    # a1 + the raw moments of a2 + the normalised moments of a3, one pass over the counts
     stats = be.vec(2 * G, np.float64)
-    norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats)
+    nstats = be.vec(2 * G, np.float64)
+    norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats, nstats)
     comm.allreduce_sum(stats)
     # a2
     hvg = be.hvg_finish(stats, G, n_cells_total, p.n_features, p.span)
@@ -172,7 +174,7 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     H = int(rows.size)
     # a3
     part = be.vec(2 * H, np.float64)
-    be.scale_stats_partial(norm, feats, part)
+    be.scale_stats_select(nstats, G, feats, part)
     comm.allreduce_sum(part)
     scaled = be.scale_fill(norm, feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
     if not p.keep_norm:

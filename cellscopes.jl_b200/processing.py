@@ -40,7 +40,8 @@ class _Session:
         self.ctx = ctx
         self.raw = None          # Sparse
         self.raw_key = None
-        self.gene_stats = None   # Vec fp64[2G]
+        self.gene_stats = None   # Vec fp64[2G] raw moments
+        self.norm_stats = None   # Vec fp64[2G] normalised moments (filled by normalize_object)
         self.norm = None         # Sparse
         self.scaled = None       # Dense
         self.scaled_rows = None  # gene ids (original order) of the scaled matrix
@@ -82,8 +83,10 @@ def normalize_object(x, scale_factor=10000, norm_method="logarithm", pseudocount
         raw = _ensure_raw(x, s)
         g = raw.shape[0]
         s.gene_stats = s.ctx.vec(2 * g, np.float64)
+        s.norm_stats = s.ctx.vec(2 * g, np.float64)
         # processing.jl:44-46: imaging objects replace NaN by 0
-        s.norm = s.ctx.normalize(raw, scale_factor, code, pseudocount, bool(getattr(x, "imaging", False)), s.gene_stats)
+        s.norm = s.ctx.normalize(raw, scale_factor, code, pseudocount, bool(getattr(x, "imaging", False)), s.gene_stats,
+                                 s.norm_stats)
         pattern = x.rawCount._mtx if sp.issparse(x.rawCount._mtx) else None
         lazy = LazyDeviceMatrix(s.norm, "sparse", raw.shape, pattern)
         x.normCount = NormCountObject(lazy, x.rawCount.cell_name, x.rawCount.gene_name, scale_factor, norm_method,
@@ -146,11 +149,14 @@ def find_variable_genes(x, nFeatures: int = 2000, span: float = 0.3, ctx=None):
 # ---------------------------------------------------------------------------------------------
 # scale_object  (processing.jl:65-93)
 # ---------------------------------------------------------------------------------------------
-def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, do_center):
+def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, do_center, norm_stats=None):
     g = norm_dev.shape[0]
     rows = np.arange(g, dtype=np.int64) if feature_idx is None else np.unique(np.asarray(feature_idx, dtype=np.int64))
     part = c.vec(2 * rows.size, np.float64)
-    c.scale_stats_partial(norm_dev, feature_idx, part)
+    if norm_stats is not None:
+        c.scale_stats_select(norm_stats, g, feature_idx, part)     # moments already taken by the normalise pass
+    else:
+        c.scale_stats_partial(norm_dev, feature_idx, part)
     dense = c.scale_fill(norm_dev, feature_idx, part, n_cells_total, scale_max, do_scale, do_center)
     return dense, rows
 
@@ -162,6 +168,7 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
         s = _session(x, ctx)
         if s.norm is None:
             s.norm = s.ctx.sparse_from_scipy(x.normCount.count_mtx)
+            s.norm_stats = None
         genes = x.normCount.gene_name
         fidx = None
         if features is not None:
@@ -172,7 +179,7 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
         eff_max = kwargs.get("scale_max", 10.0)
         eff_scale = kwargs.get("do_scale", True)
         eff_center = kwargs.get("do_center", True)
-        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center)
+        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center, s.norm_stats)
         s.scaled, s.scaled_rows = dense, rows
         lazy = LazyDeviceMatrix(dense, "dense_t", (rows.size, s.norm.shape[1]))
         x.scaleCount = ScaleCountObject(lazy, x.normCount.cell_name, [genes[i] for i in rows], do_scale, do_center,
@@ -216,9 +223,10 @@ def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=Non
         # Re-scaling the subset from normCount gives the same rows (scaling is per gene).
         if s.norm is None:
             s.norm = s.ctx.sparse_from_scipy(sc_obj.normCount.count_mtx)
+            s.norm_stats = None
         pos = {g: i for i, g in enumerate(sc_obj.normCount.gene_name)}
         fidx = np.array([pos[f] for f in features], dtype=np.int64)
-        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True)
+        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True, s.norm_stats)
     elif s.scaled is not None:
         dense = s.scaled
     else:

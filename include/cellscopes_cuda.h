@@ -73,6 +73,7 @@ enum {
   CSC_T_PCA_GRAM, CSC_T_PCA_SOLVE, CSC_T_PCA_TRANSFORM, CSC_T_KNN, CSC_T_GRAPH, CSC_T_GENERATE,
   CSC_T_KNN_SCAN, /* the all-pairs scan kernel alone (inside CSC_T_KNN): the dominant kernel of the path */
   CSC_T_GRAM_MMA, /* the tcgen05 Gram kernel alone (inside CSC_T_PCA_GRAM) */
+  CSC_T_ALLOC_HOST, /* HOST milliseconds spent inside the device allocator (pool growth shows up here) */
   CSC_T_COUNT
 };
 
@@ -125,9 +126,13 @@ csc_status csc_generate_counts(csc_ctx* ctx, int64_t n_genes, int64_t cell_lo, i
 /* ---- a1: normalize_object(mtx) src/scrna/processing.jl:15-31 ---------------------------- */
 /* out shares the sparsity pattern of raw.  nan_to_zero = the replace!(NaN=>0) of :44-46.
  * gene_stats (optional, fp64[2*n_genes]) receives += per-gene (sum x, sum x^2) of the RAW counts of this
- * shard, fused into the same pass (find_variable_genes :138-139 needs them). */
+ * shard, fused into the same pass (find_variable_genes :138-139 needs them; exact for integer counts).
+ * norm_stats (optional, fp64[2*n_genes]) receives += per-gene (sum y, sum y^2) of the NORMALISED values of
+ * this shard (scale_object :66-67 needs them for its rows), accumulated in 32-bit fixed point per CTA
+ * (resolution ~1e-6 of the value range; deterministic). */
 csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
-                         double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out);
+                         double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
+                         csc_sparse** out);
 
 /* ---- a2: find_variable_genes src/scrna/processing.jl:133-155 ---------------------------- */
 /* per-gene (sum x, sum x^2) of this shard, += into gene_stats fp64[2*n_genes] (standalone K2) */
@@ -146,6 +151,10 @@ csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_gen
  * partial: fp64[2*H] += (sum y, sum y^2) of the normalised values of this shard. */
 csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                                    csc_vec* partial);
+/* the same partial taken from the all-gene table that csc_normalize filled (norm_stats, fp64[2*n_genes]):
+ * partial[0:H] += sum y, partial[H:2H] += sum y^2 of the selected rows in original gene order */
+csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_stats, int64_t n_genes, const int64_t* features,
+                                  int64_t n_feat, csc_vec* partial);
 /* partial already summed over ranks; out = dense fp32 [n_cells_local x H], cell-major, which is the
  * memory layout of Julia's genes x cells column-major Matrix: min((y-mean)/sd, scale_max) (:69-74). */
 csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,

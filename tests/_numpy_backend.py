@@ -77,15 +77,20 @@ class NumpyBackend:
     def vec(self, n, dtype=np.float64):
         return NpVec(np.zeros(int(n), dtype=dtype))
 
-    def normalize(self, raw, scale_factor, norm_method, pseudocount, nan_to_zero, gene_stats):
+    def normalize(self, raw, scale_factor, norm_method, pseudocount, nan_to_zero, gene_stats, norm_stats=None):
         m = raw.m
+        g = m.shape[0]
         if gene_stats is not None:
-            g = m.shape[0]
             s1, s2, _, _ = oracle.gene_moments(m) if m.shape[1] else (np.zeros(g), np.zeros(g), None, None)
             gene_stats.a[:g] += s1
             gene_stats.a[g:2 * g] += s2
-        return NpSparse(oracle.normalize_object(m, scale_factor, "logarithm" if norm_method == 0 else "none",
-                                                pseudocount, nan_to_zero))
+        out = oracle.normalize_object(m, scale_factor, "logarithm" if norm_method == 0 else "none", pseudocount,
+                                      nan_to_zero)
+        if norm_stats is not None:
+            r = out.tocsr()
+            norm_stats.a[:g] += np.asarray(r.sum(axis=1)).ravel()
+            norm_stats.a[g:2 * g] += np.asarray(r.multiply(r).sum(axis=1)).ravel()
+        return NpSparse(out)
 
     def hvg_finish(self, gene_stats, n_genes, n_cells_total, n_features, span):
         s1, s2 = gene_stats.a[:n_genes], gene_stats.a[n_genes:2 * n_genes]
@@ -99,6 +104,12 @@ class NumpyBackend:
         order = np.lexsort((np.arange(n_genes), -vs))
         return {"mean": mean, "variance": var, "variance_expected": ve, "variance_standardized": vs,
                 "order": order, "features": order[:min(n_features, n_genes)].copy()}
+
+    def scale_stats_select(self, norm_stats, n_genes, features, partial):
+        rows = np.arange(n_genes) if features is None else np.unique(features)
+        h = rows.size
+        partial.a[:h] += norm_stats.a[rows]
+        partial.a[h:2 * h] += norm_stats.a[n_genes + rows]
 
     def scale_stats_partial(self, norm, features, partial):
         rows = np.unique(features)

@@ -180,6 +180,33 @@ def test_scale_matches_oracle(cs, oracle, ctx, medium_counts, kw):
         assert (want >= 10.0).any(), "the clip must actually be exercised"
 
 
+def test_fused_normalised_moments_match_standalone(cs, oracle, ctx, medium_counts):
+    """csc_normalize's fixed-point (sum y, sum y^2) table agrees with the fp64 pass over the normalised values, and
+    the scaled matrix built from it meets the same tolerance."""
+    raw = ctx.sparse_from_scipy(medium_counts)
+    g, n = medium_counts.shape
+    nst = ctx.vec(2 * g)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0, False, None, nst)
+    got = nst.download()
+    want = oracle.normalize_object(medium_counts).tocsr()
+    s1 = np.asarray(want.sum(axis=1)).ravel()
+    s2 = np.asarray(want.multiply(want).sum(axis=1)).ravel()
+    assert np.allclose(got[:g], s1, rtol=2e-6, atol=1e-4)
+    assert np.allclose(got[g:], s2, rtol=2e-6, atol=1e-3)
+    feats = np.arange(0, g, 3)
+    part = ctx.vec(2 * feats.size)
+    ctx.scale_stats_select(nst, g, feats, part)
+    z = ctx.scale_fill(norm, feats, part, n).download(np.float64).T
+    wz = oracle.scale_object(oracle.normalize_object(medium_counts)[feats])
+    assert rel_close(z, wz, 1e-5, atol=2e-6)
+    # sharding invariance: two cell ranges add up to the whole
+    a, b = ctx.sparse_from_scipy(medium_counts[:, :n // 3]), ctx.sparse_from_scipy(medium_counts[:, n // 3:])
+    nst2 = ctx.vec(2 * g)
+    ctx.normalize(a, 1e4, 0, 1.0, False, None, nst2)
+    ctx.normalize(b, 1e4, 0, 1.0, False, None, nst2)
+    assert np.allclose(nst2.download(), got, rtol=1e-6, atol=1e-3)
+
+
 def test_scale_rows_in_original_gene_order(cs, oracle, ctx, small_counts):
     """features given in rank order; rows come out in original gene order (utils.jl:72-76)."""
     dense, want, rows = _scaled_pair(cs, oracle, ctx, small_counts, 100)
