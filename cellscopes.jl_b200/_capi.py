@@ -79,6 +79,7 @@ SIGNATURES = {
     "csc_pca_transform": (_I32, [_P, _P, _P, _PP]),
     "csc_pca_free": (_I32, [_P]),
     "csc_knn": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _PP, _PP]),
+    "csc_knn_last_fallback_rows": (_I32, [_P, C.POINTER(_I64)]),
     "csc_graph_build": (_I32, [_P, _P, _I64, _I32, _I64, _I64, _I32, _F64, _PP]),
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32]),
@@ -313,6 +314,11 @@ class Context:
         self.check(self.lib.csc_knn(self.h, queries.h, keys.h, int(query_offset), int(dim_lo), int(dim_hi), int(k),
                                     int(metric), C.byref(hi), C.byref(hd)))
         return Vec(self, hi), Vec(self, hd)
+
+    def knn_last_fallback_rows(self) -> int:
+        n = _I64()
+        self.check(self.lib.csc_knn_last_fallback_rows(self.h, C.byref(n)))
+        return n.value
 
     def graph_build(self, knn_idx, n_cells_total, k, cell_lo=0, cell_hi=None, mode=GRAPH_SUM, snn_prune=0.0):
         h = C.c_void_p()

@@ -63,6 +63,7 @@ struct csc_ctx {
   size_t flush_bytes = 0;
   std::shared_ptr<bool> alive;  // cleared by csc_destroy: late frees then fall back to cudaFree
   BlockCache cache;
+  int64_t knn_fallback_rows = 0;   // rows of the last csc_knn call that needed the exact re-scan
   int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
   double trace_t0 = 0.0;
 };

@@ -152,7 +152,11 @@ __global__ void k_knn_finish(float* __restrict__ score, const float* __restrict_
 }
 
 csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
-                       int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx);
+                       int64_t query_offset, const int32_t* self_ids, int32_t k, int32_t d_eff, float* out_score,
+                       int32_t* out_idx);
+csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                        int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx,
+                        int64_t* n_fallback_out);
 
 static int pad_dim(int d) {
   if (d <= 16) return 16;
@@ -201,9 +205,11 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
               "csc_knn: queries [%lld,+%lld) are not a row range of the keys", (long long)query_offset,
               (long long)queries->n_rows);
   const int d = dim_hi - dim_lo + (metric == CSC_METRIC_EUCLIDEAN ? 1 : 0);
-  // v2 (tcgen05 + TMA + TMEM) serves k <= 32 and up to 64 dimensions; the CUDA-core kernel the rest
+  // v3 (fp16 filter on tcgen05 + proof + exact refine) serves cosine with k <= 24; v2 (3xTF32 on tcgen05) k <= 32
+  // and up to 64 dimensions; the CUDA-core kernel the rest.  CSC_KNN_IMPL = simt | tf32 forces an older path.
   const char* impl = getenv("CSC_KNN_IMPL");
   const bool use_tc = d <= 64 && k <= 32 && !(impl && strcmp(impl, "simt") == 0);
+  const bool use_f16 = use_tc && metric == CSC_METRIC_COSINE && k <= 24 && !(impl && strcmp(impl, "tf32") == 0);
   const int DP = use_tc ? 64 : pad_dim(d);
   CSC_REQUIRE(ctx, DP > 0, "csc_knn: %d dimensions not supported (max 64, 63 for euclidean)", dim_hi - dim_lo);
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -226,8 +232,14 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
   if (queries->n_rows > 0) {
     const float* qd = (const float*)qp->p;
     const float* kd = (const float*)kp->p;
-    if (use_tc) {
-      s = knn_scan_tc(ctx, qd, queries->n_rows, kd, keys->n_rows, same, query_offset, k, d, vd->as<float>(), vi->as<int32_t>());
+    if (use_f16) {
+      int64_t n_fb = 0;
+      s = knn_scan_f16(ctx, qd, queries->n_rows, kd, keys->n_rows, same, query_offset, k, d, vd->as<float>(),
+                       vi->as<int32_t>(), &n_fb);
+      ctx->knn_fallback_rows = n_fb;
+    } else if (use_tc) {
+      s = knn_scan_tc(ctx, qd, queries->n_rows, kd, keys->n_rows, same, query_offset, nullptr, k, d, vd->as<float>(),
+                      vi->as<int32_t>());
     } else {
     cudaEventRecord(ctx->ev_k0, ctx->stream);
     switch (DP) {
@@ -258,4 +270,10 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
   *dist = vd;
   return CSC_OK;
   CSC_GUARD_END(ctx)
+}
+
+extern "C" csc_status csc_knn_last_fallback_rows(csc_ctx* ctx, int64_t* n_rows) {
+  if (!ctx || !n_rows) return CSC_ERR_ARG;
+  *n_rows = ctx->knn_fallback_rows;
+  return CSC_OK;
 }

@@ -1,0 +1,490 @@
+// kNN scan v3 (cosine): filter on the tensor cores in fp16, prove, refine exactly.
+//
+//   Exact brute force needs N^2 scores but only ~k + a few survive per row, so the scores do not have to be
+//   exact -- the LIST does.  The scan computes every score once in fp16 x fp16 -> fp32 (kind::f16: twice the
+//   rate and half the operand bytes of tf32, a third of the MMAs of the 3xTF32 scan), keeps the L = 32 best
+//   per row, and the refine step re-scores those 32 exactly (fp64 accumulation over the fp32 rows) and PROVES
+//   that nothing outside the list can belong to the top k:
+//       rows are unit vectors, fp16 keeps 11 significant bits  =>  |approx - exact| <= eps = 1.0e-3  (rigorous:
+//       (2^-10 + 2^-22) * sum |q_i||k_i| <= 9.8e-4, plus fp32 accumulation)
+//       every key outside the list has approx <= a_L (the 32nd best approx score), hence exact <= a_L + eps
+//       if a_L + eps < e_k (the exact k-th best inside the list) the exact top-k is inside the list.  QED.
+//   Rows that fail the test (near-duplicate neighbourhoods, k close to L) are gathered and re-run through the
+//   exact 3xTF32 scan (knn_tc.cu), so the result is always the exact one, ties by lower id included.
+//
+// Kernel layout (320 threads, 1 CTA per SM, one CTA = 128 query rows against ALL keys):
+//   warp 0      TMA producer: key tiles [128 keys x 64 halves] (one 128-byte swizzle row per key), 6-stage ring
+//   warp 1      TMEM allocator + MMA issuer: A (queries) lives in TMEM (32 columns of packed halves),
+//               D = 3 accumulator stages of 128 columns
+//   warps 2-5   epilogue group A: even key tiles        warps 6-9   epilogue group B: odd key tiles
+//               thread = query row (TMEM lane); 4 x tcgen05.ld.x32, a FMNMX3 tree, one compare against the
+//               row's threshold; survivors go into the row's sorted list in shared memory (warp-cooperative
+//               insertion).  The two groups keep separate lists and merge them at the end.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cfloat>
+#include <climits>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                       int64_t query_offset, const int32_t* self_ids, int32_t k, int32_t d_eff, float* out_score,
+                       int32_t* out_idx);
+
+namespace {
+
+constexpr int F_TQ = 128;                 // query rows per CTA = UMMA M
+constexpr int F_BN = 128;                 // keys per tile     = UMMA N
+constexpr int F_DP = 64;                  // padded feature dimension (halves): one 128-byte swizzle row
+constexpr int F_STAGES = 6;
+constexpr int F_ACC = 3;                  // TMEM accumulator stages
+constexpr int F_TILE_BYTES = F_BN * 128;  // 16 KB
+constexpr int F_THREADS = 64 + 256;
+constexpr int F_L = 32;                   // candidates kept per row
+constexpr int F_TMEM_A = F_ACC * F_BN;    // first column of the query operand (32 columns)
+constexpr float F_SCALE = 256.f;          // operands are scaled so that small components stay normal in fp16
+constexpr float F_EPS = 1.0e-3f;          // bound on |approx - exact| for unit rows (see the header)
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// max of 32 scores held as raw bits
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = fmax3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+  m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+  const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
+  return fmax3(fmax3(a, b, c), m[9], m[10]);
+}
+
+// Candidates of one 32-key chunk -> the rows' lists.  Every lane has already written its 32 scores to the warp's
+// scratch tile (scratch[key * 32 + lane]) and built the bit mask `cm` of its scores above its threshold.
+// wl = this warp's 32 lists, [row][32] (score, id) sorted descending; lane j owns entry j of whichever row is
+// being updated, so an insertion is one LDS.64, a ballot, two shuffles and one STS.64 for the whole warp.
+// Kept out of line on purpose: inlined four times per tile the slow path outgrew the instruction cache and ran
+// ~10x slower than its instruction count (measured).
+__device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scratch, int key_base, int self0, int n_keys,
+                                                 uint2* wl, int lane, float tau, float mid, float* pub, unsigned long long* cnt) {
+  const unsigned FULL = 0xffffffffu;
+  unsigned rows = __ballot_sync(FULL, cm != 0u);
+  while (rows) {
+    const int src = __ffs(rows) - 1;
+    rows &= rows - 1;
+    unsigned mask = __shfl_sync(FULL, cm, src);
+    uint2 e = wl[src * F_L + lane];           // the row's list stays in registers while its candidates are inserted
+    float es = __uint_as_float(e.x);
+    int ei = (int)e.y;
+    bool dirty = false;
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int id = key_base + j;
+      if (id == self0 + src || id >= n_keys) continue;
+      const float cv = scratch[j * 32 + src];
+      // entries that rank before the candidate form a prefix of the sorted list
+      const int pos = __popc(__ballot_sync(FULL, es > cv || (es == cv && ei < id)));
+      if (cnt && lane == 0) {
+        atomicAdd(cnt, 1ull);
+        if (pos < F_L) atomicAdd(cnt + 1, 1ull);
+      }
+      if (pos < F_L) {
+        const float ps = __shfl_up_sync(FULL, es, 1);
+        const int pi = __shfl_up_sync(FULL, ei, 1);
+        if (lane == pos) {
+          es = cv;
+          ei = id;
+        } else if (lane > pos) {
+          es = ps;
+          ei = pi;
+        }
+        dirty = true;
+      }
+    }
+    if (dirty) {
+      wl[src * F_L + lane] = make_uint2(__float_as_uint(es), (unsigned)ei);
+      const float nt = __shfl_sync(FULL, es, F_L - 1);
+      const float nm = __shfl_sync(FULL, es, F_L / 2 - 1);
+      if (lane == src) {
+        tau = nt;
+        mid = nm;
+        pub[src] = nm;     // this group's 16th best of the row, for the other group's threshold
+      }
+    }
+  }
+  return make_float2(tau, mid);
+}
+
+// one chunk of the slow path: candidate mask, scores to the scratch tile, out-of-line insertion
+__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self0, int n_keys,
+                                           uint2* wl, int lane, float thr, float& tau, float& mid, float* pub, unsigned long long* cnt) {
+  unsigned cm = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    scratch[i * 32 + lane] = __uint_as_float(r[i]);
+    cm |= (__uint_as_float(r[i]) > thr ? 1u : 0u) << i;
+  }
+  __syncwarp();
+  const float2 t = insert_candidates(cm, scratch, key_base, self0, n_keys, wl, lane, tau, mid, pub, cnt);
+  if (cnt && lane == 0) atomicAdd(cnt + 3, 1ull);
+  tau = t.x;
+  mid = t.y;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restrict__ q16, int64_t n_q, int64_t n_keys,
+               int64_t query_offset, int32_t ksteps, float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int dbg_mode, unsigned long long* cnt) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
+  unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
+  uint2* lists = reinterpret_cast<uint2*>(sB + F_STAGES * F_TILE_BYTES);           // [2 groups][128 rows][32]
+  float* scratch_all = reinterpret_cast<float*>(lists + 2 * F_TQ * F_L);           // [8 warps][32 keys][32 lanes]
+  float* pub_all = scratch_all + 8 * 32 * 32;                                      // [2 groups][128 rows] 16th best
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pub_all + 2 * F_TQ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
+  const uint32_t bar_empty = smem_u32(bars + 8);       // [F_STAGES]
+  const uint32_t bar_tfull = smem_u32(bars + 16);      // [F_ACC]
+  const uint32_t bar_tempty = smem_u32(bars + 19);     // [F_ACC]
+  const uint32_t bar_a = smem_u32(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
+  const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < F_ACC; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 128);
+    }
+    mbar_init(bar_a, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&kmap)) : "memory");
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      const int s = (int)(t % F_STAGES);
+      mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / F_STAGES) & 1) ^ 1));
+      if (elect_one()) {
+        mbar_expect_tx(bar_full + 8 * s, F_TILE_BYTES);
+        tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, (int)(t * F_BN));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(F_TQ >> 4) << 24);
+    // K-major SWIZZLE_128B: SBO = 1024 B between 8-row groups, version 1
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    mbar_wait(bar_a, 0);
+    tc_fence_after();
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      const int s = (int)(t % F_STAGES);
+      const int a = (int)(t % F_ACC);
+      mbar_wait(bar_tempty + 8 * a, (uint32_t)(((t / F_ACC) & 1) ^ 1));
+      mbar_wait(bar_full + 8 * s, (uint32_t)((t / F_STAGES) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_addr = smem_u32(sB + (size_t)s * F_TILE_BYTES);
+        const uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * F_BN);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (ks < ksteps) {
+            // one k-step = 16 halves = 32 bytes of the swizzled row = 8 packed TMEM columns of A
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(ks * 2));
+            tc_mma_f16_ts(d_tmem, tmem_base + F_TMEM_A + (uint32_t)ks * 8u, db, idesc, ks ? 1u : 0u);
+          }
+        }
+        tc_commit(bar_empty + 8 * s);
+        tc_commit(bar_tfull + 8 * a);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: two groups, one thread = one query row =================
+    const unsigned FULL = 0xffffffffu;
+    const int grp = (warp - 2) >> 2;                    // 0: even tiles, 1: odd tiles
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const int64_t qrow = q0 + row;
+    const bool qvalid = qrow < n_q;
+    const int self0 = (int)(query_offset + q0 + quarter * 32);   // key id of this warp's row 0 (row r: self0 + r)
+    float* scratch = scratch_all + (warp - 2) * 32 * 32;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (grp == 0) {
+      // stage this thread's query row into TMEM: lane = row, 32 columns of two packed halves
+      uint32_t v[32];
+      const uint4* src = reinterpret_cast<const uint4*>(q16 + (qvalid ? qrow : 0) * F_DP);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 f = qvalid ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+        v[4 * i] = f.x;
+        v[4 * i + 1] = f.y;
+        v[4 * i + 2] = f.z;
+        v[4 * i + 3] = f.w;
+      }
+      tmem_st32(lane_base + F_TMEM_A, v);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
+    uint2* wl = lists + ((size_t)grp * F_TQ + quarter * 32) * F_L;      // this warp's 32 rows
+    for (int r = 0; r < 32; ++r) wl[r * F_L + lane] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
+    __syncwarp();
+    // Thresholds.  tau = this group's 32nd best of the row (its list's last entry); mid = its 16th best, published
+    // to the other group.  Both groups hold >= 16 scores >= min(mid_A, mid_B), so nothing at or below that value
+    // can be among the 32 best of the union: thr = max(tau, min(mid, other's mid)) filters almost as well as one
+    // shared list would, without the two groups ever writing the same list.  Published values only grow, so a
+    // stale read is merely conservative.
+    float* pub = pub_all + grp * F_TQ + quarter * 32;
+    const float* pub_other = pub_all + (grp ^ 1) * F_TQ + quarter * 32;
+    pub[lane] = -INFINITY;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float tau = qvalid ? -INFINITY : INFINITY;
+    float mid = -INFINITY;
+    for (int64_t t = grp; t < n_tiles; t += 2) {
+      const int a = (int)(t % F_ACC);
+      mbar_wait(bar_tfull + 8 * a, (uint32_t)((t / F_ACC) & 1));
+      tc_fence_after();
+      const int key0 = (int)(t * F_BN);
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld32(taddr + 64, r2);
+      tmem_ld32(taddr + 96, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the accumulator is in registers: hand the TMEM stage back before looking at the scores
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * a);
+      const float m0 = max32(r0), m1 = max32(r1), m2 = max32(r2), m3 = max32(r3);
+      const float thr = fmaxf(tau, fminf(mid, pub_other[lane]));
+      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr)) {
+        if (cnt && lane == 0) atomicAdd(cnt + 2, 1ull);
+        if (__any_sync(FULL, m0 > thr)) slow_chunk(r0, scratch, key0, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
+        if (__any_sync(FULL, m1 > thr)) slow_chunk(r1, scratch, key0 + 32, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
+        if (__any_sync(FULL, m2 > thr)) slow_chunk(r2, scratch, key0 + 64, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
+        if (__any_sync(FULL, m3 > thr)) slow_chunk(r3, scratch, key0 + 96, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
+      }
+    }
+    // merge the two groups' lists: the 32 best of the union = elementwise max of A[j] and B[31 - j] (bitonic)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const uint2* la = lists + ((size_t)quarter * 32) * F_L;
+      const uint2* lb = lists + ((size_t)F_TQ + quarter * 32) * F_L;
+      for (int r = 0; r < 32; ++r) {
+        const int64_t orow = q0 + quarter * 32 + r;
+        const uint2 ea = la[r * F_L + lane], eb = lb[r * F_L + (F_L - 1 - lane)];
+        const float sa = __uint_as_float(ea.x), sb = __uint_as_float(eb.x);
+        const bool take_a = sa > sb || (sa == sb && (int)ea.y < (int)eb.y);
+        const float s = take_a ? sa : sb;
+        const int id = take_a ? (int)ea.y : (int)eb.y;
+        float mn = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+        if (orow < n_q) {
+          out_idx[orow * F_L + lane] = id;
+          if (lane == 0) out_thr[orow] = mn * (1.f / (F_SCALE * F_SCALE));    // a_L, unscaled (-inf: list not full)
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// prepared fp32 rows [n x 64] -> fp16 rows scaled by 256
+__global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __float2half_rn(x[i] * F_SCALE);
+}
+
+// Exact re-scoring of the 32 candidates (fp64 accumulation over the fp32 operands), final ordering (descending
+// score, ties by ascending id) and the completeness proof: rows whose exact k-th score does not clear
+// a_L + eps are appended to the fallback list.  One thread per query row.
+__global__ void __launch_bounds__(128)
+k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
+                   const float* __restrict__ thr, const int32_t* __restrict__ in_idx, float* __restrict__ out_score,
+                   int32_t* __restrict__ out_idx, int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_q) return;
+  float s[F_L];
+  int id[F_L];
+  const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
+  int cnt = 0;
+  for (int j = 0; j < F_L; ++j) {
+    const int cand = in_idx[row * F_L + j];
+    if (cand == INT_MAX) continue;
+    const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)cand * 64);
+    double acc = 0.0;
+    for (int i = 0; i < (d + 3) / 4; ++i) {
+      const float4 a = __ldg(qr + i), b = __ldg(kr + i);
+      acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+    }
+    const float v = (float)acc;
+    int p = cnt++;
+#pragma unroll 1
+    while (p > 0 && (v > s[p - 1] || (v == s[p - 1] && cand < id[p - 1]))) {
+      s[p] = s[p - 1];
+      id[p] = id[p - 1];
+      --p;
+    }
+    s[p] = v;
+    id[p] = cand;
+  }
+  for (int j = 0; j < k; ++j) {
+    out_score[row * k + j] = j < cnt ? s[j] : -INFINITY;
+    out_idx[row * k + j] = j < cnt ? id[j] : INT_MAX;
+  }
+  // a_L = -inf when fewer than 32 keys exist: the list holds every key and the proof is trivial
+  const float a_l = thr[row];
+  if (cnt < k || !(a_l + F_EPS < s[k - 1])) {
+    if (a_l != -INFINITY) fallback_rows[atomicAdd(n_fallback, 1)] = (int32_t)row;
+  }
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, const int32_t* __restrict__ rows, int32_t n, int64_t row_offset,
+                              float* __restrict__ dst, int32_t* __restrict__ self_ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * 16) return;
+  const int r = (int)(i >> 4), c = (int)(i & 15);
+  reinterpret_cast<float4*>(dst)[(int64_t)r * 16 + c] = __ldg(reinterpret_cast<const float4*>(src) + (int64_t)rows[r] * 16 + c);
+  if (c == 0) self_ids[r] = (int32_t)(row_offset + rows[r]);
+}
+__global__ void k_scatter_results(const float* __restrict__ s, const int32_t* __restrict__ idx, const int32_t* __restrict__ rows,
+                                  int32_t n, int32_t k, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * k) return;
+  const int r = (int)(i / k), j = (int)(i % k);
+  out_score[(int64_t)rows[r] * k + j] = s[i];
+  out_idx[(int64_t)rows[r] * k + j] = idx[i];
+}
+
+csc_status make_map_f16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const __half* ptr, int64_t n_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)F_DP, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)F_DP * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F_DP, (cuuint32_t)F_BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled (f16 keys) failed with %d", (int)r);
+  return CSC_OK;
+}
+
+}  // namespace
+
+// Unit-norm prepared rows only (cosine).  Writes the exact k best (score, id) per query, sorted.
+csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                        int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx,
+                        int64_t* n_fallback_out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CSC_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeTiledFn)fn;
+  }
+  const int ksteps = (d_eff + 15) / 16;
+  DevPtr k16, q16, thr, cand, fb_rows, fb_count;
+  const int64_t nk_el = n_keys * F_DP, nq_el = n_q * F_DP;
+  CSC_TRY(dev_alloc(ctx, (size_t)nk_el * 2, &k16));
+  k_to_f16<<<(unsigned)ceil_div64(nk_el, 256), 256, 0, ctx->stream>>>(k_prep, nk_el, (__half*)k16->p);
+  CSC_LAUNCHED(ctx);
+  if (same) {
+    q16 = k16;
+  } else {
+    CSC_TRY(dev_alloc(ctx, (size_t)nq_el * 2, &q16));
+    k_to_f16<<<(unsigned)ceil_div64(nq_el, 256), 256, 0, ctx->stream>>>(q_prep, nq_el, (__half*)q16->p);
+    CSC_LAUNCHED(ctx);
+  }
+  CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &thr));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_q * F_L * 4, &cand));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &fb_rows));
+  CSC_TRY(dev_alloc(ctx, 4, &fb_count, true));
+  DevPtr dbg_cnt;
+  if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 64, &dbg_cnt, true));
+  CUtensorMap kmap;
+  CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
+  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)2 * F_TQ * F_L * 8 + (size_t)8 * 32 * 32 * 4 + (size_t)2 * F_TQ * 4 + 512;
+  CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEventRecord(ctx->ev_k0, ctx->stream);
+  k_knn_scan_f16<<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(
+      kmap, (const __half*)q16->p, n_q, n_keys, query_offset, ksteps, (float*)thr->p, (int32_t*)cand->p,
+      getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0, dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);
+  CSC_LAUNCHED(ctx);
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
+  k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(
+      q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, out_score, out_idx, (int32_t*)fb_rows->p,
+      (int32_t*)fb_count->p);
+  CSC_LAUNCHED(ctx);
+  int32_t n_fb = 0;
+  CSC_CUDA(ctx, cudaMemcpyAsync(&n_fb, fb_count->p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->stage_ms[CSC_T_KNN_SCAN] += ms;
+  if (n_fallback_out) *n_fallback_out = n_fb;
+  if (dbg_cnt) {
+    unsigned long long h[4];
+    cudaMemcpy(h, dbg_cnt->p, 32, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[knn f16] attempts %llu accepted %llu slow-path tile entries %llu chunk entries %llu (warps x tiles = %lld)\n", h[0], h[1], h[2], h[3],
+            (long long)(ceil_div64(n_q, F_TQ) * 4 * ceil_div64(n_keys, F_BN)));
+  }
+  if (n_fb > 0) {
+    // the unproven rows go through the exact 3xTF32 scan
+    DevPtr gq, gself, gs, gi;
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * 64 * 4, &gq));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * 4, &gself));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * k * 4, &gs));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * k * 4, &gi));
+    k_gather_rows<<<(unsigned)ceil_div64((int64_t)n_fb * 16, 256), 256, 0, ctx->stream>>>(
+        q_prep, (const int32_t*)fb_rows->p, n_fb, query_offset, (float*)gq->p, (int32_t*)gself->p);
+    CSC_LAUNCHED(ctx);
+    CSC_TRY(knn_scan_tc(ctx, (const float*)gq->p, n_fb, k_prep, n_keys, false, 0, (const int32_t*)gself->p, k, d_eff,
+                        (float*)gs->p, (int32_t*)gi->p));
+    k_scatter_results<<<(unsigned)ceil_div64((int64_t)n_fb * k, 256), 256, 0, ctx->stream>>>(
+        (const float*)gs->p, (const int32_t*)gi->p, (const int32_t*)fb_rows->p, n_fb, k, out_score, out_idx);
+    CSC_LAUNCHED(ctx);
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return CSC_OK;
+}

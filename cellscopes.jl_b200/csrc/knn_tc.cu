@@ -46,7 +46,7 @@ struct __align__(64) TcMaps {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_scan_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ q_hi, const float* __restrict__ q_lo,
-              int64_t n_q, int64_t n_keys, int64_t query_offset, int32_t kl,
+              int64_t n_q, int64_t n_keys, int64_t query_offset, const int32_t* __restrict__ self_ids, int32_t kl,
               int32_t ksteps, float* __restrict__ out_score, int32_t* __restrict__ out_idx, long long* __restrict__ trace, int64_t trace_t0) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled operand blocks
@@ -165,7 +165,8 @@ k_knn_scan_tc(const __grid_constant__ TcMaps maps, const float* __restrict__ q_h
     const int row = quarter * 32 + lane;
     const int64_t qrow = q0 + row;
     const bool qvalid = qrow < n_q;
-    const int self_i = (int)(query_offset + qrow);
+    // the key that is the query itself (excluded): a row range of the keys, or an explicit id per gathered row
+    const int self_i = self_ids ? (qvalid ? self_ids[qrow] : -1) : (int)(query_offset + qrow);
     {
       // stage this thread's query row (hi and lo parts) into the TMEM operand block: lane = row, column = feature
       const uint32_t a_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + TC_TMEM_A;
@@ -354,7 +355,8 @@ csc_status make_map(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const floa
 // q_prep / k_prep: prepared operand rows [n x 64] fp32 (knn.cu::knn_prepare with DP = 64).
 // Writes the k best (score, id) per query, exact scores, sorted.
 csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
-                       int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx) {
+                       int64_t query_offset, const int32_t* self_ids, int32_t k, int32_t d_eff, float* out_score,
+                       int32_t* out_idx) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -392,7 +394,7 @@ csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const flo
   const bool want_trace = getenv("CSC_KNN_TRACE") != nullptr;
   if (want_trace) CSC_TRY(dev_alloc(ctx, 64 * 8 * 8, &trace, true));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
-  k_knn_scan_tc<<<(unsigned)ceil_div64(n_q, TC_TQ), TC_THREADS, smem, ctx->stream>>>(maps, (const float*)qhi->p, (const float*)qlo->p, n_q, n_keys, query_offset, kl, ksteps,
+  k_knn_scan_tc<<<(unsigned)ceil_div64(n_q, TC_TQ), TC_THREADS, smem, ctx->stream>>>(maps, (const float*)qhi->p, (const float*)qlo->p, n_q, n_keys, query_offset, self_ids, kl, ksteps,
                                                                                       (float*)cs->p, (int32_t*)ci->p,
                                                                                       want_trace ? (long long*)trace->p : nullptr, want_trace ? atoll(getenv("CSC_KNN_TRACE")) : 0);
   CSC_LAUNCHED(ctx);

@@ -194,6 +194,10 @@ csc_status csc_pca_free(csc_pca* p);
 csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_dense* keys, int64_t query_offset,
                    int32_t dim_lo, int32_t dim_hi, int32_t k, int32_t metric, csc_vec** idx, csc_vec** dist);
 
+/* rows of the last csc_knn call whose fp16 filter could not prove its candidate list complete and that were
+ * re-scanned with the exact 3xTF32 kernel (diagnostic; the result is exact either way) */
+csc_status csc_knn_last_fallback_rows(csc_ctx* ctx, int64_t* n_rows);
+
 /* ---- adjacency fed to Leiden src/scrna/processing.jl:218-232, 268-278 ------------------- */
 /* knn_idx: int32 [n_cells_total x k] of ALL cells (all-gathered); builds columns [cell_lo, cell_hi). */
 csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int64_t n_cells_total, int32_t k,

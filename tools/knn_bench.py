@@ -27,4 +27,5 @@ for r in range(reps):
     ms, _ = ctx.stage_times()
     flops = 2.0 * n * n * d
     print(f"n={n} d={d} k={k}: knn {ms['knn']:.2f} ms, scan {ms['knn_scan']:.2f} ms, wall {wall:.2f} ms, "
-          f"{flops / ms['knn_scan'] / 1e9:.1f} TFLOP/s, {n * n / ms['knn_scan'] / 1e6:.1f} Gcand/s", flush=True)
+          f"{flops / ms['knn_scan'] / 1e9:.1f} TFLOP/s, {n * n / ms['knn_scan'] / 1e6:.1f} Gcand/s, "
+          f"fallback rows {ctx.knn_last_fallback_rows()}", flush=True)
