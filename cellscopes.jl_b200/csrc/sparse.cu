@@ -254,7 +254,7 @@ struct NormArgs {
 // RAW: 0 = no raw moments, 1 = S1 table only (E goes to global memory), 2 = S1 and E tables,
 //      3 = no table fits: every update goes to the fp64 table in global memory
 template <bool WRITE_NORM, int RAW, bool NSTATS>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(768, 2)
 k_normalize(const NormArgs a) {
   extern __shared__ unsigned int stab[];
   const int G = a.n_genes;
@@ -277,25 +277,27 @@ k_normalize(const NormArgs a) {
   const float pcf = (float)a.pc;
   for (int64_t c = c0 + warp; c < c1; c += nwarp) {
     const int64_t b = a.colptr[c], e = a.colptr[c + 1];
-    double inv = 0.0;
+    float scale = 0.f;
     if (WRITE_NORM || NSTATS) {
       double s = 0.0;
 #pragma unroll 4
       for (int64_t i = b + lane; i < e; i += 32) s += (double)a.raw[i];
       s = warp_sum(s);
-      inv = 1.0 / s;  // 1/0 = Inf: the reference's NaN column (processing.jl:18)
+      // (x * (1/s)) * sf of processing.jl:24 with the two cell constants folded in fp64 and applied in fp32: the
+      // stored value is fp32 anyway, the result stays within 2 ulp of it.  1/0 = Inf -> 0 * Inf = NaN: the
+      // reference's NaN column (processing.jl:18).
+      scale = (float)((1.0 / s) * a.sf);
     }
 #pragma unroll 4
     for (int64_t i = b + lane; i < e; i += 32) {
       const float x = a.raw[i];
       float y = 0.f;
       if (WRITE_NORM || NSTATS) {
-        const double t = ((double)x * inv) * a.sf;  // association order of processing.jl:24
+        const float t = x * scale;
         if (a.method == CSC_NORM_LOGARITHM) {
-          const float tf = (float)t;
-          y = pc_is_one ? log1pf(tf) : logf(tf + pcf);
+          y = pc_is_one ? log1pf(t) : logf(t + pcf);
         } else {
-          y = (float)t;
+          y = t;
         }
         if (a.nan_to_zero && y != y) y = 0.f;
         if (WRITE_NORM) __stcs(a.out + i, y);
@@ -373,7 +375,7 @@ k_norm_moments_global(const int64_t* __restrict__ colptr, const int32_t* __restr
 static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* out, double sf, double pc, int method,
                                    int nan_to_zero, double* gstats, double* nstats) {
   if (raw->n_cells == 0) return CSC_OK;
-  const int threads = 512;
+  const int threads = 768;
   const size_t G = (size_t)raw->n_genes;
   const size_t budget = (size_t)200 * 1024;
   // which tables fit: raw S1 (+E), normalised Y1/Y2
@@ -384,7 +386,7 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   if (nstats && out && (size_t)(nraw + 2) * G * 4 <= budget) nst = true;
   const int ntab = nraw + (nst ? 2 : 0);
   const size_t smem = (size_t)ntab * G * 4;
-  const int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)220 * 1024) / (smem + 1024))) : 4;
+  const int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(2, ((size_t)220 * 1024) / (smem + 1024))) : 2;
   int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
   // a CTA's u32 tables must not overflow: <= 65535 (S1) and <= 65025 (E) per entry * 65536 cells
   int64_t cells_per_cta = std::max<int64_t>(16, ceil_div64(raw->n_cells, grid));
