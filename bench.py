@@ -316,8 +316,9 @@ def run_e2e(cs, ctx, comm, dist, raw, n_genes, n_cells, lo, hi, params, offsets,
         t0 = time.perf_counter()
         if world == 1:
             # the reference-facing calls, in the atlas order of docs/scRNA_tutorial/README.md:260-280
-            m = sp.csc_matrix((nzval, rowval, colptr), shape=(n_genes, n_loc), copy=False)
-            m.has_sorted_indices = True
+            # the host matrix wraps the pinned Int64/Float64 arrays as they are (scipy's constructor would copy and
+            # down-cast the indices, i.e. un-pin them)
+            m = cs.csc_from_arrays(nzval, rowval, colptr, (n_genes, n_loc))
             obj = cs.scRNAObject.__new__(cs.scRNAObject)
             obj.rawCount = cs.RawCountObject(m, np.arange(n_loc), np.arange(n_genes))
             obj.normCount = obj.scaleCount = obj.varGene = obj.dimReduction = obj.clustData = None

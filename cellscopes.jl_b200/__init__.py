@@ -16,3 +16,4 @@ from .pipeline import LocalComm, PathParams, TorchComm, partition_cells, run_pat
 from .processing import (find_variable_genes, normalize_object, run_clustering, run_pca, scale_object)  # noqa: F401
 
 __version__ = "0.1.0"
+from ._capi import csc_from_arrays  # noqa: E402,F401

@@ -49,6 +49,8 @@ SIGNATURES = {
     "csc_timer_stop": (_I32, [_P, C.POINTER(_F64)]),
     "csc_stage_times": (_I32, [_P, C.POINTER(_F64), C.POINTER(_I64), _I32]),
     "csc_flush_l2": (_I32, [_P]),
+    "csc_host_alloc": (_I32, [_P, _I64, _PP]),
+    "csc_host_free": (_I32, [_P, _P]),
     "csc_vec_alloc": (_I32, [_P, _I64, _I32, _PP]),
     "csc_vec_wrap": (_I32, [_P, _P, _I64, _I32, _PP]),
     "csc_vec_free": (_I32, [_P]),
@@ -82,11 +84,26 @@ SIGNATURES = {
     "csc_knn_last_fallback_rows": (_I32, [_P, C.POINTER(_I64)]),
     "csc_graph_build": (_I32, [_P, _P, _I64, _I32, _I64, _I64, _I32, _F64, _PP]),
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
-    "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32]),
+    "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32, _I32]),
     "csc_graph_free": (_I32, [_P]),
 }
 
 _lib = None
+
+
+def csc_from_arrays(data, indices, indptr, shape):
+    """scipy CSC matrix around existing (already valid, sorted) arrays without the validation passes and index
+    down-casts of the constructor, which cost more than the device work for a 10^7-entry graph."""
+    import scipy.sparse as sp
+    m = sp.csc_matrix(shape, dtype=data.dtype)
+    m.data, m.indices, m.indptr = data, indices, indptr
+    m.has_sorted_indices = True
+    return m
+
+
+def _host_free(ctx, ptr):
+    if ctx.h is not None:
+        ctx.lib.csc_host_free(ctx.h, C.c_void_p(ptr))
 
 
 def load_library(path: str | None = None):
@@ -144,6 +161,21 @@ class Context:
             pass
 
     # ---- misc ------------------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.float64):
+        """Uninitialised numpy array in page-locked memory of this context's host cache (results land in it at
+        PCIe rate).  The block returns to the cache when the array (and every view of it) is garbage-collected."""
+        import weakref
+        dtype = np.dtype(dtype)
+        shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype=dtype)
+        p = C.c_void_p()
+        self.check(self.lib.csc_host_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        weakref.finalize(buf, _host_free, self, p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
     def synchronize(self):
         self.check(self.lib.csc_synchronize(self.h))
 
@@ -211,8 +243,9 @@ class Context:
 
     def sparse_from_scipy(self, m):
         import scipy.sparse as sp
-        m = sp.csc_matrix(m)
-        m.sort_indices()
+        # the SparseMatrixCSC invariant (sorted row indices) is the caller's, as in the reference; nothing on the
+        # path depends on it, so no host-side pass over the indices is made here
+        m = m if sp.isspmatrix_csc(m) else sp.csc_matrix(m)
         return self.sparse_upload(m.shape[0], m.shape[1], m.indptr, m.indices, m.data, 0)
 
     def generate_counts(self, params, cell_lo, cell_hi):
@@ -374,7 +407,7 @@ class Vec(_Handle):
     def download(self, n=None):
         total, dt, _ = self.info()
         n = total if n is None else n
-        out = np.empty(n, dtype=dt)
+        out = self.ctx.pinned_empty(n, dt) if n * np.dtype(dt).itemsize >= (1 << 20) else np.empty(n, dtype=dt)
         self.ctx.check(self.ctx.lib.csc_vec_download(self.h, _ptr(out), n))
         return out
 
@@ -410,13 +443,13 @@ class Sparse(_Handle):
         g, n, _ = self.info()
         cell_hi = n if cell_hi is None else cell_hi
         nnz = self.range_nnz(cell_lo, cell_hi)
-        val = np.empty(nnz, dtype=np.float64)
+        val = self.ctx.pinned_empty(nnz, np.float64)
         if values_only:
             self.ctx.check(self.ctx.lib.csc_sparse_download(self.h, int(cell_lo), int(cell_hi), None, None, _ptr(val),
                                                             int(index_base)))
             return val
-        colptr = np.empty(cell_hi - cell_lo + 1, dtype=np.int64)
-        rowval = np.empty(nnz, dtype=np.int64)
+        colptr = self.ctx.pinned_empty(cell_hi - cell_lo + 1, np.int64)
+        rowval = self.ctx.pinned_empty(nnz, np.int64)
         self.ctx.check(self.ctx.lib.csc_sparse_download(self.h, int(cell_lo), int(cell_hi), _ptr(colptr), _ptr(rowval),
                                                         _ptr(val), int(index_base)))
         return colptr, rowval, val
@@ -449,7 +482,7 @@ class Dense(_Handle):
     def download(self, dtype=np.float64, row_lo=0, row_hi=None):
         r, c, _ = self.info()
         row_hi = r if row_hi is None else row_hi
-        out = np.empty((row_hi - row_lo, c), dtype=dtype)
+        out = self.ctx.pinned_empty((row_hi - row_lo, c), dtype)
         self.ctx.check(self.ctx.lib.csc_dense_download(self.h, _ptr(out), _NP_DT[np.dtype(dtype)], int(row_lo), int(row_hi)))
         return out
 
@@ -484,16 +517,16 @@ class Graph(_Handle):
         self.ctx.check(self.ctx.lib.csc_graph_info(self.h, C.byref(r), C.byref(c), C.byref(z)))
         return r.value, c.value, z.value
 
-    def download(self, index_base=0):
+    def download(self, index_base=0, val_dtype=np.float64):
         r, c, z = self.info()
-        colptr = np.empty(c + 1, dtype=np.int64)
-        rowval = np.empty(z, dtype=np.int64)
-        val = np.empty(z, dtype=np.float64)
-        self.ctx.check(self.ctx.lib.csc_graph_download(self.h, _ptr(colptr), _ptr(rowval), _ptr(val), int(index_base)))
+        colptr = self.ctx.pinned_empty(c + 1, np.int64)
+        rowval = self.ctx.pinned_empty(z, np.int64)
+        val = self.ctx.pinned_empty(z, val_dtype)
+        self.ctx.check(self.ctx.lib.csc_graph_download(self.h, _ptr(colptr), _ptr(rowval), _ptr(val),
+                                                       _NP_DT[np.dtype(val_dtype)], int(index_base)))
         return colptr, rowval, val
 
-    def to_scipy(self):
-        import scipy.sparse as sp
+    def to_scipy(self, val_dtype=np.float64):
         r, c, _ = self.info()
-        colptr, rowval, val = self.download(0)
-        return sp.csc_matrix((val, rowval, colptr), shape=(r, c))
+        colptr, rowval, val = self.download(0, val_dtype)
+        return csc_from_arrays(val, rowval, colptr, (r, c))

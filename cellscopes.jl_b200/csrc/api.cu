@@ -65,9 +65,94 @@ csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero) {
   return CSC_OK;
 }
 
+static constexpr size_t BOUNCE_BYTES = (size_t)16 << 20;
+
+// is [p, p+bytes) inside a block this context handed out through csc_host_alloc?
+static bool is_ctx_pinned(csc_ctx* ctx, const void* p, size_t bytes) {
+  auto it = ctx->host_live.upper_bound(const_cast<void*>(p));
+  if (it == ctx->host_live.begin()) return false;
+  --it;
+  const char* b = (const char*)it->first;
+  return (const char*)p >= b && (const char*)p + bytes <= b + it->second;
+}
+
+csc_status d2h_copy(csc_ctx* ctx, void* host, const void* dev, size_t bytes) {
+  if (bytes == 0) return CSC_OK;
+  if (bytes <= ((size_t)1 << 20) || is_ctx_pinned(ctx, host, bytes)) {
+    CSC_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CSC_OK;
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (!ctx->bounce[b]) {
+      CSC_CUDA(ctx, cudaHostAlloc(&ctx->bounce[b], BOUNCE_BYTES, cudaHostAllocDefault));
+      CSC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_bounce[b], cudaEventDisableTiming));
+    }
+  }
+  const size_t n_chunks = (bytes + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
+  for (size_t i = 0; i <= n_chunks; ++i) {
+    const int b = (int)(i & 1);
+    if (i < n_chunks) {
+      const size_t off = i * BOUNCE_BYTES, len = std::min(BOUNCE_BYTES, bytes - off);
+      CSC_CUDA(ctx, cudaMemcpyAsync(ctx->bounce[b], (const char*)dev + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+      CSC_CUDA(ctx, cudaEventRecord(ctx->ev_bounce[b], ctx->stream));
+    }
+    if (i >= 1) {
+      const size_t off = (i - 1) * BOUNCE_BYTES, len = std::min(BOUNCE_BYTES, bytes - off);
+      CSC_CUDA(ctx, cudaEventSynchronize(ctx->ev_bounce[b ^ 1]));
+      memcpy((char*)host + off, ctx->bounce[b ^ 1], len);
+    }
+  }
+  return CSC_OK;
+}
+
 extern "C" {
 
 int32_t csc_abi_version(void) { return CSC_ABI_VERSION; }
+
+csc_status csc_host_alloc(csc_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes < 0) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t req = std::max<size_t>((size_t)bytes, 64);
+  req = (req + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);      // 1 MiB granules
+  void* p = nullptr;
+  size_t got = req;
+  auto it = ctx->host_free.lower_bound(req);
+  if (it != ctx->host_free.end() && it->first <= req + req / 4 + ((size_t)1 << 20)) {
+    p = it->second;
+    got = it->first;
+    ctx->host_free.erase(it);
+  } else {
+    cudaError_t e = cudaHostAlloc(&p, req, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);
+      ctx->host_free.clear();
+      e = cudaHostAlloc(&p, req, cudaHostAllocDefault);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return csc_fail(ctx, CSC_ERR_OOM, "cudaHostAlloc(%zu bytes) failed: %s", req, cudaGetErrorString(e));
+    }
+  }
+  ctx->host_live[p] = got;
+  *out = p;
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+csc_status csc_host_free(csc_ctx* ctx, void* p) {
+  if (!ctx) return CSC_ERR_ARG;
+  if (!p) return CSC_OK;
+  CSC_GUARD_BEGIN
+  auto it = ctx->host_live.find(p);
+  CSC_REQUIRE(ctx, it != ctx->host_live.end(), "csc_host_free: pointer was not allocated by csc_host_alloc of this context");
+  ctx->host_free.emplace(it->second, p);
+  ctx->host_live.erase(it);
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
 
 csc_status csc_create(int32_t device, csc_ctx** out) {
   if (!out) return csc_fail(nullptr, CSC_ERR_ARG, "csc_create: out is NULL");
@@ -132,6 +217,12 @@ csc_status csc_destroy(csc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->cache.release_all();
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);
+  for (auto& kv : ctx->host_live) cudaFreeHost(kv.first);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
+    if (ctx->ev_bounce[b]) cudaEventDestroy(ctx->ev_bounce[b]);
+  }
   if (ctx->ev_timer0) cudaEventDestroy(ctx->ev_timer0);
   if (ctx->ev_timer1) cudaEventDestroy(ctx->ev_timer1);
   if (ctx->ev_stage0) cudaEventDestroy(ctx->ev_stage0);
@@ -287,9 +378,7 @@ csc_status csc_vec_download(const csc_vec* v, void* host, int64_t n) {
   csc_ctx* ctx = v->ctx;
   CSC_REQUIRE(ctx, n >= 0 && n <= v->n, "csc_vec_download: n=%lld exceeds %lld", (long long)n, (long long)v->n);
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
-  CSC_CUDA(ctx, cudaMemcpyAsync(host, v->mem->p, (size_t)n * dtype_size(v->dtype), cudaMemcpyDeviceToHost, ctx->stream));
-  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return CSC_OK;
+  return d2h_copy(ctx, host, v->mem->p, (size_t)n * dtype_size(v->dtype));
 }
 
 // ---- dense --------------------------------------------------------------------------------------
@@ -368,7 +457,7 @@ csc_status csc_dense_download(const csc_dense* d, void* host, int32_t dtype, int
   const float* src = d->p() + row_lo * d->n_cols;
   if (n == 0) return CSC_OK;
   if (dtype == CSC_DT_F32) {
-    CSC_CUDA(ctx, cudaMemcpyAsync(host, src, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_TRY(d2h_copy(ctx, host, src, (size_t)n * 4));
   } else {
     // convert on the device in bounded chunks so that the staging buffer stays small
     const int64_t chunk = (int64_t)32 << 20;  // elements
@@ -379,8 +468,7 @@ csc_status csc_dense_download(const csc_dense* d, void* host, int32_t dtype, int
       k_f32_to_f64<<<(unsigned)std::min<int64_t>(ceil_div64(m, 256), 148 * 16), 256, 0, ctx->stream>>>(
           src + o, (double*)tmp->p, m);
       CSC_LAUNCHED(ctx);
-      CSC_CUDA(ctx, cudaMemcpyAsync((double*)host + o, tmp->p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      CSC_TRY(d2h_copy(ctx, (double*)host + o, tmp->p, (size_t)m * 8));
     }
   }
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -63,6 +63,12 @@ struct csc_ctx {
   size_t flush_bytes = 0;
   std::shared_ptr<bool> alive;  // cleared by csc_destroy: late frees then fall back to cudaFree
   BlockCache cache;
+  // page-locked host blocks handed to callers (csc_host_alloc): live blocks by pointer, free blocks by size
+  std::map<void*, size_t> host_live;
+  std::multimap<size_t, void*> host_free;
+  // pinned bounce buffers for device->host copies into pageable memory (see d2h_copy)
+  void* bounce[2] = {nullptr, nullptr};
+  cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   int64_t knn_fallback_rows = 0;   // rows of the last csc_knn call that needed the exact re-scan
   int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
   double trace_t0 = 0.0;
@@ -177,6 +183,9 @@ csc_status csc_fail(csc_ctx* ctx, csc_status code, const char* fmt, ...);
   } while (0)
 
 csc_status dev_alloc(csc_ctx* ctx, size_t bytes, DevPtr* out, bool zero = false);
+// device -> caller-owned (pageable) host memory through double-buffered pinned staging: the DMA of chunk i+1
+// overlaps the host memcpy of chunk i (about twice the rate of a plain cudaMemcpy into pageable memory)
+csc_status d2h_copy(csc_ctx* ctx, void* host, const void* dev, size_t bytes);
 
 // Wrap a C-ABI body so that C++ exceptions (std::bad_alloc from the host containers) become codes.
 #define CSC_GUARD_BEGIN try {

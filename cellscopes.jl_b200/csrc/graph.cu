@@ -268,11 +268,17 @@ __global__ void k_i64_add_base(const int64_t* __restrict__ in, int64_t* __restri
   if (i < n) out[i] = in[i] + base;
 }
 
-extern "C" csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, double* nzval,
+__global__ void k_f64_to_i64(const double* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)llrint(in[i]);
+}
+
+extern "C" csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, void* nzval, int32_t val_dtype,
                                          int32_t index_base) {
   if (!g) return CSC_ERR_ARG;
   csc_ctx* ctx = g->ctx;
   CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, val_dtype == CSC_DT_F64 || val_dtype == CSC_DT_I64, "csc_graph_download: val_dtype must be F64 or I64");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (colptr) {
     DevPtr tmp;
@@ -280,20 +286,25 @@ extern "C" csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, in
     k_i64_add_base<<<nblk(g->n_cols + 1), 256, 0, ctx->stream>>>((const int64_t*)g->colptr->p, (int64_t*)tmp->p, g->n_cols + 1,
                                                                   index_base);
     CSC_LAUNCHED(ctx);
-    CSC_CUDA(ctx, cudaMemcpyAsync(colptr, tmp->p, (size_t)(g->n_cols + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CSC_TRY(d2h_copy(ctx, colptr, tmp->p, (size_t)(g->n_cols + 1) * 8));
   }
   if (rowval && g->nnz > 0) {
     DevPtr tmp;
     CSC_TRY(dev_alloc(ctx, (size_t)g->nnz * 8, &tmp));
     k_i32_to_i64_base<<<nblk(g->nnz), 256, 0, ctx->stream>>>((const int32_t*)g->rowval->p, (int64_t*)tmp->p, g->nnz, index_base);
     CSC_LAUNCHED(ctx);
-    CSC_CUDA(ctx, cudaMemcpyAsync(rowval, tmp->p, (size_t)g->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CSC_TRY(d2h_copy(ctx, rowval, tmp->p, (size_t)g->nnz * 8));
   }
   if (nzval && g->nnz > 0) {
-    CSC_CUDA(ctx, cudaMemcpyAsync(nzval, g->val->p, (size_t)g->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (val_dtype == CSC_DT_F64) {
+      CSC_TRY(d2h_copy(ctx, nzval, g->val->p, (size_t)g->nnz * 8));
+    } else {
+      DevPtr tmp;
+      CSC_TRY(dev_alloc(ctx, (size_t)g->nnz * 8, &tmp));
+      k_f64_to_i64<<<nblk(g->nnz), 256, 0, ctx->stream>>>((const double*)g->val->p, (int64_t*)tmp->p, g->nnz);
+      CSC_LAUNCHED(ctx);
+      CSC_TRY(d2h_copy(ctx, nzval, tmp->p, (size_t)g->nnz * 8));
+    }
   }
   return CSC_OK;
   CSC_GUARD_END(ctx)

@@ -192,8 +192,7 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
     k_colptr_rebase<int64_t><<<grid_for(nc + 1, sm), 256, 0, ctx->stream>>>(m->cp() + cell_lo, (int64_t*)tmp->p, nc + 1,
                                                                              b - index_base);
     CSC_LAUNCHED(ctx);
-    CSC_CUDA(ctx, cudaMemcpyAsync(colptr_out, tmp->p, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CSC_TRY(d2h_copy(ctx, colptr_out, tmp->p, (size_t)(nc + 1) * 8));
   }
   const int64_t chunk = (int64_t)32 << 20;
   if ((rowval_out || nzval_out) && nnz > 0) {
@@ -203,15 +202,13 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
       int64_t cnt = std::min(chunk, nnz - o);
       k_widen_idx<<<grid_for(cnt, sm), 256, 0, ctx->stream>>>(m->rv() + b + o, (int64_t*)tmp->p, cnt, index_base);
       CSC_LAUNCHED(ctx);
-      CSC_CUDA(ctx, cudaMemcpyAsync(rowval_out + o, tmp->p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      CSC_TRY(d2h_copy(ctx, rowval_out + o, tmp->p, (size_t)cnt * 8));
     }
     for (int64_t o = 0; o < nnz && nzval_out; o += chunk) {
       int64_t cnt = std::min(chunk, nnz - o);
       k_widen_val<<<grid_for(cnt, sm), 256, 0, ctx->stream>>>(m->v() + b + o, (double*)tmp->p, cnt);
       CSC_LAUNCHED(ctx);
-      CSC_CUDA(ctx, cudaMemcpyAsync(nzval_out + o, tmp->p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      CSC_TRY(d2h_copy(ctx, nzval_out + o, tmp->p, (size_t)cnt * 8));
     }
   }
   return CSC_OK;

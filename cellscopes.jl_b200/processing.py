@@ -274,9 +274,7 @@ def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1
         graph = "binary" if n < 10000 else "sum"       # processing.jl:310-317
     mode = {"binary": _capi.GRAPH_BINARY, "sum": _capi.GRAPH_SUM, "snn": _capi.GRAPH_SNN_JACCARD}[graph]
     gdev = s.ctx.graph_build(idx, n, n_neighbors, 0, n, mode, snn_prune)
-    adj = gdev.to_scipy()
-    if graph != "snn":
-        adj = adj.astype(np.int64)
+    adj = gdev.to_scipy(np.float64 if graph == "snn" else np.int64)      # SparseMatrixCSC{Int64,Int64} in the reference
     s.knn = (idx, dist)
     clustering = None
     result = None

@@ -94,6 +94,13 @@ csc_status csc_stage_times(csc_ctx* ctx, double* ms /*[CSC_T_COUNT]*/, int64_t* 
 /* scratch-flush: overwrite a buffer larger than L2 (bench hygiene between timed iterations) */
 csc_status csc_flush_l2(csc_ctx* ctx);
 
+/* ---- pinned host memory (optional) -------------------------------------------------------
+ * Results copied into pageable memory move at ~5 GB/s (staging + first-touch page faults); into page-locked
+ * memory they move at PCIe rate.  A caller that wants that allocates its result arrays here; blocks are cached
+ * per context and handed back by csc_host_free.  Every download entry point accepts either kind of memory. */
+csc_status csc_host_alloc(csc_ctx* ctx, int64_t bytes, void** out);
+csc_status csc_host_free(csc_ctx* ctx, void* p);
+
 /* ---- device buffers (partials that the host reduces/gathers between ranks) ------------- */
 csc_status csc_vec_alloc(csc_ctx* ctx, int64_t n, int32_t dtype, csc_vec** out); /* zero-filled */
 /* non-owning view of caller-managed device memory (e.g. an all-gathered table held by torch) */
@@ -203,7 +210,8 @@ csc_status csc_knn_last_fallback_rows(csc_ctx* ctx, int64_t* n_rows);
 csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int64_t n_cells_total, int32_t k,
                            int64_t cell_lo, int64_t cell_hi, int32_t mode, double snn_prune, csc_graph** out);
 csc_status csc_graph_info(const csc_graph* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
-csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, double* nzval,
+/* nzval: fp64 or int64 [nnz] as val_dtype says (the reference's adjacency is SparseMatrixCSC{Int64,Int64}) */
+csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, void* nzval, int32_t val_dtype,
                               int32_t index_base);
 csc_status csc_graph_free(csc_graph* g);
 

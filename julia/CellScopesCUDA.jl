@@ -390,10 +390,17 @@ function adjacency(s::Session, idx::Handle, n, k, mode; snn_prune=0.0)
     g = Handle(gr[], :csc_graph_free, s.ctx)
     nz = Ref{Int64}(0)
     check(s.ctx, ccall(sym(:csc_graph_info), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), g.h, C_NULL, C_NULL, nz))
-    cp = Vector{Int64}(undef, n + 1); rv = Vector{Int64}(undef, nz[]); v = Vector{Float64}(undef, nz[])
-    GC.@preserve cp rv v check(s.ctx, ccall(sym(:csc_graph_download), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32),
-                                            g.h, pointer(cp), pointer(rv), pointer(v), Int32(1)))
-    mode == GRAPH_SNN ? SparseMatrixCSC{Float64,Int64}(n, n, cp, rv, v) : SparseMatrixCSC{Int64,Int64}(n, n, cp, rv, Int64.(v))
+    cp = Vector{Int64}(undef, n + 1); rv = Vector{Int64}(undef, nz[])
+    if mode == GRAPH_SNN
+        v = Vector{Float64}(undef, nz[])
+        GC.@preserve cp rv v check(s.ctx, ccall(sym(:csc_graph_download), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Int32, Int32),
+                                                g.h, pointer(cp), pointer(rv), pointer(v), DT_F64, Int32(1)))
+        return SparseMatrixCSC{Float64,Int64}(n, n, cp, rv, v)
+    end
+    vi = Vector{Int64}(undef, nz[])            # the reference's adjacency is SparseMatrixCSC{Int64,Int64}
+    GC.@preserve cp rv vi check(s.ctx, ccall(sym(:csc_graph_download), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Int32, Int32),
+                                             g.h, pointer(cp), pointer(rv), pointer(vi), DT_I64, Int32(1)))
+    SparseMatrixCSC{Int64,Int64}(n, n, cp, rv, vi)
 end
 
 function run_clustering(sc_obj::cs.get_object_group("All"); n_neighbors=30, metric=cs.CosineDist(), res=0.06, seed_use=1234,
