@@ -4,6 +4,7 @@
 // The local regression restates Loess.jl 0.6.3 (kd-tree vertices + cubic Hermite blending);
 // the operation order follows oracle/cellscopes_oracle.py::loess_fit so both agree to rounding.
 #include <cmath>
+#include <limits>
 #include <numeric>
 
 #include "common.cuh"
@@ -99,28 +100,56 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
   const double cell = 0.2;
   const int64_t q = std::max<int64_t>(1, (int64_t)std::floor(span * (double)n));
   const int64_t cutoff = (int64_t)std::ceil(cell * span * (double)n);
-  std::vector<double> xs(x);
-  std::stable_sort(xs.begin(), xs.end());
+  // the points sorted by (x, index): the q nearest to a vertex are a window around it, so they come out of a
+  // two-pointer walk in O(q) instead of a selection over all n points per vertex
+  std::vector<int64_t> sidx((size_t)n);
+  std::iota(sidx.begin(), sidx.end(), (int64_t)0);
+  std::stable_sort(sidx.begin(), sidx.end(), [&](int64_t i, int64_t j) { return x[i] < x[j]; });
+  std::vector<double> xs((size_t)n);
+  for (int64_t i = 0; i < n; ++i) xs[i] = x[sidx[i]];
   std::vector<double> verts;
   kd_vertices(xs, cutoff, verts);
   const size_t nv = verts.size();
   std::vector<double> val(nv), slope(nv);
-  std::vector<int64_t> order((size_t)n);
-  std::vector<double> d((size_t)n), a((size_t)q * 3), b((size_t)q);
+  std::vector<int64_t> order;
+  std::vector<double> d;
+  order.reserve((size_t)q + 64);
+  d.reserve((size_t)q + 64);
+  std::vector<double> a((size_t)q * 3), b((size_t)q);
+  const double inf = std::numeric_limits<double>::infinity();
   for (size_t vi = 0; vi < nv; ++vi) {
     const double v = verts[vi];
-    for (int64_t i = 0; i < n; ++i) d[i] = std::fabs(x[i] - v);
-    std::iota(order.begin(), order.end(), (int64_t)0);
-    // the q nearest, ties by lower index (stable)
-    auto cmp = [&](int64_t i, int64_t j) { return d[i] < d[j] || (d[i] == d[j] && i < j); };
-    if (q < n) std::nth_element(order.begin(), order.begin() + q, order.end(), cmp);
-    std::sort(order.begin(), order.begin() + q, cmp);
+    // nearest first, ties by lower index: exactly the order of a stable sort of |x - v| (the oracle's argsort)
+    int64_t R = (int64_t)(std::lower_bound(xs.begin(), xs.end(), v) - xs.begin()), L = R - 1;
+    order.clear();
+    d.clear();
+    while (true) {
+      const double dl = L >= 0 ? std::fabs(xs[L] - v) : inf;
+      const double dr = R < n ? std::fabs(xs[R] - v) : inf;
+      const double dn = std::min(dl, dr);
+      if (dn == inf) break;
+      if ((int64_t)order.size() >= q && dn > d.back()) break;     // keep every tie of the q-th distance for now
+      if (dl <= dr) {
+        order.push_back(sidx[L--]);
+        d.push_back(dl);
+      } else {
+        order.push_back(sidx[R++]);
+        d.push_back(dr);
+      }
+    }
+    // equal distances: ascending index
+    for (size_t i0 = 0; i0 < order.size();) {
+      size_t i1 = i0 + 1;
+      while (i1 < order.size() && d[i1] == d[i0]) ++i1;
+      if (i1 - i0 > 1) std::sort(order.begin() + i0, order.begin() + i1);
+      i0 = i1;
+    }
     double dmax = 0.0;
-    for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[order[i]]);
+    for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[i]);
     if (dmax == 0.0) dmax = 1.0;
     for (int64_t i = 0; i < q; ++i) {
       const int64_t p = order[i];
-      const double u = d[p] / dmax;
+      const double u = d[i] / dmax;
       const double u3 = u * u * u;
       const double t = 1.0 - u3;
       const double w = std::sqrt(t * t * t);
