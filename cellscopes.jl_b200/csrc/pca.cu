@@ -733,6 +733,29 @@ k_apply_rot(const double* __restrict__ X0, double* __restrict__ O0, const double
   }
 }
 
+// out[j] = || R[:, j] ||_2 of the H x b block R, out[b + j] = B[j][j]; one CTA per column
+__global__ void __launch_bounds__(256)
+k_block_stats(const double* __restrict__ R, int H, int b, const double* __restrict__ B, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < H; r += blockDim.x) {
+    const double v = R[(int64_t)r * b + j];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      out[j] = sqrt(v);
+      out[b + j] = B[(int64_t)j * b + j];
+    }
+  }
+}
+
 // residual norms ||Yn_i - theta_i Qn_i|| for the first k columns
 __global__ void k_resid(const double* __restrict__ Yn, const double* __restrict__ Qn, const double* __restrict__ theta, int H,
                         int b, int k, double* __restrict__ out) {
@@ -941,12 +964,11 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
       return CSC_OK;
     };
 
-    k_init_block<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(T1, nel, 42);
+    // start: a Gaussian block (well conditioned as it is), two cycles of three plain products + CholeskyQR2
+    k_init_block<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(Q, nel, 42);
     CSC_LAUNCHED(ctx);
-    CSC_TRY(chol_qr(ctx, w, T1, T2));
-    CSC_TRY(chol_qr(ctx, w, T2, Q));
     for (int c = 0; c < 2; ++c) {
-      // three plain products per cycle: growth (lambda_1/lambda_b)^3 stays far inside CholeskyQR2's range
+      // growth (lambda_1/lambda_b)^3 stays far inside CholeskyQR2's range
       CSC_TRY(dgemm(ctx, false, Gc, Q, T1, H, b, H, H, b, b));
       CSC_TRY(dgemm(ctx, false, Gc, T1, T2, H, b, H, H, b, b));
       CSC_TRY(dgemm(ctx, false, Gc, T2, T1, H, b, H, H, b, b));
@@ -954,42 +976,66 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
       CSC_TRY(chol_qr(ctx, w, T1, T2));
       CSC_TRY(chol_qr(ctx, w, T2, Q));
     }
-    CSC_TRY(rayleigh_ritz());
-    int n_rr = 1;
-    double rate_per_degree = 0.0;   // d log(resid) / d (filter degree), measured between Ritz steps
-    while (resid > tol && iters < max_iter) {
-      const double th1 = hth[0];
-      const double resid_before = resid;
-      const double beta = std::max(hth[b - 1], 1e-10 * std::fabs(th1));
-      const double c = 0.5 * beta, e = 0.5 * beta;
-      const double x1 = std::max((th1 - c) / e, 1.0 + 1e-12);
-      // A filtered guard column (error O(1)) is contaminated by the leading eigenvectors in proportion to
-      // T_m(x1)/T_m(1): keep that growth where the Cholesky pivots still have digits (growth^2 * b * eps << 1).
-      int m = (int)std::floor(std::log(4e5) / std::acosh(x1));
-      m = std::max(1, std::min(m, 24));
-      // Ritz steps are the expensive part of a cycle: once two of them have measured the convergence rate per
-      // filter degree, run as many cycles as the tolerance is predicted to need (at most 6) before the next one
-      int cycles = 1;
-      if (rate_per_degree < -1e-3) {
-        const double need = std::log(0.3 * tol / resid) / rate_per_degree;
-        cycles = (int)std::max(1.0, std::min(6.0, std::ceil(need / m)));
-      }
-      int degrees = 0;
-      for (int cyc = 0; cyc < cycles && iters < max_iter; ++cyc) {
+    // Filter cycles.  CholeskyQR orthogonalises the columns in order, so the block behaves like orthogonal (QR)
+    // iteration: its leading k columns span the dominant invariant subspace ever better while the columns
+    // themselves stay ordered.  That makes the expensive Rayleigh-Ritz step unnecessary inside the loop:
+    //   - the filter interval [0, beta] and the growth bound come from the Rayleigh quotients of the columns
+    //     (diag of Q'GcQ: beta = the smallest, theta_1 ~ the largest),
+    //   - convergence is read off the block residual (I - QQ') Gc q_j of the columns that can carry weight in a
+    //     wanted Ritz vector,
+    // both by-products of the first product of every cycle.  One Ritz step at the end turns the subspace into
+    // eigenpairs and measures the true per-vector residual; if that misses the tolerance the loop resumes with a
+    // tighter subspace target.
+    double stop_mult = 10.0;
+    DevPtr sst;
+    CSC_TRY(dev_alloc(ctx, (size_t)2 * b * 8, &sst));
+    std::vector<double> hst((size_t)2 * b);
+    while (true) {
+      while (iters < max_iter) {
+        CSC_TRY(dgemm(ctx, false, Gc, Q, T3, H, b, H, H, b, b));      // T3 = Gc Q
+        ++iters;
+        CSC_TRY(small_gram(ctx, w, Q, T3, 1, (double*)bm->p));        // B = Q' Gc Q
+        {
+          GemmEpi ep;                                                   // T1 = (I - Q Q') Gc Q = T3 - Q B
+          ep.alpha = -1.0;
+          ep.g1 = 1.0;
+          ep.X1 = T3;
+          CSC_TRY(dgemm(ctx, false, Q, (double*)bm->p, T1, H, b, b, b, b, b, ep));
+        }
+        k_block_stats<<<b, 256, 0, ctx->stream>>>(T1, H, b, (const double*)bm->p, (double*)sst->p);
+        CSC_LAUNCHED(ctx);
+        CSC_CUDA(ctx, cudaMemcpyAsync(hst.data(), sst->p, (size_t)2 * b * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // hst[0:b] = column norms of the block residual, hst[b:2b] = Rayleigh quotients of the columns
+        double th1 = 1e-300, rmin = 1e300;
+        for (int j = 0; j < b; ++j) {
+          th1 = std::max(th1, hst[b + j]);
+          rmin = std::min(rmin, hst[b + j]);
+        }
+        // the k-th largest Rayleigh quotient; every column at or above 95 % of it can carry weight in a wanted
+        // Ritz vector (that includes the partners of a near-degenerate k-th eigenvalue), so all of them must have
+        // stopped leaving the block
+        std::vector<double> rq(hst.begin() + b, hst.begin() + 2 * b);
+        std::nth_element(rq.begin(), rq.begin() + (k - 1), rq.end(), std::greater<double>());
+        const double cut = 0.95 * rq[k - 1];
+        resid = 0.0;
+        for (int j = 0; j < b; ++j)
+          if (hst[b + j] >= cut) resid = std::max(resid, hst[j]);
+        resid /= th1;
+        if (resid <= stop_mult * tol) break;
+        const double hs[3] = {0.0, rmin, th1};
+        const double beta = std::max(hs[1], 1e-10 * th1);
+        const double c = 0.5 * beta, e = 0.5 * beta;
+        // A filtered guard column (error O(1)) is contaminated by the leading eigenvectors in proportion to
+        // T_m(x1)/T_m(1): keep that growth where the Cholesky pivots still have digits (growth^2 * b * eps << 1).
+        // The largest Rayleigh quotient underestimates lambda_1 a little: 5 % head-room.
+        const double x1 = std::max((1.05 * th1 - c) / e, 1.0 + 1e-12);
+        int m = (int)std::floor(std::log(4e5) / std::acosh(x1));
+        m = std::max(1, std::min(m, 24));
         // Y0 = Q, Y1 = (Gc Q - c Q)/e
         double *Y0 = Q, *Y1 = T3;
-        if (have_gq) {
-          k_axpby_cols<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(T3, Q, 1.0 / e, -c / e, nullptr, nel, b, T3);
-          CSC_LAUNCHED(ctx);
-          have_gq = false;
-        } else {
-          GemmEpi ep;
-          ep.alpha = 1.0 / e;
-          ep.g1 = -c / e;
-          ep.X1 = Q;
-          CSC_TRY(dgemm(ctx, false, Gc, Q, T3, H, b, H, H, b, b, ep));
-          ++iters;
-        }
+        k_axpby_cols<<<(unsigned)ceil_div64(nel, 256), 256, 0, ctx->stream>>>(T3, Q, 1.0 / e, -c / e, nullptr, nel, b, T3);
+        CSC_LAUNCHED(ctx);
         for (int j = 1; j < m; ++j) {
           // Y2 = (2/e) Gc Y1 - (2c/e) Y1 - Y0, written over Y0
           GemmEpi ep;
@@ -1002,16 +1048,17 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
           ++iters;
           std::swap(Y0, Y1);
         }
-        degrees += m;
-        // Y1 holds the filtered block; orthonormalise into the other one of {Q, T3}
+        // Y1 holds the filtered block; one CholeskyQR pass into the other one of {Q, T3} is enough between cycles
         double* dst = (Y1 == T3) ? Q : T3;
-        CSC_TRY(chol_qr(ctx, w, Y1, T1));
-        CSC_TRY(chol_qr(ctx, w, T1, dst));
-        if (dst != Q) std::swap(Q, T3);      // Q now names the orthonormal block
+        CSC_TRY(chol_qr(ctx, w, Y1, dst));
+        if (dst != Q) std::swap(Q, T3);      // Q now names the (nearly) orthonormal block
       }
+      // exact orthonormality for the Ritz step, then eigenpairs and the per-vector residual
+      CSC_TRY(chol_qr(ctx, w, Q, T1));
+      std::swap(Q, T1);
       CSC_TRY(rayleigh_ritz());
-      ++n_rr;
-      rate_per_degree = (resid > 0.0 && degrees > 0) ? std::log(resid / resid_before) / (double)degrees : -1e9;
+      if (resid <= tol || iters >= max_iter) break;
+      stop_mult *= 0.1;
     }
     std::vector<double> hq((size_t)H * b);
     CSC_CUDA(ctx, cudaMemcpyAsync(hq.data(), Q, hq.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
