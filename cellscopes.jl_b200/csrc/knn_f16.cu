@@ -73,13 +73,56 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
   return fmax3(fmax3(a, b, c), m[9], m[10]);
 }
 
+// List entry j of the warp's row r lives at slot r*32 + ((j + r) & 31): one row is 32 consecutive slots for the
+// cooperative path (lane = entry), and the same entry of 32 different rows falls into 16 different banks for the
+// lane-parallel path (lane = row).
+__device__ __forceinline__ int lslot(int r, int j) { return r * 32 + ((j + r) & 31); }
+
+// Dense phases (a block's own cluster, the first tiles): most rows of the warp have several candidates in the same
+// chunk, and inserting them one row at a time with the whole warp is 32x serial.  Here every lane inserts its own
+// row's candidates into its own list (binary search + shift), all rows in parallel, no warp-level operation.
+__device__ __noinline__ float2 insert_lane_parallel(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
+                                                    uint2* wl, int lane, float tau, float mid, float* pub) {
+  int tid31 = (int)wl[lslot(lane, F_L - 1)].y;            // id of the current 32nd entry (ties: lower id ranks first)
+  bool dirty = false;
+  while (cm) {
+    const int j = __ffs(cm) - 1;
+    cm &= cm - 1;
+    const int id = key_base + j;
+    if (id == self_i || id >= n_keys) continue;
+    const float v = scratch[j * 32 + lane];
+    if (!(v > tau || (v == tau && id < tid31))) continue;  // does not beat the row's last entry
+    // number of entries ranking before the candidate (they form a prefix): binary search over [0, 31]
+    int lo = 0, hi = F_L - 1;                              // the answer is in [lo, hi]; entry 31 is beaten for sure
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      const uint2 e = wl[lslot(lane, m)];
+      const float es = __uint_as_float(e.x);
+      if (es > v || (es == v && (int)e.y < id)) lo = m + 1;
+      else hi = m;
+    }
+    for (int t = F_L - 1; t > lo; --t) wl[lslot(lane, t)] = wl[lslot(lane, t - 1)];
+    wl[lslot(lane, lo)] = make_uint2(__float_as_uint(v), (unsigned)id);
+    const uint2 last = wl[lslot(lane, F_L - 1)];
+    tau = __uint_as_float(last.x);
+    tid31 = (int)last.y;
+    dirty = true;
+  }
+  if (dirty) {
+    mid = __uint_as_float(wl[lslot(lane, F_L / 2 - 1)].x);
+    pub[lane] = mid;
+  }
+  __syncwarp();
+  return make_float2(tau, mid);
+}
+
 // Candidates of one 32-key chunk -> the rows' lists.  Every lane has already written its 32 scores to the warp's
 // scratch tile (scratch[key * 32 + lane]) and built the bit mask `cm` of its scores above its threshold.
 // wl = this warp's 32 lists, [row][32] (score, id) sorted descending; lane j owns entry j of whichever row is
 // being updated, so an insertion is one LDS.64, a ballot, two shuffles and one STS.64 for the whole warp.
 // Kept out of line on purpose: inlined four times per tile the slow path outgrew the instruction cache and ran
 // ~10x slower than its instruction count (measured).
-__device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scratch, int key_base, int self0, int n_keys,
+__device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
                                                  uint2* wl, int lane, float tau, float mid, float* pub, unsigned long long* cnt) {
   const unsigned FULL = 0xffffffffu;
   unsigned rows = __ballot_sync(FULL, cm != 0u);
@@ -87,7 +130,8 @@ __device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scrat
     const int src = __ffs(rows) - 1;
     rows &= rows - 1;
     unsigned mask = __shfl_sync(FULL, cm, src);
-    uint2 e = wl[src * F_L + lane];           // the row's list stays in registers while its candidates are inserted
+    const int self_src = __shfl_sync(FULL, self_i, src);     // the key that is row src itself
+    uint2 e = wl[lslot(src, lane)];            // the row's list stays in registers while its candidates are inserted
     float es = __uint_as_float(e.x);
     int ei = (int)e.y;
     bool dirty = false;
@@ -95,7 +139,7 @@ __device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scrat
       const int j = __ffs(mask) - 1;
       mask &= mask - 1;
       const int id = key_base + j;
-      if (id == self0 + src || id >= n_keys) continue;
+      if (id == self_src || id >= n_keys) continue;
       const float cv = scratch[j * 32 + src];
       // entries that rank before the candidate form a prefix of the sorted list
       const int pos = __popc(__ballot_sync(FULL, es > cv || (es == cv && ei < id)));
@@ -117,7 +161,7 @@ __device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scrat
       }
     }
     if (dirty) {
-      wl[src * F_L + lane] = make_uint2(__float_as_uint(es), (unsigned)ei);
+      wl[lslot(src, lane)] = make_uint2(__float_as_uint(es), (unsigned)ei);
       const float nt = __shfl_sync(FULL, es, F_L - 1);
       const float nm = __shfl_sync(FULL, es, F_L / 2 - 1);
       if (lane == src) {
@@ -131,8 +175,8 @@ __device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scrat
 }
 
 // one chunk of the slow path: candidate mask, scores to the scratch tile, out-of-line insertion
-__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self0, int n_keys,
-                                           uint2* wl, int lane, float thr, float& tau, float& mid, float* pub, unsigned long long* cnt) {
+__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self_i, int n_keys,
+                                           uint2* wl, int lane, float thr, float& tau, float& mid, float* pub, unsigned long long* cnt, int dense_min) {
   unsigned cm = 0u;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -140,7 +184,10 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scrat
     cm |= (__uint_as_float(r[i]) > thr ? 1u : 0u) << i;
   }
   __syncwarp();
-  const float2 t = insert_candidates(cm, scratch, key_base, self0, n_keys, wl, lane, tau, mid, pub, cnt);
+  // many rows with candidates: every lane works on its own row; few: the warp works on one row at a time
+  const bool dense = __popc(__ballot_sync(0xffffffffu, cm != 0u)) >= dense_min;
+  const float2 t = dense ? insert_lane_parallel(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, mid, pub)
+                         : insert_candidates(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, mid, pub, cnt);
   if (cnt && lane == 0) atomicAdd(cnt + 3, 1ull);
   tau = t.x;
   mid = t.y;
@@ -149,7 +196,8 @@ __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scrat
 
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restrict__ q16, int64_t n_q, int64_t n_keys,
-               int64_t query_offset, int32_t ksteps, float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int dbg_mode, unsigned long long* cnt) {
+               int64_t query_offset, const int32_t* __restrict__ self_pos, const int32_t* __restrict__ start_tile, int32_t ksteps,
+               float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int dbg_mode, unsigned long long* cnt) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
@@ -167,6 +215,8 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
   const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
+  // locality order (knn_order.cu): this block starts its scan near its own cluster and wraps around
+  const int64_t t_start = start_tile ? (int64_t)start_tile[blockIdx.x] % n_tiles : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < F_STAGES; ++i) {
@@ -198,7 +248,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / F_STAGES) & 1) ^ 1));
       if (elect_one()) {
         mbar_expect_tx(bar_full + 8 * s, F_TILE_BYTES);
-        tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, (int)(t * F_BN));
+        int64_t tile = t + t_start;
+        if (tile >= n_tiles) tile -= n_tiles;
+        tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, (int)(tile * F_BN));
       }
       __syncwarp();
     }
@@ -241,7 +293,8 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     const int row = quarter * 32 + lane;
     const int64_t qrow = q0 + row;
     const bool qvalid = qrow < n_q;
-    const int self0 = (int)(query_offset + q0 + quarter * 32);   // key id of this warp's row 0 (row r: self0 + r)
+    // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
+    const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
     float* scratch = scratch_all + (warp - 2) * 32 * 32;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if (grp == 0) {
@@ -262,7 +315,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       mbar_arrive(bar_a);
     }
     uint2* wl = lists + ((size_t)grp * F_TQ + quarter * 32) * F_L;      // this warp's 32 rows
-    for (int r = 0; r < 32; ++r) wl[r * F_L + lane] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
+    for (int r = 0; r < 32; ++r) wl[lslot(r, lane)] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
     __syncwarp();
     // Thresholds.  tau = this group's 32nd best of the row (its list's last entry); mid = its 16th best, published
     // to the other group.  Both groups hold >= 16 scores >= min(mid_A, mid_B), so nothing at or below that value
@@ -279,7 +332,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       const int a = (int)(t % F_ACC);
       mbar_wait(bar_tfull + 8 * a, (uint32_t)((t / F_ACC) & 1));
       tc_fence_after();
-      const int key0 = (int)(t * F_BN);
+      int64_t tile = t + t_start;
+      if (tile >= n_tiles) tile -= n_tiles;
+      const int key0 = (int)(tile * F_BN);
       uint32_t r0[32], r1[32], r2[32], r3[32];
       const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
       tmem_ld32(taddr, r0);
@@ -292,12 +347,13 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       mbar_arrive(bar_tempty + 8 * a);
       const float m0 = max32(r0), m1 = max32(r1), m2 = max32(r2), m3 = max32(r3);
       const float thr = fmaxf(tau, fminf(mid, pub_other[lane]));
+      const int dense_min = dbg_mode >= 10 ? dbg_mode - 10 : 6;
       if (dbg_mode != 1 && __any_sync(FULL, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr)) {
         if (cnt && lane == 0) atomicAdd(cnt + 2, 1ull);
-        if (__any_sync(FULL, m0 > thr)) slow_chunk(r0, scratch, key0, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
-        if (__any_sync(FULL, m1 > thr)) slow_chunk(r1, scratch, key0 + 32, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
-        if (__any_sync(FULL, m2 > thr)) slow_chunk(r2, scratch, key0 + 64, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
-        if (__any_sync(FULL, m3 > thr)) slow_chunk(r3, scratch, key0 + 96, self0, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt);
+        if (__any_sync(FULL, m0 > thr)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
+        if (__any_sync(FULL, m1 > thr)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
+        if (__any_sync(FULL, m2 > thr)) slow_chunk(r2, scratch, key0 + 64, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
+        if (__any_sync(FULL, m3 > thr)) slow_chunk(r3, scratch, key0 + 96, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
       }
     }
     // merge the two groups' lists: the 32 best of the union = elementwise max of A[j] and B[31 - j] (bitonic)
@@ -307,7 +363,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       const uint2* lb = lists + ((size_t)F_TQ + quarter * 32) * F_L;
       for (int r = 0; r < 32; ++r) {
         const int64_t orow = q0 + quarter * 32 + r;
-        const uint2 ea = la[r * F_L + lane], eb = lb[r * F_L + (F_L - 1 - lane)];
+        const uint2 ea = la[lslot(r, lane)], eb = lb[lslot(r, F_L - 1 - lane)];
         const float sa = __uint_as_float(ea.x), sb = __uint_as_float(eb.x);
         const bool take_a = sa > sb || (sa == sb && (int)ea.y < (int)eb.y);
         const float s = take_a ? sa : sb;
@@ -342,8 +398,9 @@ __global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restr
 // a_L + eps are appended to the fallback list.  One thread per query row.
 __global__ void __launch_bounds__(128)
 k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
-                   const float* __restrict__ thr, const int32_t* __restrict__ in_idx, float* __restrict__ out_score,
-                   int32_t* __restrict__ out_idx, int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
+                   const float* __restrict__ thr, const int32_t* __restrict__ in_idx, const int32_t* __restrict__ perm_k,
+                   const int32_t* __restrict__ perm_q, float* __restrict__ out_score, int32_t* __restrict__ out_idx,
+                   int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_q) return;
   float s[F_L];
@@ -351,9 +408,10 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
   const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
   int cnt = 0;
   for (int j = 0; j < F_L; ++j) {
-    const int cand = in_idx[row * F_L + j];
-    if (cand == INT_MAX) continue;
-    const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)cand * 64);
+    const int pos = in_idx[row * F_L + j];
+    if (pos == INT_MAX) continue;
+    const int cand = perm_k ? perm_k[pos] : pos;         // original key id: what is reported and what breaks ties
+    const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)pos * 64);
     double acc = 0.0;
     for (int i = 0; i < (d + 3) / 4; ++i) {
       const float4 a = __ldg(qr + i), b = __ldg(kr + i);
@@ -370,9 +428,10 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
     s[p] = v;
     id[p] = cand;
   }
+  const int64_t orow = perm_q ? perm_q[row] : row;
   for (int j = 0; j < k; ++j) {
-    out_score[row * k + j] = j < cnt ? s[j] : -INFINITY;
-    out_idx[row * k + j] = j < cnt ? id[j] : INT_MAX;
+    out_score[orow * k + j] = j < cnt ? s[j] : -INFINITY;
+    out_idx[orow * k + j] = j < cnt ? id[j] : INT_MAX;
   }
   // a_L = -inf when fewer than 32 keys exist: the list holds every key and the proof is trivial
   const float a_l = thr[row];
@@ -382,20 +441,40 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
 }
 
 __global__ void k_gather_rows(const float* __restrict__ src, const int32_t* __restrict__ rows, int32_t n, int64_t row_offset,
-                              float* __restrict__ dst, int32_t* __restrict__ self_ids) {
+                              const int32_t* __restrict__ self_pos, float* __restrict__ dst, int32_t* __restrict__ self_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n * 16) return;
   const int r = (int)(i >> 4), c = (int)(i & 15);
   reinterpret_cast<float4*>(dst)[(int64_t)r * 16 + c] = __ldg(reinterpret_cast<const float4*>(src) + (int64_t)rows[r] * 16 + c);
-  if (c == 0) self_ids[r] = (int32_t)(row_offset + rows[r]);
+  if (c == 0) self_ids[r] = self_pos ? self_pos[rows[r]] : (int32_t)(row_offset + rows[r]);
 }
+// results of the exact re-scan -> their rows; key positions -> original ids, equal scores ordered by original id.
+// One thread per re-scanned row (k <= 32).
 __global__ void k_scatter_results(const float* __restrict__ s, const int32_t* __restrict__ idx, const int32_t* __restrict__ rows,
-                                  int32_t n, int32_t k, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n * k) return;
-  const int r = (int)(i / k), j = (int)(i % k);
-  out_score[(int64_t)rows[r] * k + j] = s[i];
-  out_idx[(int64_t)rows[r] * k + j] = idx[i];
+                                  int32_t n, int32_t k, const int32_t* __restrict__ perm_k, const int32_t* __restrict__ perm_q,
+                                  float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float sc[32];
+  int id[32];
+  for (int j = 0; j < k; ++j) {
+    const float v = s[(int64_t)r * k + j];
+    const int pos = idx[(int64_t)r * k + j];
+    const int oid = (perm_k && pos != INT_MAX) ? perm_k[pos] : pos;
+    int p = j;
+    while (p > 0 && sc[p - 1] == v && id[p - 1] > oid) {      // scores arrive sorted: only ties need reordering
+      sc[p] = sc[p - 1];
+      id[p] = id[p - 1];
+      --p;
+    }
+    sc[p] = v;
+    id[p] = oid;
+  }
+  const int64_t orow = perm_q ? perm_q[rows[r]] : rows[r];
+  for (int j = 0; j < k; ++j) {
+    out_score[orow * k + j] = sc[j];
+    out_idx[orow * k + j] = id[j];
+  }
 }
 
 csc_status make_map_f16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const __half* ptr, int64_t n_rows) {
@@ -412,6 +491,10 @@ csc_status make_map_f16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const 
 }  // namespace
 
 // Unit-norm prepared rows only (cosine).  Writes the exact k best (score, id) per query, sorted.
+csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                           int64_t query_offset, int tq, int bn, DevPtr* ks, DevPtr* qs, DevPtr* perm_k, DevPtr* perm_q,
+                           DevPtr* self_pos, DevPtr* start_tile);
+
 csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
                         int64_t query_offset, int32_t k, int32_t d_eff, float* out_score, int32_t* out_idx,
                         int64_t* n_fallback_out) {
@@ -425,6 +508,20 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
     encode = (EncodeTiledFn)fn;
   }
   const int ksteps = (d_eff + 15) / 16;
+  // locality order (knn_order.cu) once the scan is long enough to pay for the clustering; CSC_KNN_ORDER=0 disables
+  DevPtr ks, qs, perm_k, perm_q, self_pos, start_tile;
+  const char* ord_env = getenv("CSC_KNN_ORDER");
+  const bool ordered = n_keys >= 32768 && n_keys < ((int64_t)1 << 31) && !(ord_env && atoi(ord_env) == 0);
+  if (ordered) {
+    CSC_TRY(knn_build_order(ctx, q_prep, n_q, k_prep, n_keys, same, query_offset, F_TQ, F_BN, &ks, &qs, &perm_k, &perm_q,
+                            &self_pos, &start_tile));
+    q_prep = (const float*)qs->p;
+    k_prep = (const float*)ks->p;
+  }
+  const int32_t* d_perm_k = ordered ? (const int32_t*)perm_k->p : nullptr;
+  const int32_t* d_perm_q = ordered ? (const int32_t*)perm_q->p : nullptr;
+  const int32_t* d_self = ordered ? (const int32_t*)self_pos->p : nullptr;
+  const int32_t* d_start = ordered ? (const int32_t*)start_tile->p : nullptr;
   DevPtr k16, q16, thr, cand, fb_rows, fb_count;
   const int64_t nk_el = n_keys * F_DP, nq_el = n_q * F_DP;
   CSC_TRY(dev_alloc(ctx, (size_t)nk_el * 2, &k16));
@@ -449,13 +546,13 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
   k_knn_scan_f16<<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(
-      kmap, (const __half*)q16->p, n_q, n_keys, query_offset, ksteps, (float*)thr->p, (int32_t*)cand->p,
+      kmap, (const __half*)q16->p, n_q, n_keys, query_offset, d_self, d_start, ksteps, (float*)thr->p, (int32_t*)cand->p,
       getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0, dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(
-      q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, out_score, out_idx, (int32_t*)fb_rows->p,
-      (int32_t*)fb_count->p);
+      q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, d_perm_k, d_perm_q, out_score, out_idx,
+      (int32_t*)fb_rows->p, (int32_t*)fb_count->p);
   CSC_LAUNCHED(ctx);
   int32_t n_fb = 0;
   CSC_CUDA(ctx, cudaMemcpyAsync(&n_fb, fb_count->p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -477,12 +574,12 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
     CSC_TRY(dev_alloc(ctx, (size_t)n_fb * k * 4, &gs));
     CSC_TRY(dev_alloc(ctx, (size_t)n_fb * k * 4, &gi));
     k_gather_rows<<<(unsigned)ceil_div64((int64_t)n_fb * 16, 256), 256, 0, ctx->stream>>>(
-        q_prep, (const int32_t*)fb_rows->p, n_fb, query_offset, (float*)gq->p, (int32_t*)gself->p);
+        q_prep, (const int32_t*)fb_rows->p, n_fb, query_offset, d_self, (float*)gq->p, (int32_t*)gself->p);
     CSC_LAUNCHED(ctx);
     CSC_TRY(knn_scan_tc(ctx, (const float*)gq->p, n_fb, k_prep, n_keys, false, 0, (const int32_t*)gself->p, k, d_eff,
                         (float*)gs->p, (int32_t*)gi->p));
-    k_scatter_results<<<(unsigned)ceil_div64((int64_t)n_fb * k, 256), 256, 0, ctx->stream>>>(
-        (const float*)gs->p, (const int32_t*)gi->p, (const int32_t*)fb_rows->p, n_fb, k, out_score, out_idx);
+    k_scatter_results<<<(unsigned)ceil_div64(n_fb, 128), 128, 0, ctx->stream>>>(
+        (const float*)gs->p, (const int32_t*)gi->p, (const int32_t*)fb_rows->p, n_fb, k, d_perm_k, d_perm_q, out_score, out_idx);
     CSC_LAUNCHED(ctx);
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }

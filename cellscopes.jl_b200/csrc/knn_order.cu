@@ -1,0 +1,230 @@
+// Locality order for the exact kNN scan.
+//
+// The brute-force scan is exact in any key order, but its cost is not order-free: a row's running top-L list
+// is updated whenever a key beats the current L-th best, which for keys in random order happens ~L ln(N/L)
+// times per row -- and list updates, not the tensor-core scores, dominate the scan (measured: 57 of 95 ms at
+// 500k cells).  If a row meets its true neighbours FIRST, its threshold is tight from the start and almost
+// nothing that follows gets through.  So: cluster the unit rows (spherical k-means, ~N/2048 clusters, a few Lloyd
+// passes on a strided sample), sort keys and queries by cluster, and let every query block start its scan a few
+// tiles before its own cluster.  Pure reordering: results are identical, ids are mapped back at the end.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int KO_D = 64;          // prepared row length (floats)
+constexpr int KO_CHUNK = 128;     // centroids staged in shared memory at a time (32 KB)
+
+// label[i] = argmax_c <x_i, cent_c>; optionally accumulates the per-cluster sums of the assigned points
+// (sample stride `stride`: point i is row i * stride)
+__global__ void __launch_bounds__(128)
+k_km_assign(const float* __restrict__ x, int64_t n, int64_t stride, const float* __restrict__ cent, int K, int32_t* __restrict__ label,
+            float* __restrict__ sums, int32_t* __restrict__ counts) {
+  __shared__ __align__(16) float sc[KO_CHUNK * KO_D];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  float xr[KO_D];
+  {
+    const float4* src = reinterpret_cast<const float4*>(x + (valid ? i * stride : 0) * KO_D);
+#pragma unroll
+    for (int j = 0; j < KO_D / 4; ++j) {
+      const float4 v = __ldg(src + j);
+      xr[4 * j] = v.x;
+      xr[4 * j + 1] = v.y;
+      xr[4 * j + 2] = v.z;
+      xr[4 * j + 3] = v.w;
+    }
+  }
+  float best = -2.f;
+  int bi = 0;
+  for (int c0 = 0; c0 < K; c0 += KO_CHUNK) {
+    const int nc = min(KO_CHUNK, K - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < nc * KO_D / 4; j += blockDim.x)
+      reinterpret_cast<float4*>(sc)[j] = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)c0 * KO_D) + j);
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+      const float4* cr = reinterpret_cast<const float4*>(sc + c * KO_D);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KO_D / 4; ++j) {
+        const float4 v = cr[j];      // same address for the whole warp: broadcast
+        a0 = fmaf(xr[4 * j], v.x, a0);
+        a1 = fmaf(xr[4 * j + 1], v.y, a1);
+        a2 = fmaf(xr[4 * j + 2], v.z, a2);
+        a3 = fmaf(xr[4 * j + 3], v.w, a3);
+      }
+      const float s = (a0 + a1) + (a2 + a3);
+      if (s > best) {
+        best = s;
+        bi = c0 + c;
+      }
+    }
+  }
+  if (!valid) return;
+  if (label) label[i] = bi;
+  if (sums) {
+    float* dst = sums + (int64_t)bi * KO_D;
+#pragma unroll
+    for (int j = 0; j < KO_D; ++j) atomicAdd(dst + j, xr[j]);
+    atomicAdd(counts + bi, 1);
+  }
+}
+
+// centroid = normalised mean of its points; an empty cluster keeps its previous centroid
+__global__ void k_km_update(const float* __restrict__ sums, const int32_t* __restrict__ counts, int K, float* __restrict__ cent) {
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x;     // 32 threads
+  if (counts[c] == 0) return;
+  const float v0 = sums[(int64_t)c * KO_D + lane], v1 = sums[(int64_t)c * KO_D + 32 + lane];
+  float s = v0 * v0 + v1 * v1;
+  s = warp_sum(s);
+  const float inv = s > 0.f ? rsqrtf(s) : 0.f;
+  cent[(int64_t)c * KO_D + lane] = v0 * inv;
+  cent[(int64_t)c * KO_D + 32 + lane] = v1 * inv;
+}
+
+__global__ void k_km_init(const float* __restrict__ x, int64_t n, int K, float* __restrict__ cent) {
+  const int c = blockIdx.x;
+  const int64_t row = (int64_t)c * (n / K) + (n / K) / 2;     // evenly strided seeds: deterministic
+  for (int j = threadIdx.x; j < KO_D; j += blockDim.x) cent[(int64_t)c * KO_D + j] = x[row * KO_D + j];
+}
+
+__global__ void k_iota(int32_t* __restrict__ a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+
+// seg_start[c] = first sorted position whose label is >= c (labels_sorted ascending); seg_start[K] = n
+__global__ void k_seg_start(const int32_t* __restrict__ labels_sorted, int64_t n, int K, int32_t* __restrict__ seg_start) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int prev = i == 0 ? -1 : labels_sorted[i - 1];
+  const int cur = i == n ? K : labels_sorted[i];
+  for (int c = prev + 1; c <= cur; ++c) seg_start[c] = (int32_t)i;
+}
+
+// dst row r = src row perm[r] (64 floats), and inv[perm[r]] = r
+__global__ void k_gather64(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, float* __restrict__ dst,
+                           int32_t* __restrict__ inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 16) return;
+  const int64_t r = i >> 4;
+  const int c = (int)(i & 15);
+  const int32_t s = perm[r];
+  reinterpret_cast<float4*>(dst)[r * 16 + c] = __ldg(reinterpret_cast<const float4*>(src) + (int64_t)s * 16 + c);
+  if (c == 0 && inv) inv[s] = (int32_t)r;
+}
+
+// self_pos[r] = sorted key position of the cell that sorted query row r is
+__global__ void k_self_pos(const int32_t* __restrict__ perm_q, const int32_t* __restrict__ inv_k, int64_t off, int64_t n,
+                           int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = inv_k[off + perm_q[i]];
+}
+
+}  // namespace
+
+static csc_status sort_by_label(csc_ctx* ctx, const int32_t* labels, int64_t n, int K, DevPtr* perm, DevPtr* labels_sorted) {
+  DevPtr idx, tmp;
+  CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &idx));
+  CSC_TRY(dev_alloc(ctx, (size_t)n * 4, perm));
+  CSC_TRY(dev_alloc(ctx, (size_t)n * 4, labels_sorted));
+  k_iota<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>((int32_t*)idx->p, n);
+  CSC_LAUNCHED(ctx);
+  int bits = 1;
+  while ((1 << bits) < K) ++bits;
+  size_t tb = 0;
+  CSC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, labels, (int32_t*)(*labels_sorted)->p, (const int32_t*)idx->p,
+                                                (int32_t*)(*perm)->p, (int)n, 0, bits, ctx->stream));
+  CSC_TRY(dev_alloc(ctx, tb, &tmp));
+  CSC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp->p, tb, labels, (int32_t*)(*labels_sorted)->p, (const int32_t*)idx->p,
+                                                (int32_t*)(*perm)->p, (int)n, 0, bits, ctx->stream));
+  ctx->launches += 3;
+  return CSC_OK;
+}
+
+// Cluster the key rows, sort keys (and queries) by cluster.  Outputs (device):
+//   ks / qs        gathered prepared rows in sorted order (qs == ks when `same`)
+//   perm_k/perm_q  sorted position -> original row;  self_pos[r] = sorted key position of query row r's own cell
+//   start_tile[b]  first key tile to scan for query block b (blocks of `tq` rows, tiles of `bn` keys)
+csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
+                           int64_t query_offset, int tq, int bn, DevPtr* ks, DevPtr* qs, DevPtr* perm_k, DevPtr* perm_q,
+                           DevPtr* self_pos, DevPtr* start_tile) {
+  int K = 16;
+  const char* kd = getenv("CSC_KNN_KDIV");
+  const int64_t per = kd ? std::max(64, atoi(kd)) : 2048;
+  while (K < 4096 && (int64_t)K * per < n_keys) K *= 2;
+  DevPtr cent, sums, counts, lab_k, lab_q, labs_k, labs_q, inv_k, seg;
+  CSC_TRY(dev_alloc(ctx, (size_t)K * KO_D * 4, &cent));
+  CSC_TRY(dev_alloc(ctx, (size_t)K * KO_D * 4, &sums));
+  CSC_TRY(dev_alloc(ctx, (size_t)K * 4, &counts));
+  k_km_init<<<K, 64, 0, ctx->stream>>>(k_prep, n_keys, K, (float*)cent->p);
+  CSC_LAUNCHED(ctx);
+  // Lloyd passes on a strided sample of at most 64k rows
+  const int64_t stride = std::max<int64_t>(1, n_keys / 65536);
+  const int64_t n_s = n_keys / stride;
+  for (int it = 0; it < 3; ++it) {
+    CSC_CUDA(ctx, cudaMemsetAsync(sums->p, 0, (size_t)K * KO_D * 4, ctx->stream));
+    CSC_CUDA(ctx, cudaMemsetAsync(counts->p, 0, (size_t)K * 4, ctx->stream));
+    k_km_assign<<<(unsigned)ceil_div64(n_s, 128), 128, 0, ctx->stream>>>(k_prep, n_s, stride, (const float*)cent->p, K, nullptr,
+                                                                      (float*)sums->p, (int32_t*)counts->p);
+    CSC_LAUNCHED(ctx);
+    k_km_update<<<K, 32, 0, ctx->stream>>>((const float*)sums->p, (const int32_t*)counts->p, K, (float*)cent->p);
+    CSC_LAUNCHED(ctx);
+  }
+  CSC_TRY(dev_alloc(ctx, (size_t)n_keys * 4, &lab_k));
+  k_km_assign<<<(unsigned)ceil_div64(n_keys, 128), 128, 0, ctx->stream>>>(k_prep, n_keys, 1, (const float*)cent->p, K,
+                                                                       (int32_t*)lab_k->p, nullptr, nullptr);
+  CSC_LAUNCHED(ctx);
+  CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_k->p, n_keys, K, perm_k, &labs_k));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_keys * KO_D * 4, ks));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_keys * 4, &inv_k));
+  k_gather64<<<(unsigned)ceil_div64(n_keys * 16, 256), 256, 0, ctx->stream>>>(k_prep, (const int32_t*)(*perm_k)->p, n_keys,
+                                                                           (float*)(*ks)->p, (int32_t*)inv_k->p);
+  CSC_LAUNCHED(ctx);
+  CSC_TRY(dev_alloc(ctx, (size_t)(K + 1) * 4, &seg));
+  k_seg_start<<<(unsigned)ceil_div64(n_keys + 1, 256), 256, 0, ctx->stream>>>((const int32_t*)labs_k->p, n_keys, K, (int32_t*)seg->p);
+  CSC_LAUNCHED(ctx);
+  const int32_t* labs_q_ptr = nullptr;
+  if (same) {
+    *qs = *ks;
+    *perm_q = *perm_k;
+    labs_q_ptr = (const int32_t*)labs_k->p;
+  } else {
+    CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &lab_q));
+    k_km_assign<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(q_prep, n_q, 1, (const float*)cent->p, K, (int32_t*)lab_q->p,
+                                                                      nullptr, nullptr);
+    CSC_LAUNCHED(ctx);
+    CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_q->p, n_q, K, perm_q, &labs_q));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_q * KO_D * 4, qs));
+    k_gather64<<<(unsigned)ceil_div64(n_q * 16, 256), 256, 0, ctx->stream>>>(q_prep, (const int32_t*)(*perm_q)->p, n_q, (float*)(*qs)->p,
+                                                                          nullptr);
+    CSC_LAUNCHED(ctx);
+    labs_q_ptr = (const int32_t*)labs_q->p;
+  }
+  // small host step: per query block, where its first row's cluster starts among the keys
+  const int64_t n_blocks = ceil_div64(n_q, tq);
+  std::vector<int32_t> h_seg((size_t)K + 1), h_lab((size_t)n_blocks), h_start((size_t)n_blocks);
+  DevPtr d_first;
+  CSC_TRY(dev_alloc(ctx, (size_t)n_blocks * 4, &d_first));
+  // first label of every block: strided device->device copy, then one small download
+  CSC_CUDA(ctx, cudaMemcpy2DAsync(d_first->p, 4, labs_q_ptr, (size_t)tq * 4, 4, (size_t)n_blocks, cudaMemcpyDeviceToDevice, ctx->stream));
+  CSC_CUDA(ctx, cudaMemcpyAsync(h_lab.data(), d_first->p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaMemcpyAsync(h_seg.data(), seg->p, (size_t)(K + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t bq = 0; bq < n_blocks; ++bq) {
+    const int64_t t = (int64_t)h_seg[h_lab[bq]] / bn - 2;     // two tiles of head-room before the cluster
+    h_start[bq] = (int32_t)std::max<int64_t>(0, t);
+  }
+  CSC_TRY(dev_alloc(ctx, (size_t)n_blocks * 4, start_tile));
+  CSC_CUDA(ctx, cudaMemcpyAsync((*start_tile)->p, h_start.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // self position of every (sorted) query row among the sorted keys
+  CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, self_pos));
+  k_self_pos<<<(unsigned)ceil_div64(n_q, 256), 256, 0, ctx->stream>>>((const int32_t*)(*perm_q)->p, (const int32_t*)inv_k->p,
+                                                                     query_offset, n_q, (int32_t*)(*self_pos)->p);
+  CSC_LAUNCHED(ctx);
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // h_start must outlive its copy
+  return CSC_OK;
+}

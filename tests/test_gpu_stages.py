@@ -383,6 +383,43 @@ def test_knn_dims_subset_and_query_shard(cs, oracle, ctx):
     _knn_check(idx, dist, widx[500:1300], wdist[500:1300])
 
 
+def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
+    """Size-independent property at a size the oracle cannot reach: the fp16 filter/prove/refine scan with the
+    locality order, the same without the order, and the exact 3xTF32 scan give IDENTICAL neighbour tables (ids
+    bit-exact, distances to rounding), for the whole set and for a query shard.  Includes exact duplicates."""
+    rng = np.random.default_rng(21)
+    n, d, k = 40000, 32, 15
+    centers = rng.normal(size=(25, d)) * 2.5
+    x = (centers[rng.integers(0, 25, n)] + rng.normal(size=(n, d))).astype(np.float32)
+    x[1000:1200] = x[3000:3200]                          # exact duplicates: ties must resolve by lower id
+    keys = ctx.dense_upload(x)
+
+    def run(env):
+        for kk in ("CSC_KNN_ORDER", "CSC_KNN_IMPL"):
+            monkeypatch.delenv(kk, raising=False)
+        for kk, v in env.items():
+            monkeypatch.setenv(kk, v)
+        i, dd = ctx.knn(keys, keys, k)
+        fb = ctx.knn_last_fallback_rows()
+        q = ctx.dense_upload(x[12345:23456])
+        iq, dq = ctx.knn(q, keys, k, query_offset=12345)
+        return (i.download().reshape(n, k), dd.download().reshape(n, k), iq.download().reshape(-1, k),
+                dq.download().reshape(-1, k), fb)
+
+    a = run({})
+    b = run({"CSC_KNN_ORDER": "0"})
+    c = run({"CSC_KNN_IMPL": "tf32"})
+    assert a[4] < n // 20, "the proof should cover almost every row"
+    for other in (b, c):
+        assert np.array_equal(a[0], other[0])
+        assert np.array_equal(a[2], other[2])
+        assert np.allclose(a[1], other[1], atol=1e-6) and np.allclose(a[3], other[3], atol=1e-6)
+    assert np.array_equal(a[2], a[0][12345:23456])
+    assert np.all(a[0] != np.arange(n)[:, None])
+    # duplicates: row 1000+j and 3000+j are each other's nearest neighbour at distance 0
+    assert np.array_equal(a[0][1000:1200, 0], np.arange(3000, 3200)) and np.all(a[1][1000:1200, 0] <= 1e-6)
+
+
 def test_knn_bad_k(cs, ctx):
     x = ctx.dense_upload(np.random.default_rng(0).normal(size=(10, 4)).astype(np.float32))
     with pytest.raises(cs.CellScopesCudaError):
