@@ -12,14 +12,15 @@
 //   Rows that fail the test (near-duplicate neighbourhoods, k close to L) are gathered and re-run through the
 //   exact 3xTF32 scan (knn_tc.cu), so the result is always the exact one, ties by lower id included.
 //
-// Kernel layout (320 threads, 1 CTA per SM, one CTA = 128 query rows against ALL keys):
+// Kernel layout (320 threads, 1 CTA per SM, one CTA = 256 query rows = two 128-row blocks against ALL keys; the two
+// blocks share every key tile, which halves the L2 traffic per score -- the scan is L2-bandwidth bound otherwise):
 //   warp 0      TMA producer: key tiles [128 keys x 64 halves] (one 128-byte swizzle row per key), 6-stage ring
-//   warp 1      TMEM allocator + MMA issuer: A (queries) lives in TMEM (32 columns of packed halves),
-//               D = 3 accumulator stages of 128 columns
-//   warps 2-5   epilogue group A: even key tiles        warps 6-9   epilogue group B: odd key tiles
-//               thread = query row (TMEM lane); 4 x tcgen05.ld.x32, a FMNMX3 tree, one compare against the
-//               row's threshold; survivors go into the row's sorted list in shared memory (warp-cooperative
-//               insertion).  The two groups keep separate lists and merge them at the end.
+//   warp 1      TMEM allocator + MMA issuer: A (queries, both blocks) lives in TMEM (2 x 32 columns of packed halves),
+//               D = 3 accumulator stages x 2 blocks x 64 columns; the unit of work is a half tile of 64 keys
+//   warps 2-5   epilogue of block 0, warps 6-9 epilogue of block 1: thread = query row (TMEM lane); per half tile
+//               2 x tcgen05.ld.x32, a FMNMX3 tree, one compare against the row's threshold; survivors go into the row's
+//               sorted list in shared memory (warp-cooperative insertion when few rows have candidates, one lane per
+//               row when many do).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -37,15 +38,16 @@ csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const flo
 
 namespace {
 
-constexpr int F_TQ = 128;                 // query rows per CTA = UMMA M
-constexpr int F_BN = 128;                 // keys per tile     = UMMA N
+constexpr int F_TQ = 256;                 // query rows per CTA: two blocks of UMMA M = 128
+constexpr int F_BN = 128;                 // keys per shared-memory tile
+constexpr int F_HN = 64;                  // keys per MMA / accumulator stage (half a tile) = UMMA N
 constexpr int F_DP = 64;                  // padded feature dimension (halves): one 128-byte swizzle row
 constexpr int F_STAGES = 6;
 constexpr int F_ACC = 3;                  // TMEM accumulator stages
 constexpr int F_TILE_BYTES = F_BN * 128;  // 16 KB
 constexpr int F_THREADS = 64 + 256;
 constexpr int F_L = 32;                   // candidates kept per row
-constexpr int F_TMEM_A = F_ACC * F_BN;    // first column of the query operand (32 columns)
+constexpr int F_TMEM_A = F_ACC * 2 * F_HN; // first column of the query operands (2 blocks x 32 columns)
 constexpr float F_SCALE = 256.f;          // operands are scaled so that small components stay normal in fp16
 constexpr float F_EPS = 1.0e-3f;          // bound on |approx - exact| for unit rows (see the header)
 
@@ -81,8 +83,8 @@ __device__ __forceinline__ int lslot(int r, int j) { return r * 32 + ((j + r) & 
 // Dense phases (a block's own cluster, the first tiles): most rows of the warp have several candidates in the same
 // chunk, and inserting them one row at a time with the whole warp is 32x serial.  Here every lane inserts its own
 // row's candidates into its own list (binary search + shift), all rows in parallel, no warp-level operation.
-__device__ __noinline__ float2 insert_lane_parallel(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
-                                                    uint2* wl, int lane, float tau, float mid, float* pub) {
+__device__ __noinline__ float insert_lane_parallel(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
+                                                    uint2* wl, int lane, float tau) {
   int tid31 = (int)wl[lslot(lane, F_L - 1)].y;            // id of the current 32nd entry (ties: lower id ranks first)
   bool dirty = false;
   while (cm) {
@@ -108,12 +110,9 @@ __device__ __noinline__ float2 insert_lane_parallel(unsigned cm, const float* sc
     tid31 = (int)last.y;
     dirty = true;
   }
-  if (dirty) {
-    mid = __uint_as_float(wl[lslot(lane, F_L / 2 - 1)].x);
-    pub[lane] = mid;
-  }
+  (void)dirty;
   __syncwarp();
-  return make_float2(tau, mid);
+  return tau;
 }
 
 // Candidates of one 32-key chunk -> the rows' lists.  Every lane has already written its 32 scores to the warp's
@@ -122,8 +121,8 @@ __device__ __noinline__ float2 insert_lane_parallel(unsigned cm, const float* sc
 // being updated, so an insertion is one LDS.64, a ballot, two shuffles and one STS.64 for the whole warp.
 // Kept out of line on purpose: inlined four times per tile the slow path outgrew the instruction cache and ran
 // ~10x slower than its instruction count (measured).
-__device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
-                                                 uint2* wl, int lane, float tau, float mid, float* pub, unsigned long long* cnt) {
+__device__ __noinline__ float insert_candidates(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
+                                                uint2* wl, int lane, float tau, unsigned long long* cnt) {
   const unsigned FULL = 0xffffffffu;
   unsigned rows = __ballot_sync(FULL, cm != 0u);
   while (rows) {
@@ -163,34 +162,27 @@ __device__ __noinline__ float2 insert_candidates(unsigned cm, const float* scrat
     if (dirty) {
       wl[lslot(src, lane)] = make_uint2(__float_as_uint(es), (unsigned)ei);
       const float nt = __shfl_sync(FULL, es, F_L - 1);
-      const float nm = __shfl_sync(FULL, es, F_L / 2 - 1);
-      if (lane == src) {
-        tau = nt;
-        mid = nm;
-        pub[src] = nm;     // this group's 16th best of the row, for the other group's threshold
-      }
+      if (lane == src) tau = nt;
     }
   }
-  return make_float2(tau, mid);
+  return tau;
 }
 
 // one chunk of the slow path: candidate mask, scores to the scratch tile, out-of-line insertion
 __device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self_i, int n_keys,
-                                           uint2* wl, int lane, float thr, float& tau, float& mid, float* pub, unsigned long long* cnt, int dense_min) {
+                                           uint2* wl, int lane, float& tau, unsigned long long* cnt, int dense_min) {
   unsigned cm = 0u;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     scratch[i * 32 + lane] = __uint_as_float(r[i]);
-    cm |= (__uint_as_float(r[i]) > thr ? 1u : 0u) << i;
+    cm |= (__uint_as_float(r[i]) > tau ? 1u : 0u) << i;
   }
   __syncwarp();
   // many rows with candidates: every lane works on its own row; few: the warp works on one row at a time
   const bool dense = __popc(__ballot_sync(0xffffffffu, cm != 0u)) >= dense_min;
-  const float2 t = dense ? insert_lane_parallel(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, mid, pub)
-                         : insert_candidates(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, mid, pub, cnt);
+  tau = dense ? insert_lane_parallel(cm, scratch, key_base, self_i, n_keys, wl, lane, tau)
+              : insert_candidates(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, cnt);
   if (cnt && lane == 0) atomicAdd(cnt + 3, 1ull);
-  tau = t.x;
-  mid = t.y;
   __syncwarp();
 }
 
@@ -201,10 +193,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
-  uint2* lists = reinterpret_cast<uint2*>(sB + F_STAGES * F_TILE_BYTES);           // [2 groups][128 rows][32]
-  float* scratch_all = reinterpret_cast<float*>(lists + 2 * F_TQ * F_L);           // [8 warps][32 keys][32 lanes]
-  float* pub_all = scratch_all + 8 * 32 * 32;                                      // [2 groups][128 rows] 16th best
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pub_all + 2 * F_TQ);
+  uint2* lists = reinterpret_cast<uint2*>(sB + F_STAGES * F_TILE_BYTES);           // [256 rows][32]
+  float* scratch_all = reinterpret_cast<float*>(lists + F_TQ * F_L);               // [8 warps][32 keys][32 lanes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + 8 * 32 * 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
   const uint32_t bar_empty = smem_u32(bars + 8);       // [F_STAGES]
@@ -215,6 +206,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
   const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
+  const int64_t n_half = 2 * n_tiles;
   // locality order (knn_order.cu): this block starts its scan near its own cluster and wraps around
   const int64_t t_start = start_tile ? (int64_t)start_tile[blockIdx.x] % n_tiles : 0;
 
@@ -225,9 +217,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     }
     for (int i = 0; i < F_ACC; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 128);
+      mbar_init(bar_tempty + 8 * i, 256);
     }
-    mbar_init(bar_a, 128);
+    mbar_init(bar_a, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -256,49 +248,56 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = 128, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(F_TQ >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(F_HN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // K-major SWIZZLE_128B: SBO = 1024 B between 8-row groups, version 1
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     mbar_wait(bar_a, 0);
     tc_fence_after();
-    for (int64_t t = 0; t < n_tiles; ++t) {
+    for (int64_t h = 0; h < n_half; ++h) {
+      const int64_t t = h >> 1;
+      const int half = (int)(h & 1);
       const int s = (int)(t % F_STAGES);
-      const int a = (int)(t % F_ACC);
-      mbar_wait(bar_tempty + 8 * a, (uint32_t)(((t / F_ACC) & 1) ^ 1));
-      mbar_wait(bar_full + 8 * s, (uint32_t)((t / F_STAGES) & 1));
+      const int a = (int)(h % F_ACC);
+      mbar_wait(bar_tempty + 8 * a, (uint32_t)(((h / F_ACC) & 1) ^ 1));
+      if (half == 0) mbar_wait(bar_full + 8 * s, (uint32_t)((t / F_STAGES) & 1));
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t b_addr = smem_u32(sB + (size_t)s * F_TILE_BYTES);
+        // keys [64 half, +64) of the tile: 8 swizzle groups of 1024 bytes further
+        const uint32_t b_addr = smem_u32(sB + (size_t)s * F_TILE_BYTES) + (uint32_t)half * (F_HN * 128);
         const uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (1u << 16);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * F_BN);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          if (ks < ksteps) {
-            // one k-step = 16 halves = 32 bytes of the swizzled row = 8 packed TMEM columns of A
-            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(ks * 2));
-            tc_mma_f16_ts(d_tmem, tmem_base + F_TMEM_A + (uint32_t)ks * 8u, db, idesc, ks ? 1u : 0u);
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((a * 2 + blk) * F_HN);
+          const uint32_t a_tmem = tmem_base + F_TMEM_A + (uint32_t)blk * 32u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps) {
+              // one k-step = 16 halves = 32 bytes of the swizzled row = 8 packed TMEM columns of A
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(ks * 2));
+              tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, db, idesc, ks ? 1u : 0u);
+            }
           }
         }
-        tc_commit(bar_empty + 8 * s);
+        if (half == 1) tc_commit(bar_empty + 8 * s);     // the key stage is reusable once both halves were read
         tc_commit(bar_tfull + 8 * a);
       }
       __syncwarp();
     }
   } else {
-    // ================= epilogue: two groups, one thread = one query row =================
+    // ================= epilogue: one thread = one query row =================
     const unsigned FULL = 0xffffffffu;
-    const int grp = (warp - 2) >> 2;                    // 0: even tiles, 1: odd tiles
+    const int blk = (warp - 2) >> 2;                    // which 128-row block
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
+    const int row = blk * 128 + quarter * 32 + lane;
     const int64_t qrow = q0 + row;
     const bool qvalid = qrow < n_q;
     // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
     const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
     float* scratch = scratch_all + (warp - 2) * 32 * 32;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    if (grp == 0) {
-      // stage this thread's query row into TMEM: lane = row, 32 columns of two packed halves
+    {
+      // stage this thread's query row into TMEM: lane = row within the block, 32 columns of two packed halves
       uint32_t v[32];
       const uint4* src = reinterpret_cast<const uint4*>(q16 + (qvalid ? qrow : 0) * F_DP);
 #pragma unroll
@@ -309,72 +308,48 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
         v[4 * i + 2] = f.z;
         v[4 * i + 3] = f.w;
       }
-      tmem_st32(lane_base + F_TMEM_A, v);
+      tmem_st32(lane_base + F_TMEM_A + (uint32_t)blk * 32u, v);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_a);
     }
-    uint2* wl = lists + ((size_t)grp * F_TQ + quarter * 32) * F_L;      // this warp's 32 rows
+    uint2* wl = lists + (size_t)(blk * 128 + quarter * 32) * F_L;       // this warp's 32 rows
     for (int r = 0; r < 32; ++r) wl[lslot(r, lane)] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
     __syncwarp();
-    // Thresholds.  tau = this group's 32nd best of the row (its list's last entry); mid = its 16th best, published
-    // to the other group.  Both groups hold >= 16 scores >= min(mid_A, mid_B), so nothing at or below that value
-    // can be among the 32 best of the union: thr = max(tau, min(mid, other's mid)) filters almost as well as one
-    // shared list would, without the two groups ever writing the same list.  Published values only grow, so a
-    // stale read is merely conservative.
-    float* pub = pub_all + grp * F_TQ + quarter * 32;
-    const float* pub_other = pub_all + (grp ^ 1) * F_TQ + quarter * 32;
-    pub[lane] = -INFINITY;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float tau = qvalid ? -INFINITY : INFINITY;
-    float mid = -INFINITY;
-    for (int64_t t = grp; t < n_tiles; t += 2) {
-      const int a = (int)(t % F_ACC);
-      mbar_wait(bar_tfull + 8 * a, (uint32_t)((t / F_ACC) & 1));
+    float tau = qvalid ? -INFINITY : INFINITY;          // the row's 32nd best so far (its list's last entry)
+    const int dense_min = dbg_mode >= 10 ? dbg_mode - 10 : 6;
+    // (The loop is bound by the TMEM read rate -- every fp32 score has to come out of tensor memory once, ~94 B/clk
+    // per SM measured -- so prefetching the next half tile into a second register set bought nothing and spilled.)
+    for (int64_t h = 0; h < n_half; ++h) {
+      const int a = (int)(h % F_ACC);
+      mbar_wait(bar_tfull + 8 * a, (uint32_t)((h / F_ACC) & 1));
       tc_fence_after();
-      int64_t tile = t + t_start;
+      int64_t tile = (h >> 1) + t_start;
       if (tile >= n_tiles) tile -= n_tiles;
-      const int key0 = (int)(tile * F_BN);
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
+      const int key0 = (int)(tile * F_BN) + (int)(h & 1) * F_HN;
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = lane_base + (uint32_t)((a * 2 + blk) * F_HN);
       tmem_ld32(taddr, r0);
       tmem_ld32(taddr + 32, r1);
-      tmem_ld32(taddr + 64, r2);
-      tmem_ld32(taddr + 96, r3);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       // the accumulator is in registers: hand the TMEM stage back before looking at the scores
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * a);
-      const float m0 = max32(r0), m1 = max32(r1), m2 = max32(r2), m3 = max32(r3);
-      const float thr = fmaxf(tau, fminf(mid, pub_other[lane]));
-      const int dense_min = dbg_mode >= 10 ? dbg_mode - 10 : 6;
-      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr)) {
+      const float m0 = max32(r0), m1 = max32(r1);
+      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(m0, m1) > tau)) {
         if (cnt && lane == 0) atomicAdd(cnt + 2, 1ull);
-        if (__any_sync(FULL, m0 > thr)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
-        if (__any_sync(FULL, m1 > thr)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
-        if (__any_sync(FULL, m2 > thr)) slow_chunk(r2, scratch, key0 + 64, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
-        if (__any_sync(FULL, m3 > thr)) slow_chunk(r3, scratch, key0 + 96, self_i, (int)n_keys, wl, lane, thr, tau, mid, pub, cnt, dense_min);
+        if (__any_sync(FULL, m0 > tau)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, wl, lane, tau, cnt, dense_min);
+        if (__any_sync(FULL, m1 > tau)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, wl, lane, tau, cnt, dense_min);
       }
     }
-    // merge the two groups' lists: the 32 best of the union = elementwise max of A[j] and B[31 - j] (bitonic)
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (grp == 0) {
-      const uint2* la = lists + ((size_t)quarter * 32) * F_L;
-      const uint2* lb = lists + ((size_t)F_TQ + quarter * 32) * F_L;
-      for (int r = 0; r < 32; ++r) {
-        const int64_t orow = q0 + quarter * 32 + r;
-        const uint2 ea = la[lslot(r, lane)], eb = lb[lslot(r, F_L - 1 - lane)];
-        const float sa = __uint_as_float(ea.x), sb = __uint_as_float(eb.x);
-        const bool take_a = sa > sb || (sa == sb && (int)ea.y < (int)eb.y);
-        const float s = take_a ? sa : sb;
-        const int id = take_a ? (int)ea.y : (int)eb.y;
-        float mn = s;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
-        if (orow < n_q) {
-          out_idx[orow * F_L + lane] = id;
-          if (lane == 0) out_thr[orow] = mn * (1.f / (F_SCALE * F_SCALE));    // a_L, unscaled (-inf: list not full)
-        }
+    __syncwarp();
+    // the row's 32 candidates (sorted by approximate score) and a_L = the last one's score
+    for (int r = 0; r < 32; ++r) {
+      const int64_t orow = q0 + blk * 128 + quarter * 32 + r;
+      const uint2 e = wl[lslot(r, lane)];
+      if (orow < n_q) {
+        out_idx[orow * F_L + lane] = (int)e.y;
+        if (lane == F_L - 1) out_thr[orow] = __uint_as_float(e.x) * (1.f / (F_SCALE * F_SCALE));   // -inf: list not full
       }
     }
   }
@@ -542,7 +517,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 64, &dbg_cnt, true));
   CUtensorMap kmap;
   CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
-  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)2 * F_TQ * F_L * 8 + (size_t)8 * 32 * 32 * 4 + (size_t)2 * F_TQ * 4 + 512;
+  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_TQ * F_L * 8 + (size_t)8 * 32 * 32 * 4 + 512;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
   k_knn_scan_f16<<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(
