@@ -79,6 +79,7 @@ SIGNATURES = {
     "csc_pca_solve": (_I32, [_P, _P, _P, _I64, _I64, _I32, _F64, _I32, _PP, C.POINTER(_I32), C.POINTER(_F64)]),
     "csc_pca_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I32), _P, C.POINTER(_F64), _P, _P]),
     "csc_pca_transform": (_I32, [_P, _P, _P, _PP]),
+    "csc_pca_transform_sparse": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _P, _PP]),
     "csc_pca_free": (_I32, [_P]),
     "csc_knn": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _PP, _PP]),
     "csc_knn_last_fallback_rows": (_I32, [_P, C.POINTER(_I64)]),
@@ -338,6 +339,15 @@ class Context:
     def pca_transform(self, scaled, pca):
         h = C.c_void_p()
         self.check(self.lib.csc_pca_transform(self.h, scaled.h, pca.h, C.byref(h)))
+        return Dense(self, h)
+
+    def pca_transform_sparse(self, norm, features, partial, n_cells_total, pca, scale_max=10.0, do_scale=True,
+                             do_center=True):
+        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_pca_transform_sparse(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h,
+                                                     int(n_cells_total), float(scale_max), 1 if do_scale else 0,
+                                                     1 if do_center else 0, pca.h, C.byref(h)))
         return Dense(self, h)
 
     def knn(self, queries, keys, k, query_offset=0, dim_lo=0, dim_hi=None, metric=METRIC_COSINE):

@@ -177,9 +177,6 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     be.scale_stats_select(nstats, G, feats, part)
     comm.allreduce_sum(part)
     scaled = be.scale_fill(norm, feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
-    if not p.keep_norm:
-        norm.free()
-        norm = None
     # a4
     colsum = be.vec(H, np.float64)
     gram = be.vec(H * H, np.float64)
@@ -187,7 +184,14 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     comm.allreduce_sum(colsum)
     comm.allreduce_sum(gram)
     pca = be.pca_solve(colsum, gram, H, n_cells_total, p.n_pcs, p.pca_tol, p.pca_max_iter)
-    emb = be.pca_transform(scaled, pca)
+    # the embedding comes straight from the sparse normalised matrix (Z = S + 1 z0' is sparse-plus-rank-one)
+    if hasattr(be, "pca_transform_sparse"):
+        emb = be.pca_transform_sparse(norm, feats, part, n_cells_total, pca, p.scale_max, p.do_scale, p.do_center)
+    else:
+        emb = be.pca_transform(scaled, pca)
+    if not p.keep_norm:
+        norm.free()
+        norm = None
     # a5/a6
     keys = comm.allgather_rows(be, emb, offsets)
     idx, dist = be.knn(emb, keys, p.k, query_offset=cell_offset, metric=metric_code(p.metric))

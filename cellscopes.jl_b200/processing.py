@@ -45,6 +45,7 @@ class _Session:
         self.norm = None         # Sparse
         self.scaled = None       # Dense
         self.scaled_rows = None  # gene ids (original order) of the scaled matrix
+        self.scale_args = None   # (feature_idx, partial Vec, scale_max, do_scale, do_center) that define `scaled`
         self.pca = None
         self.emb = None
         self.knn = None
@@ -158,7 +159,7 @@ def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, 
     else:
         c.scale_stats_partial(norm_dev, feature_idx, part)
     dense = c.scale_fill(norm_dev, feature_idx, part, n_cells_total, scale_max, do_scale, do_center)
-    return dense, rows
+    return dense, rows, (feature_idx, part, scale_max, do_scale, do_center)
 
 
 def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_center: bool = True, ctx=None, **kwargs):
@@ -179,8 +180,8 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
         eff_max = kwargs.get("scale_max", 10.0)
         eff_scale = kwargs.get("do_scale", True)
         eff_center = kwargs.get("do_center", True)
-        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center, s.norm_stats)
-        s.scaled, s.scaled_rows = dense, rows
+        dense, rows, sargs = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center, s.norm_stats)
+        s.scaled, s.scaled_rows, s.scale_args = dense, rows, sargs
         lazy = LazyDeviceMatrix(dense, "dense_t", (rows.size, s.norm.shape[1]))
         x.scaleCount = ScaleCountObject(lazy, x.normCount.cell_name, [genes[i] for i in rows], do_scale, do_center,
                                         scale_max)
@@ -190,7 +191,7 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
     m = x.count_mtx if isinstance(x, NormCountObject) else x
     m = sp.csc_matrix(m) if not sp.issparse(m) else m.tocsc()
     dev = c.sparse_from_scipy(m)
-    dense, _ = _scale_device(c, dev, None, m.shape[1], scale_max, do_scale, do_center)
+    dense, _, _ = _scale_device(c, dev, None, m.shape[1], scale_max, do_scale, do_center)
     out = dense.download(np.float64).T
     if isinstance(x, NormCountObject):
         return ScaleCountObject(out, x.cell_name, x.gene_name, do_scale, do_center, scale_max)
@@ -200,13 +201,19 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
 # ---------------------------------------------------------------------------------------------
 # run_pca  (processing.jl:164-193)
 # ---------------------------------------------------------------------------------------------
-def _pca_device(c, dense, n_cells_total, maxoutdim, tol=1e-9, max_iter=500):
+def _pca_device(c, dense, n_cells_total, maxoutdim, tol=1e-9, max_iter=500, sparse_src=None):
+    """``sparse_src = (norm, (feature_idx, partial, scale_max, do_scale, do_center))``: the normalised device matrix and
+    the scale arguments that produced ``dense``; the embedding is then taken from the sparse matrix (far less work)."""
     h = dense.shape[1]
     colsum = c.vec(h, np.float64)
     gram = c.vec(h * h, np.float64)
     c.pca_partial(dense, colsum, gram)
     model = c.pca_solve(colsum, gram, h, n_cells_total, maxoutdim, tol, max_iter)
-    emb = c.pca_transform(dense, model)
+    if sparse_src is not None:
+        norm, (fidx, part, smax, dsc, dct) = sparse_src
+        emb = c.pca_transform_sparse(norm, fidx, part, n_cells_total, model, smax, dsc, dct)
+    else:
+        emb = c.pca_transform(dense, model)
     return model, emb
 
 
@@ -226,13 +233,16 @@ def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=Non
             s.norm_stats = None
         pos = {g: i for i, g in enumerate(sc_obj.normCount.gene_name)}
         fidx = np.array([pos[f] for f in features], dtype=np.int64)
-        dense, rows = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True, s.norm_stats)
+        dense, rows, sargs = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True, s.norm_stats)
+        sparse_src = (s.norm, sargs)
     elif s.scaled is not None:
         dense = s.scaled
+        sparse_src = (s.norm, s.scale_args) if (s.norm is not None and s.scale_args is not None) else None
     else:
+        sparse_src = None
         dense = s.ctx.dense_upload(np.ascontiguousarray(np.asarray(sc_obj.scaleCount.count_mtx).T))
     n = dense.shape[0]
-    model, emb = _pca_device(s.ctx, dense, n, maxoutdim)
+    model, emb = _pca_device(s.ctx, dense, n, maxoutdim, sparse_src=sparse_src)
     s.pca, s.emb = model, emb
     info = model.info()
     proj = emb.download(np.float64)                     # N x k Float64 (utils.jl:108-117, int_objects.jl:153)

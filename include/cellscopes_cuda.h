@@ -191,6 +191,12 @@ csc_status csc_pca_info(const csc_pca* p, int64_t* n_feat, int32_t* k, double* p
                         double* loadings /*[n_feat*k], column-major H x k*/, double* mean /*[n_feat]*/);
 /* embedding of the local cells: (Z - 1 m') U_k, dense fp32 [n_cells_local x k] */
 csc_status csc_pca_transform(csc_ctx* ctx, const csc_dense* scaled, const csc_pca* p, csc_dense** out);
+/* the same embedding straight from the normalised sparse matrix: the scaled matrix is sparse-plus-rank-one
+ * (z = s + 1 z0'), so (Z - 1 m')U = S U + 1 ((z0 - m)'U) costs ~nnz(selected rows) x k multiply-adds instead of
+ * N x H x k.  Arguments as csc_scale_fill (features/partial/scale parameters define Z) plus the model. */
+csc_status csc_pca_transform_sparse(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                                    const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
+                                    int32_t do_center, const csc_pca* p, csc_dense** out);
 csc_status csc_pca_free(csc_pca* p);
 
 /* ---- a5/a6: kNN inside run_clustering src/scrna/processing.jl:195-201, 263-266 ----------- */

@@ -300,6 +300,32 @@ def test_pca_on_pipeline_data(cs, oracle, ctx, medium_counts):
     print("pipeline-data PCA: max err", err.max(), "min gap", gaps.min(), "iters", model.iters)
 
 
+def test_sparse_transform_equals_dense_transform(cs, oracle, ctx, medium_counts):
+    """(Z - 1m')U taken from the sparse normalised matrix (Z = S + 1 z0') equals the dense product, also with a
+    component count that is not a multiple of 32 and with clipping active."""
+    raw = ctx.sparse_from_scipy(medium_counts)
+    g, n = medium_counts.shape
+    nst = ctx.vec(2 * g)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0, False, None, nst)
+    feats = np.arange(1, g, 2)
+    part = ctx.vec(2 * feats.size)
+    ctx.scale_stats_select(nst, g, feats, part)
+    for k, smax in ((20, 10.0), (50, 10.0), (33, 1.5)):
+        dense = ctx.scale_fill(norm, feats, part, n, smax)
+        colsum, gram = ctx.vec(feats.size), ctx.vec(feats.size ** 2)
+        ctx.pca_partial(dense, colsum, gram)
+        model = ctx.pca_solve(colsum, gram, feats.size, n, k)
+        a = ctx.pca_transform(dense, model).download(np.float64)
+        b = ctx.pca_transform_sparse(norm, feats, part, n, model, smax).download(np.float64)
+        scale = np.abs(a).max(axis=0)
+        assert np.all(np.abs(a - b).max(axis=0) <= 2e-5 * scale), (k, smax, np.abs(a - b).max(axis=0) / scale)
+        # and against the fp64 product of the downloaded matrix
+        z = dense.download(np.float64)
+        info = model.info()
+        want = (z - info["mean"]) @ info["loadings"]
+        assert np.all(np.abs(b - want).max(axis=0) <= 2e-5 * scale)
+
+
 def test_gram_partials_add_up(cs, ctx):
     """Sharding invariance: partials of two cell ranges sum to the partial of the whole (multi-GPU allreduce)."""
     rng = np.random.default_rng(5)
