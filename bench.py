@@ -46,6 +46,15 @@ WORKLOAD_DESC = {
 }
 
 
+def workload_config(name, world, graph):
+    """The `config` object of the JSON line: identical for the b200 arm and the reference arm."""
+    n_genes, n_cells, density, n_features, n_pcs, k = WORKLOADS[name]
+    return {"workload": WORKLOAD_DESC[name], "n_genes": n_genes, "n_cells": n_cells, "density": density,
+            "n_features": n_features, "n_pcs": n_pcs, "k": k, "graph": graph,
+            "parallelism": f"cells sharded over {world} GPU(s)",
+            "l2": "inputs larger than L2 (CSC shard >= 1 GB) and a 256 MiB flush between iterations"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -134,7 +143,7 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "cells/sec counts->PCA->kNN/SNN", "value": v, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "n_features": n_features, "n_pcs": n_pcs, "k": k},
+        "config": workload_config(args.workload, args.gpus, args.graph),
         "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample} cells of the workload, full path incl. exact LAPACK SVD and "
                                    f"exact brute-force kNN; restated reference algorithm (NumPy/SciPy/OpenBLAS), "
@@ -236,19 +245,38 @@ def main():
             "lambda_1": float(info["principalvars"][0]), "lambda_k": float(info["principalvars"][-1]),
             "min_rel_gap": float(np.min(-np.diff(info["principalvars"]) / info["principalvars"][:-1])),
             "nnz_local": int(nnz_local)}
-    del last, out
-
     # ---- roofline of the dominant kernel (kNN scan) -------------------------------------------
     peaks, peak_kind = measured_peaks()
     scan_ms = stage_ms["knn_scan"] / args.steps
     flops = 2.0 * (hi - lo) * n_cells * n_pcs
     achieved = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
-    # TF32 tensor rate is half the bf16 rate on this part; the kernel runs inside a long step -> sustained figure
-    peak_tf32 = 0.5 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    roofline = {"bound": "tensor", "kernel": "k_knn_scan", "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf32, "traffic": None, "peak_kind": f"{peak_kind} bf16 sustained / 2 (tf32)",
+    # the scan runs on tcgen05 kind::f16 (fp16 operands, fp32 accumulate): same rate as the measured bf16 GEMM; it
+    # runs inside a long step -> the sustained figure
+    peak_f16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"k_knn_scan_f16@{args.workload}x{world}")
+    roofline = {"bound": "tensor", "kernel": "k_knn_scan_f16", "achieved": achieved, "peak": peak_f16, "unit": "TFLOP/s",
+                "frac": achieved / peak_f16, "traffic": traffic,
+                "peak_kind": f"{peak_kind} bf16 sustained (kind::f16 rate)",
                 "ms_per_launch": scan_ms, "share_of_step": scan_ms / ms_per_step,
-                "candidates_per_s": (hi - lo) * n_cells / (scan_ms * 1e-3) if scan_ms > 0 else 0.0}
+                "candidates_per_s": (hi - lo) * n_cells / (scan_ms * 1e-3) if scan_ms > 0 else 0.0,
+                "note": "algorithmic flops 2*Nq*Nkeys*n_pcs (K padded 50->64 on the MMA); the kernel is bound by reading "
+                        "every fp32 score out of TMEM once (~100 B/clk/SM measured) and by the top-k list updates, not "
+                        "by the tensor pipe (ncu sm__pipe_tensor 7 %): see DESIGN.md"}
+    # the PCA Gram kernel against the TF32 tensor peak (half the bf16 rate)
+    tensor_stages = {}
+    gm = stage_ms.get("gram_mma", 0.0) / args.steps
+    if gm > 0:
+        H = int(last["pca"].info()["n_feat"])
+        gf = 2.0 * (hi - lo) * H * H
+        tensor_stages["k_gram_tc"] = {"algorithmic_TFLOP/s": gf / (gm * 1e-3) / 1e12, "ms": gm,
+                                      "issued_TFLOP/s_3xTF32_upper_tiles": 3 * 0.5625 * gf / (gm * 1e-3) / 1e12,
+                                      "tf32_peak": 0.5 * peak_f16,
+                                      "frac_issued": 3 * 0.5625 * gf / (gm * 1e-3) / 1e12 / (0.5 * peak_f16)}
+    del last, out
     # sparse stages against the HBM roofline (context for the dominant-kernel figure)
     hbm = {}
     per_step = {kk: v / args.steps for kk, v in stage_ms.items()}
@@ -276,14 +304,11 @@ def main():
             "metric": "cells/sec counts->PCA->kNN/SNN", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "n_genes": n_genes, "n_cells": n_cells,
-                       "density": density, "n_features": n_features, "n_pcs": n_pcs, "k": k, "graph": args.graph,
-                       "parallelism": f"cells sharded over {world} GPU(s)",
-                       "l2": "inputs larger than L2 (CSC shard >= 1 GB) and a 256 MiB flush between iterations"},
+            "config": workload_config(args.workload, world, args.graph),
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": {kk: round(v, 3) for kk, v in per_step.items() if v > 0}, "step_ms": [round(x, 2) for x in step_ms],
-            "hbm_stages": hbm, "diag": diag,
+            "hbm_stages": hbm, "tensor_stages": tensor_stages, "diag": diag,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -75,115 +75,87 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
   return fmax3(fmax3(a, b, c), m[9], m[10]);
 }
 
-// List entry j of the warp's row r lives at slot r*32 + ((j + r) & 31): one row is 32 consecutive slots for the
-// cooperative path (lane = entry), and the same entry of 32 different rows falls into 16 different banks for the
-// lane-parallel path (lane = row).
-__device__ __forceinline__ int lslot(int r, int j) { return r * 32 + ((j + r) & 31); }
+// Per-row candidate set: 32 (score, id) slots in shared memory, UNSORTED (the refine kernel orders by exact score
+// anyway), slot-major so that lane = row is bank-conflict free: sc[slot * 256 + row], id[slot * 256 + row].
+// The only thing the scan needs from a row's set is its minimum (the threshold tau) and where it sits.  The owner
+// thread keeps a two-level minimum in registers: the minimum and its slot of each group of 8 slots; a new candidate
+// overwrites the global minimum's slot and only that group's minimum is recomputed (8 LDS) -- ~35 instructions per
+// insertion, no warp-level operation, so the rows of a warp insert independently (dense phases) and a single row
+// costs the same (sparse phases).  Ties of the approximate score are irrelevant: a candidate enters only if it is
+// strictly better than tau, so everything outside the set is <= tau, which is all the proof needs.
+struct RowState {
+  float tau;        // min over the 32 slots
+  int slot;         // where that minimum sits
+  float gm[4];      // min of slots [8g, 8g+8)
+  int gs[4];        // its slot
+};
 
-// Dense phases (a block's own cluster, the first tiles): most rows of the warp have several candidates in the same
-// chunk, and inserting them one row at a time with the whole warp is 32x serial.  Here every lane inserts its own
-// row's candidates into its own list (binary search + shift), all rows in parallel, no warp-level operation.
-__device__ __noinline__ float insert_lane_parallel(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
-                                                    uint2* wl, int lane, float tau) {
-  int tid31 = (int)wl[lslot(lane, F_L - 1)].y;            // id of the current 32nd entry (ties: lower id ranks first)
-  bool dirty = false;
+__device__ __forceinline__ void row_insert(RowState& st, float* sc, int* ids, int row, float v, int id) {
+  const int s = st.slot;
+  sc[s * F_TQ + row] = v;
+  ids[s * F_TQ + row] = id;
+  const int g = s >> 3;
+  float m = sc[(g * 8) * F_TQ + row];
+  int ms = g * 8;
+#pragma unroll
+  for (int u = 1; u < 8; ++u) {
+    const float x = sc[(g * 8 + u) * F_TQ + row];
+    if (x < m) {
+      m = x;
+      ms = g * 8 + u;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q == g) {
+      st.gm[q] = m;
+      st.gs[q] = ms;
+    }
+  float t = st.gm[0];
+  int ts = st.gs[0];
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (st.gm[q] < t) {
+      t = st.gm[q];
+      ts = st.gs[q];
+    }
+  st.tau = t;
+  st.slot = ts;
+}
+
+// one 32-key chunk of the slow path: scores to the warp's scratch tile (the candidate loop needs them by a run-time
+// index), candidate mask, then every lane inserts its own row's candidates
+__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self_i, int n_keys,
+                                           float* sc, int* ids, int row, int lane, RowState& st, unsigned long long* cnt) {
+  unsigned cm = 0u;
+  const float tau0 = st.tau;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    scratch[i * 32 + lane] = __uint_as_float(r[i]);
+    cm |= (__uint_as_float(r[i]) > tau0 ? 1u : 0u) << i;
+  }
+  const long long t0 = cnt ? clock64() : 0;
+  int ncand = 0;
   while (cm) {
     const int j = __ffs(cm) - 1;
     cm &= cm - 1;
     const int id = key_base + j;
-    if (id == self_i || id >= n_keys) continue;
     const float v = scratch[j * 32 + lane];
-    if (!(v > tau || (v == tau && id < tid31))) continue;  // does not beat the row's last entry
-    // number of entries ranking before the candidate (they form a prefix): binary search over [0, 31]
-    int lo = 0, hi = F_L - 1;                              // the answer is in [lo, hi]; entry 31 is beaten for sure
-    while (lo < hi) {
-      const int m = (lo + hi) >> 1;
-      const uint2 e = wl[lslot(lane, m)];
-      const float es = __uint_as_float(e.x);
-      if (es > v || (es == v && (int)e.y < id)) lo = m + 1;
-      else hi = m;
-    }
-    for (int t = F_L - 1; t > lo; --t) wl[lslot(lane, t)] = wl[lslot(lane, t - 1)];
-    wl[lslot(lane, lo)] = make_uint2(__float_as_uint(v), (unsigned)id);
-    const uint2 last = wl[lslot(lane, F_L - 1)];
-    tau = __uint_as_float(last.x);
-    tid31 = (int)last.y;
-    dirty = true;
-  }
-  (void)dirty;
-  __syncwarp();
-  return tau;
-}
-
-// Candidates of one 32-key chunk -> the rows' lists.  Every lane has already written its 32 scores to the warp's
-// scratch tile (scratch[key * 32 + lane]) and built the bit mask `cm` of its scores above its threshold.
-// wl = this warp's 32 lists, [row][32] (score, id) sorted descending; lane j owns entry j of whichever row is
-// being updated, so an insertion is one LDS.64, a ballot, two shuffles and one STS.64 for the whole warp.
-// Kept out of line on purpose: inlined four times per tile the slow path outgrew the instruction cache and ran
-// ~10x slower than its instruction count (measured).
-__device__ __noinline__ float insert_candidates(unsigned cm, const float* scratch, int key_base, int self_i, int n_keys,
-                                                uint2* wl, int lane, float tau, unsigned long long* cnt) {
-  const unsigned FULL = 0xffffffffu;
-  unsigned rows = __ballot_sync(FULL, cm != 0u);
-  while (rows) {
-    const int src = __ffs(rows) - 1;
-    rows &= rows - 1;
-    unsigned mask = __shfl_sync(FULL, cm, src);
-    const int self_src = __shfl_sync(FULL, self_i, src);     // the key that is row src itself
-    uint2 e = wl[lslot(src, lane)];            // the row's list stays in registers while its candidates are inserted
-    float es = __uint_as_float(e.x);
-    int ei = (int)e.y;
-    bool dirty = false;
-    while (mask) {
-      const int j = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int id = key_base + j;
-      if (id == self_src || id >= n_keys) continue;
-      const float cv = scratch[j * 32 + src];
-      // entries that rank before the candidate form a prefix of the sorted list
-      const int pos = __popc(__ballot_sync(FULL, es > cv || (es == cv && ei < id)));
-      if (cnt && lane == 0) {
-        atomicAdd(cnt, 1ull);
-        if (pos < F_L) atomicAdd(cnt + 1, 1ull);
-      }
-      if (pos < F_L) {
-        const float ps = __shfl_up_sync(FULL, es, 1);
-        const int pi = __shfl_up_sync(FULL, ei, 1);
-        if (lane == pos) {
-          es = cv;
-          ei = id;
-        } else if (lane > pos) {
-          es = ps;
-          ei = pi;
-        }
-        dirty = true;
-      }
-    }
-    if (dirty) {
-      wl[lslot(src, lane)] = make_uint2(__float_as_uint(es), (unsigned)ei);
-      const float nt = __shfl_sync(FULL, es, F_L - 1);
-      if (lane == src) tau = nt;
+    if (v > st.tau && id != self_i && id < n_keys) {
+      row_insert(st, sc, ids, row, v, id);
+      ++ncand;
     }
   }
-  return tau;
-}
-
-// one chunk of the slow path: candidate mask, scores to the scratch tile, out-of-line insertion
-__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self_i, int n_keys,
-                                           uint2* wl, int lane, float& tau, unsigned long long* cnt, int dense_min) {
-  unsigned cm = 0u;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    scratch[i * 32 + lane] = __uint_as_float(r[i]);
-    cm |= (__uint_as_float(r[i]) > tau ? 1u : 0u) << i;
+  __syncwarp();
+  if (cnt) {
+    int tot = ncand;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) {
+      atomicAdd(cnt + 3, 1ull);
+      atomicAdd(cnt + 7, (unsigned long long)(clock64() - t0));
+      atomicAdd(cnt + 9, (unsigned long long)tot);
+    }
   }
-  __syncwarp();
-  // many rows with candidates: every lane works on its own row; few: the warp works on one row at a time
-  const bool dense = __popc(__ballot_sync(0xffffffffu, cm != 0u)) >= dense_min;
-  tau = dense ? insert_lane_parallel(cm, scratch, key_base, self_i, n_keys, wl, lane, tau)
-              : insert_candidates(cm, scratch, key_base, self_i, n_keys, wl, lane, tau, cnt);
-  if (cnt && lane == 0) atomicAdd(cnt + 3, 1ull);
-  __syncwarp();
 }
 
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -193,8 +165,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
-  uint2* lists = reinterpret_cast<uint2*>(sB + F_STAGES * F_TILE_BYTES);           // [256 rows][32]
-  float* scratch_all = reinterpret_cast<float*>(lists + F_TQ * F_L);               // [8 warps][32 keys][32 lanes]
+  float* l_sc = reinterpret_cast<float*>(sB + F_STAGES * F_TILE_BYTES);            // [32 slots][256 rows] scores
+  int* l_id = reinterpret_cast<int*>(l_sc + F_L * F_TQ);                           // [32 slots][256 rows] key ids
+  float* scratch_all = reinterpret_cast<float*>(l_id + F_L * F_TQ);                // [8 warps][32 keys][32 lanes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + 8 * 32 * 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
@@ -313,11 +286,19 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       tc_fence_before();
       mbar_arrive(bar_a);
     }
-    uint2* wl = lists + (size_t)(blk * 128 + quarter * 32) * F_L;       // this warp's 32 rows
-    for (int r = 0; r < 32; ++r) wl[lslot(r, lane)] = make_uint2(__float_as_uint(-INFINITY), (unsigned)INT_MAX);
+    RowState st;
+    for (int j = 0; j < F_L; ++j) {
+      l_sc[j * F_TQ + row] = -INFINITY;
+      l_id[j * F_TQ + row] = INT_MAX;
+    }
+    st.tau = qvalid ? -INFINITY : INFINITY;             // the row's 32nd best so far (the minimum of its set)
+    st.slot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      st.gm[q] = -INFINITY;
+      st.gs[q] = q * 8;
+    }
     __syncwarp();
-    float tau = qvalid ? -INFINITY : INFINITY;          // the row's 32nd best so far (its list's last entry)
-    const int dense_min = dbg_mode >= 10 ? dbg_mode - 10 : 6;
     // (The loop is bound by the TMEM read rate -- every fp32 score has to come out of tensor memory once, ~94 B/clk
     // per SM measured -- so prefetching the next half tile into a second register set bought nothing and spilled.)
     for (int64_t h = 0; h < n_half; ++h) {
@@ -336,21 +317,21 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * a);
       const float m0 = max32(r0), m1 = max32(r1);
-      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(m0, m1) > tau)) {
-        if (cnt && lane == 0) atomicAdd(cnt + 2, 1ull);
-        if (__any_sync(FULL, m0 > tau)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, wl, lane, tau, cnt, dense_min);
-        if (__any_sync(FULL, m1 > tau)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, wl, lane, tau, cnt, dense_min);
+      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(m0, m1) > st.tau)) {
+        const long long ts = cnt ? clock64() : 0;
+        if (__any_sync(FULL, m0 > st.tau)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, l_sc, l_id, row, lane, st, cnt);
+        if (__any_sync(FULL, m1 > st.tau)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, l_sc, l_id, row, lane, st, cnt);
+        if (cnt && lane == 0) {
+          atomicAdd(cnt + 2, 1ull);
+          atomicAdd(cnt + 4, (unsigned long long)(clock64() - ts));
+        }
       }
     }
     __syncwarp();
-    // the row's 32 candidates (sorted by approximate score) and a_L = the last one's score
-    for (int r = 0; r < 32; ++r) {
-      const int64_t orow = q0 + blk * 128 + quarter * 32 + r;
-      const uint2 e = wl[lslot(r, lane)];
-      if (orow < n_q) {
-        out_idx[orow * F_L + lane] = (int)e.y;
-        if (lane == F_L - 1) out_thr[orow] = __uint_as_float(e.x) * (1.f / (F_SCALE * F_SCALE));   // -inf: list not full
-      }
+    // the row's 32 candidates (unsorted) and a_L = the smallest approximate score among them
+    if (qvalid) {
+      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = l_id[j * F_TQ + row];
+      out_thr[qrow] = st.tau * (1.f / (F_SCALE * F_SCALE));    // -inf: fewer than 32 keys
     }
   }
   tc_fence_before();
@@ -514,7 +495,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &fb_rows));
   CSC_TRY(dev_alloc(ctx, 4, &fb_count, true));
   DevPtr dbg_cnt;
-  if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 64, &dbg_cnt, true));
+  if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 128, &dbg_cnt, true));
   CUtensorMap kmap;
   CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
   const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_TQ * F_L * 8 + (size_t)8 * 32 * 32 * 4 + 512;
@@ -536,10 +517,14 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->stage_ms[CSC_T_KNN_SCAN] += ms;
   if (n_fallback_out) *n_fallback_out = n_fb;
   if (dbg_cnt) {
-    unsigned long long h[4];
-    cudaMemcpy(h, dbg_cnt->p, 32, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[knn f16] attempts %llu accepted %llu slow-path tile entries %llu chunk entries %llu (warps x tiles = %lld)\n", h[0], h[1], h[2], h[3],
-            (long long)(ceil_div64(n_q, F_TQ) * 4 * ceil_div64(n_keys, F_BN)));
+    unsigned long long h[11];
+    cudaMemcpy(h, dbg_cnt->p, sizeof(h), cudaMemcpyDeviceToHost);
+    const double wt = (double)ceil_div64(n_q, F_TQ) * 8 * (double)(2 * ceil_div64(n_keys, F_BN));
+    fprintf(stderr, "[knn f16] warp x half-tiles %.3g; slow entries %llu (%.2f%%), cycles in slow path %.3g (%.0f per entry)\n", wt, h[2],
+            100.0 * h[2] / wt, (double)h[4], h[2] ? (double)h[4] / h[2] : 0.0);
+    fprintf(stderr, "[knn f16] dense chunks %llu: %.3g cycles (%.0f each), %.3g candidates (%.1f each); sparse chunks %llu: %.3g cycles (%.0f each), %.3g candidates; cooperative attempts %llu accepted %llu\n",
+            h[5], (double)h[7], h[5] ? (double)h[7] / h[5] : 0.0, (double)h[9], h[5] ? (double)h[9] / h[5] : 0.0, h[6], (double)h[8],
+            h[6] ? (double)h[8] / h[6] : 0.0, (double)h[10], h[0], h[1]);
   }
   if (n_fb > 0) {
     // the unproven rows go through the exact 3xTF32 scan
