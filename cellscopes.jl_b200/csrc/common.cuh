@@ -48,6 +48,7 @@ struct BlockCache {
   }
 };
 
+struct DevMem;
 struct csc_ctx {
   int device = 0;
   int sm_count = 0;
@@ -69,6 +70,7 @@ struct csc_ctx {
   // pinned bounce buffers for device->host copies into pageable memory (see d2h_copy)
   void* bounce[2] = {nullptr, nullptr};
   cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
+  std::shared_ptr<DevMem> gemm_ws;   // split-K partials of the fp64 GEMM (grow-only)
   int64_t knn_fallback_rows = 0;   // rows of the last csc_knn call that needed the exact re-scan
   int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
   double trace_t0 = 0.0;

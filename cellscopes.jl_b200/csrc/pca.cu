@@ -281,7 +281,8 @@ k_dgemm(const double* __restrict__ A, const double* __restrict__ B, double* C, i
 // (one barrier per K-step).  Needs even lda/ldb/ldc/K/N and 16-byte aligned bases; dgemm() checks.
 __global__ void __launch_bounds__(128)
 k_dgemm_nn(const double* __restrict__ A, const double* __restrict__ B, double* C, int M, int N, int K, int lda, int ldb,
-           int ldc, double alpha, double g1, const double* __restrict__ X1, double g2, const double* X2) {
+           int ldc, double alpha, double g1, const double* __restrict__ X1, double g2, const double* X2, int kchunk,
+           double* __restrict__ P) {
   __shared__ __align__(16) double As[2][16][32 + 2];   // [kk][m]
   __shared__ __align__(16) double Bs[2][16][64 + 2];   // [kk][n]
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -319,19 +320,24 @@ k_dgemm_nn(const double* __restrict__ A, const double* __restrict__ B, double* C
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  load_tiles(0);
+  // split-K: blockIdx.z owns K range [kbeg, K) with K clipped to its chunk; the raw partial goes to P[z]
+  const int kbeg = kchunk > 0 ? blockIdx.z * kchunk : 0;
+  if (kchunk > 0) K = min(K, kbeg + kchunk);
+  load_tiles(kbeg);
   store_tiles(0);
   __syncthreads();
   int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
     const bool more = k0 + 16 < K;
     if (more) load_tiles(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 4 + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 4 + 2]);
+      // a thread owns rows {2ty, 2ty+1, 16+2ty, 17+2ty} and columns {2tx, 2tx+1, 32+2tx, 33+2tx}: the 16 lanes of a
+      // half-warp then read 256 contiguous bytes per LDS.128 (the blocked 4-in-a-row ownership was a 5-way conflict)
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 2]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[buf][kk][16 + ty * 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[buf][kk][tx * 2]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[buf][kk][32 + tx * 2]);
       const double a[4] = {a01.x, a01.y, a23.x, a23.y};
       const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
@@ -347,12 +353,16 @@ k_dgemm_nn(const double* __restrict__ A, const double* __restrict__ B, double* C
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+    const int m = m0 + (i < 2 ? ty * 2 + i : 16 + ty * 2 + (i - 2));
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; j += 2) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + (j < 2 ? tx * 2 : 32 + tx * 2);
       if (n >= N) continue;
+      if (kchunk > 0) {
+        *reinterpret_cast<double2*>(P + ((int64_t)blockIdx.z * M + m) * N + n) = make_double2(acc[i][j], acc[i][j + 1]);
+        continue;
+      }
       const int64_t o = (int64_t)m * ldc + n;
       double2 v = make_double2(alpha * acc[i][j], alpha * acc[i][j + 1]);
       if (X1) {
@@ -370,6 +380,143 @@ k_dgemm_nn(const double* __restrict__ A, const double* __restrict__ B, double* C
   }
 }
 
+// The same product on the fp64 tensor cores (mma.sync m8n8k4): a warp owns a 32 x 32 block of C as 16 DMMA tiles and
+// needs one shared-memory load per operand fragment for 256 multiply-adds of the warp, eight times less shared-memory
+// traffic than the register-blocked CUDA-core kernel, which ncu showed waiting on shared memory (fp64 pipe 23 %).
+// CTA = 4 warps = 64 x 64 tile; K in steps of 16 through double-buffered shared memory; split-K over blockIdx.z
+// (kchunk > 0: raw partial to P[z]).  Same argument conventions and alignment requirements as k_dgemm_nn.
+__global__ void __launch_bounds__(128)
+k_dgemm_mma(const double* __restrict__ A, const double* __restrict__ B, double* C, int M, int N, int K, int lda, int ldb,
+            int ldc, double alpha, double g1, const double* __restrict__ X1, double g2, const double* X2, int kchunk,
+            double* __restrict__ P) {
+  constexpr int S = 72;                                 // B row stride (doubles): 72 mod 16 == 8 -> fragment loads at 2 wavefronts
+  constexpr int SA = 18;                                // A row stride: tile kept [m][k], stores and fragment loads conflict-free
+  __shared__ __align__(16) double As[2][64][SA];        // [m][kk]
+  __shared__ __align__(16) double Bs[2][16][S];         // [kk][n]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = kchunk > 0 ? blockIdx.z * kchunk : 0;
+  if (kchunk > 0) K = min(K, kbeg + kchunk);
+  double2 ra[4], rb[4];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                       // A: 64 rows x 16 k = 512 double2
+      const int idx = t + 128 * u, row = idx >> 3, kc = (idx & 7) * 2;
+      const int gm = m0 + row, gk = k0 + kc;
+      ra[u] = (gm < M && gk < K) ? __ldg(reinterpret_cast<const double2*>(A + (int64_t)gm * lda + gk)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                       // B: 16 k x 64 cols = 512 double2
+      const int idx = t + 128 * u, kk = idx >> 5, nc = (idx & 31) * 2;
+      const int gk = k0 + kk, gn = n0 + nc;
+      rb[u] = (gk < K && gn < N) ? *reinterpret_cast<const double2*>(B + (int64_t)gk * ldb + gn) : make_double2(0.0, 0.0);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + 128 * u, row = idx >> 3, kc = (idx & 7) * 2;
+      *reinterpret_cast<double2*>(&As[buf][row][kc]) = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + 128 * u, kk = idx >> 5, nc = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(&Bs[buf][kk][nc]) = rb[u];
+    }
+  };
+  double acc[4][4][2];                                  // [m-block][n-block][2 columns of the lane]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int fr = lane >> 2, fc = lane & 3;              // fragment coordinates of the lane
+  load_tiles(kbeg);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) load_tiles(k0 + 16);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[buf][wm + i * 8 + fr][ks * 4 + fc];     // A[m = fr][k = fc]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[buf][ks * 4 + fc][wn + j * 8 + fr];     // B[k = fc][n = fr]
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  // C fragment: lane holds C[row = fr][cols 2 fc, 2 fc + 1] of every 8 x 8 tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm + i * 8 + fr;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + wn + j * 8 + 2 * fc;
+      if (n >= N) continue;
+      if (kchunk > 0) {
+        *reinterpret_cast<double2*>(P + ((int64_t)blockIdx.z * M + m) * N + n) = make_double2(acc[i][j][0], acc[i][j][1]);
+        continue;
+      }
+      const int64_t o = (int64_t)m * ldc + n;
+      double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+      if (X1) {
+        const double2 x = *reinterpret_cast<const double2*>(X1 + o);
+        v.x = fma(g1, x.x, v.x);
+        v.y = fma(g1, x.y, v.y);
+      }
+      if (X2) {
+        const double2 x = *reinterpret_cast<const double2*>(X2 + o);
+        v.x = fma(g2, x.x, v.x);
+        v.y = fma(g2, x.y, v.y);
+      }
+      *reinterpret_cast<double2*>(C + o) = v;
+    }
+  }
+}
+
+// C = alpha * sum_z P[z] + g1 * X1 + g2 * X2 (the epilogue of a split-K k_dgemm_nn; fixed summation order)
+__global__ void __launch_bounds__(256)
+k_dgemm_combine(const double* __restrict__ P, int nz, double* C, int M, int N, int ldc, double alpha, double g1,
+                const double* __restrict__ X1, double g2, const double* X2) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= (int64_t)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  double2 s = make_double2(0.0, 0.0);
+  for (int z = 0; z < nz; ++z) {
+    const double2 p = *reinterpret_cast<const double2*>(P + (int64_t)z * M * N + i);
+    s.x += p.x;
+    s.y += p.y;
+  }
+  const int64_t o = (int64_t)m * ldc + n;
+  double2 v = make_double2(alpha * s.x, alpha * s.y);
+  if (X1) {
+    const double2 x = *reinterpret_cast<const double2*>(X1 + o);
+    v.x = fma(g1, x.x, v.x);
+    v.y = fma(g1, x.y, v.y);
+  }
+  if (X2) {
+    const double2 x = *reinterpret_cast<const double2*>(X2 + o);
+    v.x = fma(g2, x.x, v.x);
+    v.y = fma(g2, x.y, v.y);
+  }
+  *reinterpret_cast<double2*>(C + o) = v;
+}
+
 struct GemmEpi {
   double alpha = 1.0;
   double g1 = 0.0;
@@ -385,8 +532,26 @@ static csc_status dgemm(csc_ctx* ctx, bool ta, const double* A, const double* B,
   auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
   if (!ta && kchunk == 0 && !e.colscale && ((lda | ldb | ldc | K | N) & 1) == 0 && al16(A) && al16(B) && al16(C) &&
       al16(e.X1) && al16(e.X2)) {
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 31) / 32));
-    k_dgemm_nn<<<grid, 128, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2);
+    // 64 x 64 tiles on the fp64 tensor cores; a grid below two CTAs per SM leaves the pipes waiting on one warp per
+    // scheduler, so K is split over blockIdx.z and the partials are summed in a second small kernel (fixed order)
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+    const int n_cta = (int)(grid.x * grid.y);
+    int nsplit = K >= 512 ? std::min(8, (2 * ctx->sm_count) / std::max(1, n_cta)) : 1;
+    if (nsplit > 1) {
+      const int kc = ((K + nsplit - 1) / nsplit + 15) / 16 * 16;
+      nsplit = (K + kc - 1) / kc;
+      const size_t need = (size_t)nsplit * M * N * 8;
+      if (!ctx->gemm_ws || ctx->gemm_ws->bytes < need) CSC_TRY(dev_alloc(ctx, need, &ctx->gemm_ws));
+      grid.z = (unsigned)nsplit;
+      k_dgemm_mma<<<grid, 128, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2, kc,
+                                                 (double*)ctx->gemm_ws->p);
+      CSC_LAUNCHED(ctx);
+      k_dgemm_combine<<<(unsigned)(((int64_t)M * N / 2 + 255) / 256), 256, 0, ctx->stream>>>(
+          (const double*)ctx->gemm_ws->p, nsplit, C, M, N, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2);
+      CSC_LAUNCHED(ctx);
+      return CSC_OK;
+    }
+    k_dgemm_mma<<<grid, 128, 0, ctx->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, e.alpha, e.g1, e.X1, e.g2, e.X2, 0, nullptr);
     CSC_LAUNCHED(ctx);
     return CSC_OK;
   }
@@ -470,7 +635,7 @@ k_chol_inv(const double* __restrict__ S, int b, double* __restrict__ Rinv) {
   for (int j = 0; j < b; ++j) {
     const double d = A[j * ld + j];
     const bool ok = d > rel * d0[j] && d > 0.0;
-    const double invd = ok ? 1.0 / d : 0.0;
+    const double invd = ok ? __drcp_rn(d) : 0.0;      // every thread needs it: the short reciprocal, not a full division
     if (t == 0) rs[j] = ok ? rsqrt(d) : 0.0;
     for (int r = j + 1 + warp; r < b; r += nwarp) {
       const double f = A[j * ld + r] * invd;
@@ -487,7 +652,10 @@ k_chol_inv(const double* __restrict__ S, int b, double* __restrict__ Rinv) {
   // independent: no block barrier).  X' is stored in the unused lower triangle, X[l][c] at A[c][l]; the
   // diagonal of R is read from a copy.
   double* rd = d0 + b;
-  for (int i = t; i < b; i += nt) rd[i] = A[i * ld + i];
+  for (int i = t; i < b; i += nt) {
+    const double rii = A[i * ld + i];
+    rd[i] = rii != 0.0 ? 1.0 / rii : 0.0;      // reciprocal diagonal: the substitution below multiplies
+  }
   __syncthreads();
   {
     const int grp = t >> 3, gl = t & 7;
@@ -500,10 +668,7 @@ k_chol_inv(const double* __restrict__ S, int b, double* __restrict__ Rinv) {
         acc += __shfl_xor_sync(gmask, acc, 2);
         acc += __shfl_xor_sync(gmask, acc, 4);
         __syncwarp(gmask);
-        if (gl == 0) {
-          const double rii = rd[i];
-          A[c * ld + i] = rii != 0.0 ? ((i == c ? 1.0 : 0.0) - acc) / rii : 0.0;
-        }
+        if (gl == 0) A[c * ld + i] = ((i == c ? 1.0 : 0.0) - acc) * rd[i];
         __syncwarp(gmask);
       }
     }
