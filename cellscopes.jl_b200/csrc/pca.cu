@@ -1177,12 +1177,16 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
           th1 = std::max(th1, hst[b + j]);
           rmin = std::min(rmin, hst[b + j]);
         }
-        // the k-th largest Rayleigh quotient; every column at or above 95 % of it can carry weight in a wanted
-        // Ritz vector (that includes the partners of a near-degenerate k-th eigenvalue), so all of them must have
-        // stopped leaving the block
+        // the columns that can carry weight in a wanted Ritz vector: the k with the largest Rayleigh quotients plus at
+        // most 8 more (the partners of a near-degenerate k-th eigenvalue); all of them must have stopped leaving the
+        // block.  A relative window on the quotients instead would swallow the whole block on a flat spectrum
+        // (0.5 % dense VisiumHD-like counts: lambda_k = 1.03 over a bulk at 1.0) and never report convergence.
         std::vector<double> rq(hst.begin() + b, hst.begin() + 2 * b);
-        std::nth_element(rq.begin(), rq.begin() + (k - 1), rq.end(), std::greater<double>());
-        const double cut = 0.95 * rq[k - 1];
+        const int kk = std::min(b, k + 8);
+        std::nth_element(rq.begin(), rq.begin() + (kk - 1), rq.end(), std::greater<double>());
+        std::nth_element(rq.begin(), rq.begin() + (k - 1), rq.begin() + kk, std::greater<double>());
+        // ... and of those only the ones within 5 % of the k-th quotient: a clear gap after lambda_k ends the set there
+        const double cut = std::max(rq[kk - 1], 0.95 * rq[k - 1]);
         resid = 0.0;
         for (int j = 0; j < b; ++j)
           if (hst[b + j] >= cut) resid = std::max(resid, hst[j]);
