@@ -6,6 +6,7 @@
 #include <cmath>
 #include <limits>
 #include <numeric>
+#include <thread>
 
 #include "common.cuh"
 
@@ -102,67 +103,101 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
   const int64_t cutoff = (int64_t)std::ceil(cell * span * (double)n);
   // the points sorted by (x, index): the q nearest to a vertex are a window around it, so they come out of a
   // two-pointer walk in O(q) instead of a selection over all n points per vertex
+  std::vector<std::pair<double, int64_t>> px((size_t)n);
+  for (int64_t i = 0; i < n; ++i) px[i] = std::make_pair(x[i], i);
+  std::sort(px.begin(), px.end());                       // by (x, index) == a stable sort by x
   std::vector<int64_t> sidx((size_t)n);
-  std::iota(sidx.begin(), sidx.end(), (int64_t)0);
-  std::stable_sort(sidx.begin(), sidx.end(), [&](int64_t i, int64_t j) { return x[i] < x[j]; });
   std::vector<double> xs((size_t)n);
-  for (int64_t i = 0; i < n; ++i) xs[i] = x[sidx[i]];
+  for (int64_t i = 0; i < n; ++i) {
+    xs[i] = px[i].first;
+    sidx[i] = px[i].second;
+  }
   std::vector<double> verts;
   kd_vertices(xs, cutoff, verts);
   const size_t nv = verts.size();
   std::vector<double> val(nv), slope(nv);
-  std::vector<int64_t> order;
-  std::vector<double> d;
-  order.reserve((size_t)q + 64);
-  d.reserve((size_t)q + 64);
-  std::vector<double> a((size_t)q * 3), b((size_t)q);
   const double inf = std::numeric_limits<double>::infinity();
-  for (size_t vi = 0; vi < nv; ++vi) {
-    const double v = verts[vi];
-    // nearest first, ties by lower index: exactly the order of a stable sort of |x - v| (the oracle's argsort)
-    int64_t R = (int64_t)(std::lower_bound(xs.begin(), xs.end(), v) - xs.begin()), L = R - 1;
-    order.clear();
-    d.clear();
-    while (true) {
-      const double dl = L >= 0 ? std::fabs(xs[L] - v) : inf;
-      const double dr = R < n ? std::fabs(xs[R] - v) : inf;
-      const double dn = std::min(dl, dr);
-      if (dn == inf) break;
-      if ((int64_t)order.size() >= q && dn > d.back()) break;     // keep every tie of the q-th distance for now
-      if (dl <= dr) {
-        order.push_back(sidx[L--]);
-        d.push_back(dl);
-      } else {
-        order.push_back(sidx[R++]);
-        d.push_back(dr);
+  // the local fits are independent: a few host threads take the vertices round-robin (33 k genes give 33 fits over
+  // 10 k points each; one thread needs ~15 ms for them)
+  auto fit_range = [&](size_t v_begin, size_t v_step) {
+    std::vector<int64_t> order;
+    std::vector<double> d;
+    order.reserve((size_t)q + 64);
+    d.reserve((size_t)q + 64);
+    std::vector<double> a((size_t)q * 3), b((size_t)q);
+    for (size_t vi = v_begin; vi < nv; vi += v_step) {
+      const double v = verts[vi];
+      // nearest first, ties by lower index: exactly the order of a stable sort of |x - v| (the oracle's argsort)
+      int64_t R = (int64_t)(std::lower_bound(xs.begin(), xs.end(), v) - xs.begin()), L = R - 1;
+      order.clear();
+      d.clear();
+      while (true) {
+        const double dl = L >= 0 ? std::fabs(xs[L] - v) : inf;
+        const double dr = R < n ? std::fabs(xs[R] - v) : inf;
+        const double dn = std::min(dl, dr);
+        if (dn == inf) break;
+        if ((int64_t)order.size() >= q && dn > d.back()) break;     // keep every tie of the q-th distance for now
+        if (dl <= dr) {
+          order.push_back(sidx[L--]);
+          d.push_back(dl);
+        } else {
+          order.push_back(sidx[R++]);
+          d.push_back(dr);
+        }
       }
+      // equal distances: ascending index
+      for (size_t i0 = 0; i0 < order.size();) {
+        size_t i1 = i0 + 1;
+        while (i1 < order.size() && d[i1] == d[i0]) ++i1;
+        if (i1 - i0 > 1) std::sort(order.begin() + i0, order.begin() + i1);
+        i0 = i1;
+      }
+      double dmax = 0.0;
+      for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[i]);
+      if (dmax == 0.0) dmax = 1.0;
+      for (int64_t i = 0; i < q; ++i) {
+        const int64_t p = order[i];
+        const double u = d[i] / dmax;
+        const double u3 = u * u * u;
+        const double t = 1.0 - u3;
+        const double w = std::sqrt(t * t * t);
+        const double xc = x[p] - v;
+        a[i] = w;
+        a[(size_t)q + i] = w * xc;
+        a[(size_t)2 * q + i] = w * xc * xc;
+        b[i] = y[p] * w;
+      }
+      double coef[3];
+      pivoted_qr_solve3(a, b, q, coef);
+      val[vi] = coef[0];
+      slope[vi] = coef[1];
     }
-    // equal distances: ascending index
-    for (size_t i0 = 0; i0 < order.size();) {
-      size_t i1 = i0 + 1;
-      while (i1 < order.size() && d[i1] == d[i0]) ++i1;
-      if (i1 - i0 > 1) std::sort(order.begin() + i0, order.begin() + i1);
-      i0 = i1;
+  };
+  const size_t n_thr = (n >= 8000 && nv >= 8) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (n_thr <= 1) {
+    fit_range(0, 1);
+  } else {
+    // no exception may leave a thread (it would terminate the process): record it and rethrow after the join
+    std::vector<int> failed(n_thr, 0);
+    auto guarded = [&](size_t tix) {
+      try {
+        fit_range(tix, n_thr);
+      } catch (...) {
+        failed[tix] = 1;
+      }
+    };
+    std::vector<std::thread> pool;
+    size_t started = 1;
+    try {
+      for (; started < n_thr; ++started) pool.emplace_back(guarded, started);
+    } catch (...) {
+      // could not start every thread: the vertices of the missing ones are done here
     }
-    double dmax = 0.0;
-    for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[i]);
-    if (dmax == 0.0) dmax = 1.0;
-    for (int64_t i = 0; i < q; ++i) {
-      const int64_t p = order[i];
-      const double u = d[i] / dmax;
-      const double u3 = u * u * u;
-      const double t = 1.0 - u3;
-      const double w = std::sqrt(t * t * t);
-      const double xc = x[p] - v;
-      a[i] = w;
-      a[(size_t)q + i] = w * xc;
-      a[(size_t)2 * q + i] = w * xc * xc;
-      b[i] = y[p] * w;
-    }
-    double coef[3];
-    pivoted_qr_solve3(a, b, q, coef);
-    val[vi] = coef[0];
-    slope[vi] = coef[1];
+    guarded(0);
+    for (auto& th : pool) th.join();
+    for (size_t tix = started; tix < n_thr; ++tix) guarded(tix);
+    for (size_t tix = 0; tix < n_thr; ++tix)
+      if (failed[tix]) throw std::bad_alloc();
   }
   out.resize((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
@@ -229,10 +264,11 @@ csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, in
   if (var_exp) std::copy(ve.begin(), ve.end(), var_exp);
   if (var_std) std::copy(vs.begin(), vs.end(), var_std);
   if (order) {
-    std::vector<int64_t> ord((size_t)n_genes);
-    std::iota(ord.begin(), ord.end(), (int64_t)0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int64_t i, int64_t j) { return vs[i] > vs[j]; });
-    std::copy(ord.begin(), ord.end(), order);
+    // descending variance_standardized, ties by ascending gene index (= the stable sort of processing.jl:152)
+    std::vector<std::pair<double, int64_t>> pv((size_t)n_genes);
+    for (int64_t g = 0; g < n_genes; ++g) pv[g] = std::make_pair(-vs[g], g);
+    std::sort(pv.begin(), pv.end());
+    for (int64_t g = 0; g < n_genes; ++g) order[g] = pv[g].second;
   }
   (void)ctx;
   return CSC_OK;
