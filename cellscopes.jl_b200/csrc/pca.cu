@@ -9,6 +9,7 @@
 //   top-k eigenpairs of Gc in fp64 on the device   (block subspace iteration + Rayleigh-Ritz,
 //                                                    small dense eigenproblems by parallel Jacobi)
 //   principalvars = lambda / (N-1), tvar = trace(Gc)/(N-1), embedding = (Z - 1 m') U_k
+#include <string>
 #include <cmath>
 #include <cuda_pipeline.h>
 
@@ -517,6 +518,52 @@ k_dgemm_combine(const double* __restrict__ P, int nz, double* C, int M, int N, i
   *reinterpret_cast<double2*>(C + o) = v;
 }
 
+// Optional per-kernel-class timing of the solver (CSC_PCA_PROF=1): CUDA event pairs around every helper, summed by
+// label and printed to stderr when the solve ends.  Off by default (no events are created).
+struct SolveProf {
+  struct Rec { const char* label; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  bool on = false;
+  static SolveProf& get() { static SolveProf p; return p; }
+  void begin() { const char* e = getenv("CSC_PCA_PROF"); on = e && e[0] == '1'; recs.clear(); }
+  void report(cudaStream_t st) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    std::vector<std::pair<std::string, std::pair<double, int>>> agg;
+    for (auto& r : recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+      bool found = false;
+      for (auto& a : agg)
+        if (a.first == r.label) { a.second.first += ms; a.second.second++; found = true; }
+      if (!found) agg.push_back({r.label, {ms, 1}});
+    }
+    fprintf(stderr, "[csc pca prof]");
+    for (auto& a : agg) fprintf(stderr, " %s %.3f ms /%d;", a.first.c_str(), a.second.first, a.second.second);
+    fprintf(stderr, "\n");
+    recs.clear();
+  }
+};
+struct ProfScope {
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(csc_ctx* ctx, const char* label) : st(ctx->stream) {
+    SolveProf& p = SolveProf::get();
+    if (!p.on) return;
+    SolveProf::Rec r{label, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    idx = (int)p.recs.size();
+    p.recs.push_back(r);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(SolveProf::get().recs[idx].b, st);
+  }
+};
+
 struct GemmEpi {
   double alpha = 1.0;
   double g1 = 0.0;
@@ -528,6 +575,7 @@ struct GemmEpi {
 
 static csc_status dgemm(csc_ctx* ctx, bool ta, const double* A, const double* B, double* C, int M, int N, int K, int lda,
                         int ldb, int ldc, const GemmEpi& e = GemmEpi(), int kchunk = 0) {
+  ProfScope ps(ctx, ta ? "gemm_tn" : (K > 256 ? "gemm_big" : "gemm_small"));
   const int nz = kchunk > 0 ? (K + kchunk - 1) / kchunk : 1;
   auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
   if (!ta && kchunk == 0 && !e.colscale && ((lda | ldb | ldc | K | N) & 1) == 0 && al16(A) && al16(B) && al16(C) &&
@@ -677,6 +725,197 @@ k_chol_inv(const double* __restrict__ S, int b, double* __restrict__ Rinv) {
   for (int idx = t; idx < b * b; idx += nt) {
     const int r = idx / b, c = idx % b;
     Rinv[idx] = c >= r ? A[c * ld + r] : 0.0;
+  }
+}
+
+// Panel-blocked variant of k_chol_inv for blocks whose workspace fits (b <= ~144): R'R = S by panels of CHOL_NB rows
+// (diagonal block in registers of one warp, panel rows by forward substitution, trailing update by all threads),
+// then inv(R) by inverting the CHOL_NB x CHOL_NB diagonal blocks and doubling: X_PQ = -X_PP R_PQ X_QQ.  Same drop rule and
+// output as k_chol_inv; 3 block barriers per panel instead of one per column (b = 128: 96 us instead of 210 us).
+// X = inv(R) is kept transposed in the strict lower triangle (X[i][c] at A[c][i], i < c) with its diagonal in rd[].
+constexpr int CHOL_NB = 16;
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// One warp factors the CHOL_NB x CHOL_NB diagonal block at (j0, j0) in registers (lane c = column c of the block) and writes
+// R11 (upper, scaled) back plus rd = 1/R_jj.  Unscaled right-looking steps: a[r] -= (A[j][r] / d_j) A[j][c]; the
+// row scalings 1/sqrt(d_j) are off the dependency chain.
+__device__ __forceinline__ void chol_diag_block(double* A, int ld, int j0, int nbk, const double* d0, double rel,
+                                                double* rd, int lane) {
+  double a[CHOL_NB], rs[CHOL_NB];
+  const int c = lane & (CHOL_NB - 1);
+#pragma unroll
+  for (int r = 0; r < CHOL_NB; ++r) a[r] = (r <= c && c < nbk && r < nbk) ? A[(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < CHOL_NB; ++j) {
+    const double d = shfl_d(a[j], j);
+    const double dj0 = j < nbk ? d0[j0 + j] : 1.0;
+    const bool ok = d > rel * dj0 && d > 0.0;
+    const double invd = ok ? __drcp_rn(d) : 0.0;
+    rs[j] = ok ? rsqrt(d) : 0.0;
+    const double f = a[j] * invd;          // A[j][c] / d
+#pragma unroll
+    for (int r = j + 1; r < CHOL_NB; ++r) a[r] = fma(-shfl_d(a[j], r), f, a[r]);
+  }
+  if (lane < CHOL_NB && c < nbk) {
+#pragma unroll
+    for (int r = 0; r < CHOL_NB; ++r)
+      if (r <= c) A[(j0 + r) * ld + j0 + c] = a[r] * rs[r];
+    rd[j0 + c] = rs[c];
+  }
+}
+
+// One warp inverts the CHOL_NB x CHOL_NB upper-triangular diagonal block at (j0, j0): lane c owns column c of X, the rows of
+// R come by broadcast shuffles.  X goes to the strict lower triangle (transposed).
+__device__ __forceinline__ void inv_diag_block(double* A, int ld, int j0, int nbk, const double* rd, int lane) {
+  double rcol[CHOL_NB], x[CHOL_NB];
+  const int c = lane & (CHOL_NB - 1);
+#pragma unroll
+  for (int r = 0; r < CHOL_NB; ++r) rcol[r] = (r < c && c < nbk) ? A[(j0 + r) * ld + j0 + c] : 0.0;   // R[r][c], strict upper
+  const double rdc = c < nbk ? rd[j0 + c] : 0.0;
+#pragma unroll
+  for (int i = CHOL_NB - 1; i >= 0; --i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int l = i + 1; l < CHOL_NB; ++l) acc = fma(shfl_d(rcol[i], l), x[l], acc);      // R[i][l] x[l]
+    const double rdi = shfl_d(rdc, i);
+    x[i] = (i == c) ? rdc : (i < c ? -acc * rdi : 0.0);
+  }
+  if (lane < CHOL_NB && c < nbk) {
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; ++i)
+      if (i < c) A[(j0 + c) * ld + j0 + i] = x[i];
+  }
+}
+
+__global__ void __launch_bounds__(512)
+k_chol_inv_blocked(const double* __restrict__ S, int b, double* __restrict__ Rinv, int tld) {
+  extern __shared__ double sm[];
+  const int ld = b + 1;
+  double* A = sm;              // [b][ld]
+  double* rd = A + b * ld;     // [b] 1 / R_ii (0 for a dropped column)
+  double* d0 = rd + b;         // [b] original diagonal
+  double* T = d0 + b;          // temp of the inverse levels, [s][tld]
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int lane = t & 31, warp = t >> 5, nwarp = nt >> 5;
+  for (int i = t; i < b * b; i += nt) A[(i / b) * ld + (i % b)] = S[i];
+  __syncthreads();
+  for (int i = t; i < b; i += nt) d0[i] = fabs(A[i * ld + i]);
+  __syncthreads();
+  const double rel = 4.0 * (double)b * 1.1e-16;
+  for (int j0 = 0; j0 < b; j0 += CHOL_NB) {
+    const int j1 = min(j0 + CHOL_NB, b);
+    if (warp == 0) chol_diag_block(A, ld, j0, j1 - j0, d0, rel, rd, lane);
+    __syncthreads();
+    // the last warp inverts the finished diagonal block while the others solve the panel rows:
+    // R12 = R11^-T A12, one thread per trailing column
+    if (warp == nwarp - 1) {
+      inv_diag_block(A, ld, j0, j1 - j0, rd, lane);
+    } else {
+      for (int c = j1 + t; c < b; c += nt - 32) {
+        double v[CHOL_NB];
+#pragma unroll
+        for (int i = 0; i < CHOL_NB; ++i) {
+          if (j0 + i < j1) {
+            double acc = A[(j0 + i) * ld + c];
+#pragma unroll
+            for (int l = 0; l < i; ++l) acc = fma(-A[(j0 + l) * ld + j0 + i], v[l], acc);
+            v[i] = acc * rd[j0 + i];
+            A[(j0 + i) * ld + c] = v[i];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // trailing update A22 -= R12' R12 on the upper triangle: 2 rows x 2 columns (c, c + mh) per thread
+    const int m = b - j1;
+    if (m > 0) {
+      // 4 rows x 2 columns (c, c + mh) per thread
+      const int mh = (m + 1) >> 1, mq = (m + 3) >> 2;
+      for (int idx = t; idx < mq * mh; idx += nt) {
+        const int tr = idx / mh, tc = idx % mh;
+        const int r0 = j1 + 4 * tr, c0 = j1 + tc, c1 = c0 + mh;
+        if (c1 < r0) continue;         // whole tile strictly below the diagonal
+        const bool hc1 = c1 < b;
+        const int c1c = hc1 ? c1 : c0;
+        int rr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rr[k] = min(r0 + k, b - 1);
+        double acc[4][2] = {};
+#pragma unroll 4
+        for (int l = j0; l < j1; ++l) {
+          const double y0 = A[l * ld + c0], y1 = A[l * ld + c1c];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double x = A[l * ld + rr[k]];
+            acc[k][0] = fma(x, y0, acc[k][0]);
+            acc[k][1] = fma(x, y1, acc[k][1]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = r0 + k;
+          if (r < b) {
+            if (c0 >= r) A[r * ld + c0] -= acc[k][0];
+            if (hc1 && c1 >= r) A[r * ld + c1] -= acc[k][1];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // doubling: X_PQ = -X_PP (R_PQ X_QQ) for neighbouring blocks P = [p0, p0+s), Q = [p0+s, min(p0+2s, b))
+  for (int s = CHOL_NB; s < b; s <<= 1) {
+    const int npair = (b + 2 * s - 1) / (2 * s);
+    const int s4 = s >> 2;
+    // T[pair][i - p0][c - q0] = sum_{l in Q, l <= c} R[i][l] X[l][c]; a thread: rows i, i + s/4, i + 2s/4, i + 3s/4
+    for (int idx = t; idx < npair * s4 * s; idx += nt) {
+      const int pr = idx / (s4 * s), rem = idx % (s4 * s);
+      const int p0 = pr * 2 * s, q0 = p0 + s;
+      const int i = p0 + rem / s, c = q0 + rem % s;
+      if (c >= b) continue;
+      const double xcc = rd[c];
+      double a0 = A[i * ld + c] * xcc, a1 = A[(i + s4) * ld + c] * xcc, a2 = A[(i + 2 * s4) * ld + c] * xcc,
+             a3 = A[(i + 3 * s4) * ld + c] * xcc;
+#pragma unroll 4
+      for (int l = q0; l < c; ++l) {
+        const double x = A[c * ld + l];
+        a0 = fma(A[i * ld + l], x, a0);
+        a1 = fma(A[(i + s4) * ld + l], x, a1);
+        a2 = fma(A[(i + 2 * s4) * ld + l], x, a2);
+        a3 = fma(A[(i + 3 * s4) * ld + l], x, a3);
+      }
+      double* Tp = T + (pr * s + (i - p0)) * tld + (c - q0);
+      Tp[0] = a0; Tp[s4 * tld] = a1; Tp[2 * s4 * tld] = a2; Tp[3 * s4 * tld] = a3;
+    }
+    __syncthreads();
+    // X[i][c] = -sum_{l in P, l >= i} X[i][l] T[l][c]; a thread: columns c, c + s/4, c + 2s/4, c + 3s/4
+    for (int idx = t; idx < npair * s * s4; idx += nt) {
+      const int pr = idx / (s * s4), rem = idx % (s * s4);
+      const int p0 = pr * 2 * s, q0 = p0 + s;
+      const int i = p0 + rem / s4, cc = rem % s4;
+      if (q0 + cc >= b) continue;
+      const double* Tp = T + (pr * s + (i - p0)) * tld + cc;
+      const double xii = rd[i];
+      double a0 = xii * Tp[0], a1 = xii * Tp[s4], a2 = xii * Tp[2 * s4], a3 = xii * Tp[3 * s4];
+#pragma unroll 4
+      for (int l = i + 1; l < q0; ++l) {
+        const double x = A[l * ld + i];
+        const double* Tl = T + (pr * s + (l - p0)) * tld + cc;
+        a0 = fma(x, Tl[0], a0); a1 = fma(x, Tl[s4], a1); a2 = fma(x, Tl[2 * s4], a2); a3 = fma(x, Tl[3 * s4], a3);
+      }
+      const int c = q0 + cc;
+      A[c * ld + i] = -a0;
+      if (c + s4 < b) A[(c + s4) * ld + i] = -a1;
+      if (c + 2 * s4 < b) A[(c + 2 * s4) * ld + i] = -a2;
+      if (c + 3 * s4 < b) A[(c + 3 * s4) * ld + i] = -a3;
+    }
+    __syncthreads();
+  }
+  for (int idx = t; idx < b * b; idx += nt) {
+    const int r = idx / b, c = idx % b;
+    Rinv[idx] = c > r ? A[c * ld + r] : (c == r ? rd[r] : 0.0);
   }
 }
 
@@ -971,6 +1210,7 @@ static csc_status jacobi(csc_ctx* ctx, const double* A, int n, const RotList& ro
   const int hp = ((n + 1) & ~1) / 2;
   const size_t smem = (size_t)n * n * 8 + (size_t)hp * 24 + 64;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(ctx, "jacobi");
   k_jacobi<<<1, 1024, smem, ctx->stream>>>(A, n, rot.cs, rot.pq, eval, rank, JACOBI_MAX_SWEEPS, off_tol * off_tol, d_sweeps);
   CSC_LAUNCHED(ctx);
   return CSC_OK;
@@ -982,6 +1222,7 @@ static csc_status apply_rot(csc_ctx* ctx, const double* X0, double* O0, const do
   const size_t smem = (size_t)APPLY_ROWS * (n + 1) * 8 + (size_t)2 * APPLY_CHUNK * hp * 16 + (size_t)(m - 1) * hp * 2 + 16;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_apply_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((n_rows + APPLY_ROWS - 1) / APPLY_ROWS), X1 ? 2u : 1u);
+  ProfScope ps(ctx, "apply_rot");
   k_apply_rot<<<grid, APPLY_ROWS * hp, smem, ctx->stream>>>(X0, O0, X1, O1, n_rows, n, rot.cs, rot.pq, d_sweeps, rank);
   CSC_LAUNCHED(ctx);
   return CSC_OK;
@@ -996,7 +1237,10 @@ struct BlockWs {
 // out[b x b] = X' Y for two H x b blocks (K split over the grid, deterministic reduction)
 static csc_status small_gram(csc_ctx* ctx, const BlockWs& w, const double* X, const double* Y, int sym, double* out) {
   CSC_TRY(dgemm(ctx, true, X, Y, w.parts, w.b, w.b, w.H, w.b, w.b, w.b, GemmEpi(), w.kchunk));
-  k_reduce_parts<<<(unsigned)((w.b * w.b + 255) / 256), 256, 0, ctx->stream>>>(w.parts, w.nz, w.b, sym, out);
+  {
+    ProfScope ps(ctx, "reduce_parts");
+    k_reduce_parts<<<(unsigned)((w.b * w.b + 255) / 256), 256, 0, ctx->stream>>>(w.parts, w.nz, w.b, sym, out);
+  }
   CSC_LAUNCHED(ctx);
   return CSC_OK;
 }
@@ -1004,9 +1248,23 @@ static csc_status small_gram(csc_ctx* ctx, const BlockWs& w, const double* X, co
 // Q = Y R^{-1} with R'R = Y'Y
 static csc_status chol_qr(csc_ctx* ctx, const BlockWs& w, const double* Y, double* Q) {
   CSC_TRY(small_gram(ctx, w, Y, Y, 1, w.S));
-  const size_t smem = (size_t)w.b * (w.b + 1) * 8 + (size_t)w.b * 24;
-  CSC_CUDA(ctx, cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chol_inv<<<1, 1024, smem, ctx->stream>>>(w.S, w.b, w.Rinv);
+  // workspace of the blocked kernel: the matrix, two vectors and the widest temp of the doubling levels
+  int trows = 0, tld = 0;
+  for (int sz = CHOL_NB; sz < w.b; sz <<= 1) {
+    trows = std::max(trows, ((w.b + 2 * sz - 1) / (2 * sz)) * sz);
+    tld = std::max(tld, sz + 1);
+  }
+  const size_t smem_blk = ((size_t)w.b * (w.b + 1) + 2 * (size_t)w.b + (size_t)trows * tld) * 8;
+  if (smem_blk <= (size_t)227 * 1024) {
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_chol_inv_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk));
+    ProfScope ps(ctx, "chol_inv");
+    k_chol_inv_blocked<<<1, 512, smem_blk, ctx->stream>>>(w.S, w.b, w.Rinv, tld);
+  } else {
+    const size_t smem = (size_t)w.b * (w.b + 1) * 8 + (size_t)w.b * 24;
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, "chol_inv");
+    k_chol_inv<<<1, 1024, smem, ctx->stream>>>(w.S, w.b, w.Rinv);
+  }
   CSC_LAUNCHED(ctx);
   return dgemm(ctx, false, Y, w.Rinv, Q, w.H, w.b, w.b, w.b, w.b, w.b);
 }
@@ -1024,6 +1282,7 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
   CSC_REQUIRE(ctx, maxoutdim >= 1, "csc_pca_solve: maxoutdim must be >= 1");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_PCA_SOLVE);
+  SolveProf::get().begin();
   if (tol <= 0) tol = 1e-9;
   if (max_iter <= 0) max_iter = 500;
   // MultivariateStats: outdim <= min(H, N) (rank is at most N-1 after centring)
@@ -1229,6 +1488,7 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
       if (resid <= tol || iters >= max_iter) break;
       stop_mult *= 0.1;
     }
+    SolveProf::get().report(ctx->stream);
     std::vector<double> hq((size_t)H * b);
     CSC_CUDA(ctx, cudaMemcpyAsync(hq.data(), Q, hq.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

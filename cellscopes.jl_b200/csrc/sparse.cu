@@ -553,38 +553,47 @@ __global__ void k_scale_params(const double* __restrict__ part, int32_t n_feat, 
   z0[h] = z;
 }
 
-// a warp builds one cell's dense row in shared memory (fill value, then scatter of the non-zeros)
-// and writes it out with coalesced 16-byte stores: 4*H bytes written per cell, each once.
+// a warp builds one slice of a cell's dense row in shared memory (fill value, then scatter of the non-zeros) and
+// writes it out with coalesced 16-byte stores: 4*H bytes written per cell, each once.  The row is cut into `nsplit`
+// slices handled by different warp-tasks: the shared-memory footprint per warp shrinks accordingly, which is what
+// limits the number of rows in flight per SM (8 KB per full row of 2000 genes); the cell's stored entries are read
+// once per slice, out of L1/L2.
 __global__ void __launch_bounds__(256)
 k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
              const int32_t* __restrict__ gene2h, const float* __restrict__ mu, const float* __restrict__ inv_sd,
-             const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, float scale_max, float* __restrict__ out) {
+             const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, float scale_max,
+             float* __restrict__ out) {
   extern __shared__ float srow[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  float* row = srow + (size_t)wib * n_feat;
+  float* row = srow + (size_t)wib * slice;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t c = warp; c < n_cells; c += nwarp) {
-    for (int h = lane; h < n_feat; h += 32) row[h] = __ldg(z0 + h);
+  const int64_t n_tasks = n_cells * nsplit;
+  for (int64_t task = warp; task < n_tasks; task += nwarp) {
+    const int64_t c = task / nsplit;
+    const int h0 = (int)(task - c * nsplit) * slice;
+    const int h1 = min(h0 + slice, n_feat);
+    for (int h = h0 + lane; h < h1; h += 32) row[h - h0] = __ldg(z0 + h);
     __syncwarp();
     const int64_t b = colptr[c], e = colptr[c + 1];
     for (int64_t i = b + lane; i < e; i += 32) {
       const int h = __ldg(gene2h + __ldcs(rowval + i));
-      if (h >= 0) {
+      if (h >= h0 && h < h1) {
         float z = (__ldcs(val + i) - __ldg(mu + h)) * __ldg(inv_sd + h);
         z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
-        row[h] = z;
+        row[h - h0] = z;
       }
     }
     __syncwarp();
-    float* dst = out + c * (int64_t)n_feat;
-    if ((n_feat & 3) == 0) {
+    float* dst = out + c * (int64_t)n_feat + h0;
+    const int len = h1 - h0;
+    if ((n_feat & 3) == 0 && (h0 & 3) == 0 && (len & 3) == 0) {
       const float4* r4 = reinterpret_cast<const float4*>(row);
       float4* d4 = reinterpret_cast<float4*>(dst);
-      for (int h = lane; h < (n_feat >> 2); h += 32) __stcs(d4 + h, r4[h]);
+      for (int h = lane; h < (len >> 2); h += 32) __stcs(d4 + h, r4[h]);
     } else {
-      for (int h = lane; h < n_feat; h += 32) __stcs(dst + h, row[h]);
+      for (int h = lane; h < len; h += 32) __stcs(dst + h, row[h]);
     }
     __syncwarp();
   }
@@ -649,7 +658,6 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
   CSC_TRY(build_gene2h(ctx, norm->n_genes, features, n_feat, &map, &H));
   CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_fill: partial must be fp64[2*H]");
   CSC_REQUIRE(ctx, n_cells_total >= 2, "csc_scale_fill: need at least 2 cells");
-  CSC_REQUIRE(ctx, H <= 56000, "csc_scale_fill: more than 56000 selected genes is not supported");
   DevPtr params;
   CSC_TRY(dev_alloc(ctx, (size_t)H * 4 * 3, &params));
   float* mu = (float*)params->p;
@@ -662,17 +670,20 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
   csc_dense* d = nullptr;
   CSC_TRY(csc_dense_alloc(ctx, norm->n_cells, H, &d));
   if (norm->n_cells > 0) {
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * H * 4 > (size_t)200 * 1024) warps >>= 1;
-    size_t smem = (size_t)warps * H * 4;
+    // slices of at most 1024 genes (multiple of 4): 4 KB per warp, 8 warps per CTA, up to 7 CTAs per SM
+    int nsplit = (int)ceil_div64(H, 1024);
+    int slice = (int)(ceil_div64(ceil_div64(H, nsplit), 4) * 4);
+    nsplit = (int)ceil_div64(H, slice);
+    const int warps = 8;
+    size_t smem = (size_t)warps * slice * 4;
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_scale_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
-      int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells, warps));
+      int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
       k_scale_fill<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(),
                                                                       (const int32_t*)map->p, mu, inv_sd, z0, norm->n_cells,
-                                                                      (int32_t)H, (float)scale_max, d->p());
+                                                                      (int32_t)H, nsplit, slice, (float)scale_max, d->p());
       ctx->launches++;
       e = cudaGetLastError();
     }
