@@ -173,7 +173,7 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
       slope[vi] = coef[1];
     }
   };
-  const size_t n_thr = (n >= 8000 && nv >= 8) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  const size_t n_thr = (n >= 2000 && nv >= 8) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
   if (n_thr <= 1) {
     fit_range(0, 1);
   } else {

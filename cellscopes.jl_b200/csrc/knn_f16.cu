@@ -12,15 +12,20 @@
 //   Rows that fail the test (near-duplicate neighbourhoods, k close to L) are gathered and re-run through the
 //   exact 3xTF32 scan (knn_tc.cu), so the result is always the exact one, ties by lower id included.
 //
-// Kernel layout (320 threads, 1 CTA per SM, one CTA = 256 query rows = two 128-row blocks against ALL keys; the two
+// Kernel layout (576 threads, 1 CTA per SM, one CTA = 256 query rows = two 128-row blocks against ALL keys; the two
 // blocks share every key tile, which halves the L2 traffic per score -- the scan is L2-bandwidth bound otherwise):
-//   warp 0      TMA producer: key tiles [128 keys x 64 halves] (one 128-byte swizzle row per key), 6-stage ring
+//   warp 0      TMA producer: key tiles [128 keys x 64 halves] (one 128-byte swizzle row per key), 3-stage ring
 //   warp 1      TMEM allocator + MMA issuer: A (queries, both blocks) lives in TMEM (2 x 32 columns of packed halves),
 //               D = 3 accumulator stages x 2 blocks x 64 columns; the unit of work is a half tile of 64 keys
-//   warps 2-5   epilogue of block 0, warps 6-9 epilogue of block 1: thread = query row (TMEM lane); per half tile
-//               2 x tcgen05.ld.x32, a FMNMX3 tree, one compare against the row's threshold; survivors go into the row's
-//               sorted list in shared memory (warp-cooperative insertion when few rows have candidates, one lane per
-//               row when many do).
+//   warps 2-17  epilogue, 16 warps = 2 blocks x 2 column parts x 4 TMEM lane quarters: thread = (query row, part);
+//               per half tile of 64 keys part p reads columns [32p, 32p+32) with ONE tcgen05.ld.x32, runs a FMNMX3 tree
+//               and one compare against its threshold; survivors go into the thread's own 16-slot candidate set in
+//               shared memory.  A warp gets ~43 B/clk out of TMEM however many loads it has in flight (x32 = 96 cycles;
+//               tools/micro/tmem_ld_bench.cu: 4 warps 171, 8 warps 310, 16 warps 420 B/clk/SM), and it cannot look at
+//               scores while it waits for them, so the rate at which a CTA drains its accumulators is set by the
+//               number of epilogue warps per scheduler: 4 per scheduler instead of 2 halves the time per half tile.
+//               The two parts of a row keep separate sets (no communication in the loop); everything outside both is
+//               <= max(tau_0, tau_1), which is the bound the proof uses.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -39,15 +44,16 @@ csc_status knn_scan_tc(csc_ctx* ctx, const float* q_prep, int64_t n_q, const flo
 namespace {
 
 constexpr int F_TQ = 256;                 // query rows per CTA: two blocks of UMMA M = 128
-constexpr int F_BN = 128;                 // keys per shared-memory tile
-constexpr int F_HN = 64;                  // keys per MMA / accumulator stage (half a tile) = UMMA N
+constexpr int F_BN = 128;                 // keys per shared-memory tile = UMMA N: one MMA unit is (key tile, block)
 constexpr int F_DP = 64;                  // padded feature dimension (halves): one 128-byte swizzle row
-constexpr int F_STAGES = 6;
-constexpr int F_ACC = 3;                  // TMEM accumulator stages
+constexpr int F_STAGES = 6;               // key tile ring (the MMA loop is unrolled over one turn of it)
+constexpr int F_ACC = 3;                  // TMEM accumulators of 128 columns, used round-robin by the units
 constexpr int F_TILE_BYTES = F_BN * 128;  // 16 KB
-constexpr int F_THREADS = 64 + 256;
+constexpr int F_PAIRS = 8;                // (block, TMEM lane quarter): 32 query rows each
+constexpr int F_THREADS = 64 + 2 * F_PAIRS * 32;   // producer, MMA issuer, 8 drain warps, 8 insert warps
 constexpr int F_L = 32;                   // candidates kept per row
-constexpr int F_TMEM_A = F_ACC * 2 * F_HN; // first column of the query operands (2 blocks x 32 columns)
+constexpr int F_QS = 3;                   // parked chunks per pair (slots of 32 keys x 32 rows x 4 bytes)
+constexpr int F_TMEM_A = F_ACC * F_BN;    // first column of the query operands (2 blocks x 32 columns)
 constexpr float F_SCALE = 256.f;          // operands are scaled so that small components stay normal in fp16
 constexpr float F_EPS = 1.0e-3f;          // bound on |approx - exact| for unit rows (see the header)
 
@@ -75,111 +81,89 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
   return fmax3(fmax3(a, b, c), m[9], m[10]);
 }
 
-// Per-row candidate set: 32 (score, id) slots in shared memory, UNSORTED (the refine kernel orders by exact score
-// anyway), slot-major so that lane = row is bank-conflict free: sc[slot * 256 + row], id[slot * 256 + row].
-// The only thing the scan needs from a row's set is its minimum (the threshold tau) and where it sits.  The owner
-// thread keeps a two-level minimum in registers: the minimum and its slot of each group of 8 slots; a new candidate
-// overwrites the global minimum's slot and only that group's minimum is recomputed (8 LDS) -- ~35 instructions per
-// insertion, no warp-level operation, so the rows of a warp insert independently (dense phases) and a single row
-// costs the same (sparse phases).  Ties of the approximate score are irrelevant: a candidate enters only if it is
-// strictly better than tau, so everything outside the set is <= tau, which is all the proof needs.
-struct RowState {
-  float tau;        // min over the 32 slots
-  int slot;         // where that minimum sits
-  float gm[4];      // min of slots [8g, 8g+8)
-  int gs[4];        // its slot
-};
+// Candidate sets.  A pair of warps serves 32 query rows, thread = row in both.  The DRAIN warp empties the accumulators
+// and only asks "does any row of mine have a score above its threshold in these 32 keys?"; if so it PARKS the 32 x 32
+// chunk in the pair's queue in shared memory (8 x STS.128 per lane plus each row's mask of candidate columns) and returns
+// to the accumulator stream at once.  The INSERT warp works the queue off concurrently and owns the sets: F_L = 32
+// (score, key id) slots per row in REGISTERS of the row's thread, unsorted (the refine kernel orders by exact score
+// anyway).  Each score carries its slot number in the 5 low mantissa bits, so the set's minimum -- the threshold tau --
+// and the slot it sits in come out of one FMNMX3 tree; a new candidate overwrites that slot by predicated moves and the
+// tree is redone: ~100 instructions without a dependent memory access.  Ties of the approximate score are irrelevant: a
+// candidate enters only if it beats tau, so everything outside the set is <= tau up to the packing perturbation (< 32 ulp
+// per value, < 64 ulp accumulated: 7.7e-6 relative), which the reported bound adds back (F_PACK_SLACK).
+//   (Inserting inside the drain loop cost ~1800 cycles per chunk with a candidate, and since a TMEM buffer is refilled
+//   only after all warps of its block have let go of it, one such warp per unit -- 69 % of the units have one -- held up
+//   the tensor pipe for everybody: the scan ran at the pace of the slowest warp.  A warp-cooperative insert (lane = slot,
+//   shuffles and warp reductions) is worse still: ~600 cycles per insertion, its collectives form one long dependent chain.)
+constexpr float F_PACK_SLACK = 1.0e-5f;   // cosine units; |score| <= 1 so 64 ulp < 7.7e-6
+constexpr float F_EMPTY = -3.0e38f;       // empty slot (finite: -inf with slot bits would be a NaN)
 
-__device__ __forceinline__ void row_insert(RowState& st, float* sc, int* ids, int row, float v, int id) {
-  const int s = st.slot;
-  sc[s * F_TQ + row] = v;
-  ids[s * F_TQ + row] = id;
-  const int g = s >> 3;
-  float m = sc[(g * 8) * F_TQ + row];
-  int ms = g * 8;
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float set_min(const float (&x)[F_L]) {
+  static_assert(F_L == 32, "tree written for 32 slots");
+  float m[11];
 #pragma unroll
-  for (int u = 1; u < 8; ++u) {
-    const float x = sc[(g * 8 + u) * F_TQ + row];
-    if (x < m) {
-      m = x;
-      ms = g * 8 + u;
-    }
+  for (int i = 0; i < 10; ++i) m[i] = fmin3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+  m[10] = fminf(x[30], x[31]);
+  const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
+  return fmin3(fmin3(a, b, c), m[9], m[10]);
+}
+// v beats tau: it replaces the set's minimum
+__device__ __forceinline__ void set_insert(float (&x)[F_L], int (&ids)[F_L], float& tau, float v, int id) {
+  const uint32_t slot = __float_as_uint(tau) & (F_L - 1);
+  const float vp = __uint_as_float((__float_as_uint(v) & ~(uint32_t)(F_L - 1)) | slot);
+#pragma unroll
+  for (int q = 0; q < F_L; ++q) {
+    const bool here = slot == (uint32_t)q;
+    x[q] = here ? vp : x[q];
+    ids[q] = here ? id : ids[q];
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (q == g) {
-      st.gm[q] = m;
-      st.gs[q] = ms;
-    }
-  float t = st.gm[0];
-  int ts = st.gs[0];
-#pragma unroll
-  for (int q = 1; q < 4; ++q)
-    if (st.gm[q] < t) {
-      t = st.gm[q];
-      ts = st.gs[q];
-    }
-  st.tau = t;
-  st.slot = ts;
+  tau = set_min(x);
 }
 
-// one 32-key chunk of the slow path: scores to the warp's scratch tile (the candidate loop needs them by a run-time
-// index), candidate mask, then every lane inserts its own row's candidates
-__device__ __forceinline__ void slow_chunk(const uint32_t (&r)[32], float* scratch, int key_base, int self_i, int n_keys,
-                                           float* sc, int* ids, int row, int lane, RowState& st, unsigned long long* cnt) {
-  unsigned cm = 0u;
-  const float tau0 = st.tau;
+// slot layout: [8 column quads][32 lanes] float4, then [32 lanes] candidate-column masks
+constexpr int F_SLOT_BYTES = 8 * 32 * 16 + 32 * 4;
+__device__ __forceinline__ void park_chunk(const uint32_t (&r)[32], float tau, unsigned char* slot, int lane) {
+  float4* sv = reinterpret_cast<float4*>(slot);
+  unsigned cm4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    scratch[i * 32 + lane] = __uint_as_float(r[i]);
-    cm |= (__uint_as_float(r[i]) > tau0 ? 1u : 0u) << i;
+  for (int i = 0; i < 8; ++i) {
+    sv[i * 32 + lane] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                    __uint_as_float(r[4 * i + 3]));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cm4[c] |= (__uint_as_float(r[4 * i + c]) > tau ? 1u : 0u) << (4 * i + c);
   }
-  const long long t0 = cnt ? clock64() : 0;
-  int ncand = 0;
-  while (cm) {
-    const int j = __ffs(cm) - 1;
-    cm &= cm - 1;
-    const int id = key_base + j;
-    const float v = scratch[j * 32 + lane];
-    if (v > st.tau && id != self_i && id < n_keys) {
-      row_insert(st, sc, ids, row, v, id);
-      ++ncand;
-    }
-  }
-  __syncwarp();
-  if (cnt) {
-    int tot = ncand;
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) {
-      atomicAdd(cnt + 3, 1ull);
-      atomicAdd(cnt + 7, (unsigned long long)(clock64() - t0));
-      atomicAdd(cnt + 9, (unsigned long long)tot);
-    }
-  }
+  reinterpret_cast<unsigned*>(slot + 8 * 32 * 16)[lane] = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]);
 }
 
+template <int KS>   // k-steps of 16 halves: ceil(d / 16)
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restrict__ q16, int64_t n_q, int64_t n_keys,
-               int64_t query_offset, const int32_t* __restrict__ self_pos, const int32_t* __restrict__ start_tile, int32_t ksteps,
+               int64_t query_offset, const int32_t* __restrict__ self_pos, const int32_t* __restrict__ start_tile,
                float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int dbg_mode, unsigned long long* cnt) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
-  float* l_sc = reinterpret_cast<float*>(sB + F_STAGES * F_TILE_BYTES);            // [32 slots][256 rows] scores
-  int* l_id = reinterpret_cast<int*>(l_sc + F_L * F_TQ);                           // [32 slots][256 rows] key ids
-  float* scratch_all = reinterpret_cast<float*>(l_id + F_L * F_TQ);                // [8 warps][32 keys][32 lanes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + 8 * 32 * 32);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  unsigned char* q_slots = sB + F_STAGES * F_TILE_BYTES;                            // [8 pairs][F_QS] parked chunks
+  float* s_tau = reinterpret_cast<float*>(q_slots + F_PAIRS * F_QS * F_SLOT_BYTES);   // [256 rows] thresholds, insert -> drain
+  int* q_key = reinterpret_cast<int*>(s_tau + F_TQ);                                  // [8 pairs][F_QS] first key of a parked chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_key + F_PAIRS * F_QS);
   const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
   const uint32_t bar_empty = smem_u32(bars + 8);       // [F_STAGES]
   const uint32_t bar_tfull = smem_u32(bars + 16);      // [F_ACC]
   const uint32_t bar_tempty = smem_u32(bars + 19);     // [F_ACC]
   const uint32_t bar_a = smem_u32(bars + 22);
+  const uint32_t bar_qfull = smem_u32(bars + 24);      // [8 pairs][F_QS]  drain -> insert: slot holds a chunk
+  const uint32_t bar_qempty = smem_u32(bars + 24 + F_PAIRS * F_QS);   // insert -> drain: slot may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24 + 2 * F_PAIRS * F_QS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
   const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
-  const int64_t n_half = 2 * n_tiles;
   // locality order (knn_order.cu): this block starts its scan near its own cluster and wraps around
   const int64_t t_start = start_tile ? (int64_t)start_tile[blockIdx.x] % n_tiles : 0;
 
@@ -190,11 +174,16 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     }
     for (int i = 0; i < F_ACC; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 256);
+      mbar_init(bar_tempty + 8 * i, 4);                   // the 4 drain warps of the unit's block
     }
     mbar_init(bar_a, 256);
+    for (int i = 0; i < F_PAIRS * F_QS; ++i) {
+      mbar_init(bar_qfull + 8 * i, 1);
+      mbar_init(bar_qempty + 8 * i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < F_TQ) s_tau[threadIdx.x] = F_EMPTY;     // "no threshold yet": every score is a candidate
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
@@ -203,7 +192,10 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 columns, so the allocation starts at lane 0, column 0: addresses below are compile-time
+  // constants (the MMA warp would otherwise move every one of them into a uniform register before each use).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -221,53 +213,63 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = 64, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(F_HN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // One unit = (key tile, block): D[128 rows x 128 keys] = A_blk (TMEM) x tile' in ksteps MMAs of K = 16.  Unit
+    // u = 2 * tile + blk accumulates into TMEM buffer u % 3; a single in-order issuer keeps the buffer hand-over safe
+    // (a block's epilogue cannot be ahead of the other block's commit on the same buffer).
+    // This warp's instruction stream is the critical path of the whole kernel: a lone warp retires one dependent
+    // instruction every ~4 cycles, and with run-time stage / buffer indices one 64-key step cost ~180 instructions
+    // (R2UR moves, index arithmetic, barrier bookkeeping) = ~750 cycles against 256 of tensor work.  Hence N = 128
+    // per MMA and a loop unrolled over one turn of the key ring (6 tiles = 12 units = 4 turns of the buffers): every
+    // descriptor, TMEM address and barrier parity but one is a compile-time constant.
+    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // K-major SWIZZLE_128B: SBO = 1024 B between 8-row groups, version 1
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFF) | (1u << 16);
     mbar_wait(bar_a, 0);
     tc_fence_after();
-    for (int64_t h = 0; h < n_half; ++h) {
-      const int64_t t = h >> 1;
-      const int half = (int)(h & 1);
-      const int s = (int)(t % F_STAGES);
-      const int a = (int)(h % F_ACC);
-      mbar_wait(bar_tempty + 8 * a, (uint32_t)(((h / F_ACC) & 1) ^ 1));
-      if (half == 0) mbar_wait(bar_full + 8 * s, (uint32_t)((t / F_STAGES) & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        // keys [64 half, +64) of the tile: 8 swizzle groups of 1024 bytes further
-        const uint32_t b_addr = smem_u32(sB + (size_t)s * F_TILE_BYTES) + (uint32_t)half * (F_HN * 128);
-        const uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (1u << 16);
+    uint32_t ring_par = 0;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += F_STAGES, ring_par ^= 1u) {
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)((a * 2 + blk) * F_HN);
-          const uint32_t a_tmem = tmem_base + F_TMEM_A + (uint32_t)blk * 32u;
+      for (int j = 0; j < F_STAGES; ++j) {
+        if (t0 + j < n_tiles) {
+          mbar_wait(bar_full + 8 * j, ring_par);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (ks < ksteps) {
-              // one k-step = 16 halves = 32 bytes of the swizzled row = 8 packed TMEM columns of A
-              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(ks * 2));
-              tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, db, idesc, ks ? 1u : 0u);
+          for (int blk = 0; blk < 2; ++blk) {
+            constexpr int kUnitsPerTurn = 2 * F_STAGES;
+            static_assert(kUnitsPerTurn % F_ACC == 0 && ((kUnitsPerTurn / F_ACC) & 1) == 0,
+                          "buffer parities must repeat every turn of the key ring");
+            const int u = 2 * j + blk;
+            const int a = u % F_ACC;
+            const uint32_t kpar = (uint32_t)((u / F_ACC) & 1);
+            mbar_wait(bar_tempty + 8 * a, kpar ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(a * F_BN);
+              const uint32_t a_tmem = tmem_base + F_TMEM_A + (uint32_t)blk * 32u;
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                // one k-step = 16 halves = 32 bytes of the swizzled row = 8 packed TMEM columns of A
+                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(j * (F_TILE_BYTES >> 4) + ks * 2));
+                tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, db, idesc, ks ? 1u : 0u);
+              }
+              if (blk == 1) tc_commit(bar_empty + 8 * j);     // the key stage is reusable once both blocks have read it
+              tc_commit(bar_tfull + 8 * a);
             }
+            __syncwarp();
           }
         }
-        if (half == 1) tc_commit(bar_empty + 8 * s);     // the key stage is reusable once both halves were read
-        tc_commit(bar_tfull + 8 * a);
       }
-      __syncwarp();
     }
-  } else {
-    // ================= epilogue: one thread = one query row =================
+  } else if (warp < 2 + F_PAIRS) {
+    // ================= drain: one thread = one query row, accumulators -> registers -> "any candidate?" =================
     const unsigned FULL = 0xffffffffu;
     const int blk = (warp - 2) >> 2;                    // which 128-row block
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int pair = blk * 4 + quarter;
     const int row = blk * 128 + quarter * 32 + lane;
     const int64_t qrow = q0 + row;
     const bool qvalid = qrow < n_q;
-    // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
-    const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
-    float* scratch = scratch_all + (warp - 2) * 32 * 32;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     {
       // stage this thread's query row into TMEM: lane = row within the block, 32 columns of two packed halves
@@ -286,52 +288,131 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       tc_fence_before();
       mbar_arrive(bar_a);
     }
-    RowState st;
-    for (int j = 0; j < F_L; ++j) {
-      l_sc[j * F_TQ + row] = -INFINITY;
-      l_id[j * F_TQ + row] = INT_MAX;
-    }
-    st.tau = qvalid ? -INFINITY : INFINITY;             // the row's 32nd best so far (the minimum of its set)
-    st.slot = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      st.gm[q] = -INFINITY;
-      st.gs[q] = q * 8;
-    }
-    __syncwarp();
-    // (The loop is bound by the TMEM read rate -- every fp32 score has to come out of tensor memory once, ~94 B/clk
-    // per SM measured -- so prefetching the next half tile into a second register set bought nothing and spilled.)
-    for (int64_t h = 0; h < n_half; ++h) {
-      const int a = (int)(h % F_ACC);
-      mbar_wait(bar_tfull + 8 * a, (uint32_t)((h / F_ACC) & 1));
+    unsigned char* my_slots = q_slots + pair * (F_QS * F_SLOT_BYTES);
+    const volatile float* my_tau = s_tau + row;
+    int qs = 0;                                         // next queue slot to fill
+    uint32_t qpar = 1u;                                 // parity that says "slot qs is free" (fresh barriers pass 1)
+    // look at a chunk; if some row has a candidate: wait for the slot, dump, publish
+#define F_LOOK(r, kb)                                                                  \
+  do {                                                                                 \
+    if (__any_sync(FULL, max32(r) > tau) && dbg_mode != 1) {                            \
+      const long long tw0 = cnt ? clock64() : 0;                                       \
+      mbar_wait(bar_qempty + 8 * (pair * F_QS + qs), qpar);                             \
+      if (cnt && lane == 0) {                                                          \
+        atomicAdd(cnt + 0, 1ull);                                                      \
+        atomicAdd(cnt + 2, (unsigned long long)(clock64() - tw0));                     \
+      }                                                                                \
+      park_chunk(r, tau, my_slots + qs * F_SLOT_BYTES, lane);                           \
+      if (lane == 0) q_key[pair * F_QS + qs] = (kb);                                    \
+      __syncwarp();                                                                    \
+      if (lane == 0) mbar_arrive(bar_qfull + 8 * (pair * F_QS + qs));                   \
+      if (++qs == F_QS) {                                                              \
+        qs = 0;                                                                        \
+        qpar ^= 1u;                                                                    \
+      }                                                                                \
+    }                                                                                  \
+  } while (0)
+    // unit u = 2 * tile + blk lives in buffer u % 3.  The four 32-column chunks of a unit go through two register sets:
+    // a chunk is examined while the next one is on its way out of TMEM.
+    int a = blk;
+    uint32_t kpar = 0;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      const float tau = qvalid ? *my_tau : INFINITY;    // may lag behind the insert warp: only ever too low
+      mbar_wait(bar_tfull + 8 * a, kpar);
       tc_fence_after();
-      int64_t tile = (h >> 1) + t_start;
+      int64_t tile = t + t_start;
       if (tile >= n_tiles) tile -= n_tiles;
-      const int key0 = (int)(tile * F_BN) + (int)(h & 1) * F_HN;
-      uint32_t r0[32], r1[32];
-      const uint32_t taddr = lane_base + (uint32_t)((a * 2 + blk) * F_HN);
-      tmem_ld32(taddr, r0);
-      tmem_ld32(taddr + 32, r1);
+      const int key0 = (int)(tile * F_BN);
+      const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
+      uint32_t rA[32], rB[32];
+      tmem_ld32(taddr, rA);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // the accumulator is in registers: hand the TMEM stage back before looking at the scores
+      tmem_ld32(taddr + 32, rB);
+      F_LOOK(rA, key0);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(taddr + 64, rA);
+      F_LOOK(rB, key0 + 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(taddr + 96, rB);
+      F_LOOK(rA, key0 + 64);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the whole accumulator has been read: hand the TMEM buffer back
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * a);
-      const float m0 = max32(r0), m1 = max32(r1);
-      if (dbg_mode != 1 && __any_sync(FULL, fmaxf(m0, m1) > st.tau)) {
-        const long long ts = cnt ? clock64() : 0;
-        if (__any_sync(FULL, m0 > st.tau)) slow_chunk(r0, scratch, key0, self_i, (int)n_keys, l_sc, l_id, row, lane, st, cnt);
-        if (__any_sync(FULL, m1 > st.tau)) slow_chunk(r1, scratch, key0 + 32, self_i, (int)n_keys, l_sc, l_id, row, lane, st, cnt);
-        if (cnt && lane == 0) {
-          atomicAdd(cnt + 2, 1ull);
-          atomicAdd(cnt + 4, (unsigned long long)(clock64() - ts));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
+      a += 2;
+      if (a >= F_ACC) {
+        a -= F_ACC;
+        kpar ^= 1u;
+      }
+      F_LOOK(rB, key0 + 96);
+    }
+    // end of stream
+    mbar_wait(bar_qempty + 8 * (pair * F_QS + qs), qpar);
+    if (lane == 0) {
+      q_key[pair * F_QS + qs] = -1;
+      mbar_arrive(bar_qfull + 8 * (pair * F_QS + qs));
+    }
+#undef F_LOOK
+  } else {
+    // ================= insert: one thread = one query row, owns the row's candidate set =================
+    const int pair = warp - (2 + F_PAIRS);
+    const int row = pair * 32 + lane;                   // pair = blk * 4 + quarter
+    const int64_t qrow = q0 + row;
+    const bool qvalid = qrow < n_q;
+    // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
+    const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
+    float x[F_L];
+    int ids[F_L];
+#pragma unroll
+    for (int j = 0; j < F_L; ++j) {
+      x[j] = __uint_as_float((__float_as_uint(F_EMPTY) & ~(uint32_t)(F_L - 1)) | (uint32_t)j);
+      ids[j] = INT_MAX;
+    }
+    float tau = set_min(x);
+    const unsigned char* my_slots = q_slots + pair * (F_QS * F_SLOT_BYTES);
+    int qs = 0;
+    uint32_t qpar = 0u;
+    while (true) {
+      mbar_wait(bar_qfull + 8 * (pair * F_QS + qs), qpar);
+      const int key_base = q_key[pair * F_QS + qs];
+      if (key_base < 0) break;
+      const long long tp0 = cnt ? clock64() : 0;
+      int n_ins = 0;
+      const unsigned char* slot = my_slots + qs * F_SLOT_BYTES;
+      const float* sv = reinterpret_cast<const float*>(slot);
+      unsigned cm = reinterpret_cast<const unsigned*>(slot + 8 * 32 * 16)[lane];    // columns that beat the drain side's tau
+      while (cm) {
+        const int j = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int id = key_base + j;
+        const float v = sv[((j >> 2) * 32 + lane) * 4 + (j & 3)];
+        if (v > tau && id != self_i && id < (int)n_keys) {
+          set_insert(x, ids, tau, v, id);
+          ++n_ins;
         }
       }
+      s_tau[row] = tau;
+      __syncwarp();
+      if (cnt) {
+        for (int o = 16; o > 0; o >>= 1) n_ins += __shfl_xor_sync(0xffffffffu, n_ins, o);
+        if (lane == 0) {
+          atomicAdd(cnt + 3, (unsigned long long)(clock64() - tp0));
+          atomicAdd(cnt + 4, (unsigned long long)n_ins);
+        }
+      }
+      if (lane == 0) mbar_arrive(bar_qempty + 8 * (pair * F_QS + qs));
+      if (++qs == F_QS) {
+        qs = 0;
+        qpar ^= 1u;
+      }
     }
-    __syncwarp();
-    // the row's 32 candidates (unsorted) and a_L = the smallest approximate score among them
+    // the row's 32 candidates (unsorted) and the bound on every score outside the set
     if (qvalid) {
-      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = l_id[j * F_TQ + row];
-      out_thr[qrow] = st.tau * (1.f / (F_SCALE * F_SCALE));    // -inf: fewer than 32 keys
+#pragma unroll
+      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = ids[j];
+      // a set that never filled up reports -inf: it holds every key
+      out_thr[qrow] = tau < -1.0e37f ? -INFINITY : tau * (1.f / (F_SCALE * F_SCALE)) + F_PACK_SLACK;
     }
   }
   tc_fence_before();
@@ -498,12 +579,23 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 128, &dbg_cnt, true));
   CUtensorMap kmap;
   CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
-  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_TQ * F_L * 8 + (size_t)8 * 32 * 32 * 4 + 512;
-  CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_PAIRS * F_QS * F_SLOT_BYTES + (size_t)F_TQ * 4 + 128 + (24 + 2 * F_PAIRS * F_QS) * 8 + 64;
+  const int dbg_mode = getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0;
   cudaEventRecord(ctx->ev_k0, ctx->stream);
-  k_knn_scan_f16<<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(
-      kmap, (const __half*)q16->p, n_q, n_keys, query_offset, d_self, d_start, ksteps, (float*)thr->p, (int32_t*)cand->p,
-      getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0, dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);
+#define F_LAUNCH(KS)                                                                                                     \
+  do {                                                                                                                   \
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_knn_scan_f16<KS><<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(                                \
+        kmap, (const __half*)q16->p, n_q, n_keys, query_offset, d_self, d_start, (float*)thr->p, (int32_t*)cand->p,       \
+        dbg_mode, dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);                                                   \
+  } while (0)
+  switch (ksteps) {
+    case 1: F_LAUNCH(1); break;
+    case 2: F_LAUNCH(2); break;
+    case 3: F_LAUNCH(3); break;
+    default: F_LAUNCH(4); break;
+  }
+#undef F_LAUNCH
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(
@@ -519,12 +611,13 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (dbg_cnt) {
     unsigned long long h[11];
     cudaMemcpy(h, dbg_cnt->p, sizeof(h), cudaMemcpyDeviceToHost);
-    const double wt = (double)ceil_div64(n_q, F_TQ) * 8 * (double)(2 * ceil_div64(n_keys, F_BN));
-    fprintf(stderr, "[knn f16] warp x half-tiles %.3g; slow entries %llu (%.2f%%), cycles in slow path %.3g (%.0f per entry)\n", wt, h[2],
-            100.0 * h[2] / wt, (double)h[4], h[2] ? (double)h[4] / h[2] : 0.0);
-    fprintf(stderr, "[knn f16] dense chunks %llu: %.3g cycles (%.0f each), %.3g candidates (%.1f each); sparse chunks %llu: %.3g cycles (%.0f each), %.3g candidates; cooperative attempts %llu accepted %llu\n",
-            h[5], (double)h[7], h[5] ? (double)h[7] / h[5] : 0.0, (double)h[9], h[5] ? (double)h[9] / h[5] : 0.0, h[6], (double)h[8],
-            h[6] ? (double)h[8] / h[6] : 0.0, (double)h[10], h[0], h[1]);
+    const double units = (double)ceil_div64(n_q, F_TQ) * F_PAIRS * (double)ceil_div64(n_keys, F_BN);   // (drain warp, key tile)
+    fprintf(stderr,
+            "[knn f16] %.3g warp-units; parked chunks %llu (%.3f per warp-unit), rows flagged per chunk %.2f, drain cycles "
+            "blocked on a full queue %.3g (%.0f per park); insert warps: %.0f cycles per chunk, %.2f insertions per chunk, "
+            "%.1f insertions per row\n",
+            units, h[0], (double)h[0] / units, h[0] ? (double)h[1] / h[0] : 0.0, (double)h[2], h[0] ? (double)h[2] / h[0] : 0.0,
+            h[0] ? (double)h[3] / h[0] : 0.0, h[0] ? (double)h[4] / h[0] : 0.0, (double)h[4] / (double)n_q);
   }
   if (n_fb > 0) {
     // the unproven rows go through the exact 3xTF32 scan
