@@ -263,9 +263,10 @@ def main():
                 "peak_kind": f"{peak_kind} bf16 sustained (kind::f16 rate)",
                 "ms_per_launch": scan_ms, "share_of_step": scan_ms / ms_per_step,
                 "candidates_per_s": (hi - lo) * n_cells / (scan_ms * 1e-3) if scan_ms > 0 else 0.0,
-                "note": "algorithmic flops 2*Nq*Nkeys*n_pcs (K padded 50->64 on the MMA); the kernel is bound by reading "
-                        "every fp32 score out of TMEM once (~100 B/clk/SM measured) and by the top-k list updates, not "
-                        "by the tensor pipe (ncu sm__pipe_tensor 7 %): see DESIGN.md"}
+                "note": "algorithmic flops 2*Nq*Nkeys*n_pcs (K padded 50->64 on the MMA).  Every fp32 score has to come out "
+                        "of TMEM and through a max tree once; the scan is bound by the instruction streams that do that "
+                        "(drain warps: ALU pipe 52 %, and the single MMA-issuing warp), not by the tensor pipe (ncu "
+                        "sm__pipe_tensor 38 %) or by TMEM bandwidth (95 of 310 B/clk/SM): see DESIGN.md"}
     # the PCA Gram kernel against the TF32 tensor peak (half the bf16 rate)
     tensor_stages = {}
     gm = stage_ms.get("gram_mma", 0.0) / args.steps
