@@ -296,8 +296,16 @@ def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1
         clustering = pd.DataFrame({"cluster": labels, "cell_id": sc_obj.rawCount.cell_name})
         sc_obj.metaData["cluster"] = labels
     cl = ClusteringObject(clustering, str(metric), adj, result, res)
-    cl.knn_indices = idx.download().reshape(n, n_neighbors).T + 1        # k x n, 1-based
-    cl.knn_distances = dist.download().reshape(n, n_neighbors).T.astype(np.float64)
+    # k x n like the reference's knn_matrices, 1-based; a Julia k x n matrix is column-major, i.e. the device's
+    # [n][k] layout: convert on the contiguous buffers and hand out transposed VIEWS (arithmetic on the transposed
+    # view would copy with a stride of k elements)
+    hi = idx.download()
+    hi += 1
+    cl.knn_indices = hi.reshape(n, n_neighbors).T
+    d32 = dist.download()
+    d64 = s.ctx.pinned_empty(d32.size, np.float64)     # cached pinned pages: no page faults on 80 MB of fresh memory
+    np.copyto(d64, d32)
+    cl.knn_distances = d64.reshape(n, n_neighbors).T
     cl.device_graph = gdev
     sc_obj.clustData = cl
     return sc_obj
