@@ -1330,7 +1330,7 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
     }
   } else {
     // Chebyshev-filtered block subspace iteration with Rayleigh-Ritz:
-    //   block of b >= 2k+28 vectors; two plain power cycles and a first Rayleigh-Ritz step give Ritz values
+    //   block of b >= k+14 vectors; two plain power cycles and a first Rayleigh-Ritz step give Ritz values
     //   theta_1 >= ... >= theta_b.  Every following cycle applies the degree-m Chebyshev polynomial that is
     //   bounded by 1 on [0, theta_b] (three-term recurrence, one Gc product per degree, fused epilogue) and
     //   re-orthonormalises by CholeskyQR2.  m is chosen so that the growth T_m(x_1) of the leading direction,
@@ -1338,7 +1338,15 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
     //   Rayleigh-Ritz step (Jacobi on the b x b projection, rotations replayed on [Q; Gc Q]) follows every
     //   second cycle and yields the residuals that stop the iteration.  All arithmetic fp64 on the device;
     //   the host sees only the b Ritz values and k residual norms per Ritz step.
-    int b = std::min(H, std::max(64, ((2 * k + 28 + 31) / 32) * 32));
+    // Block width: k wanted vectors + 14 guard columns, in steps of 16 (k = 50 -> 64).  The b x b kernels (Cholesky,
+    // Jacobi, rotation replay) cost O(b^3) on ONE SM and dominated the solve at b = 128 (5.2 of 7.6 ms); the narrower
+    // block needs more filter products (40 instead of 33 on the bench matrix, 217 instead of 88 on a flat VisiumHD-like
+    // spectrum) but every product and every small kernel is cheaper: 4.0 instead of 7.6 ms, never slower.
+    int b = std::min(H, std::max(64, ((k + 14 + 15) / 16) * 16));
+    if (const char* eb = getenv("CSC_PCA_BLOCK")) {      // tuning knob: block width (multiple of 16, >= k + 8)
+      const int v = atoi(eb);
+      if (v >= k + 8 && v <= H) b = v;
+    }
     b = std::min(b, PCA_SMALL_MAX);
     CSC_REQUIRE(ctx, k <= b, "csc_pca_solve: maxoutdim=%d too large for the block solver (max %d)", k, b);
     BlockWs w;
