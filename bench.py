@@ -267,16 +267,18 @@ def main():
                         "of TMEM and through a max tree once; the scan is bound by the instruction streams that do that "
                         "(drain warps: ALU pipe 52 %, and the single MMA-issuing warp), not by the tensor pipe (ncu "
                         "sm__pipe_tensor 38 %) or by TMEM bandwidth (95 of 310 B/clk/SM): see DESIGN.md"}
-    # the PCA Gram kernel against the TF32 tensor peak (half the bf16 rate)
+    # the PCA Gram kernel against the 16-bit tensor peak: three fp16 passes (hi'hi, hi'lo, lo'hi) over the upper-triangle
+    # tiles (0.5625 of the full square for H = 2000)
     tensor_stages = {}
     gm = stage_ms.get("gram_mma", 0.0) / args.steps
     if gm > 0:
         H = int(last["pca"].info()["n_feat"])
         gf = 2.0 * (hi - lo) * H * H
+        issued = 3 * 0.5625 * gf / (gm * 1e-3) / 1e12
         tensor_stages["k_gram_tc"] = {"algorithmic_TFLOP/s": gf / (gm * 1e-3) / 1e12, "ms": gm,
-                                      "issued_TFLOP/s_3xTF32_upper_tiles": 3 * 0.5625 * gf / (gm * 1e-3) / 1e12,
-                                      "tf32_peak": 0.5 * peak_f16,
-                                      "frac_issued": 3 * 0.5625 * gf / (gm * 1e-3) / 1e12 / (0.5 * peak_f16)}
+                                      "issued_TFLOP/s_3_fp16_passes_upper_tiles": issued, "f16_peak": peak_f16,
+                                      "frac_issued": issued / peak_f16,
+                                      "operand_GB_from_L2": 144 * ((hi - lo) / 2 / 16) * 24576 / 1e9}
     del last, out
     # sparse stages against the HBM roofline (context for the dominant-kernel figure)
     hbm = {}

@@ -4,16 +4,22 @@
 //
 //   Z is the cell-major scaled matrix [N cells][H genes] fp32.  G[a][b] = sum_c Z[c][a] Z[c][b]: the contraction
 //   runs over cells, i.e. over the SLOW index of Z, so both MMA operands are "MN-major" (the 128-byte rows that
-//   TMA lays down in shared memory run along the gene axis).  tcgen05 kind::tf32 takes MN-major operands
-//   directly (in the 128-byte swizzle with 32-byte atomicity), so no transpose is ever materialised.
+//   TMA lays down in shared memory run along the gene axis).  tcgen05 takes MN-major operands directly (16-bit:
+//   plain 128-byte swizzle; tf32 would need the 32-byte-atomicity variant), so no transpose is ever materialised.
 //
-//   3xTF32: Z = hi + lo with hi = tf32(Z), lo = Z - hi (k_split_colsum, fused with the fp64 column sums that
-//   the centring needs);  Z'Z ~= hi'hi + hi'lo + lo'hi, three MMA passes into one fp32 TMEM accumulator.
+//   Split precision: Z = hi + lo with hi = fp16(Z), lo = fp16(Z - hi) (k_split_colsum, fused with the fp64 column
+//   sums that the centring needs): 22 significant bits, the same as the tf32 hi / fp32 lo split of 3xTF32.
+//   Z'Z ~= hi'hi + hi'lo + lo'hi, three kind::f16 MMA passes into one fp32 TMEM accumulator; products of 11-bit
+//   factors are exact in fp32, so nothing is lost that 3xTF32 keeps -- but a K = 16 fp16 MMA does the work of two
+//   K = 8 tf32 MMAs in the time of one, and the operands are half as many bytes.  The second point mattered as much
+//   as the first: with fp32 operands the kernel pulled 108 GB per launch out of L2 (48 KB per 16 cells and CTA,
+//   9.8 TB/s) and was L2-bound at 0.9 of what looked like the TF32 tensor peak.
+//   (|Z| <= scale_max = 10: no overflow; values below fp16's normal range lose bits, an ABSOLUTE error <= 3e-8.)
 //
 //   Accumulation.  The tensor core adds into its fp32 accumulator with truncation, so a long same-sign sum (a
 //   diagonal entry, a pair of correlated genes) picks up a relative bias proportional to the number of MMAs it
 //   went through: 3e-5 after 4096 cells (measured), far too much for eigenvectors that must hold 1e-4.  The
-//   kernel therefore lets the tensor core accumulate only 32 cells (12 MMAs, bias < 1e-6), then the flush warps
+//   kernel therefore lets the tensor core accumulate only 32 cells (6 MMAs, bias < 1e-6), then the flush warps
 //   pull the tile out of TMEM and add it, round-to-nearest, into fp32 REGISTER accumulators (128 x 256 tile =
 //   128 registers in each of 256 threads); TMEM is double-buffered so the tensor pipe never waits for that.
 //   Every 4096 cells the registers are added into the CTA's private fp64 tile in global memory (plain
@@ -24,10 +30,11 @@
 //   contiguous range of cells ("split"): 72 tiles x 2 splits = 144 CTAs for H = 2000.
 //
 // Warp roles (320 threads, 1 CTA per SM):
-//   warp 0      TMA producer: [16 cells x 32 genes] boxes (SWIZZLE_128B_ATOM_32B) of hi and lo into a 4-stage ring
+//   warp 0      TMA producer: [16 cells x 64 genes] fp16 boxes (SWIZZLE_128B, MN-major) of hi and lo into a 6-stage ring
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
 //   warps 2-9   flush: tcgen05.ld -> register accumulators -> fp64 tile
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -39,10 +46,10 @@ namespace {
 constexpr int GT_BM = 128;                            // tile rows  = UMMA M
 constexpr int GT_BN = 256;                            // tile cols  = UMMA N
 constexpr int GT_BK = 16;                             // cells per pipeline stage
-constexpr int GT_STAGES = 4;
-constexpr int GT_ATOM_BYTES = GT_BK * 128;            // [16 cells][32 genes] fp32, one 128-byte row per cell
-constexpr int GT_PART_BYTES = 12 * GT_ATOM_BYTES;     // A: atoms 0-3 (128 genes), B: atoms 4-11 (256 genes)
-constexpr int GT_STAGE_BYTES = 2 * GT_PART_BYTES;     // hi | lo  = 48 KB
+constexpr int GT_STAGES = 6;
+constexpr int GT_ATOM_BYTES = GT_BK * 128;            // [16 cells][64 genes] fp16: one 128-byte row per cell
+constexpr int GT_PART_BYTES = 6 * GT_ATOM_BYTES;      // hi or lo: A atoms 0-1 (128 genes), B atoms 2-5 (256 genes)
+constexpr int GT_STAGE_BYTES = 2 * GT_PART_BYTES;     // hi | lo = 24 KB
 constexpr int GT_THREADS = 64 + 256;
 constexpr int GT_TC_STAGES = 2;                       // stages (32 cells) accumulated inside the tensor core
 constexpr int GT_FLUSH_CHUNKS = 128;                  // chunks (4096 cells) accumulated in fp32 registers
@@ -59,11 +66,11 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* stages = base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)GT_STAGES * GT_STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const uint32_t bar_full = smem_u32(bars + 0);      // [GT_STAGES]
-  const uint32_t bar_empty = smem_u32(bars + 4);     // [GT_STAGES]
-  const uint32_t bar_tfull = smem_u32(bars + 8);     // [2] TMEM buffer holds a finished chunk
-  const uint32_t bar_tempty = smem_u32(bars + 10);   // [2] TMEM buffer drained
+  const uint32_t bar_empty = smem_u32(bars + 8);     // [GT_STAGES]
+  const uint32_t bar_tfull = smem_u32(bars + 16);    // [2] TMEM buffer holds a finished chunk
+  const uint32_t bar_tempty = smem_u32(bars + 18);   // [2] TMEM buffer drained
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int2 pr = pairs[blockIdx.x];
@@ -102,7 +109,7 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.hi)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.lo)) : "memory");
     }
-    const uint32_t tx_bytes = diag ? 2u * 8u * GT_ATOM_BYTES : 2u * 12u * GT_ATOM_BYTES;
+    const uint32_t tx_bytes = diag ? 8u * GT_ATOM_BYTES : 12u * GT_ATOM_BYTES;
     for (int64_t st = 0; st < n_stages; ++st) {
       const int s = (int)(st % GT_STAGES);
       mbar_wait(bar_empty + 8 * s, (uint32_t)(((st / GT_STAGES) & 1) ^ 1));
@@ -116,26 +123,26 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
           const uint32_t pd = dst + (uint32_t)p * GT_PART_BYTES;
           if (!diag) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) tma_load_2d(pd + (uint32_t)a * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.x * GT_BM + a * 32, cell);
+            for (int a = 0; a < 2; ++a) tma_load_2d(pd + (uint32_t)a * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.x * GT_BM + a * 64, cell);
           }
 #pragma unroll
-          for (int a = 0; a < 8; ++a)
-            tma_load_2d(pd + (uint32_t)(4 + a) * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.y * GT_BN + a * 32, cell);
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d(pd + (uint32_t)(2 + a) * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.y * GT_BN + a * 64, cell);
         }
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // instruction descriptor: D = F32, A = B = TF32, both MN-major (bits 15, 16), N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GT_BN >> 3) << 17) |
-                           ((uint32_t)(GT_BM >> 4) << 24);
-    // shared-memory descriptor: MN-major tf32 operands exist only in the "128-byte swizzle with 32-byte
-    // atomicity" layout (type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose K-atom is 4 rows of 128 bytes:
-    // LBO = distance between 32-gene atoms, SBO = distance between 4-cell groups (512 bytes), version 1
-    const uint32_t desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (1u << 29);
+    // instruction descriptor: D = F32, A = B = F16 (format 0), both MN-major (bits 15, 16), N = 256, M = 128; one
+    // instruction covers K = 16 cells.  Shared-memory descriptors: 128-byte swizzle (layout type 2), MN-major:
+    // LBO = distance between 64-gene atoms, SBO = distance between 8-cell groups (1024 bytes), version 1.
+    // (kind::tf32 MN-major operands exist only in the "128-byte swizzle with 32-byte atomicity" layout, type 1, TMA
+    // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, K-atom = 4 rows: with the plain swizzle that MMA silently produced zeros.)
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(GT_BN >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t lbo = (uint32_t)(GT_ATOM_BYTES >> 4) << 16;
-    const uint32_t a_atom = diag ? 4u + (uint32_t)(pr.x & 1) * 4u : 0u;
+    const uint32_t a_atom = diag ? 2u + (uint32_t)(pr.x & 1) * 2u : 0u;
     for (int64_t st = 0; st < n_stages; ++st) {
       const int s = (int)(st % GT_STAGES);
       const int64_t chunk = st / GT_TC_STAGES;
@@ -152,16 +159,13 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
         const uint32_t sb = smem_u32(stages + (size_t)s * GT_STAGE_BYTES);
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * GT_BN;
 #pragma unroll
-        for (int kg = 0; kg < GT_BK / 8; ++kg) {
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            // pass 0: hi'hi   pass 1: hi'lo   pass 2: lo'hi
-            const uint32_t a_addr = sb + (pass == 2 ? GT_PART_BYTES : 0) + a_atom * GT_ATOM_BYTES + (uint32_t)kg * 1024u;
-            const uint32_t b_addr = sb + (pass == 1 ? GT_PART_BYTES : 0) + 4u * GT_ATOM_BYTES + (uint32_t)kg * 1024u;
-            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFF) | lbo);
-            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFF) | lbo);
-            tc_mma_tf32_ss(d_tmem, da, db, idesc, (chunk_first && kg == 0 && pass == 0) ? 0u : 1u);
-          }
+        for (int pass = 0; pass < 3; ++pass) {
+          // pass 0: hi'hi   pass 1: hi'lo   pass 2: lo'hi
+          const uint32_t a_addr = sb + (pass == 2 ? GT_PART_BYTES : 0) + a_atom * GT_ATOM_BYTES;
+          const uint32_t b_addr = sb + (pass == 1 ? GT_PART_BYTES : 0) + 2u * GT_ATOM_BYTES;
+          const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFF) | lbo);
+          const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFF) | lbo);
+          tc_mma_f16_ss(d_tmem, da, db, idesc, (chunk_first && pass == 0) ? 0u : 1u);
         }
         tc_commit(bar_empty + 8 * s);
         if (chunk_last) tc_commit(bar_tfull + 8 * buf);
@@ -241,11 +245,11 @@ k_gram_reduce(const double* __restrict__ part, const int2* __restrict__ pairs, i
   if ((pr.x >> 1) != pr.y) gram[(int64_t)b * H + a] += s;
 }
 
-// hi = tf32(z) (round to nearest, low 13 bits zero), lo = z - hi (exact), written with row pitch Hp;
-// colsum[h] += sum over rows of z (fp64).  One thread = 4 consecutive columns of a block of rows.
+// hi = fp16(z) (round to nearest), lo = fp16(z - hi), written with row pitch Hp; colsum[h] += sum over rows of z (fp64).
+// One thread = 4 consecutive columns of a block of rows.
 __global__ void __launch_bounds__(256)
-k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64_t rows_per_cta, float* __restrict__ hi,
-               float* __restrict__ lo, double* __restrict__ colsum) {
+k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64_t rows_per_cta, __half* __restrict__ hi16,
+               __half* __restrict__ lo16, double* __restrict__ colsum) {
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c0 >= Hp) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
@@ -266,31 +270,32 @@ k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64
       for (int j = 0; j < 4; ++j)
         if (c0 + j < H) v[j] = __ldcs(src + j);
     }
-    float h[4], l[4];
+    __half h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t u;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
-      h[j] = __uint_as_float(u);
-      l[j] = v[j] - h[j];
+      h[j] = __float2half_rn(v[j]);
+      l[j] = __float2half_rn(v[j] - __half2float(h[j]));
       s[j] += (double)v[j];
     }
-    *reinterpret_cast<float4*>(hi + r * (int64_t)Hp + c0) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(lo + r * (int64_t)Hp + c0) = make_float4(l[0], l[1], l[2], l[3]);
+    __half2 p0 = __halves2half2(h[0], h[1]), p1 = __halves2half2(h[2], h[3]);
+    *reinterpret_cast<uint2*>(hi16 + r * (int64_t)Hp + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    p0 = __halves2half2(l[0], l[1]);
+    p1 = __halves2half2(l[2], l[3]);
+    *reinterpret_cast<uint2*>(lo16 + r * (int64_t)Hp + c0) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (c0 + j < H) atomicAdd(colsum + c0 + j, s[j]);
 }
 
-csc_status gram_make_map(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const float* ptr, int64_t n_rows, int H, int Hp) {
+csc_status gram_make_map16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const __half* ptr, int64_t n_rows, int H, int Hp) {
   cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)n_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Hp * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)GT_BK};
+  cuuint64_t strides[1] = {(cuuint64_t)Hp * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)GT_BK};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled (gram) failed with %d", (int)r);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled (gram, fp16) failed with %d", (int)r);
   return CSC_OK;
 }
 
@@ -307,14 +312,14 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
       return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     encode = (EncodeTiledFn)fn;
   }
-  const int Hp = (H + 3) & ~3;
-  DevPtr hi, lo, d_pairs, part;
-  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 4, &hi));
-  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 4, &lo));
+  const int Hp = (H + 7) & ~7;      // fp16 rows must keep the 16-byte pitch TMA asks for
+  DevPtr hi16, lo16, d_pairs, part;
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &hi16));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &lo16));
   {
     const int64_t rows_per_cta = 256;
     dim3 grid((unsigned)((Hp / 4 + 255) / 256), (unsigned)ceil_div64(n_rows, rows_per_cta));
-    k_split_colsum<<<grid, 256, 0, ctx->stream>>>(z, n_rows, H, Hp, rows_per_cta, (float*)hi->p, (float*)lo->p, colsum);
+    k_split_colsum<<<grid, 256, 0, ctx->stream>>>(z, n_rows, H, Hp, rows_per_cta, (__half*)hi16->p, (__half*)lo16->p, colsum);
     CSC_LAUNCHED(ctx);
   }
   const int ntm = (H + GT_BM - 1) / GT_BM, ntn = (H + GT_BN - 1) / GT_BN;
@@ -333,8 +338,8 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
   CSC_CUDA(ctx, cudaMemcpyAsync(d_pairs->p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   CSC_TRY(dev_alloc(ctx, (size_t)n_pairs * n_splits * GT_TILE_ELEMS * 8, &part));
   GramMaps maps;
-  CSC_TRY(gram_make_map(ctx, encode, &maps.hi, (const float*)hi->p, n_rows, H, Hp));
-  CSC_TRY(gram_make_map(ctx, encode, &maps.lo, (const float*)lo->p, n_rows, H, Hp));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi, (const __half*)hi16->p, n_rows, H, Hp));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo, (const __half*)lo16->p, n_rows, H, Hp));
   const size_t smem = 1024 + (size_t)GT_STAGES * GT_STAGE_BYTES + 256;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
