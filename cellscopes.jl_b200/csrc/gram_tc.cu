@@ -56,7 +56,7 @@ constexpr int GT_FLUSH_CHUNKS = 128;                  // chunks (4096 cells) acc
 constexpr int GT_TILE_ELEMS = GT_BM * GT_BN;
 
 struct __align__(64) GramMaps {
-  CUtensorMap hi, lo;
+  CUtensorMap hi_a, lo_a, hi_b, lo_b;     // boxes of 2 atoms (A operand) and of 4 atoms (B operand)
 };
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -101,14 +101,20 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // the CTA owns all 512 columns: the allocation starts at column 0 and TMEM addresses are compile-time constants
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.hi)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.hi_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.lo_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.hi_b)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.lo_b)) : "memory");
     }
+    // one box = [atoms][16 cells][64 genes]: the B operand (4 atoms) and, off the diagonal, the A operand (2 atoms) of hi
+    // and of lo -- four TMA instructions per stage (a lone warp's instruction stream is what paces these kernels)
     const uint32_t tx_bytes = diag ? 8u * GT_ATOM_BYTES : 12u * GT_ATOM_BYTES;
     for (int64_t st = 0; st < n_stages; ++st) {
       const int s = (int)(st % GT_STAGES);
@@ -117,18 +123,12 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
         mbar_expect_tx(bar_full + 8 * s, tx_bytes);
         const uint32_t dst = smem_u32(stages + (size_t)s * GT_STAGE_BYTES);
         const int cell = (int)(c_begin + st * GT_BK);
-#pragma unroll 1
-        for (int p = 0; p < 2; ++p) {
-          const CUtensorMap* map = p ? &maps.lo : &maps.hi;
-          const uint32_t pd = dst + (uint32_t)p * GT_PART_BYTES;
-          if (!diag) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) tma_load_2d(pd + (uint32_t)a * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.x * GT_BM + a * 64, cell);
-          }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            tma_load_2d(pd + (uint32_t)(2 + a) * GT_ATOM_BYTES, map, bar_full + 8 * s, pr.y * GT_BN + a * 64, cell);
+        if (!diag) {
+          tma_load_3d(dst, &maps.hi_a, bar_full + 8 * s, 0, cell, pr.x * 2);
+          tma_load_3d(dst + GT_PART_BYTES, &maps.lo_a, bar_full + 8 * s, 0, cell, pr.x * 2);
         }
+        tma_load_3d(dst + 2u * GT_ATOM_BYTES, &maps.hi_b, bar_full + 8 * s, 0, cell, pr.y * 4);
+        tma_load_3d(dst + GT_PART_BYTES + 2u * GT_ATOM_BYTES, &maps.lo_b, bar_full + 8 * s, 0, cell, pr.y * 4);
       }
       __syncwarp();
     }
@@ -143,34 +143,45 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t lbo = (uint32_t)(GT_ATOM_BYTES >> 4) << 16;
     const uint32_t a_atom = diag ? 2u + (uint32_t)(pr.x & 1) * 2u : 0u;
-    for (int64_t st = 0; st < n_stages; ++st) {
-      const int s = (int)(st % GT_STAGES);
-      const int64_t chunk = st / GT_TC_STAGES;
-      const int buf = (int)(chunk & 1);
-      const bool chunk_first = (st % GT_TC_STAGES) == 0;
-      const bool chunk_last = ((st + 1) % GT_TC_STAGES) == 0 || st + 1 == n_stages;
-      if (chunk_first) {
-        mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((chunk >> 1) & 1) ^ 1));
-        tc_fence_after();
-      }
-      mbar_wait(bar_full + 8 * s, (uint32_t)((st / GT_STAGES) & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sb = smem_u32(stages + (size_t)s * GT_STAGE_BYTES);
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * GT_BN;
+    // The loop is unrolled over two turns of the stage ring (12 stages = 6 chunks = 3 turns of the two TMEM buffers), so
+    // that stage, buffer, descriptors and all barrier parities but one are compile-time constants: with run-time indices
+    // this warp spent ~950 cycles per stage on ~100 instructions while the tensor pipe needed 384 (pipe 46 % active).
+    static_assert(GT_STAGES == 6 && GT_TC_STAGES == 2, "unrolling below assumes a 6-stage ring and 2 stages per chunk");
+    const uint32_t sb0 = smem_u32(stages);
+    uint32_t gpar = 0;                                     // parity of the group index g: 12 g stages are behind us
+    for (int64_t st0 = 0; st0 < n_stages; st0 += 12, gpar ^= 1u) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          // pass 0: hi'hi   pass 1: hi'lo   pass 2: lo'hi
-          const uint32_t a_addr = sb + (pass == 2 ? GT_PART_BYTES : 0) + a_atom * GT_ATOM_BYTES;
-          const uint32_t b_addr = sb + (pass == 1 ? GT_PART_BYTES : 0) + 2u * GT_ATOM_BYTES;
-          const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFF) | lbo);
-          const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFF) | lbo);
-          tc_mma_f16_ss(d_tmem, da, db, idesc, (chunk_first && pass == 0) ? 0u : 1u);
+      for (int j = 0; j < 12; ++j) {
+        if (st0 + j < n_stages) {
+          const int s = j % GT_STAGES;
+          const int buf = (j >> 1) & 1;
+          const bool chunk_first = (j & 1) == 0;
+          const bool chunk_last = (j & 1) == 1 || st0 + j + 1 == n_stages;
+          if (chunk_first) {
+            // chunk c = 6 g + j/2 uses buffer c & 1 for the (c >> 1)-th time: parity (3 g + (j >> 2)) & 1
+            mbar_wait(bar_tempty + 8 * buf, ((gpar + (uint32_t)(j >> 2)) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          mbar_wait(bar_full + 8 * s, (uint32_t)((j / GT_STAGES) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sb = sb0 + (uint32_t)(s * GT_STAGE_BYTES);
+            const uint32_t d_tmem = (uint32_t)buf * GT_BN;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              // pass 0: hi'hi   pass 1: hi'lo   pass 2: lo'hi
+              const uint32_t a_addr = sb + (pass == 2 ? GT_PART_BYTES : 0) + a_atom * GT_ATOM_BYTES;
+              const uint32_t b_addr = sb + (pass == 1 ? GT_PART_BYTES : 0) + 2u * GT_ATOM_BYTES;
+              const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFF) | lbo);
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFF) | lbo);
+              tc_mma_f16_ss(d_tmem, da, db, idesc, (chunk_first && pass == 0) ? 0u : 1u);
+            }
+            tc_commit(bar_empty + 8 * s);
+            if (chunk_last) tc_commit(bar_tfull + 8 * buf);
+          }
+          __syncwarp();
         }
-        tc_commit(bar_empty + 8 * s);
-        if (chunk_last) tc_commit(bar_tfull + 8 * buf);
       }
-      __syncwarp();
     }
   } else {
     // ================= flush warps: TMEM -> fp32 registers -> private fp64 tile =================
@@ -259,7 +270,9 @@ k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64
   for (int64_t r = r0; r < r1; ++r) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const float* src = z + r * (int64_t)H + c0;
-    if (vec) {
+    if (c0 >= H) {
+      // padding columns up to the next whole atom: zeros
+    } else if (vec) {
       const float4 f = __ldcs(reinterpret_cast<const float4*>(src));
       v[0] = f.x;
       v[1] = f.y;
@@ -288,12 +301,14 @@ k_split_colsum(const float* __restrict__ z, int64_t n_rows, int H, int Hp, int64
     if (c0 + j < H) atomicAdd(colsum + c0 + j, s[j]);
 }
 
-csc_status gram_make_map16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const __half* ptr, int64_t n_rows, int H, int Hp) {
-  cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)n_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Hp * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)GT_BK};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+// 3-D view of a [n_rows][Hp] fp16 matrix (Hp a multiple of 64, zero padded): (gene within atom, cell, atom); a box of
+// `atoms` atoms lands in shared memory as [atom][16 cells][64 genes], each 128-byte row swizzled (SWIZZLE_128B)
+csc_status gram_make_map16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, const __half* ptr, int64_t n_rows, int Hp, int atoms) {
+  cuuint64_t dims[3] = {64, (cuuint64_t)n_rows, (cuuint64_t)(Hp / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)Hp * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)GT_BK, (cuuint32_t)atoms};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled (gram, fp16) failed with %d", (int)r);
   return CSC_OK;
@@ -312,7 +327,7 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
       return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     encode = (EncodeTiledFn)fn;
   }
-  const int Hp = (H + 7) & ~7;      // fp16 rows must keep the 16-byte pitch TMA asks for
+  const int Hp = (H + 63) & ~63;    // whole 64-gene atoms, zero padded (the 3-D tensor maps step over atoms)
   DevPtr hi16, lo16, d_pairs, part;
   CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &hi16));
   CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &lo16));
@@ -338,8 +353,10 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
   CSC_CUDA(ctx, cudaMemcpyAsync(d_pairs->p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   CSC_TRY(dev_alloc(ctx, (size_t)n_pairs * n_splits * GT_TILE_ELEMS * 8, &part));
   GramMaps maps;
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi, (const __half*)hi16->p, n_rows, H, Hp));
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo, (const __half*)lo16->p, n_rows, H, Hp));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_a, (const __half*)hi16->p, n_rows, Hp, 2));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_a, (const __half*)lo16->p, n_rows, Hp, 2));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_b, (const __half*)hi16->p, n_rows, Hp, 4));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_b, (const __half*)lo16->p, n_rows, Hp, 4));
   const size_t smem = 1024 + (size_t)GT_STAGES * GT_STAGE_BYTES + 256;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
