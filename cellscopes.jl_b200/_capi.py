@@ -69,6 +69,7 @@ SIGNATURES = {
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
     "csc_scale_stats_select": (_I32, [_P, _P, _I64, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
+    "csc_scale_gram_partial": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _P, _P]),
     "csc_dense_alloc": (_I32, [_P, _I64, _I64, _PP]),
     "csc_dense_upload": (_I32, [_P, _P, _I32, _I64, _I64, _PP]),
     "csc_dense_download": (_I32, [_P, _P, _I32, _I64, _I64]),
@@ -303,6 +304,14 @@ class Context:
                                            int(n_cells_total), float(scale_max), 1 if do_scale else 0,
                                            1 if do_center else 0, C.byref(h)))
         return Dense(self, h)
+
+    def scale_gram_partial(self, norm, features, partial, n_cells_total, colsum, gram, scale_max=10.0, do_scale=True,
+                           do_center=True):
+        """scale_fill + pca_partial without the dense scaled matrix: colsum += column sums, gram += Z'Z of this shard."""
+        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        self.check(self.lib.csc_scale_gram_partial(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h,
+                                                   int(n_cells_total), float(scale_max), 1 if do_scale else 0,
+                                                   1 if do_center else 0, colsum.h, gram.h))
 
     def dense_upload(self, arr):
         arr = np.ascontiguousarray(arr)

@@ -241,17 +241,22 @@ k_gram_tc(const __grid_constant__ GramMaps maps, const int2* __restrict__ pairs,
   }
 }
 
-// gram[a][b] (+)= sum over splits of the tile entries; tiles that do not straddle the diagonal are mirrored
+// gram[a][b] (+)= sum over splits of the tile entries; tiles that do not straddle the diagonal are mirrored.  With
+// `colsum` the operands carry a column of ones at index H: that column of the extended Gram is Z'1.
 __global__ void __launch_bounds__(256)
 k_gram_reduce(const double* __restrict__ part, const int2* __restrict__ pairs, int n_pairs, int n_splits, int H,
-              double* __restrict__ gram) {
+              double* __restrict__ gram, double* __restrict__ colsum) {
   const int2 pr = pairs[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // entry of the 128 x 256 tile
   const int r = idx / GT_BN, c = idx % GT_BN;
   const int a = pr.x * GT_BM + r, b = pr.y * GT_BN + c;
-  if (a >= H || b >= H) return;
+  if (a >= H || b > H || (b == H && !colsum)) return;
   double s = 0.0;
   for (int z = 0; z < n_splits; ++z) s += part[((size_t)z * n_pairs + blockIdx.y) * (size_t)GT_TILE_ELEMS + idx];
+  if (b == H) {
+    colsum[a] += s;
+    return;
+  }
   gram[(int64_t)a * H + b] += s;
   if ((pr.x >> 1) != pr.y) gram[(int64_t)b * H + a] += s;
 }
@@ -316,8 +321,13 @@ csc_status gram_make_map16(csc_ctx* ctx, EncodeTiledFn fn, CUtensorMap* map, con
 
 }  // namespace
 
-// colsum[H] += column sums of z; gram[H*H] += z'z (full symmetric), both fp64.
-csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* colsum, double* gram) {
+// gram[H*H] += hi'hi + hi'lo + lo'hi for operands that are split already: hi16 / lo16 are [n_rows][Hp] fp16 with
+// Hp = gram_split_pitch(columns), padding columns zero -- except, with `colsum_from_ones`, column H, which holds 1 in
+// hi (0 in lo) in every row: colsum[H] += Z'1 then comes out of the same MMAs.
+int gram_split_pitch(int H) { return (H + 63) & ~63; }   // whole 64-gene atoms (the 3-D tensor maps step over atoms)
+
+csc_status gram_tc_split(csc_ctx* ctx, const __half* hi16p, const __half* lo16p, int64_t n_rows, int H, int Hp, double* gram,
+                         double* colsum_from_ones) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -327,17 +337,9 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
       return csc_fail(ctx, CSC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     encode = (EncodeTiledFn)fn;
   }
-  const int Hp = (H + 63) & ~63;    // whole 64-gene atoms, zero padded (the 3-D tensor maps step over atoms)
-  DevPtr hi16, lo16, d_pairs, part;
-  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &hi16));
-  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &lo16));
-  {
-    const int64_t rows_per_cta = 256;
-    dim3 grid((unsigned)((Hp / 4 + 255) / 256), (unsigned)ceil_div64(n_rows, rows_per_cta));
-    k_split_colsum<<<grid, 256, 0, ctx->stream>>>(z, n_rows, H, Hp, rows_per_cta, (__half*)hi16->p, (__half*)lo16->p, colsum);
-    CSC_LAUNCHED(ctx);
-  }
-  const int ntm = (H + GT_BM - 1) / GT_BM, ntn = (H + GT_BN - 1) / GT_BN;
+  DevPtr d_pairs, part;
+  const int Hx = colsum_from_ones ? H + 1 : H;     // columns the tiles have to cover
+  const int ntm = (H + GT_BM - 1) / GT_BM, ntn = (Hx + GT_BN - 1) / GT_BN;
   std::vector<int2> pairs;
   for (int tj = 0; tj < ntn; ++tj)
     for (int ti = 0; ti < ntm && ti <= 2 * tj + 1; ++ti) pairs.push_back(make_int2(ti, tj));
@@ -353,10 +355,10 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
   CSC_CUDA(ctx, cudaMemcpyAsync(d_pairs->p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   CSC_TRY(dev_alloc(ctx, (size_t)n_pairs * n_splits * GT_TILE_ELEMS * 8, &part));
   GramMaps maps;
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_a, (const __half*)hi16->p, n_rows, Hp, 2));
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_a, (const __half*)lo16->p, n_rows, Hp, 2));
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_b, (const __half*)hi16->p, n_rows, Hp, 4));
-  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_b, (const __half*)lo16->p, n_rows, Hp, 4));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_a, hi16p, n_rows, Hp, 2));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_a, lo16p, n_rows, Hp, 2));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.hi_b, hi16p, n_rows, Hp, 4));
+  CSC_TRY(gram_make_map16(ctx, encode, &maps.lo_b, lo16p, n_rows, Hp, 4));
   const size_t smem = 1024 + (size_t)GT_STAGES * GT_STAGE_BYTES + 256;
   CSC_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEventRecord(ctx->ev_k0, ctx->stream);
@@ -365,11 +367,24 @@ csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* 
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_gram_reduce<<<dim3(GT_TILE_ELEMS / 256, (unsigned)n_pairs), 256, 0, ctx->stream>>>(
-      (const double*)part->p, (const int2*)d_pairs->p, n_pairs, n_splits, H, gram);
+      (const double*)part->p, (const int2*)d_pairs->p, n_pairs, n_splits, H, gram, colsum_from_ones);
   CSC_LAUNCHED(ctx);
   // the pageable pair table must outlive the async copy
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->stage_ms[CSC_T_GRAM_MMA] += ms;
   return CSC_OK;
+}
+
+// colsum[H] += column sums of z; gram[H*H] += z'z (full symmetric), both fp64.
+csc_status gram_tc(csc_ctx* ctx, const float* z, int64_t n_rows, int H, double* colsum, double* gram) {
+  const int Hp = gram_split_pitch(H);
+  DevPtr hi16, lo16;
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &hi16));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_rows * Hp * 2, &lo16));
+  const int64_t rows_per_cta = 256;
+  dim3 grid((unsigned)((Hp / 4 + 255) / 256), (unsigned)ceil_div64(n_rows, rows_per_cta));
+  k_split_colsum<<<grid, 256, 0, ctx->stream>>>(z, n_rows, H, Hp, rows_per_cta, (__half*)hi16->p, (__half*)lo16->p, colsum);
+  CSC_LAUNCHED(ctx);
+  return gram_tc_split(ctx, (const __half*)hi16->p, (const __half*)lo16->p, n_rows, H, Hp, gram, nullptr);
 }

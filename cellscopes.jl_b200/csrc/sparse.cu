@@ -3,6 +3,8 @@
 // non-zeros of the column, with warp-shuffle reductions for the per-cell sums.
 #include <cmath>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -599,6 +601,70 @@ k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row
   }
 }
 
+// The same row builder for the PCA Gram without a dense fp32 matrix in HBM: the finished slice leaves as the two fp16
+// halves of the split-precision operand (hi = fp16(z), lo = fp16(z - hi); gram_tc.cu) with the row pitch the Gram
+// kernel's tensor maps expect.  Column n_feat of every row is set to 1 and the rest of the padding to 0: the Gram of
+// the extended matrix then carries the column sums Z'1 (which the centring needs) in its last column -- the tensor
+// core sums them on the way, with the same split-precision accuracy as every other entry.
+template <int NV>   // groups of 8 genes per lane and slice: slice <= 256 * NV genes
+__global__ void __launch_bounds__(256)
+k_scale_split(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+              const int32_t* __restrict__ gene2h, const float* __restrict__ mu, const float* __restrict__ inv_sd,
+              const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, int32_t row_len,
+              int32_t pitch, float scale_max, __half* __restrict__ hi16, __half* __restrict__ lo16) {
+  extern __shared__ float srow[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  float* row = srow + (size_t)wib * row_len;            // row_len >= slice: the last slice carries the padding
+  const int64_t warp = (int64_t)blockIdx.x * nw + wib;
+  const int64_t nwarp = (int64_t)gridDim.x * nw;
+  const int64_t n_tasks = n_cells * nsplit;
+  for (int64_t task = warp; task < n_tasks; task += nwarp) {
+    const int64_t c = task / nsplit;
+    const int sl = (int)(task - c * nsplit);
+    const int h0 = sl * slice;                          // slice is a multiple of 8
+    const int h1 = min(h0 + slice, n_feat);
+    const int hw = (sl == nsplit - 1) ? pitch : h1;     // the last slice also writes the padding up to the row pitch
+    const int len8 = (hw - h0) >> 3;
+    for (int h = h0 + lane; h < hw; h += 32) row[h - h0] = h < n_feat ? __ldg(z0 + h) : (h == n_feat ? 1.f : 0.f);
+    __syncwarp();
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const int h = __ldg(gene2h + __ldcs(rowval + i));
+      if (h >= h0 && h < h1) {
+        float z = (__ldcs(val + i) - __ldg(mu + h)) * __ldg(inv_sd + h);
+        z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
+        row[h - h0] = z;
+      }
+    }
+    __syncwarp();
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    uint4* dh = reinterpret_cast<uint4*>(hi16 + c * (int64_t)pitch + h0);
+    uint4* dl = reinterpret_cast<uint4*>(lo16 + c * (int64_t)pitch + h0);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int q = j * 32 + lane;
+      if (q < len8) {
+        const float4 v0 = r4[2 * q], v1 = r4[2 * q + 1];
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __half a0 = __float2half_rn(v[2 * u]), a1 = __float2half_rn(v[2 * u + 1]);
+          __half2 p = __halves2half2(a0, a1);
+          ph[u] = *reinterpret_cast<uint32_t*>(&p);
+          p = __floats2half2_rn(v[2 * u] - __half2float(a0), v[2 * u + 1] - __half2float(a1));
+          pl[u] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        __stcs(dh + q, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+        __stcs(dl + q, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // features (any order, 0-based) -> gene2h lookup in ORIGINAL gene order (utils.jl:72-76)
 static csc_status build_gene2h(csc_ctx* ctx, int64_t n_genes, const int64_t* features, int64_t n_feat, DevPtr* d_map,
                                int64_t* n_rows_out) {
@@ -695,6 +761,80 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
   }
   *out = d;
   return CSC_OK;
+  CSC_GUARD_END(ctx)
+}
+
+int gram_split_pitch(int H);
+csc_status gram_tc_split(csc_ctx* ctx, const __half* hi16, const __half* lo16, int64_t n_rows, int H, int pitch, double* gram,
+                         double* colsum_from_ones);
+
+// a3 + a4 fused for callers that only need the PCA of the scaled matrix: colsum[H] += column sums of Z, gram[H*H] += Z'Z
+// without a dense Z in HBM (csc_scale_fill followed by csc_pca_partial writes 4 H bytes per cell, reads them back and
+// writes the split operands; here the split operands are written once).  Falls back to those two calls when H is not
+// a multiple of 4 or exceeds what one CTA's column table holds.
+extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                                             const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
+                                             int32_t do_center, csc_vec* colsum, csc_vec* gram) {
+  if (!ctx || !norm || !partial || !colsum || !gram) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevPtr map;
+  int64_t H = 0;
+  CSC_TRY(build_gene2h(ctx, norm->n_genes, features, n_feat, &map, &H));
+  CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_gram_partial: partial must be fp64[2*H]");
+  CSC_REQUIRE(ctx, n_cells_total >= 2, "csc_scale_gram_partial: need at least 2 cells");
+  CSC_REQUIRE(ctx, colsum->dtype == CSC_DT_F64 && colsum->n >= H, "csc_scale_gram_partial: colsum must be fp64[H]");
+  CSC_REQUIRE(ctx, gram->dtype == CSC_DT_F64 && gram->n >= H * H, "csc_scale_gram_partial: gram must be fp64[H*H]");
+  const char* impl = getenv("CSC_GRAM_IMPL");
+  if ((H & 3) != 0 || H > 8192 || (impl && strcmp(impl, "simt") == 0)) {
+    csc_dense* z = nullptr;
+    CSC_TRY(csc_scale_fill(ctx, norm, features, n_feat, partial, n_cells_total, scale_max, do_scale, do_center, &z));
+    const csc_status rc = csc_pca_partial(ctx, z, colsum, gram);
+    csc_dense_free(z);
+    return rc;
+  }
+  if (norm->n_cells == 0) return CSC_OK;
+  DevPtr params, hi16, lo16;
+  const int pitch = gram_split_pitch((int)H + 1);      // room for the column of ones
+  {
+    StageTimer st(ctx, CSC_T_SCALE_FILL);
+    CSC_TRY(dev_alloc(ctx, (size_t)H * 4 * 3, &params));
+    float* mu = (float*)params->p;
+    float* inv_sd = mu + H;
+    float* z0 = inv_sd + H;
+    k_scale_params<<<(unsigned)ceil_div64(H, 256), 256, 0, ctx->stream>>>(partial->as<double>(), (int32_t)H,
+                                                                          (double)n_cells_total, (float)scale_max, do_scale,
+                                                                          do_center, mu, inv_sd, z0);
+    CSC_LAUNCHED(ctx);
+    CSC_TRY(dev_alloc(ctx, (size_t)norm->n_cells * pitch * 2, &hi16));
+    CSC_TRY(dev_alloc(ctx, (size_t)norm->n_cells * pitch * 2, &lo16));
+    int nsplit = (int)ceil_div64(H, 1024);
+    int slice = (int)(ceil_div64(ceil_div64(H, nsplit), 8) * 8);
+    nsplit = (int)ceil_div64(H, slice);
+    const int last = pitch - (nsplit - 1) * slice;      // the last slice runs to the row pitch
+    const int srow_len = std::max(slice, last);
+    const int warps = 8;
+    const size_t smem = (size_t)warps * srow_len * 4;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
+    int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
+#define CSC_SPLIT_LAUNCH(NV)                                                                                             \
+  do {                                                                                                                   \
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_scale_split<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    k_scale_split<NV><<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(                                                 \
+        norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0, norm->n_cells, (int32_t)H, nsplit,     \
+        slice, srow_len, pitch, (float)scale_max, (__half*)hi16->p, (__half*)lo16->p);                                    \
+  } while (0)
+    if (srow_len <= 256) CSC_SPLIT_LAUNCH(1);
+    else if (srow_len <= 512) CSC_SPLIT_LAUNCH(2);
+    else if (srow_len <= 1024) CSC_SPLIT_LAUNCH(4);
+    else CSC_SPLIT_LAUNCH(5);
+#undef CSC_SPLIT_LAUNCH
+    CSC_LAUNCHED(ctx);
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  StageTimer st2(ctx, CSC_T_PCA_GRAM);
+  return gram_tc_split(ctx, (const __half*)hi16->p, (const __half*)lo16->p, norm->n_cells, (int)H, pitch, gram->as<double>(),
+                       colsum->as<double>());
   CSC_GUARD_END(ctx)
 }
 

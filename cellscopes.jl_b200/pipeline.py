@@ -41,6 +41,7 @@ class PathParams:
     pca_tol: float = 1e-9
     pca_max_iter: int = 500
     keep_norm: bool = False
+    keep_scaled: bool = False      # materialise the dense scaled matrix (scaleCount) as well
 
 
 _NORM = {"logarithm": _capi.NORM_LOGARITHM, "none": _capi.NORM_NONE}
@@ -176,11 +177,16 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     part = be.vec(2 * H, np.float64)
     be.scale_stats_select(nstats, G, feats, part)
     comm.allreduce_sum(part)
-    scaled = be.scale_fill(norm, feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
-    # a4
     colsum = be.vec(H, np.float64)
     gram = be.vec(H * H, np.float64)
-    be.pca_partial(scaled, colsum, gram)
+    if p.keep_scaled or not hasattr(be, "scale_gram_partial"):
+        scaled = be.scale_fill(norm, feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
+        # a4
+        be.pca_partial(scaled, colsum, gram)
+    else:
+        # a3 + a4 fused: nothing after the Gram reads the dense scaled matrix (the embedding comes from the sparse one)
+        scaled = None
+        be.scale_gram_partial(norm, feats, part, n_cells_total, colsum, gram, p.scale_max, p.do_scale, p.do_center)
     comm.allreduce_sum(colsum)
     comm.allreduce_sum(gram)
     pca = be.pca_solve(colsum, gram, H, n_cells_total, p.n_pcs, p.pca_tol, p.pca_max_iter)

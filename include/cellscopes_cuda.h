@@ -167,6 +167,14 @@ csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_stats, int64
 csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                           const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
                           int32_t do_center, csc_dense** out);
+/* a3 + a4 fused for callers that only need the PCA of the scaled matrix (run_pca after scale_object when scaleCount
+ * itself is not asked for; src/scrna/processing.jl:162-191 -> MultivariateStats.fit(PCA, ...)): adds the column sums
+ * of this shard's scaled matrix into colsum[H] and its Gram matrix Z'Z into gram[H*H] (both fp64, cells of this shard
+ * only, ready for the all-reduce) without materialising the dense matrix.  Same arguments as csc_scale_fill. */
+csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
+                                  const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
+                                  int32_t do_center, csc_vec* colsum, csc_vec* gram);
+
 
 /* ---- dense cell-major matrices: scaleCount.count_mtx', pca.cell_embedding ---------------- */
 csc_status csc_dense_alloc(csc_ctx* ctx, int64_t n_rows, int64_t n_cols, csc_dense** out);

@@ -304,6 +304,23 @@ end
 # ------------------------------------------------------------------------------------------------
 # a4  run_pca (processing.jl:164-193)
 # ------------------------------------------------------------------------------------------------
+
+"""
+    scale_gram_partial!(ctx, norm, features0, part, n_cells, colsum, gram; scale_max=10.0, do_scale=true, do_center=true)
+
+`scale_object` fused with the covariance accumulation of `run_pca` for callers that do not keep `scaleCount`: adds the
+column sums and `Z'Z` of this process's cells into `colsum` / `gram` (device fp64 vectors, ready for the all-reduce)
+without a dense scaled matrix in device memory.  `features0` are 0-based gene ids.
+"""
+function scale_gram_partial!(ctx, norm, features0::Vector{Int64}, part, n_cells::Integer, colsum, gram;
+                             scale_max::Real=10.0, do_scale::Bool=true, do_center::Bool=true)
+    GC.@preserve features0 check(ctx, ccall(sym(:csc_scale_gram_partial), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}, Int64, Float64, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}),
+        ctx.h, norm.h, pointer(features0), length(features0), part.h, n_cells, Float64(scale_max), Int32(do_scale),
+        Int32(do_center), colsum.h, gram.h))
+    return nothing
+end
+
 function run_pca(sc_obj::cs.get_object_group("All"); method=:svd, pratio=1, maxoutdim=10, package="MLJ", ctx=nothing)
     s = session(sc_obj; ctx)
     features = sc_obj.varGene.var_gene

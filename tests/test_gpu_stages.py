@@ -326,6 +326,39 @@ def test_sparse_transform_equals_dense_transform(cs, oracle, ctx, medium_counts)
         assert np.all(np.abs(b - want).max(axis=0) <= 2e-5 * scale)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("nfeat,kw", [(2000, {}), (2000, {"scale_max": 3.0}), (333, {}), (1200, {"do_center": False})])
+def test_fused_scale_gram_equals_fill_then_gram(cs, oracle, ctx, medium_counts, nfeat, kw):
+    """csc_scale_gram_partial (no dense scaled matrix) == csc_scale_fill + csc_pca_partial, and both == the fp64 Gram of
+    the oracle's scaled matrix.  333 features exercise the fallback (H not a multiple of 4), 1200 the zero-padded atom."""
+    raw = ctx.sparse_from_scipy(medium_counts)
+    G, N = medium_counts.shape
+    st, ns = ctx.vec(2 * G), ctx.vec(2 * G)
+    norm = ctx.normalize(raw, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, st, ns)
+    feats = ctx.hvg_finish(st, G, N, nfeat, 0.3)["features"]
+    H = np.unique(feats).size
+    part = ctx.vec(2 * H)
+    ctx.scale_stats_select(ns, G, feats, part)
+    args = dict(scale_max=10.0, do_scale=True, do_center=True)
+    args.update(kw)
+    c1, g1 = ctx.vec(H), ctx.vec(H * H)
+    scaled = ctx.scale_fill(norm, feats, part, N, args["scale_max"], args["do_scale"], args["do_center"])
+    ctx.pca_partial(scaled, c1, g1)
+    c2, g2 = ctx.vec(H), ctx.vec(H * H)
+    ctx.scale_gram_partial(norm, feats, part, N, c2, g2, args["scale_max"], args["do_scale"], args["do_center"])
+    z = scaled.download(np.float64)
+    ref_g = z.T @ z
+    ref_c = z.sum(0)
+    scale = np.sqrt(np.outer(np.diag(ref_g), np.diag(ref_g))) + 1e-30
+    for c, g in ((c1, g1), (c2, g2)):
+        gg = g.download().reshape(H, H)
+        assert np.abs(gg - ref_g).max() / scale.max() < 2e-6
+        # the fused path takes the column sums out of the Gram kernel (a column of ones): split-precision accuracy
+        assert np.allclose(c.download(), ref_c, rtol=0, atol=1e-6 * np.sqrt(N * np.diag(ref_g)).max())
+    assert np.abs(g1.download() - g2.download()).max() / scale.max() < 1e-6
+
+
+
 def test_gram_partials_add_up(cs, ctx):
     """Sharding invariance: partials of two cell ranges sum to the partial of the whole (multi-GPU allreduce)."""
     rng = np.random.default_rng(5)
