@@ -46,13 +46,13 @@ namespace {
 constexpr int F_TQ = 256;                 // query rows per CTA: two blocks of UMMA M = 128
 constexpr int F_BN = 128;                 // keys per shared-memory tile = UMMA N: one MMA unit is (key tile, block)
 constexpr int F_DP = 64;                  // padded feature dimension (halves): one 128-byte swizzle row
-constexpr int F_STAGES = 6;               // key tile ring (the MMA loop is unrolled over one turn of it)
+constexpr int F_STAGES = 3;               // key tile ring (the MMA loop is unrolled over one turn of it)
 constexpr int F_ACC = 3;                  // TMEM accumulators of 128 columns, used round-robin by the units
 constexpr int F_TILE_BYTES = F_BN * 128;  // 16 KB
 constexpr int F_PAIRS = 8;                // (block, TMEM lane quarter): 32 query rows each
 constexpr int F_THREADS = 64 + 2 * F_PAIRS * 32;   // producer, MMA issuer, 8 drain warps, 8 insert warps
 constexpr int F_L = 32;                   // candidates kept per row
-constexpr int F_QS = 3;                   // parked chunks per pair (slots of 32 keys x 32 rows x 4 bytes)
+constexpr int F_QS = 4;                   // parked chunks per pair (slots of 32 keys x 32 rows x 4 bytes)
 constexpr int F_TMEM_A = F_ACC * F_BN;    // first column of the query operands (2 blocks x 32 columns)
 constexpr float F_SCALE = 256.f;          // operands are scaled so that small components stay normal in fp16
 constexpr float F_EPS = 1.0e-3f;          // bound on |approx - exact| for unit rows (see the header)
@@ -83,9 +83,8 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
 
 // Candidate sets.  A pair of warps serves 32 query rows, thread = row in both.  The DRAIN warp empties the accumulators
 // and only asks "does any row of mine have a score above its threshold in these 32 keys?"; if so it PARKS the 32 x 32
-// chunk in the pair's queue in shared memory (8 x STS.128 per lane plus each row's mask of candidate columns) and returns
-// to the accumulator stream at once.  The INSERT warp works the queue off concurrently and owns the sets: F_L = 32
-// (score, key id) slots per row in REGISTERS of the row's thread, unsorted (the refine kernel orders by exact score
+// chunk in the pair's queue in shared memory (8 x STS.128 per lane) and returns to the accumulator stream at once.  The INSERT warp works the queue off concurrently and owns the sets: F_L = 32
+// slots per row -- scores in REGISTERS of the row's thread, key ids in shared memory --, unsorted (the refine kernel orders by exact score
 // anyway).  Each score carries its slot number in the 5 low mantissa bits, so the set's minimum -- the threshold tau --
 // and the slot it sits in come out of one FMNMX3 tree; a new candidate overwrites that slot by predicated moves and the
 // tree is redone: ~100 instructions without a dependent memory access.  Ties of the approximate score are irrelevant: a
@@ -112,32 +111,25 @@ __device__ __forceinline__ float set_min(const float (&x)[F_L]) {
   const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
   return fmin3(fmin3(a, b, c), m[9], m[10]);
 }
-// v beats tau: it replaces the set's minimum
-__device__ __forceinline__ void set_insert(float (&x)[F_L], int (&ids)[F_L], float& tau, float v, int id) {
+// v beats tau: it replaces the set's minimum.  ids = the row's column of the [slot][256 rows] id array in shared memory
+// (one store with a run-time slot instead of 32 predicated register moves).
+__device__ __forceinline__ void set_insert(float (&x)[F_L], int* ids, float& tau, float v, int id) {
   const uint32_t slot = __float_as_uint(tau) & (F_L - 1);
   const float vp = __uint_as_float((__float_as_uint(v) & ~(uint32_t)(F_L - 1)) | slot);
 #pragma unroll
-  for (int q = 0; q < F_L; ++q) {
-    const bool here = slot == (uint32_t)q;
-    x[q] = here ? vp : x[q];
-    ids[q] = here ? id : ids[q];
-  }
+  for (int q = 0; q < F_L; ++q) x[q] = (slot == (uint32_t)q) ? vp : x[q];
+  ids[slot * F_TQ] = id;
   tau = set_min(x);
 }
 
-// slot layout: [8 column quads][32 lanes] float4, then [32 lanes] candidate-column masks
-constexpr int F_SLOT_BYTES = 8 * 32 * 16 + 32 * 4;
-__device__ __forceinline__ void park_chunk(const uint32_t (&r)[32], float tau, unsigned char* slot, int lane) {
+// slot layout: [8 column quads][32 lanes] float4
+constexpr int F_SLOT_BYTES = 8 * 32 * 16;
+__device__ __forceinline__ void park_chunk(const uint32_t (&r)[32], unsigned char* slot, int lane) {
   float4* sv = reinterpret_cast<float4*>(slot);
-  unsigned cm4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 8; ++i)
     sv[i * 32 + lane] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                                     __uint_as_float(r[4 * i + 3]));
-#pragma unroll
-    for (int c = 0; c < 4; ++c) cm4[c] |= (__uint_as_float(r[4 * i + c]) > tau ? 1u : 0u) << (4 * i + c);
-  }
-  reinterpret_cast<unsigned*>(slot + 8 * 32 * 16)[lane] = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]);
 }
 
 template <int KS>   // k-steps of 16 halves: ceil(d / 16)
@@ -149,7 +141,8 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
   unsigned char* q_slots = sB + F_STAGES * F_TILE_BYTES;                            // [8 pairs][F_QS] parked chunks
-  float* s_tau = reinterpret_cast<float*>(q_slots + F_PAIRS * F_QS * F_SLOT_BYTES);   // [256 rows] thresholds, insert -> drain
+  int* l_id = reinterpret_cast<int*>(q_slots + F_PAIRS * F_QS * F_SLOT_BYTES);        // [32 slots][256 rows] candidate key ids
+  float* s_tau = reinterpret_cast<float*>(l_id + F_L * F_TQ);                         // [256 rows] thresholds, insert -> drain
   int* q_key = reinterpret_cast<int*>(s_tau + F_TQ);                                  // [8 pairs][F_QS] first key of a parked chunk
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_key + F_PAIRS * F_QS);
   const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
@@ -302,7 +295,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
         atomicAdd(cnt + 0, 1ull);                                                      \
         atomicAdd(cnt + 2, (unsigned long long)(clock64() - tw0));                     \
       }                                                                                \
-      park_chunk(r, tau, my_slots + qs * F_SLOT_BYTES, lane);                           \
+      park_chunk(r, my_slots + qs * F_SLOT_BYTES, lane);                                \
       if (lane == 0) q_key[pair * F_QS + qs] = (kb);                                    \
       __syncwarp();                                                                    \
       if (lane == 0) mbar_arrive(bar_qfull + 8 * (pair * F_QS + qs));                   \
@@ -363,11 +356,11 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
     const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
     float x[F_L];
-    int ids[F_L];
+    int* ids = l_id + row;                              // [slot * F_TQ]
 #pragma unroll
     for (int j = 0; j < F_L; ++j) {
       x[j] = __uint_as_float((__float_as_uint(F_EMPTY) & ~(uint32_t)(F_L - 1)) | (uint32_t)j);
-      ids[j] = INT_MAX;
+      ids[j * F_TQ] = INT_MAX;
     }
     float tau = set_min(x);
     const unsigned char* my_slots = q_slots + pair * (F_QS * F_SLOT_BYTES);
@@ -381,7 +374,16 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       int n_ins = 0;
       const unsigned char* slot = my_slots + qs * F_SLOT_BYTES;
       const float* sv = reinterpret_cast<const float*>(slot);
-      unsigned cm = reinterpret_cast<const unsigned*>(slot + 8 * 32 * 16)[lane];    // columns that beat the drain side's tau
+      unsigned cm4[4] = {0u, 0u, 0u, 0u};                 // columns that beat tau (four independent partial masks)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(slot)[i * 32 + lane];
+        cm4[0] |= (v.x > tau ? 1u : 0u) << (4 * i);
+        cm4[1] |= (v.y > tau ? 1u : 0u) << (4 * i + 1);
+        cm4[2] |= (v.z > tau ? 1u : 0u) << (4 * i + 2);
+        cm4[3] |= (v.w > tau ? 1u : 0u) << (4 * i + 3);
+      }
+      unsigned cm = (cm4[0] | cm4[1]) | (cm4[2] | cm4[3]);
       while (cm) {
         const int j = __ffs(cm) - 1;
         cm &= cm - 1;
@@ -410,7 +412,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     // the row's 32 candidates (unsorted) and the bound on every score outside the set
     if (qvalid) {
 #pragma unroll
-      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = ids[j];
+      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = ids[j * F_TQ];
       // a set that never filled up reports -inf: it holds every key
       out_thr[qrow] = tau < -1.0e37f ? -INFINITY : tau * (1.f / (F_SCALE * F_SCALE)) + F_PACK_SLACK;
     }
@@ -579,7 +581,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 128, &dbg_cnt, true));
   CUtensorMap kmap;
   CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
-  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_PAIRS * F_QS * F_SLOT_BYTES + (size_t)F_TQ * 4 + 128 + (24 + 2 * F_PAIRS * F_QS) * 8 + 64;
+  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_PAIRS * F_QS * F_SLOT_BYTES + (size_t)F_L * F_TQ * 4 + (size_t)F_TQ * 4 + 128 + (24 + 2 * F_PAIRS * F_QS) * 8 + 64;
   const int dbg_mode = getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0;
   cudaEventRecord(ctx->ev_k0, ctx->stream);
 #define F_LAUNCH(KS)                                                                                                     \
