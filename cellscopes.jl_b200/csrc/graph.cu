@@ -3,33 +3,34 @@
 //
 // Column i of the result = kNN(i) U { j : i in kNN(j) }.  Every directed kNN edge contributes the two
 // COO entries (idx, i) and (i, idx) exactly like the reference's push! loop; they are encoded as 64-bit
-// keys (column << 32 | row), radix-sorted, and run-length encoded: the run length (1 or 2) is the value
+// keys (column << row_bits | row, only as many bits as the sizes need: 39 for 500k cells, i.e. 5 radix passes
+// instead of 8), radix-sorted, and run-length encoded: the run length (1 or 2) is the value
 // the reference's sparse(I, J, V) would have summed.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
 
-#define KEY_SENTINEL 0xFFFFFFFFFFFFFFFFull
 
 // forward entries (col = local cell, row = neighbour) and reverse entries (col = neighbour if local, row = cell)
-__global__ void k_graph_keys(const int32_t* __restrict__ idx, int64_t n_total, int32_t k, int64_t lo, int64_t hi,
-                             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ n_valid) {
+__global__ void k_graph_keys(const int32_t* __restrict__ idx, int64_t n_total, int32_t k, int64_t lo, int64_t hi, int row_bits,
+                             unsigned long long sentinel, unsigned long long* __restrict__ keys,
+                             unsigned long long* __restrict__ n_valid) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n_fwd = (hi - lo) * k;
   const int64_t n_all = n_fwd + n_total * k;
-  unsigned long long key = KEY_SENTINEL;
+  unsigned long long key = sentinel;             // sorts after every valid key
   if (e < n_fwd) {
     const int64_t cell = lo + e / k;
     const int32_t nb = idx[cell * k + e % k];
-    key = ((unsigned long long)(cell - lo) << 32) | (unsigned int)nb;
+    key = ((unsigned long long)(cell - lo) << row_bits) | (unsigned int)nb;
   } else if (e < n_all) {
     const int64_t r = e - n_fwd;
     const int64_t cell = r / k;
     const int32_t nb = idx[r];
-    if (nb >= lo && nb < hi) key = ((unsigned long long)(nb - lo) << 32) | (unsigned int)cell;
+    if (nb >= lo && nb < hi) key = ((unsigned long long)(nb - lo) << row_bits) | (unsigned int)cell;
   }
   if (e < n_all) keys[e] = key;
-  const unsigned valid = __ballot_sync(0xffffffffu, key != KEY_SENTINEL);
+  const unsigned valid = __ballot_sync(0xffffffffu, key != sentinel);
   if ((threadIdx.x & 31) == 0 && valid) atomicAdd(n_valid, (unsigned long long)__popc(valid));
 }
 
@@ -71,7 +72,7 @@ __global__ void k_sort_lists(const int32_t* __restrict__ idx, int64_t n_total, i
 
 // value of every unique entry; keep flag for pruning
 __global__ void k_graph_values(const unsigned long long* __restrict__ ukeys, const int32_t* __restrict__ mult, int64_t nnz,
-                               int64_t lo, int32_t k, int mode, double prune, const int32_t* __restrict__ lists,
+                               int64_t lo, int32_t k, int mode, double prune, const int32_t* __restrict__ lists, int row_bits,
                                double* __restrict__ val, int64_t* __restrict__ keep) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nnz) return;
@@ -81,8 +82,8 @@ __global__ void k_graph_values(const unsigned long long* __restrict__ ukeys, con
   } else if (mode == CSC_GRAPH_SUM) {
     v = (double)mult[e];
   } else {
-    const int64_t col = (int64_t)(ukeys[e] >> 32) + lo;
-    const int64_t row = (int64_t)(ukeys[e] & 0xFFFFFFFFull);
+    const int64_t col = (int64_t)(ukeys[e] >> row_bits) + lo;
+    const int64_t row = (int64_t)(ukeys[e] & ((1ull << row_bits) - 1));
     const int32_t* a = lists + col * (k + 1);
     const int32_t* b = lists + row * (k + 1);
     int i = 0, j = 0, inter = 0;
@@ -105,14 +106,14 @@ __global__ void k_graph_values(const unsigned long long* __restrict__ ukeys, con
 }
 
 __global__ void k_graph_emit(const unsigned long long* __restrict__ ukeys, const double* __restrict__ val,
-                             const int64_t* __restrict__ keep, const int64_t* __restrict__ pos, int64_t nnz,
+                             const int64_t* __restrict__ keep, const int64_t* __restrict__ pos, int64_t nnz, int row_bits,
                              int32_t* __restrict__ rowval, double* __restrict__ out_val, int32_t* __restrict__ out_col) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nnz || !keep[e]) return;
   const int64_t p = pos[e];
-  rowval[p] = (int32_t)(ukeys[e] & 0xFFFFFFFFull);
+  rowval[p] = (int32_t)(ukeys[e] & ((1ull << row_bits) - 1));
   out_val[p] = val[e];
-  out_col[p] = (int32_t)(ukeys[e] >> 32);
+  out_col[p] = (int32_t)(ukeys[e] >> row_bits);
 }
 
 // colptr[c] = first entry whose column >= c (entries are sorted by column)
@@ -174,22 +175,24 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   CSC_TRY(dev_alloc(ctx, (size_t)n_all * 8, &keys_b));
   CSC_TRY(dev_alloc(ctx, 8, &counter, true));
   CSC_TRACE(ctx, "graph: alloc keys");
-  k_graph_keys<<<nblk(n_all), 256, 0, ctx->stream>>>(idx, n_cells_total, k, cell_lo, cell_hi, (unsigned long long*)keys_a->p,
-                                                      (unsigned long long*)counter->p);
+  int row_bits = 1, col_bits = 1;
+  while (((int64_t)1 << row_bits) < n_cells_total) ++row_bits;
+  while (((int64_t)1 << col_bits) < n_loc) ++col_bits;
+  const unsigned long long sentinel = 1ull << (row_bits + col_bits);
+  k_graph_keys<<<nblk(n_all), 256, 0, ctx->stream>>>(idx, n_cells_total, k, cell_lo, cell_hi, row_bits, sentinel,
+                                                      (unsigned long long*)keys_a->p, (unsigned long long*)counter->p);
   CSC_LAUNCHED(ctx);
   {
-    int col_bits = 1;
-    while (((int64_t)1 << col_bits) < n_loc) ++col_bits;
+    const int key_bits = row_bits + col_bits + 1;      // the sentinel owns the top bit
     size_t tmp_bytes = 0;
     CSC_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)keys_a->p,
-                                                 (unsigned long long*)keys_b->p, n_all, 0, 64, ctx->stream));
+                                                 (unsigned long long*)keys_b->p, n_all, 0, key_bits, ctx->stream));
     DevPtr tmp;
     CSC_TRY(dev_alloc(ctx, tmp_bytes, &tmp));
-    // sentinels (all ones) sort last in a full 64-bit sort
+    // sentinels sort last
     CSC_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp->p, tmp_bytes, (const unsigned long long*)keys_a->p,
-                                                 (unsigned long long*)keys_b->p, n_all, 0, 64, ctx->stream));
-    ctx->launches += 8;
-    (void)col_bits;
+                                                 (unsigned long long*)keys_b->p, n_all, 0, key_bits, ctx->stream));
+    ctx->launches += 1 + (key_bits + 7) / 8;
   }
   CSC_TRACE(ctx, "graph: keys+sort");
   unsigned long long n_valid = 0;
@@ -225,8 +228,8 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   }
   k_graph_values<<<nblk(n_unique), 256, 0, ctx->stream>>>((const unsigned long long*)ukeys->p, (const int32_t*)mult->p,
                                                            n_unique, cell_lo, k, mode, snn_prune,
-                                                           lists ? (const int32_t*)lists->p : nullptr, (double*)val->p,
-                                                           (int64_t*)keep->p);
+                                                           lists ? (const int32_t*)lists->p : nullptr, row_bits,
+                                                           (double*)val->p, (int64_t*)keep->p);
   CSC_LAUNCHED(ctx);
   CSC_TRY(exclusive_scan(ctx, (const int64_t*)keep->p, (int64_t*)kpos->p, n_unique + 1));
   CSC_TRACE(ctx, "graph: compact+values+scan");
@@ -239,7 +242,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   CSC_TRY(dev_alloc(ctx, (size_t)nnz * 8, &g->val));
   CSC_TRY(dev_alloc(ctx, (size_t)nnz * 4, &cols));
   k_graph_emit<<<nblk(n_unique), 256, 0, ctx->stream>>>((const unsigned long long*)ukeys->p, (const double*)val->p,
-                                                         (const int64_t*)keep->p, (const int64_t*)kpos->p, n_unique,
+                                                         (const int64_t*)keep->p, (const int64_t*)kpos->p, n_unique, row_bits,
                                                          (int32_t*)g->rowval->p, (double*)g->val->p, (int32_t*)cols->p);
   CSC_LAUNCHED(ctx);
   k_graph_colptr<<<nblk(n_loc + 1), 256, 0, ctx->stream>>>((const int32_t*)cols->p, nnz, n_loc, (int64_t*)g->colptr->p);
