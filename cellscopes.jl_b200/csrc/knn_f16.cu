@@ -157,7 +157,8 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
   const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
-  // locality order (knn_order.cu): this block starts its scan near its own cluster and wraps around
+  // locality order (knn_order.cu): the scan fans out from the middle of the block's own cluster, tiles c, c+1, c-1,
+  // c+2, ... (the key order is circular), so that similar keys come early and the thresholds settle
   const int64_t t_start = start_tile ? (int64_t)start_tile[blockIdx.x] % n_tiles : 0;
 
   if (threadIdx.x == 0) {
@@ -198,8 +199,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / F_STAGES) & 1) ^ 1));
       if (elect_one()) {
         mbar_expect_tx(bar_full + 8 * s, F_TILE_BYTES);
-        int64_t tile = t + t_start;
+        int64_t tile = (t & 1) ? t_start + ((t + 1) >> 1) : t_start - ((t + 1) >> 1);
         if (tile >= n_tiles) tile -= n_tiles;
+        if (tile < 0) tile += n_tiles;
         tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, (int)(tile * F_BN));
       }
       __syncwarp();
@@ -313,8 +315,9 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       const float tau = qvalid ? *my_tau : INFINITY;    // may lag behind the insert warp: only ever too low
       mbar_wait(bar_tfull + 8 * a, kpar);
       tc_fence_after();
-      int64_t tile = t + t_start;
+      int64_t tile = (t & 1) ? t_start + ((t + 1) >> 1) : t_start - ((t + 1) >> 1);
       if (tile >= n_tiles) tile -= n_tiles;
+      if (tile < 0) tile += n_tiles;
       const int key0 = (int)(tile * F_BN);
       const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
       uint32_t rA[32], rB[32];

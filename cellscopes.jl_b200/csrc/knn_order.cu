@@ -7,6 +7,7 @@
 // nothing that follows gets through.  So: cluster the unit rows (spherical k-means, ~N/2048 clusters, a few Lloyd
 // passes on a strided sample), sort keys and queries by cluster, and let every query block start its scan a few
 // tiles before its own cluster.  Pure reordering: results are identical, ids are mapped back at the end.
+#include <cmath>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -126,6 +127,12 @@ __global__ void k_self_pos(const int32_t* __restrict__ perm_q, const int32_t* __
 
 }  // namespace
 
+// label <- rank[label]: clusters renumbered so that neighbours in the new numbering are neighbours on the sphere
+__global__ void k_relabel(int32_t* __restrict__ label, int64_t n, const int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) label[i] = __ldg(rank + label[i]);
+}
+
 static csc_status sort_by_label(csc_ctx* ctx, const int32_t* labels, int64_t n, int K, DevPtr* perm, DevPtr* labels_sorted) {
   DevPtr idx, tmp;
   CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &idx));
@@ -148,7 +155,8 @@ static csc_status sort_by_label(csc_ctx* ctx, const int32_t* labels, int64_t n, 
 // Cluster the key rows, sort keys (and queries) by cluster.  Outputs (device):
 //   ks / qs        gathered prepared rows in sorted order (qs == ks when `same`)
 //   perm_k/perm_q  sorted position -> original row;  self_pos[r] = sorted key position of query row r's own cell
-//   start_tile[b]  first key tile to scan for query block b (blocks of `tq` rows, tiles of `bn` keys)
+//   start_tile[b]  key tile in the middle of query block b's cluster: its scan fans out from there (blocks of `tq`
+//                  rows, tiles of `bn` keys)
 csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const float* k_prep, int64_t n_keys, bool same,
                            int64_t query_offset, int tq, int bn, DevPtr* ks, DevPtr* qs, DevPtr* perm_k, DevPtr* perm_q,
                            DevPtr* self_pos, DevPtr* start_tile) {
@@ -174,9 +182,29 @@ csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const
     k_km_update<<<K, 32, 0, ctx->stream>>>((const float*)sums->p, (const int32_t*)counts->p, K, (float*)cent->p);
     CSC_LAUNCHED(ctx);
   }
+  // Number the clusters by the angle of their centroid in the plane of the two leading components (the rows are unit
+  // vectors of the PCA embedding): a circular order in which neighbouring numbers are neighbouring directions, so that
+  // a scan that fans out from a row's own cluster (knn_f16.cu visits tiles c, c+1, c-1, c+2, ...) meets the similar
+  // clusters first and its thresholds settle early.
+  DevPtr rank;
+  {
+    std::vector<float> hc((size_t)K * KO_D);
+    CSC_CUDA(ctx, cudaMemcpyAsync(hc.data(), cent->p, hc.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<float, int32_t>> ang((size_t)K);
+    for (int c = 0; c < K; ++c) ang[c] = std::make_pair(std::atan2(hc[(size_t)c * KO_D + 1], hc[(size_t)c * KO_D]), (int32_t)c);
+    std::sort(ang.begin(), ang.end());
+    std::vector<int32_t> hr((size_t)K);
+    for (int p = 0; p < K; ++p) hr[ang[p].second] = p;
+    CSC_TRY(dev_alloc(ctx, (size_t)K * 4, &rank));
+    CSC_CUDA(ctx, cudaMemcpyAsync(rank->p, hr.data(), (size_t)K * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   CSC_TRY(dev_alloc(ctx, (size_t)n_keys * 4, &lab_k));
   k_km_assign<<<(unsigned)ceil_div64(n_keys, 128), 128, 0, ctx->stream>>>(k_prep, n_keys, 1, (const float*)cent->p, K,
                                                                        (int32_t*)lab_k->p, nullptr, nullptr);
+  CSC_LAUNCHED(ctx);
+  k_relabel<<<(unsigned)ceil_div64(n_keys, 256), 256, 0, ctx->stream>>>((int32_t*)lab_k->p, n_keys, (const int32_t*)rank->p);
   CSC_LAUNCHED(ctx);
   CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_k->p, n_keys, K, perm_k, &labs_k));
   CSC_TRY(dev_alloc(ctx, (size_t)n_keys * KO_D * 4, ks));
@@ -197,6 +225,8 @@ csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const
     k_km_assign<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(q_prep, n_q, 1, (const float*)cent->p, K, (int32_t*)lab_q->p,
                                                                       nullptr, nullptr);
     CSC_LAUNCHED(ctx);
+    k_relabel<<<(unsigned)ceil_div64(n_q, 256), 256, 0, ctx->stream>>>((int32_t*)lab_q->p, n_q, (const int32_t*)rank->p);
+    CSC_LAUNCHED(ctx);
     CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_q->p, n_q, K, perm_q, &labs_q));
     CSC_TRY(dev_alloc(ctx, (size_t)n_q * KO_D * 4, qs));
     k_gather64<<<(unsigned)ceil_div64(n_q * 16, 256), 256, 0, ctx->stream>>>(q_prep, (const int32_t*)(*perm_q)->p, n_q, (float*)(*qs)->p,
@@ -215,7 +245,8 @@ csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const
   CSC_CUDA(ctx, cudaMemcpyAsync(h_seg.data(), seg->p, (size_t)(K + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int64_t bq = 0; bq < n_blocks; ++bq) {
-    const int64_t t = (int64_t)h_seg[h_lab[bq]] / bn - 2;     // two tiles of head-room before the cluster
+    // the tile in the middle of the block's cluster: the scan fans out from there
+    const int64_t t = ((int64_t)h_seg[h_lab[bq]] + (int64_t)h_seg[h_lab[bq] + 1]) / 2 / bn;
     h_start[bq] = (int32_t)std::max<int64_t>(0, t);
   }
   CSC_TRY(dev_alloc(ctx, (size_t)n_blocks * 4, start_tile));
