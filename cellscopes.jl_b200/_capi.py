@@ -64,8 +64,10 @@ SIGNATURES = {
     "csc_sparse_free": (_I32, [_P]),
     "csc_generate_counts": (_I32, [_P, _I64, _I64, _I64, _U64, _P, _P, _P, _P, _I32, _I32, _F32, _F32, _F32, _PP]),
     "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _P, _PP]),
+    "csc_normalize_fuses_norm_stats": (_I32, [_I64]),
     "csc_gene_stats_partial": (_I32, [_P, _P, _P]),
     "csc_hvg_finish": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
+    "csc_sparse_select_rows": (_I32, [_P, _P, _P, _I64, _PP]),
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
     "csc_scale_stats_select": (_I32, [_P, _P, _I64, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
@@ -272,6 +274,9 @@ class Context:
                                           norm_stats.h if norm_stats is not None else None, C.byref(h)))
         return Sparse(self, h)
 
+    def normalize_fuses_norm_stats(self, n_genes):
+        return bool(self.lib.csc_normalize_fuses_norm_stats(int(n_genes)))
+
     def gene_stats_partial(self, raw, gene_stats):
         self.check(self.lib.csc_gene_stats_partial(self.h, raw.h, gene_stats.h))
 
@@ -286,6 +291,13 @@ class Context:
         out["order"] = order
         out["features"] = order[:min(int(n_features), g)].copy()
         return out
+
+    def select_rows(self, m, features):
+        """subset_count on the device: rows `features` in original gene order, renumbered 0..H-1"""
+        f = np.ascontiguousarray(features, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_sparse_select_rows(self.h, m.h, _ptr(f), f.size, C.byref(h)))
+        return Sparse(self, h)
 
     def scale_stats_partial(self, norm, features, partial):
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)

@@ -5,6 +5,8 @@
 
 #include <cuda_fp16.h>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -440,6 +442,14 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   return CSC_OK;
 }
 
+// 1 when csc_normalize can keep the all-gene normalised moments in per-CTA shared-memory tables (four 32-bit tables of
+// n_genes entries within 200 KB: n_genes <= 12800); otherwise its norm_stats output costs a pass of global fp64
+// atomics over every stored entry, and a caller that only needs the moments of the selected genes is better off
+// with csc_scale_stats_partial after the selection.
+extern "C" int32_t csc_normalize_fuses_norm_stats(int64_t n_genes) {
+  return (size_t)n_genes * 16 <= (size_t)200 * 1024 ? 1 : 0;
+}
+
 extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
                                     double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
                                     csc_sparse** out) {
@@ -689,6 +699,100 @@ static csc_status build_gene2h(csc_ctx* ctx, int64_t n_genes, const int64_t* fea
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *n_rows_out = H;
   return CSC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// subset_count (src/scrna/utils.jl:59-87) on the device: the rows `features` of a CSC matrix, in ORIGINAL gene
+// order, renumbered 0..H-1.  A whole-transcriptome matrix keeps ~6 % of its rows (2000 of 33 k genes); the scale,
+// fill and transform passes then read the subset instead of looking every stored entry up again.
+// A warp owns a cell: count pass, exclusive scan, then an order-preserving compaction by warp votes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_select_count(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const int32_t* __restrict__ gene2h,
+               int64_t n_cells, int64_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    int n = 0;
+    for (int64_t i = b + lane; i < e; i += 32) n += __ldg(gene2h + __ldcs(rowval + i)) >= 0 ? 1 : 0;
+    n = (int)warp_sum((double)n);
+    if (lane == 0) counts[c] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_select_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+              const int32_t* __restrict__ gene2h, int64_t n_cells, const int64_t* __restrict__ out_colptr,
+              int32_t* __restrict__ out_rowval, float* __restrict__ out_val) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    int64_t o = out_colptr[c];
+    for (int64_t i0 = b; i0 < e; i0 += 32) {
+      const int64_t i = i0 + lane;
+      const int h = i < e ? __ldg(gene2h + __ldcs(rowval + i)) : -1;
+      const unsigned m = __ballot_sync(FULL, h >= 0);
+      if (h >= 0) {
+        const int64_t p = o + __popc(m & ((1u << lane) - 1u));
+        out_rowval[p] = h;
+        out_val[p] = __ldcs(val + i);
+      }
+      o += __popc(m);
+    }
+  }
+}
+
+extern "C" csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, const int64_t* features, int64_t n_feat,
+                                             csc_sparse** out) {
+  if (!ctx || !m || !out) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_SCALE_STATS);
+  DevPtr map, counts;
+  int64_t H = 0;
+  CSC_TRY(build_gene2h(ctx, m->n_genes, features, n_feat, &map, &H));
+  std::unique_ptr<csc_sparse> r(new csc_sparse());
+  r->ctx = ctx;
+  r->n_genes = H;
+  r->n_cells = m->n_cells;
+  r->nnz = 0;
+  CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &counts, true));
+  CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &r->colptr));
+  if (m->n_cells > 0) {
+    k_select_count<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->cp(), m->rv(), (const int32_t*)map->p, m->n_cells,
+                                                                (int64_t*)counts->p);
+    CSC_LAUNCHED(ctx);
+  }
+  {
+    size_t tb = 0;
+    CSC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int64_t*)counts->p, (int64_t*)r->colptr->p,
+                                                (int)(m->n_cells + 1), ctx->stream));
+    DevPtr tmp;
+    CSC_TRY(dev_alloc(ctx, tb, &tmp));
+    CSC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp->p, tb, (const int64_t*)counts->p, (int64_t*)r->colptr->p,
+                                                (int)(m->n_cells + 1), ctx->stream));
+    ctx->launches += 2;
+    int64_t nnz = 0;
+    CSC_CUDA(ctx, cudaMemcpyAsync(&nnz, (const int64_t*)r->colptr->p + m->n_cells, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->nnz = nnz;
+  }
+  CSC_TRY(dev_alloc(ctx, (size_t)r->nnz * 4, &r->rowval));
+  CSC_TRY(dev_alloc(ctx, (size_t)r->nnz * 4, &r->val));
+  if (r->nnz > 0) {
+    k_select_fill<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->cp(), m->rv(), m->v(), (const int32_t*)map->p, m->n_cells,
+                                                               r->cp(), (int32_t*)r->rowval->p, r->v());
+    CSC_LAUNCHED(ctx);
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *out = r.release();
+  return CSC_OK;
+  CSC_GUARD_END(ctx)
 }
 
 extern "C" csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features,

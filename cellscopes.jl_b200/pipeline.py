@@ -165,7 +165,10 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
         offsets = np.array([0, n_cells_total], dtype=np.int64)
     # a1 + the raw moments of a2 + the normalised moments of a3, one pass over the counts
     stats = be.vec(2 * G, np.float64)
-    nstats = be.vec(2 * G, np.float64)
+    # the normalised moments of ALL genes ride along only while their tables fit in shared memory (<= 12800 genes);
+    # a whole-transcriptome matrix takes the moments of the selected genes in a pass of its own after the selection
+    fused_nstats = be.normalize_fuses_norm_stats(G) if hasattr(be, "normalize_fuses_norm_stats") else True
+    nstats = be.vec(2 * G, np.float64) if fused_nstats else None
     norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats, nstats)
     comm.allreduce_sum(stats)
     # a2
@@ -175,26 +178,35 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     H = int(rows.size)
     # a3
     part = be.vec(2 * H, np.float64)
-    be.scale_stats_select(nstats, G, feats, part)
+    src, src_feats = norm, feats                  # what the scale / Gram / transform passes read
+    if not fused_nstats and hasattr(be, "select_rows") and G >= 4 * H:
+        # whole-transcriptome matrix: subset_count first (few of the rows are kept), everything after reads the subset
+        src, src_feats = be.select_rows(norm, feats), None
+    if fused_nstats:
+        be.scale_stats_select(nstats, G, feats, part)
+    else:
+        be.scale_stats_partial(src, src_feats, part)
     comm.allreduce_sum(part)
     colsum = be.vec(H, np.float64)
     gram = be.vec(H * H, np.float64)
     if p.keep_scaled or not hasattr(be, "scale_gram_partial"):
-        scaled = be.scale_fill(norm, feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
+        scaled = be.scale_fill(src, src_feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
         # a4
         be.pca_partial(scaled, colsum, gram)
     else:
         # a3 + a4 fused: nothing after the Gram reads the dense scaled matrix (the embedding comes from the sparse one)
         scaled = None
-        be.scale_gram_partial(norm, feats, part, n_cells_total, colsum, gram, p.scale_max, p.do_scale, p.do_center)
+        be.scale_gram_partial(src, src_feats, part, n_cells_total, colsum, gram, p.scale_max, p.do_scale, p.do_center)
     comm.allreduce_sum(colsum)
     comm.allreduce_sum(gram)
     pca = be.pca_solve(colsum, gram, H, n_cells_total, p.n_pcs, p.pca_tol, p.pca_max_iter)
     # the embedding comes straight from the sparse normalised matrix (Z = S + 1 z0' is sparse-plus-rank-one)
     if hasattr(be, "pca_transform_sparse"):
-        emb = be.pca_transform_sparse(norm, feats, part, n_cells_total, pca, p.scale_max, p.do_scale, p.do_center)
+        emb = be.pca_transform_sparse(src, src_feats, part, n_cells_total, pca, p.scale_max, p.do_scale, p.do_center)
     else:
         emb = be.pca_transform(scaled, pca)
+    if src is not norm:
+        src.free()
     if not p.keep_norm:
         norm.free()
         norm = None

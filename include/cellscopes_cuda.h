@@ -140,6 +140,9 @@ csc_status csc_generate_counts(csc_ctx* ctx, int64_t n_genes, int64_t cell_lo, i
 csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
                          double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
                          csc_sparse** out);
+/* 1 when csc_normalize fills norm_stats from shared-memory tables in the same pass (n_genes <= 12800); with more genes
+ * norm_stats costs a pass of global atomics and csc_scale_stats_partial on the selected genes is the cheaper route. */
+int32_t csc_normalize_fuses_norm_stats(int64_t n_genes);
 
 /* ---- a2: find_variable_genes src/scrna/processing.jl:133-155 ---------------------------- */
 /* per-gene (sum x, sum x^2) of this shard, += into gene_stats fp64[2*n_genes] (standalone K2) */
@@ -151,6 +154,12 @@ csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw, csc_vec* 
 csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
                           int64_t n_features, double span, double* mean, double* variance,
                           double* variance_expected, double* variance_standardized, int64_t* order);
+
+/* subset_count (src/scrna/utils.jl:59-87): the rows features[n_feat] (0-based, any order) of m in ORIGINAL gene order,
+ * renumbered 0..H-1, as a new matrix with the same cells.  scale_object works on this subset in the reference; here it
+ * pays off when few of the genes are kept (whole-transcriptome matrices): the passes after it take features == NULL. */
+csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, const int64_t* features, int64_t n_feat,
+                                  csc_sparse** out);
 
 /* ---- a3: scale_object src/scrna/processing.jl:65-93 ------------------------------------- */
 /* features[n_feat]: 0-based gene ids in any order; rows are taken in ORIGINAL gene order like

@@ -327,6 +327,24 @@ def test_sparse_transform_equals_dense_transform(cs, oracle, ctx, medium_counts)
 
 
 @pytest.mark.gpu
+def test_select_rows_is_subset_count(cs, oracle, ctx, medium_counts):
+    """csc_sparse_select_rows == rows of the matrix in ORIGINAL gene order (src/scrna/utils.jl:59-87), bit for bit; an
+    empty selection of a cell stays an empty column; unsorted and repeated feature ids are fine."""
+    raw = ctx.sparse_from_scipy(medium_counts)
+    G, N = medium_counts.shape
+    rng = np.random.default_rng(3)
+    feats = rng.choice(G, size=137, replace=False)
+    feats = np.r_[feats, feats[:5]]                       # repeats
+    sub = ctx.select_rows(raw, feats).to_scipy()
+    rows = np.unique(feats)
+    want = medium_counts.tocsr()[rows].tocsc()
+    want.sort_indices()
+    assert sub.shape == (rows.size, N)
+    assert np.array_equal(sub.indptr, want.indptr) and np.array_equal(sub.indices, want.indices)
+    assert np.array_equal(sub.data, want.data.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("nfeat,kw", [(2000, {}), (2000, {"scale_max": 3.0}), (333, {}), (1200, {"do_center": False})])
 def test_fused_scale_gram_equals_fill_then_gram(cs, oracle, ctx, medium_counts, nfeat, kw):
     """csc_scale_gram_partial (no dense scaled matrix) == csc_scale_fill + csc_pca_partial, and both == the fp64 Gram of
