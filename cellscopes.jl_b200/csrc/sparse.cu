@@ -716,8 +716,9 @@ k_select_count(const int64_t* __restrict__ colptr, const int32_t* __restrict__ r
   for (int64_t c = warp; c < n_cells; c += nwarp) {
     const int64_t b = colptr[c], e = colptr[c + 1];
     int n = 0;
+#pragma unroll 8
     for (int64_t i = b + lane; i < e; i += 32) n += __ldg(gene2h + __ldcs(rowval + i)) >= 0 ? 1 : 0;
-    n = (int)warp_sum((double)n);
+    n = __reduce_add_sync(0xffffffffu, n);
     if (lane == 0) counts[c] = n;
   }
 }
@@ -733,6 +734,7 @@ k_select_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   for (int64_t c = warp; c < n_cells; c += nwarp) {
     const int64_t b = colptr[c], e = colptr[c + 1];
     int64_t o = out_colptr[c];
+#pragma unroll 4
     for (int64_t i0 = b; i0 < e; i0 += 32) {
       const int64_t i = i0 + lane;
       const int h = i < e ? __ldg(gene2h + __ldcs(rowval + i)) : -1;
