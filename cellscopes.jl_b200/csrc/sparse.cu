@@ -50,6 +50,18 @@ static inline unsigned grid_for(int64_t n, int sm) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256), (int64_t)sm * 16));
 }
 
+// CTAs of `kern` that are resident per SM at this block size and dynamic shared memory: the persistent kernels divide
+// their tasks statically over the grid, so a grid above the resident count runs a thin second wave
+template <typename K>
+static int resident_ctas(K kern, int threads, size_t smem, int fallback) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fallback;
+  }
+  return n;
+}
+
 static size_t dt_size(int32_t dt) { return (dt == CSC_DT_F32 || dt == CSC_DT_I32) ? 4 : 8; }
 
 // stage `n` host elements through a bounded device buffer and run `conv(dev_src, offset, count)` on each chunk
@@ -235,7 +247,23 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 //   Y2 = sum round(y^2 s2) u32, fixed point
 // Integer sums are order-independent, so the result is deterministic; the raw moments are exact.
 // HBM traffic: 4 B value read + 4 B value written + 4 B row index per non-zero.
+// What bounds the pass (tools/micro/norm_bench.cu, C2 shape): without the table updates it streams at 0.76 of the
+// HBM rate; the 3.4 shared-memory atomics per entry run at ~7 lanes/clk/SM (bank conflicts of 32 random genes),
+// 0.22 ms on their own, and go through the same load/store unit as the global accesses.  The compiler does not move
+// a global load across an atomic, so a loop of load -> update -> load exposes one DRAM latency per entry group: the
+// loads of UN entries per lane are therefore issued first (0.74 -> 0.52 ms), the next cell's lines are prefetched
+// into L2, and log1p of arguments >= 1 uses the hardware logarithm (-> 0.46 ms).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// lanes 0-15: the 128-byte lines of val[b, e); lanes 16-31: those of rowval[b, e)
+__device__ __forceinline__ void prefetch_column_l2(const int32_t* rowval, const float* val, int64_t b, int64_t e, int lane) {
+  const char* base = lane < 16 ? reinterpret_cast<const char*>(val) : reinterpret_cast<const char*>(rowval);
+  if (base == nullptr) return;
+  const int64_t hi = e * 4;
+  for (int64_t off = ((b * 4) & ~(int64_t)127) + 128 * (lane & 15); off < hi; off += 128 * 16) prefetch_l2(base + off);
+}
+
 struct NormArgs {
   const int64_t* colptr;
   const int32_t* rowval;
@@ -276,8 +304,15 @@ k_normalize(const NormArgs a) {
   const int64_t c1 = min(c0 + a.cells_per_cta, a.n_cells);
   const bool pc_is_one = (a.pc == 1.0);
   const float pcf = (float)a.pc;
+  constexpr int UN = 4;   // entries per lane whose loads are issued before the first update (see the header comment)
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (c0 + warp < c1) { b = a.colptr[c0 + warp]; e = a.colptr[c0 + warp + 1]; }
+  if (c0 + warp + nwarp < c1) { nb = a.colptr[c0 + warp + nwarp]; ne = a.colptr[c0 + warp + nwarp + 1]; }
   for (int64_t c = c0 + warp; c < c1; c += nwarp) {
-    const int64_t b = a.colptr[c], e = a.colptr[c + 1];
+    // column bounds two cells ahead, the next cell's lines on their way into L2 while this one is processed
+    int64_t nnb = 0, nne = 0;
+    if (c + 2 * nwarp < c1) { nnb = a.colptr[c + 2 * nwarp]; nne = a.colptr[c + 2 * nwarp + 1]; }
+    if (nb < ne) prefetch_column_l2((RAW > 0 || NSTATS) ? a.rowval : nullptr, a.raw, nb, ne, lane);
     float scale = 0.f;
     if (WRITE_NORM || NSTATS) {
       double s = 0.0;
@@ -289,51 +324,67 @@ k_normalize(const NormArgs a) {
       // reference's NaN column (processing.jl:18).
       scale = (float)((1.0 / s) * a.sf);
     }
-#pragma unroll 4
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const float x = a.raw[i];
-      float y = 0.f;
-      if (WRITE_NORM || NSTATS) {
-        const float t = x * scale;
-        if (a.method == CSC_NORM_LOGARITHM) {
-          y = pc_is_one ? log1pf(t) : logf(t + pcf);
-        } else {
-          y = t;
-        }
-        if (a.nan_to_zero && y != y) y = 0.f;
-        if (WRITE_NORM) __stcs(a.out + i, y);
+    for (int64_t i0 = b + lane; i0 < e; i0 += 32 * UN) {
+      float xs[UN];
+      int gs[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t i = i0 + 32 * u;
+        xs[u] = i < e ? a.raw[i] : 0.f;
+        gs[u] = ((RAW > 0 || NSTATS) && i < e) ? __ldcs(a.rowval + i) : 0;
       }
-      if (RAW > 0 || NSTATS) {
-        const int g = __ldcs(a.rowval + i);
-        if (RAW > 0) {
-          const float xr = rintf(x);
-          if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
-            const unsigned int xi = (unsigned int)x;
-            atomicAdd(&s1tab[g], xi);
-            if (RAW == 2 && xi <= 255u) {
-              if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
-            } else if (xi >= 2u) {
-              const double xd = (double)x;
-              atomicAdd(&a.gstats[(int64_t)G + g], xd * xd - xd);
-            }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t i = i0 + 32 * u;
+        if (i >= e) break;
+        const float x = xs[u];
+        float y = 0.f;
+        if (WRITE_NORM || NSTATS) {
+          const float t = x * scale;
+          if (a.method == CSC_NORM_LOGARITHM) {
+            // log(1 + t): from t = 1 on, 1 + t is at least 2, where __logf is good to 3 ulp and the rounding of the
+            // sum costs 2^-24 / log 2 relative (4.5e-7 together, against the 1e-5 the path promises); below, and
+            // for any other pseudocount, the library functions
+            y = pc_is_one ? (t >= 1.f ? __logf(1.f + t) : log1pf(t)) : logf(t + pcf);
           } else {
-            const double xd = (double)x;
-            atomicAdd(&a.gstats[g], xd);
-            atomicAdd(&a.gstats[(int64_t)G + g], xd * xd);
+            y = t;
           }
+          if (a.nan_to_zero && y != y) y = 0.f;
+          if (WRITE_NORM) __stcs(a.out + i, y);
         }
-        if (NSTATS) {
-          if (fabsf(y) <= a.ymax) {   // false for NaN / Inf / out-of-range values
-            atomicAdd(&y1tab[g], __float2int_rn(y * a.s1));
-            atomicAdd(&y2tab[g], __float2uint_rn(y * y * a.s2));
-          } else {
-            const double yd = (double)y;
-            atomicAdd(&a.nstats[g], yd);
-            atomicAdd(&a.nstats[(int64_t)G + g], yd * yd);
+        if (RAW > 0 || NSTATS) {
+          const int g = gs[u];
+          if (RAW > 0) {
+            const float xr = rintf(x);
+            if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
+              const unsigned int xi = (unsigned int)x;
+              atomicAdd(&s1tab[g], xi);
+              if (RAW == 2 && xi <= 255u) {
+                if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
+              } else if (xi >= 2u) {
+                const double xd = (double)x;
+                atomicAdd(&a.gstats[(int64_t)G + g], xd * xd - xd);
+              }
+            } else {
+              const double xd = (double)x;
+              atomicAdd(&a.gstats[g], xd);
+              atomicAdd(&a.gstats[(int64_t)G + g], xd * xd);
+            }
+          }
+          if (NSTATS) {
+            if (fabsf(y) <= a.ymax) {   // false for NaN / Inf / out-of-range values
+              atomicAdd(&y1tab[g], __float2int_rn(y * a.s1));
+              atomicAdd(&y2tab[g], __float2uint_rn(y * y * a.s2));
+            } else {
+              const double yd = (double)y;
+              atomicAdd(&a.nstats[g], yd);
+              atomicAdd(&a.nstats[(int64_t)G + g], yd * yd);
+            }
           }
         }
       }
     }
+    b = nb; e = ne; nb = nnb; ne = nne;
   }
   if (NTAB > 0) {
     __syncthreads();
@@ -570,11 +621,57 @@ __global__ void k_scale_params(const double* __restrict__ part, int32_t n_feat, 
 // slices handled by different warp-tasks: the shared-memory footprint per warp shrinks accordingly, which is what
 // limits the number of rows in flight per SM (8 KB per full row of 2000 genes); the cell's stored entries are read
 // once per slice, out of L1/L2.
-__global__ void __launch_bounds__(256)
-k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
-             const int32_t* __restrict__ gene2h, const float* __restrict__ mu, const float* __restrict__ inv_sd,
-             const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, float scale_max,
-             float* __restrict__ out) {
+// The same row builder for the PCA Gram without a dense fp32 matrix in HBM: the finished slice leaves as the two fp16
+// halves of the split-precision operand (hi = fp16(z), lo = fp16(z - hi); gram_tc.cu) with the row pitch the Gram
+// kernel's tensor maps expect.  Column n_feat of every row is set to 1 and the rest of the padding to 0: the Gram of
+// the extended matrix then carries the column sums Z'1 (which the centring needs) in its last column -- the tensor
+// core sums them on the way, with the same split-precision accuracy as every other entry.
+// Both are built around the memory latency that bounded their first version (ncu: long-scoreboard stalls 27 per
+// issued instruction; 1.78 / 1.91 ms at C2): (1) the column bounds of a warp's next two tasks are loaded ahead, (2) the
+// lines of the NEXT task's column (values and row indices) are prefetched into L2 while the current row is built,
+// (3) the scatter loads a group of UN entries (index, value, then the gene2h look-ups) before the first dependent
+// use, (4) the fill value goes to shared memory with 16-byte stores, (5) the grid is the number of CTAs that are
+// actually resident (the tasks are divided statically over the grid): 1.31 / 1.44 ms, bit-identical results.
+struct ScaleSrc {
+  const int64_t* colptr;
+  const int32_t* rowval;
+  const float* val;
+  const int32_t* gene2h;
+  const float* mu;
+  const float* inv_sd;
+  const float* z0;
+};
+
+template <int UN>
+__device__ __forceinline__ void scatter_scaled(const ScaleSrc& s, float* row, int h0, int h1, int64_t b, int64_t e, int lane,
+                                               float scale_max) {
+  for (int64_t i0 = b + lane; i0 < e; i0 += 32 * UN) {
+    int g[UN];
+    float x[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + 32 * u;
+      const bool ok = i < e;
+      g[u] = ok ? __ldcs(s.rowval + i) : -1;
+      x[u] = ok ? __ldcs(s.val + i) : 0.f;
+    }
+    int h[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) h[u] = g[u] >= 0 ? __ldg(s.gene2h + g[u]) : -1;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (h[u] >= h0 && h[u] < h1) {
+        float z = (x[u] - __ldg(s.mu + h[u])) * __ldg(s.inv_sd + h[u]);
+        z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
+        row[h[u] - h0] = z;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_scale_fill(const ScaleSrc s, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, float scale_max,
+              float* __restrict__ out) {
   extern __shared__ float srow[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -582,25 +679,30 @@ k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t n_tasks = n_cells * nsplit;
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (warp < n_tasks) { const int64_t c = warp / nsplit; b = s.colptr[c]; e = s.colptr[c + 1]; }
+  if (warp + nwarp < n_tasks) { const int64_t c = (warp + nwarp) / nsplit; nb = s.colptr[c]; ne = s.colptr[c + 1]; }
+  const bool vec_ok = (n_feat & 3) == 0 && (slice & 3) == 0;
   for (int64_t task = warp; task < n_tasks; task += nwarp) {
+    int64_t nnb = 0, nne = 0;
+    if (task + 2 * nwarp < n_tasks) { const int64_t c2 = (task + 2 * nwarp) / nsplit; nnb = s.colptr[c2]; nne = s.colptr[c2 + 1]; }
+    if (nb < ne) prefetch_column_l2(s.rowval, s.val, nb, ne, lane);
     const int64_t c = task / nsplit;
     const int h0 = (int)(task - c * nsplit) * slice;
     const int h1 = min(h0 + slice, n_feat);
-    for (int h = h0 + lane; h < h1; h += 32) row[h - h0] = __ldg(z0 + h);
-    __syncwarp();
-    const int64_t b = colptr[c], e = colptr[c + 1];
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const int h = __ldg(gene2h + __ldcs(rowval + i));
-      if (h >= h0 && h < h1) {
-        float z = (__ldcs(val + i) - __ldg(mu + h)) * __ldg(inv_sd + h);
-        z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
-        row[h - h0] = z;
-      }
+    const int len = h1 - h0;
+    if (vec_ok && (len & 3) == 0) {
+      const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
+      float4* r4 = reinterpret_cast<float4*>(row);
+      for (int q = lane; q < (len >> 2); q += 32) r4[q] = __ldg(z4 + q);
+    } else {
+      for (int h = h0 + lane; h < h1; h += 32) row[h - h0] = __ldg(s.z0 + h);
     }
     __syncwarp();
+    scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max);
+    __syncwarp();
     float* dst = out + c * (int64_t)n_feat + h0;
-    const int len = h1 - h0;
-    if ((n_feat & 3) == 0 && (h0 & 3) == 0 && (len & 3) == 0) {
+    if (vec_ok && (len & 3) == 0) {
       const float4* r4 = reinterpret_cast<const float4*>(row);
       float4* d4 = reinterpret_cast<float4*>(dst);
       for (int h = lane; h < (len >> 2); h += 32) __stcs(d4 + h, r4[h]);
@@ -608,20 +710,14 @@ k_scale_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ row
       for (int h = lane; h < len; h += 32) __stcs(dst + h, row[h]);
     }
     __syncwarp();
+    b = nb; e = ne; nb = nnb; ne = nne;
   }
 }
 
-// The same row builder for the PCA Gram without a dense fp32 matrix in HBM: the finished slice leaves as the two fp16
-// halves of the split-precision operand (hi = fp16(z), lo = fp16(z - hi); gram_tc.cu) with the row pitch the Gram
-// kernel's tensor maps expect.  Column n_feat of every row is set to 1 and the rest of the padding to 0: the Gram of
-// the extended matrix then carries the column sums Z'1 (which the centring needs) in its last column -- the tensor
-// core sums them on the way, with the same split-precision accuracy as every other entry.
 template <int NV>   // groups of 8 genes per lane and slice: slice <= 256 * NV genes
-__global__ void __launch_bounds__(256)
-k_scale_split(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
-              const int32_t* __restrict__ gene2h, const float* __restrict__ mu, const float* __restrict__ inv_sd,
-              const float* __restrict__ z0, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, int32_t row_len,
-              int32_t pitch, float scale_max, __half* __restrict__ hi16, __half* __restrict__ lo16) {
+__global__ void __launch_bounds__(256, 4)
+k_scale_split(const ScaleSrc s, int64_t n_cells, int32_t n_feat, int32_t nsplit, int32_t slice, int32_t row_len,
+               int32_t pitch, float scale_max, __half* __restrict__ hi16, __half* __restrict__ lo16) {
   extern __shared__ float srow[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -630,24 +726,29 @@ k_scale_split(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   const int64_t warp = (int64_t)blockIdx.x * nw + wib;
   const int64_t nwarp = (int64_t)gridDim.x * nw;
   const int64_t n_tasks = n_cells * nsplit;
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (warp < n_tasks) { const int64_t c = warp / nsplit; b = s.colptr[c]; e = s.colptr[c + 1]; }
+  if (warp + nwarp < n_tasks) { const int64_t c = (warp + nwarp) / nsplit; nb = s.colptr[c]; ne = s.colptr[c + 1]; }
   for (int64_t task = warp; task < n_tasks; task += nwarp) {
+    int64_t nnb = 0, nne = 0;
+    if (task + 2 * nwarp < n_tasks) { const int64_t c2 = (task + 2 * nwarp) / nsplit; nnb = s.colptr[c2]; nne = s.colptr[c2 + 1]; }
+    if (nb < ne) prefetch_column_l2(s.rowval, s.val, nb, ne, lane);
     const int64_t c = task / nsplit;
     const int sl = (int)(task - c * nsplit);
     const int h0 = sl * slice;                          // slice is a multiple of 8
     const int h1 = min(h0 + slice, n_feat);
     const int hw = (sl == nsplit - 1) ? pitch : h1;     // the last slice also writes the padding up to the row pitch
     const int len8 = (hw - h0) >> 3;
-    for (int h = h0 + lane; h < hw; h += 32) row[h - h0] = h < n_feat ? __ldg(z0 + h) : (h == n_feat ? 1.f : 0.f);
-    __syncwarp();
-    const int64_t b = colptr[c], e = colptr[c + 1];
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const int h = __ldg(gene2h + __ldcs(rowval + i));
-      if (h >= h0 && h < h1) {
-        float z = (__ldcs(val + i) - __ldg(mu + h)) * __ldg(inv_sd + h);
-        z = (z != z) ? z : fminf(z, scale_max);  // min.(x, scale_max): upper clip only, NaN propagates
-        row[h - h0] = z;
-      }
+    {
+      // n_feat is a multiple of 4 here (the caller falls back otherwise): whole float4 groups of z0, then the tail
+      const int nfull = (h1 - h0) >> 2;
+      const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
+      float4* r4 = reinterpret_cast<float4*>(row);
+      for (int q = lane; q < nfull; q += 32) r4[q] = __ldg(z4 + q);
+      for (int h = h0 + 4 * nfull + lane; h < hw; h += 32) row[h - h0] = h < n_feat ? __ldg(s.z0 + h) : (h == n_feat ? 1.f : 0.f);
     }
+    __syncwarp();
+    scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max);
     __syncwarp();
     const float4* r4 = reinterpret_cast<const float4*>(row);
     uint4* dh = reinterpret_cast<uint4*>(hi16 + c * (int64_t)pitch + h0);
@@ -672,6 +773,7 @@ k_scale_split(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
       }
     }
     __syncwarp();
+    b = nb; e = ne; nb = nnb; ne = nne;
   }
 }
 
@@ -851,11 +953,12 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_scale_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
-      int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
-      k_scale_fill<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(),
-                                                                      (const int32_t*)map->p, mu, inv_sd, z0, norm->n_cells,
-                                                                      (int32_t)H, nsplit, slice, (float)scale_max, d->p());
+      const int ctas_per_sm = resident_ctas(k_scale_fill, warps * 32, smem,
+                                            (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024))));
+      const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
+      const ScaleSrc src{norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0};
+      k_scale_fill<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(src, norm->n_cells, (int32_t)H, nsplit, slice,
+                                                                      (float)scale_max, d->p());
       ctx->launches++;
       e = cudaGetLastError();
     }
@@ -921,14 +1024,17 @@ extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* nor
     const int srow_len = std::max(slice, last);
     const int warps = 8;
     const size_t smem = (size_t)warps * srow_len * 4;
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
-    int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
+    const int ctas_guess = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
+    const int64_t n_wtasks = ceil_div64(norm->n_cells * nsplit, warps);
+    const ScaleSrc src{norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0};
 #define CSC_SPLIT_LAUNCH(NV)                                                                                             \
   do {                                                                                                                   \
     CSC_CUDA(ctx, cudaFuncSetAttribute(k_scale_split<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    k_scale_split<NV><<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(                                                 \
-        norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0, norm->n_cells, (int32_t)H, nsplit,     \
-        slice, srow_len, pitch, (float)scale_max, (__half*)hi16->p, (__half*)lo16->p);                                    \
+    const int64_t grid = std::min<int64_t>(                                                                              \
+        (int64_t)ctx->sm_count * resident_ctas(k_scale_split<NV>, warps * 32, smem, ctas_guess), n_wtasks);               \
+    k_scale_split<NV><<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(src, norm->n_cells, (int32_t)H, nsplit, slice,   \
+                                                                         srow_len, pitch, (float)scale_max,              \
+                                                                         (__half*)hi16->p, (__half*)lo16->p);             \
   } while (0)
     if (srow_len <= 256) CSC_SPLIT_LAUNCH(1);
     else if (srow_len <= 512) CSC_SPLIT_LAUNCH(2);
@@ -974,6 +1080,13 @@ extern "C" csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_s
 // ~100 multiply-adds per component and cell instead of H = 2000, and 8 B per stored entry read instead of 4 H
 // bytes per cell.  A warp owns a cell; lanes own components (lane, lane + 32, ...); the stored entries are
 // loaded 32 at a time (coalesced) and broadcast by shuffle; the loading rows come out of L1/L2.
+// (Measured dead end: a 1024-thread CTA per SM with a 1000-row slice of U and the scaling parameters in shared
+// memory, selected entries compacted into a per-warp staging area, loads pipelined two batches ahead and the next
+// chunk prefetched into L2 -- 1.45 to 1.85 ms against 1.36 ms for this kernel: with 8 warps per scheduler the
+// per-batch ballot / compaction / dependent shared-memory chain costs more than the L2 gathers it removes.  Nor is
+// this kernel latency-bound: prefetching the next column, pipelining the loads and four loading rows in flight per
+// round left it at 1.6 ms.  It moves 50 M selected entries x 256 B of U = 12.8 GB out of L1/L2 in 1.36 ms, i.e. it
+// sits on the L2 gather bandwidth.)
 // ------------------------------------------------------------------------------------------
 template <int NJ>   // kpad = 32 * NJ components
 __global__ void __launch_bounds__(256)
@@ -1010,7 +1123,8 @@ k_transform_sparse(const int64_t* __restrict__ colptr, const int32_t* __restrict
         const float sj = __shfl_sync(FULL, sv, src);
         const float* ur = U + (int64_t)hj * kpad + lane;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[j] = fmaf(sj, __ldg(ur + 32 * j), acc[j]);
+        for (int j = 0; j < NJ; ++j)      // lanes past k skip the load: the kernel is bound by these L2 sectors
+          if (lane + 32 * j < k) acc[j] = fmaf(sj, __ldg(ur + 32 * j), acc[j]);
       }
     }
 #pragma unroll
