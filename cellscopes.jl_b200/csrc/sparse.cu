@@ -644,7 +644,7 @@ struct ScaleSrc {
 
 template <int UN>
 __device__ __forceinline__ void scatter_scaled(const ScaleSrc& s, float* row, int h0, int h1, int64_t b, int64_t e, int lane,
-                                               float scale_max) {
+                                               float scale_max, bool last_use) {
   for (int64_t i0 = b + lane; i0 < e; i0 += 32 * UN) {
     int g[UN];
     float x[UN];
@@ -652,8 +652,9 @@ __device__ __forceinline__ void scatter_scaled(const ScaleSrc& s, float* row, in
     for (int u = 0; u < UN; ++u) {
       const int64_t i = i0 + 32 * u;
       const bool ok = i < e;
-      g[u] = ok ? __ldcs(s.rowval + i) : -1;
-      x[u] = ok ? __ldcs(s.val + i) : 0.f;
+      // the column is read once per slice by the same warp: cached loads until the last slice, streaming there
+      g[u] = ok ? (last_use ? __ldcs(s.rowval + i) : __ldg(s.rowval + i)) : -1;
+      x[u] = ok ? (last_use ? __ldcs(s.val + i) : __ldg(s.val + i)) : 0.f;
     }
     int h[UN];
 #pragma unroll
@@ -678,38 +679,39 @@ k_scale_fill(const ScaleSrc s, int64_t n_cells, int32_t n_feat, int32_t nsplit, 
   float* row = srow + (size_t)wib * slice;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t n_tasks = n_cells * nsplit;
+  // a warp owns a cell and builds its slices one after the other (the column comes from HBM once, then from L1/L2)
   int64_t b = 0, e = 0, nb = 0, ne = 0;
-  if (warp < n_tasks) { const int64_t c = warp / nsplit; b = s.colptr[c]; e = s.colptr[c + 1]; }
-  if (warp + nwarp < n_tasks) { const int64_t c = (warp + nwarp) / nsplit; nb = s.colptr[c]; ne = s.colptr[c + 1]; }
+  if (warp < n_cells) { b = s.colptr[warp]; e = s.colptr[warp + 1]; }
+  if (warp + nwarp < n_cells) { nb = s.colptr[warp + nwarp]; ne = s.colptr[warp + nwarp + 1]; }
   const bool vec_ok = (n_feat & 3) == 0 && (slice & 3) == 0;
-  for (int64_t task = warp; task < n_tasks; task += nwarp) {
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
     int64_t nnb = 0, nne = 0;
-    if (task + 2 * nwarp < n_tasks) { const int64_t c2 = (task + 2 * nwarp) / nsplit; nnb = s.colptr[c2]; nne = s.colptr[c2 + 1]; }
+    if (c + 2 * nwarp < n_cells) { nnb = s.colptr[c + 2 * nwarp]; nne = s.colptr[c + 2 * nwarp + 1]; }
     if (nb < ne) prefetch_column_l2(s.rowval, s.val, nb, ne, lane);
-    const int64_t c = task / nsplit;
-    const int h0 = (int)(task - c * nsplit) * slice;
-    const int h1 = min(h0 + slice, n_feat);
-    const int len = h1 - h0;
-    if (vec_ok && (len & 3) == 0) {
-      const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
-      float4* r4 = reinterpret_cast<float4*>(row);
-      for (int q = lane; q < (len >> 2); q += 32) r4[q] = __ldg(z4 + q);
-    } else {
-      for (int h = h0 + lane; h < h1; h += 32) row[h - h0] = __ldg(s.z0 + h);
+    for (int sl = 0; sl < nsplit; ++sl) {
+      const int h0 = sl * slice;
+      const int h1 = min(h0 + slice, n_feat);
+      const int len = h1 - h0;
+      if (vec_ok && (len & 3) == 0) {
+        const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
+        float4* r4 = reinterpret_cast<float4*>(row);
+        for (int q = lane; q < (len >> 2); q += 32) r4[q] = __ldg(z4 + q);
+      } else {
+        for (int h = h0 + lane; h < h1; h += 32) row[h - h0] = __ldg(s.z0 + h);
+      }
+      __syncwarp();
+      scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max, sl == nsplit - 1);
+      __syncwarp();
+      float* dst = out + c * (int64_t)n_feat + h0;
+      if (vec_ok && (len & 3) == 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int h = lane; h < (len >> 2); h += 32) __stcs(d4 + h, r4[h]);
+      } else {
+        for (int h = lane; h < len; h += 32) __stcs(dst + h, row[h]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max);
-    __syncwarp();
-    float* dst = out + c * (int64_t)n_feat + h0;
-    if (vec_ok && (len & 3) == 0) {
-      const float4* r4 = reinterpret_cast<const float4*>(row);
-      float4* d4 = reinterpret_cast<float4*>(dst);
-      for (int h = lane; h < (len >> 2); h += 32) __stcs(d4 + h, r4[h]);
-    } else {
-      for (int h = lane; h < len; h += 32) __stcs(dst + h, row[h]);
-    }
-    __syncwarp();
     b = nb; e = ne; nb = nnb; ne = nne;
   }
 }
@@ -725,54 +727,54 @@ k_scale_split(const ScaleSrc s, int64_t n_cells, int32_t n_feat, int32_t nsplit,
   float* row = srow + (size_t)wib * row_len;            // row_len >= slice: the last slice carries the padding
   const int64_t warp = (int64_t)blockIdx.x * nw + wib;
   const int64_t nwarp = (int64_t)gridDim.x * nw;
-  const int64_t n_tasks = n_cells * nsplit;
+  // a warp owns a cell and builds its slices one after the other (the column comes from HBM once, then from L1/L2)
   int64_t b = 0, e = 0, nb = 0, ne = 0;
-  if (warp < n_tasks) { const int64_t c = warp / nsplit; b = s.colptr[c]; e = s.colptr[c + 1]; }
-  if (warp + nwarp < n_tasks) { const int64_t c = (warp + nwarp) / nsplit; nb = s.colptr[c]; ne = s.colptr[c + 1]; }
-  for (int64_t task = warp; task < n_tasks; task += nwarp) {
+  if (warp < n_cells) { b = s.colptr[warp]; e = s.colptr[warp + 1]; }
+  if (warp + nwarp < n_cells) { nb = s.colptr[warp + nwarp]; ne = s.colptr[warp + nwarp + 1]; }
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
     int64_t nnb = 0, nne = 0;
-    if (task + 2 * nwarp < n_tasks) { const int64_t c2 = (task + 2 * nwarp) / nsplit; nnb = s.colptr[c2]; nne = s.colptr[c2 + 1]; }
+    if (c + 2 * nwarp < n_cells) { nnb = s.colptr[c + 2 * nwarp]; nne = s.colptr[c + 2 * nwarp + 1]; }
     if (nb < ne) prefetch_column_l2(s.rowval, s.val, nb, ne, lane);
-    const int64_t c = task / nsplit;
-    const int sl = (int)(task - c * nsplit);
-    const int h0 = sl * slice;                          // slice is a multiple of 8
-    const int h1 = min(h0 + slice, n_feat);
-    const int hw = (sl == nsplit - 1) ? pitch : h1;     // the last slice also writes the padding up to the row pitch
-    const int len8 = (hw - h0) >> 3;
-    {
-      // n_feat is a multiple of 4 here (the caller falls back otherwise): whole float4 groups of z0, then the tail
-      const int nfull = (h1 - h0) >> 2;
-      const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
-      float4* r4 = reinterpret_cast<float4*>(row);
-      for (int q = lane; q < nfull; q += 32) r4[q] = __ldg(z4 + q);
-      for (int h = h0 + 4 * nfull + lane; h < hw; h += 32) row[h - h0] = h < n_feat ? __ldg(s.z0 + h) : (h == n_feat ? 1.f : 0.f);
-    }
-    __syncwarp();
-    scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max);
-    __syncwarp();
-    const float4* r4 = reinterpret_cast<const float4*>(row);
-    uint4* dh = reinterpret_cast<uint4*>(hi16 + c * (int64_t)pitch + h0);
-    uint4* dl = reinterpret_cast<uint4*>(lo16 + c * (int64_t)pitch + h0);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int q = j * 32 + lane;
-      if (q < len8) {
-        const float4 v0 = r4[2 * q], v1 = r4[2 * q + 1];
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const __half a0 = __float2half_rn(v[2 * u]), a1 = __float2half_rn(v[2 * u + 1]);
-          __half2 p = __halves2half2(a0, a1);
-          ph[u] = *reinterpret_cast<uint32_t*>(&p);
-          p = __floats2half2_rn(v[2 * u] - __half2float(a0), v[2 * u + 1] - __half2float(a1));
-          pl[u] = *reinterpret_cast<uint32_t*>(&p);
-        }
-        __stcs(dh + q, make_uint4(ph[0], ph[1], ph[2], ph[3]));
-        __stcs(dl + q, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+    for (int sl = 0; sl < nsplit; ++sl) {
+      const int h0 = sl * slice;                          // slice is a multiple of 8
+      const int h1 = min(h0 + slice, n_feat);
+      const int hw = (sl == nsplit - 1) ? pitch : h1;     // the last slice also writes the padding up to the row pitch
+      const int len8 = (hw - h0) >> 3;
+      {
+        // n_feat is a multiple of 4 here (the caller falls back otherwise): whole float4 groups of z0, then the tail
+        const int nfull = (h1 - h0) >> 2;
+        const float4* z4 = reinterpret_cast<const float4*>(s.z0 + h0);
+        float4* r4 = reinterpret_cast<float4*>(row);
+        for (int q = lane; q < nfull; q += 32) r4[q] = __ldg(z4 + q);
+        for (int h = h0 + 4 * nfull + lane; h < hw; h += 32) row[h - h0] = h < n_feat ? __ldg(s.z0 + h) : (h == n_feat ? 1.f : 0.f);
       }
+      __syncwarp();
+      scatter_scaled<4>(s, row, h0, h1, b, e, lane, scale_max, sl == nsplit - 1);
+      __syncwarp();
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      uint4* dh = reinterpret_cast<uint4*>(hi16 + c * (int64_t)pitch + h0);
+      uint4* dl = reinterpret_cast<uint4*>(lo16 + c * (int64_t)pitch + h0);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int q = j * 32 + lane;
+        if (q < len8) {
+          const float4 v0 = r4[2 * q], v1 = r4[2 * q + 1];
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const __half a0 = __float2half_rn(v[2 * u]), a1 = __float2half_rn(v[2 * u + 1]);
+            __half2 p = __halves2half2(a0, a1);
+            ph[u] = *reinterpret_cast<uint32_t*>(&p);
+            p = __floats2half2_rn(v[2 * u] - __half2float(a0), v[2 * u + 1] - __half2float(a1));
+            pl[u] = *reinterpret_cast<uint32_t*>(&p);
+          }
+          __stcs(dh + q, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+          __stcs(dl + q, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
     b = nb; e = ne; nb = nnb; ne = nne;
   }
 }
@@ -955,7 +957,7 @@ extern "C" csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const
     if (e == cudaSuccess) {
       const int ctas_per_sm = resident_ctas(k_scale_fill, warps * 32, smem,
                                             (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024))));
-      const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells * nsplit, warps));
+      const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * ctas_per_sm, ceil_div64(norm->n_cells, warps));
       const ScaleSrc src{norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0};
       k_scale_fill<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(src, norm->n_cells, (int32_t)H, nsplit, slice,
                                                                       (float)scale_max, d->p());
@@ -1025,7 +1027,7 @@ extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* nor
     const int warps = 8;
     const size_t smem = (size_t)warps * srow_len * 4;
     const int ctas_guess = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 * 1024) / (smem + 1024)));
-    const int64_t n_wtasks = ceil_div64(norm->n_cells * nsplit, warps);
+    const int64_t n_wtasks = ceil_div64(norm->n_cells, warps);
     const ScaleSrc src{norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, mu, inv_sd, z0};
 #define CSC_SPLIT_LAUNCH(NV)                                                                                             \
   do {                                                                                                                   \
