@@ -286,6 +286,16 @@ def main():
     if per_step["normalize"] > 0:
         hbm["normalize_fused_stats"] = {"bytes_per_nnz": 12, "GB/s": 12.0 * nnz_local / (per_step["normalize"] * 1e-3) / 1e9}
         hbm["normalize_fused_stats"]["frac"] = hbm["normalize_fused_stats"]["GB/s"] / peaks["hbm_gbs"]
+    if per_step["scale_fill"] > 0:
+        # scale -> fp16 hi/lo operands of the Gram: 8 B per stored entry read, 4 B per (cell, selected gene) written
+        b_scale = 8.0 * nnz_local + 4.0 * params.n_features * (hi - lo)
+        hbm["scale_split"] = {"bytes": b_scale, "GB/s": b_scale / (per_step["scale_fill"] * 1e-3) / 1e9}
+        hbm["scale_split"]["frac"] = hbm["scale_split"]["GB/s"] / peaks["hbm_gbs"]
+    if per_step["pca_transform"] > 0:
+        b_tr = 8.0 * nnz_local + 4.0 * params.n_pcs * (hi - lo)
+        hbm["pca_transform_sparse"] = {"bytes": b_tr, "GB/s": b_tr / (per_step["pca_transform"] * 1e-3) / 1e9,
+                                       "note": "bound by the L2 gathers of the loading rows, not by HBM"}
+        hbm["pca_transform_sparse"]["frac"] = hbm["pca_transform_sparse"]["GB/s"] / peaks["hbm_gbs"]
 
     # ---- e2e: host buffers through the reference-facing API -----------------------------------
     e2e = None

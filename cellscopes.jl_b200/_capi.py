@@ -57,6 +57,7 @@ SIGNATURES = {
     "csc_vec_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I32), _PP]),
     "csc_vec_upload": (_I32, [_P, _P, _I64]),
     "csc_vec_download": (_I32, [_P, _P, _I64]),
+    "csc_vec_download_as": (_I32, [_P, _P, _I64, _I32, _I64]),
     "csc_sparse_upload": (_I32, [_P, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _PP]),
     "csc_sparse_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_sparse_range_nnz": (_I32, [_P, _I64, _I64, C.POINTER(_I64)]),
@@ -440,6 +441,15 @@ class Vec(_Handle):
         n = total if n is None else n
         out = self.ctx.pinned_empty(n, dt) if n * np.dtype(dt).itemsize >= (1 << 20) else np.empty(n, dtype=dt)
         self.ctx.check(self.ctx.lib.csc_vec_download(self.h, _ptr(out), n))
+        return out
+
+    def download_as(self, dtype, add=0, n=None):
+        """Download converted on the device first: int32 -> int32/int64 with ``add`` on every element, float32 -> float64."""
+        total, _, _ = self.info()
+        n = total if n is None else n
+        dtype = np.dtype(dtype)
+        out = self.ctx.pinned_empty(n, dtype) if n * dtype.itemsize >= (1 << 20) else np.empty(n, dtype=dtype)
+        self.ctx.check(self.ctx.lib.csc_vec_download_as(self.h, _ptr(out), n, _NP_DT[dtype], int(add)))
         return out
 
     @property

@@ -394,6 +394,38 @@ __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ 
   for (; i < n; i += stride) out[i] = (double)in[i];
 }
 
+__global__ void k_i32_add(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int32_t add) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[i] + add;
+}
+__global__ void k_i32_to_i64_add(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n, int64_t add) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (int64_t)in[i] + add;
+}
+csc_status csc_vec_download_as(const csc_vec* v, void* host, int64_t n, int32_t out_dtype, int64_t add) {
+  if (!v || !host) return CSC_ERR_ARG;
+  csc_ctx* ctx = v->ctx;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, n >= 0 && n <= v->n, "csc_vec_download_as: n=%lld exceeds %lld", (long long)n, (long long)v->n);
+  if (out_dtype == v->dtype && add == 0) return csc_vec_download(v, host, n);
+  const bool ok = (v->dtype == CSC_DT_I32 && (out_dtype == CSC_DT_I32 || out_dtype == CSC_DT_I64)) ||
+                  (v->dtype == CSC_DT_F32 && out_dtype == CSC_DT_F64 && add == 0);
+  CSC_REQUIRE(ctx, ok, "csc_vec_download_as: unsupported conversion %d -> %d (add %lld)", v->dtype, out_dtype, (long long)add);
+  if (n == 0) return CSC_OK;
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevPtr tmp;
+  CSC_TRY(dev_alloc(ctx, (size_t)n * dtype_size(out_dtype), &tmp));
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(n, 256), (int64_t)ctx->sm_count * 16);
+  if (out_dtype == CSC_DT_I32) k_i32_add<<<grid, 256, 0, ctx->stream>>>(v->as<int32_t>(), (int32_t*)tmp->p, n, (int32_t)add);
+  else if (out_dtype == CSC_DT_I64) k_i32_to_i64_add<<<grid, 256, 0, ctx->stream>>>(v->as<int32_t>(), (int64_t*)tmp->p, n, add);
+  else k_f32_to_f64<<<grid, 256, 0, ctx->stream>>>(v->as<float>(), (double*)tmp->p, n);
+  CSC_LAUNCHED(ctx);
+  return d2h_copy(ctx, host, tmp->p, (size_t)n * dtype_size(out_dtype));
+  CSC_GUARD_END(ctx)
+}
+
 csc_status csc_dense_alloc(csc_ctx* ctx, int64_t n_rows, int64_t n_cols, csc_dense** out) {
   if (!ctx || !out) return CSC_ERR_ARG;
   CSC_GUARD_BEGIN

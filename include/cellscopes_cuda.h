@@ -109,6 +109,10 @@ csc_status csc_vec_free(csc_vec* v);
 csc_status csc_vec_info(const csc_vec* v, int64_t* n, int32_t* dtype, void** device_ptr);
 csc_status csc_vec_upload(csc_vec* v, const void* host, int64_t n);
 csc_status csc_vec_download(const csc_vec* v, void* host, int64_t n);
+/* download with the conversion the host side of the reference needs done on the device first: out_dtype I32|I64 for an
+ * I32 vector (every element + add: the 1-based k x N neighbour table of knn_matrices, processing.jl:196-201), F64 for
+ * an F32 vector (the distance table); out_dtype == the vector's dtype with add == 0 is csc_vec_download. */
+csc_status csc_vec_download_as(const csc_vec* v, void* host, int64_t n, int32_t out_dtype, int64_t add);
 
 /* ---- sparse count matrix: rawCount.count_mtx (src/scrna/objects.jl:10-24) --------------- */
 /* colptr[n_cells+1], rowval[nnz], nzval[nnz] of a SparseMatrixCSC; idx_dtype I64|I32,

@@ -394,8 +394,12 @@ function knn(sc_obj; n_neighbors=30, metric="cosine", ctx=nothing)
         s.ctx.h, s.emb.h, s.emb.h, 0, Int32(0), Int32(d), Int32(n_neighbors), metric_code(metric), ir, dr))
     idx = Handle(ir[], :csc_vec_free, s.ctx); dist = Handle(dr[], :csc_vec_free, s.ctx)
     # [n x k] row-major == k x n column-major, the layout of knn_matrices (processing.jl:201)
-    indices = reshape(Int64.(vec_download(s.ctx, idx, Int32, n * n_neighbors)) .+ 1, n_neighbors, n)
-    dists = reshape(Float64.(vec_download(s.ctx, dist, Float32, n * n_neighbors)), n_neighbors, n)
+    # Int64 / 1-based / Float64 on the device before the copy (csc_vec_download_as), straight into the Julia arrays
+    indices = Matrix{Int64}(undef, n_neighbors, n); dists = Matrix{Float64}(undef, n_neighbors, n)
+    GC.@preserve indices check(s.ctx, ccall(sym(:csc_vec_download_as), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int64),
+                                            idx.h, pointer(indices), n * n_neighbors, DT_I64, 1))
+    GC.@preserve dists check(s.ctx, ccall(sym(:csc_vec_download_as), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int64),
+                                          dist.h, pointer(dists), n * n_neighbors, DT_F64, 0))
     indices, dists, idx
 end
 

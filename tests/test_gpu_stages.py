@@ -551,3 +551,21 @@ def test_device_generator_density_and_determinism(cs, ctx):
     # statistically the same model as the NumPy twin
     twin = cs.synth.sample_counts(p, 1000, 3000)
     assert abs(twin.nnz - ma.nnz) / ma.nnz < 0.02
+
+
+def test_vec_download_as_converts_on_the_device(cs, ctx):
+    """csc_vec_download_as: the 1-based / Int64 neighbour table and the Float64 distance table of knn_matrices
+    (processing.jl:196-201) leave the device already converted; bit-exact against the host conversion."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 1000, 300_001):          # below and above the pinned-buffer threshold
+        i32 = rng.integers(0, 2 ** 31 - 2, size=n, dtype=np.int32)
+        f32 = rng.normal(size=n).astype(np.float32)
+        vi, vf = ctx.vec_from(i32), ctx.vec_from(f32)
+        assert np.array_equal(vi.download_as(np.int32, add=1), i32 + 1)
+        a = vi.download_as(np.int64, add=1)
+        assert a.dtype == np.int64 and np.array_equal(a, i32.astype(np.int64) + 1)
+        b = vf.download_as(np.float64)
+        assert b.dtype == np.float64 and np.array_equal(b, f32.astype(np.float64))
+        assert np.array_equal(vf.download_as(np.float32), f32)
+    with pytest.raises(Exception):
+        ctx.vec_from(np.zeros(4, np.float32)).download_as(np.int64)
