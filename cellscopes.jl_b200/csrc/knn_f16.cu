@@ -437,48 +437,66 @@ __global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restr
 
 // Exact re-scoring of the 32 candidates (fp64 accumulation over the fp32 operands), final ordering (descending
 // score, ties by ascending id) and the completeness proof: rows whose exact k-th score does not clear
-// a_L + eps are appended to the fallback list.  One thread per query row.
-__global__ void __launch_bounds__(128)
+// a_L + eps are appended to the fallback list.  One WARP per query row, one lane per candidate (F_L = 32): the
+// candidate list is read coalesced, the 32 key rows are gathered side by side, and the order comes from a bitonic
+// network over the lanes.  (One thread per row with an insertion sort kept its 32-entry lists in local memory and
+// read the candidate table with a 128-byte stride: 2.6 ms at 500k rows.)
+static_assert(F_L == 32, "k_knn_refine_prove maps one candidate to one lane");
+__device__ __forceinline__ bool ranks_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+
+__global__ void __launch_bounds__(256)
 k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
                    const float* __restrict__ thr, const int32_t* __restrict__ in_idx, const int32_t* __restrict__ perm_k,
                    const int32_t* __restrict__ perm_q, float* __restrict__ out_score, int32_t* __restrict__ out_idx,
                    int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_q) return;
-  float s[F_L];
-  int id[F_L];
-  const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
-  int cnt = 0;
-  for (int j = 0; j < F_L; ++j) {
-    const int pos = in_idx[row * F_L + j];
-    if (pos == INT_MAX) continue;
-    const int cand = perm_k ? perm_k[pos] : pos;         // original key id: what is reported and what breaks ties
+  const int pos = in_idx[row * F_L + lane];
+  const bool valid = pos != INT_MAX;
+  const int cnt = __popc(__ballot_sync(FULL, valid));
+  float v = -INFINITY;
+  int id = INT_MAX;                                       // original key id: what is reported and what breaks ties
+  if (valid) {
+    id = perm_k ? perm_k[pos] : pos;
+    const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
     const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)pos * 64);
     double acc = 0.0;
     for (int i = 0; i < (d + 3) / 4; ++i) {
       const float4 a = __ldg(qr + i), b = __ldg(kr + i);
       acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
     }
-    const float v = (float)acc;
-    int p = cnt++;
-#pragma unroll 1
-    while (p > 0 && (v > s[p - 1] || (v == s[p - 1] && cand < id[p - 1]))) {
-      s[p] = s[p - 1];
-      id[p] = id[p - 1];
-      --p;
+    v = (float)acc;
+  }
+  // bitonic network: afterwards lane j holds the j-th best candidate
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, v, j);
+      const int oid = __shfl_xor_sync(FULL, id, j);
+      const bool keep_first = ((lane & j) == 0) == ((lane & k2) == 0);
+      const bool other_first = ranks_before(ov, oid, v, id);
+      const bool mine_first = ranks_before(v, id, ov, oid);
+      if (keep_first ? other_first : mine_first) {
+        v = ov;
+        id = oid;
+      }
     }
-    s[p] = v;
-    id[p] = cand;
   }
   const int64_t orow = perm_q ? perm_q[row] : row;
-  for (int j = 0; j < k; ++j) {
-    out_score[orow * k + j] = j < cnt ? s[j] : -INFINITY;
-    out_idx[orow * k + j] = j < cnt ? id[j] : INT_MAX;
+  if (lane < k) {
+    out_score[orow * k + lane] = lane < cnt ? v : -INFINITY;
+    out_idx[orow * k + lane] = lane < cnt ? id : INT_MAX;
   }
   // a_L = -inf when fewer than 32 keys exist: the list holds every key and the proof is trivial
-  const float a_l = thr[row];
-  if (cnt < k || !(a_l + F_EPS < s[k - 1])) {
-    if (a_l != -INFINITY) fallback_rows[atomicAdd(n_fallback, 1)] = (int32_t)row;
+  const float s_k = __shfl_sync(FULL, v, (k - 1) & 31);
+  if (lane == 0) {
+    const float a_l = thr[row];
+    if (cnt < k || !(a_l + F_EPS < s_k)) {
+      if (a_l != -INFINITY) fallback_rows[atomicAdd(n_fallback, 1)] = (int32_t)row;
+    }
   }
 }
 
@@ -603,7 +621,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
 #undef F_LAUNCH
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
-  k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(
+  k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 8), 256, 0, ctx->stream>>>(
       q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, d_perm_k, d_perm_q, out_score, out_idx,
       (int32_t*)fb_rows->p, (int32_t*)fb_count->p);
   CSC_LAUNCHED(ctx);
