@@ -151,10 +151,30 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the JSON line
+    goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -323,7 +343,7 @@ def main():
             "stage_ms": {kk: round(v, 3) for kk, v in per_step.items() if v > 0}, "step_ms": [round(x, 2) for x in step_ms],
             "hbm_stages": hbm, "tensor_stages": tensor_stages, "diag": diag,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
