@@ -136,7 +136,8 @@ template <int KS>   // k-steps of 16 halves: ceil(d / 16)
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restrict__ q16, int64_t n_q, int64_t n_keys,
                int64_t query_offset, const int32_t* __restrict__ self_pos, const int32_t* __restrict__ start_tile,
-               float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int dbg_mode, unsigned long long* cnt) {
+               float* __restrict__ out_thr, int32_t* __restrict__ out_idx, int n_whole, int n_parts,
+               float* __restrict__ xtr_thr, int32_t* __restrict__ xtr_idx, int dbg_mode, unsigned long long* cnt) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
@@ -155,11 +156,24 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24 + 2 * F_PAIRS * F_QS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q0 = (int64_t)blockIdx.x * F_TQ;
-  const int64_t n_tiles = (n_keys + F_BN - 1) / F_BN;
+  // CTAs [0, n_whole) scan every key tile for their 256 rows.  The blocks behind them -- the thin last wave of a grid
+  // that is not a multiple of the SM count -- are cut into n_parts CTAs each, every part scanning its share of the
+  // key tiles with its own candidate sets: list 0 goes to the row's usual place, lists 1.. to the extra arrays, and
+  // the refine kernel merges them (the completeness proof takes the largest of the parts' bounds).
+  const int xi = (int)blockIdx.x - n_whole;
+  const int qblock = xi < 0 ? (int)blockIdx.x : n_whole + xi / n_parts;
+  const int part = xi < 0 ? 0 : xi % n_parts;
+  const int64_t q0 = (int64_t)qblock * F_TQ;
+  const int64_t n_tiles_all = (n_keys + F_BN - 1) / F_BN;
+  const int64_t tile_lo = xi < 0 ? 0 : n_tiles_all * part / n_parts;
+  const int64_t tile_hi = xi < 0 ? n_tiles_all : n_tiles_all * (part + 1) / n_parts;
+  const int64_t n_tiles = tile_hi - tile_lo;            // tiles THIS CTA scans; tile numbers below are relative to tile_lo
+  const int key_lo = (int)(tile_lo * F_BN);             // first key of the CTA's range
   // locality order (knn_order.cu): the scan fans out from the middle of the block's own cluster, tiles c, c+1, c-1,
-  // c+2, ... (the key order is circular), so that similar keys come early and the thresholds settle
-  const int64_t t_start = start_tile ? (int64_t)start_tile[blockIdx.x] % n_tiles : 0;
+  // c+2, ... (the key order is circular), so that similar keys come early and the thresholds settle; a part starts at
+  // the tile of its range that is nearest to the cluster
+  int64_t t_start = start_tile ? (int64_t)start_tile[qblock] % n_tiles_all : 0;
+  t_start = min(max(t_start, tile_lo), tile_hi - 1) - tile_lo;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < F_STAGES; ++i) {
@@ -202,7 +216,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
         int64_t tile = (t & 1) ? t_start + ((t + 1) >> 1) : t_start - ((t + 1) >> 1);
         if (tile >= n_tiles) tile -= n_tiles;
         if (tile < 0) tile += n_tiles;
-        tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, (int)(tile * F_BN));
+        tma_load_2d(smem_u32(sB + (size_t)s * F_TILE_BYTES), &kmap, bar_full + 8 * s, 0, key_lo + (int)(tile * F_BN));
       }
       __syncwarp();
     }
@@ -318,7 +332,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
       int64_t tile = (t & 1) ? t_start + ((t + 1) >> 1) : t_start - ((t + 1) >> 1);
       if (tile >= n_tiles) tile -= n_tiles;
       if (tile < 0) tile += n_tiles;
-      const int key0 = (int)(tile * F_BN);
+      const int key0 = key_lo + (int)(tile * F_BN);
       const uint32_t taddr = lane_base + (uint32_t)(a * F_BN);
       uint32_t rA[32], rB[32];
       tmem_ld32(taddr, rA);
@@ -414,10 +428,14 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     }
     // the row's 32 candidates (unsorted) and the bound on every score outside the set
     if (qvalid) {
+      // list 0 at the row's place; list p >= 1 of a split block at [(p - 1) * split rows + row within the split blocks]
+      const int64_t split_rows = ((int64_t)gridDim.x - n_whole) / max(n_parts, 1) * F_TQ;
+      const int64_t xrow = (int64_t)(part - 1) * split_rows + (qrow - (int64_t)n_whole * F_TQ);
+      int32_t* oi = part == 0 ? out_idx + qrow * F_L : xtr_idx + xrow * F_L;
 #pragma unroll
-      for (int j = 0; j < F_L; ++j) out_idx[qrow * F_L + j] = ids[j * F_TQ];
-      // a set that never filled up reports -inf: it holds every key
-      out_thr[qrow] = tau < -1.0e37f ? -INFINITY : tau * (1.f / (F_SCALE * F_SCALE)) + F_PACK_SLACK;
+      for (int j = 0; j < F_L; ++j) oi[j] = ids[j * F_TQ];
+      // a set that never filled up reports -inf: it holds every key (of the part's range)
+      (part == 0 ? out_thr + qrow : xtr_thr + xrow)[0] = tau < -1.0e37f ? -INFINITY : tau * (1.f / (F_SCALE * F_SCALE)) + F_PACK_SLACK;
     }
   }
   tc_fence_before();
@@ -444,34 +462,12 @@ __global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restr
 static_assert(F_L == 32, "k_knn_refine_prove maps one candidate to one lane");
 __device__ __forceinline__ bool ranks_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
-__global__ void __launch_bounds__(256)
-k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
-                   const float* __restrict__ thr, const int32_t* __restrict__ in_idx, const int32_t* __restrict__ perm_k,
-                   const int32_t* __restrict__ perm_q, float* __restrict__ out_score, int32_t* __restrict__ out_idx,
-                   int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
+// sorts (v, id) over the 32 lanes: afterwards lane j holds the j-th best
+__device__ __forceinline__ void bitonic_sort32(float& v, int& id, int lane, int first_k2) {
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= n_q) return;
-  const int pos = in_idx[row * F_L + lane];
-  const bool valid = pos != INT_MAX;
-  const int cnt = __popc(__ballot_sync(FULL, valid));
-  float v = -INFINITY;
-  int id = INT_MAX;                                       // original key id: what is reported and what breaks ties
-  if (valid) {
-    id = perm_k ? perm_k[pos] : pos;
-    const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
-    const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)pos * 64);
-    double acc = 0.0;
-    for (int i = 0; i < (d + 3) / 4; ++i) {
-      const float4 a = __ldg(qr + i), b = __ldg(kr + i);
-      acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
-    }
-    v = (float)acc;
-  }
-  // bitonic network: afterwards lane j holds the j-th best candidate
 #pragma unroll
   for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    if (k2 < first_k2) continue;                          // first_k2 = 32: only the last merge (the input is bitonic)
 #pragma unroll
     for (int j = k2 >> 1; j > 0; j >>= 1) {
       const float ov = __shfl_xor_sync(FULL, v, j);
@@ -485,15 +481,67 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
       }
     }
   }
+}
+
+// Rows from split_row0 on have n_lists candidate lists (the key-range parts of the scan's last wave): list 0 in
+// in_idx / thr, list p >= 1 in xtr_idx / xtr_thr at row (p - 1) * split_rows + (row - split_row0).
+__global__ void __launch_bounds__(256)
+k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
+                   const float* __restrict__ thr, const int32_t* __restrict__ in_idx, int64_t split_row0, int64_t split_rows,
+                   int32_t n_lists, const float* __restrict__ xtr_thr, const int32_t* __restrict__ xtr_idx,
+                   const int32_t* __restrict__ perm_k, const int32_t* __restrict__ perm_q, float* __restrict__ out_score,
+                   int32_t* __restrict__ out_idx, int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_q) return;
+  const int lists = row >= split_row0 ? n_lists : 1;
+  const float4* qr = reinterpret_cast<const float4*>(q + row * 64);
+  float v = -INFINITY;                                    // running best 32, sorted over the lanes
+  int id = INT_MAX;                                       // original key id: what is reported and what breaks ties
+  int cnt = 0;
+  float a_l = -INFINITY;
+  for (int l = 0; l < lists; ++l) {
+    const int64_t xrow = (int64_t)(l - 1) * split_rows + (row - split_row0);
+    const int pos = l == 0 ? in_idx[row * F_L + lane] : xtr_idx[xrow * F_L + lane];
+    a_l = fmaxf(a_l, l == 0 ? thr[row] : xtr_thr[xrow]);
+    const bool valid = pos != INT_MAX;
+    cnt += __popc(__ballot_sync(FULL, valid));
+    float cv = -INFINITY;
+    int cid = INT_MAX;
+    if (valid) {
+      cid = perm_k ? perm_k[pos] : pos;
+      const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)pos * 64);
+      double acc = 0.0;
+      for (int i = 0; i < (d + 3) / 4; ++i) {
+        const float4 a = __ldg(qr + i), b = __ldg(kr + i);
+        acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+      }
+      cv = (float)acc;
+    }
+    bitonic_sort32(cv, cid, lane, 2);
+    if (l == 0) {
+      v = cv;
+      id = cid;
+    } else {
+      // best 32 of two sorted lists: the better of (mine, the other list reversed) per lane is a bitonic sequence
+      const float rv = __shfl_sync(FULL, cv, 31 - lane);
+      const int rid = __shfl_sync(FULL, cid, 31 - lane);
+      if (ranks_before(rv, rid, v, id)) {
+        v = rv;
+        id = rid;
+      }
+      bitonic_sort32(v, id, lane, 32);
+    }
+  }
   const int64_t orow = perm_q ? perm_q[row] : row;
   if (lane < k) {
     out_score[orow * k + lane] = lane < cnt ? v : -INFINITY;
     out_idx[orow * k + lane] = lane < cnt ? id : INT_MAX;
   }
-  // a_L = -inf when fewer than 32 keys exist: the list holds every key and the proof is trivial
+  // a_L = -inf when a list never filled up: it holds every key of its range and the proof is trivial for it
   const float s_k = __shfl_sync(FULL, v, (k - 1) & 31);
   if (lane == 0) {
-    const float a_l = thr[row];
     if (cnt < k || !(a_l + F_EPS < s_k)) {
       if (a_l != -INFINITY) fallback_rows[atomicAdd(n_fallback, 1)] = (int32_t)row;
     }
@@ -596,6 +644,28 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   }
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &thr));
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * F_L * 4, &cand));
+  // The scan runs one CTA per SM.  When the number of 256-row blocks is not a multiple of the SM count, the last wave
+  // is thin (1954 blocks on 148 SMs: 13 full waves and 30 CTAs that take as long as a full wave).  Those blocks are
+  // cut into n_parts CTAs over the key range instead (see the kernel); CSC_KNN_SPLIT=0 disables.
+  const int64_t n_blocks = ceil_div64(n_q, F_TQ);
+  const int64_t n_key_tiles = ceil_div64(n_keys, F_BN);
+  int64_t n_split_blocks = n_blocks % ctx->sm_count;
+  int n_parts = 1;
+  if (n_split_blocks > 0 && !(getenv("CSC_KNN_SPLIT") && atoi(getenv("CSC_KNN_SPLIT")) == 0)) {
+    n_parts = (int)std::min<int64_t>(std::min<int64_t>(8, ctx->sm_count / n_split_blocks), n_key_tiles / 8);
+    if (const char* force = getenv("CSC_KNN_SPLIT")) n_parts = std::max(1, std::min<int>(atoi(force), (int)std::max<int64_t>(1, n_key_tiles)));
+  }
+  if (n_parts < 2) {
+    n_parts = 1;
+    n_split_blocks = 0;
+  }
+  const int64_t n_whole = n_blocks - n_split_blocks;
+  const int64_t split_rows = n_split_blocks * F_TQ;
+  DevPtr xthr, xcand;
+  if (n_parts > 1) {
+    CSC_TRY(dev_alloc(ctx, (size_t)(n_parts - 1) * split_rows * 4, &xthr));
+    CSC_TRY(dev_alloc(ctx, (size_t)(n_parts - 1) * split_rows * F_L * 4, &xcand));
+  }
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &fb_rows));
   CSC_TRY(dev_alloc(ctx, 4, &fb_count, true));
   DevPtr dbg_cnt;
@@ -608,9 +678,10 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
 #define F_LAUNCH(KS)                                                                                                     \
   do {                                                                                                                   \
     CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_knn_scan_f16<KS><<<(unsigned)ceil_div64(n_q, F_TQ), F_THREADS, smem, ctx->stream>>>(                                \
+    k_knn_scan_f16<KS><<<(unsigned)(n_whole + n_split_blocks * n_parts), F_THREADS, smem, ctx->stream>>>(                 \
         kmap, (const __half*)q16->p, n_q, n_keys, query_offset, d_self, d_start, (float*)thr->p, (int32_t*)cand->p,       \
-        dbg_mode, dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);                                                   \
+        (int)n_whole, n_parts, xthr ? (float*)xthr->p : nullptr, xcand ? (int32_t*)xcand->p : nullptr, dbg_mode,          \
+        dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);                                                             \
   } while (0)
   switch (ksteps) {
     case 1: F_LAUNCH(1); break;
@@ -622,7 +693,8 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 8), 256, 0, ctx->stream>>>(
-      q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, d_perm_k, d_perm_q, out_score, out_idx,
+      q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, n_whole * F_TQ, split_rows, n_parts,
+      xthr ? (const float*)xthr->p : nullptr, xcand ? (const int32_t*)xcand->p : nullptr, d_perm_k, d_perm_q, out_score, out_idx,
       (int32_t*)fb_rows->p, (int32_t*)fb_count->p);
   CSC_LAUNCHED(ctx);
   int32_t n_fb = 0;

@@ -462,8 +462,9 @@ def test_knn_dims_subset_and_query_shard(cs, oracle, ctx):
 
 def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
     """Size-independent property at a size the oracle cannot reach: the fp16 filter/prove/refine scan with the
-    locality order, the same without the order, and the exact 3xTF32 scan give IDENTICAL neighbour tables (ids
-    bit-exact, distances to rounding), for the whole set and for a query shard.  Includes exact duplicates."""
+    locality order, the same without the order, with and without the key-range split of the last wave, and the exact
+    3xTF32 scan give IDENTICAL neighbour tables (ids bit-exact, distances to rounding), for the whole set and for a
+    query shard.  Includes exact duplicates."""
     rng = np.random.default_rng(21)
     n, d, k = 40000, 32, 15
     centers = rng.normal(size=(25, d)) * 2.5
@@ -472,7 +473,7 @@ def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
     keys = ctx.dense_upload(x)
 
     def run(env):
-        for kk in ("CSC_KNN_ORDER", "CSC_KNN_IMPL"):
+        for kk in ("CSC_KNN_ORDER", "CSC_KNN_IMPL", "CSC_KNN_SPLIT"):
             monkeypatch.delenv(kk, raising=False)
         for kk, v in env.items():
             monkeypatch.setenv(kk, v)
@@ -486,8 +487,12 @@ def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
     a = run({})
     b = run({"CSC_KNN_ORDER": "0"})
     c = run({"CSC_KNN_IMPL": "tf32"})
+    # the blocks of the scan's thin last wave cut into key-range parts (default: on, 157 blocks -> 9 blocks x 8 parts):
+    # off, and forced to 2, 3 and 8 parts with and without the locality order
+    splits = [run({"CSC_KNN_SPLIT": "0"}), run({"CSC_KNN_SPLIT": "2"}), run({"CSC_KNN_SPLIT": "3", "CSC_KNN_ORDER": "0"}),
+              run({"CSC_KNN_SPLIT": "8"})]
     assert a[4] < n // 20, "the proof should cover almost every row"
-    for other in (b, c):
+    for other in [b, c] + splits:
         assert np.array_equal(a[0], other[0])
         assert np.array_equal(a[2], other[2])
         assert np.allclose(a[1], other[1], atol=1e-6) and np.allclose(a[3], other[3], atol=1e-6)
