@@ -576,25 +576,57 @@ extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, in
 // ------------------------------------------------------------------------------------------
 // K4  scale_object (processing.jl:65-93)
 // ------------------------------------------------------------------------------------------
-// per-gene sum y / sum y^2 of the normalised values of the selected rows
+// per-gene sum y / sum y^2 of the normalised values of the selected rows, exact fp64 sums (a constant gene must come
+// out with variance exactly 0: processing.jl:66-67 then divides 0 by 0).  Every CTA adds into its OWN fp64 table in
+// global memory (`priv`, [gridDim.x][2 n_feat], zeroed by the caller): atomics of different CTAs never meet at an
+// address (the shared table serialised the whole grid on the popular genes: 6.5 ms at C3), k_scale_stats_reduce adds
+// the tables up.  Loads of four entries per lane are issued before the look-ups, the next column is prefetched.
 __global__ void __launch_bounds__(256)
 k_scale_stats(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
-              const int32_t* __restrict__ gene2h, int64_t n_cells, int32_t n_feat, double* __restrict__ part) {
+              const int32_t* __restrict__ gene2h, int64_t n_cells, int32_t n_feat, double* __restrict__ priv) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double* part = priv + (int64_t)blockIdx.x * 2 * n_feat;
+  constexpr int UN = 4;
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (warp < n_cells) { b = colptr[warp]; e = colptr[warp + 1]; }
+  if (warp + nwarp < n_cells) { nb = colptr[warp + nwarp]; ne = colptr[warp + nwarp + 1]; }
   for (int64_t c = warp; c < n_cells; c += nwarp) {
-    const int64_t b = colptr[c], e = colptr[c + 1];
-#pragma unroll 4
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const int h = __ldg(gene2h + __ldcs(rowval + i));
-      if (h >= 0) {
-        const double y = (double)__ldcs(val + i);
-        atomicAdd(&part[h], y);
-        atomicAdd(&part[n_feat + h], y * y);
+    int64_t nnb = 0, nne = 0;
+    if (c + 2 * nwarp < n_cells) { nnb = colptr[c + 2 * nwarp]; nne = colptr[c + 2 * nwarp + 1]; }
+    if (nb < ne) prefetch_column_l2(rowval, val, nb, ne, lane);
+    for (int64_t i0 = b + lane; i0 < e; i0 += 32 * UN) {
+      int g[UN];
+      float x[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t i = i0 + 32 * u;
+        g[u] = i < e ? __ldcs(rowval + i) : -1;
+        x[u] = i < e ? __ldcs(val + i) : 0.f;
+      }
+      int h[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) h[u] = g[u] >= 0 ? __ldg(gene2h + g[u]) : -1;
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (h[u] >= 0) {
+          const double y = (double)x[u];
+          atomicAdd(&part[h[u]], y);
+          atomicAdd(&part[n_feat + h[u]], y * y);
+        }
       }
     }
+    b = nb; e = ne; nb = nnb; ne = nne;
   }
+}
+
+__global__ void k_scale_stats_reduce(const double* __restrict__ priv, int32_t n_tab, int32_t n_entries, double* __restrict__ part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  double s = 0.0;
+  for (int t = 0; t < n_tab; ++t) s += priv[(int64_t)t * n_entries + i];
+  part[i] += s;
 }
 
 // mean / 1/sd / fill value per selected gene from the (already all-reduced) sums
@@ -835,21 +867,38 @@ k_select_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int UN = 4;   // groups of 32 entries whose loads (index, value, look-up) are in flight together
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (warp < n_cells) { b = colptr[warp]; e = colptr[warp + 1]; }
+  if (warp + nwarp < n_cells) { nb = colptr[warp + nwarp]; ne = colptr[warp + nwarp + 1]; }
   for (int64_t c = warp; c < n_cells; c += nwarp) {
-    const int64_t b = colptr[c], e = colptr[c + 1];
+    int64_t nnb = 0, nne = 0;
+    if (c + 2 * nwarp < n_cells) { nnb = colptr[c + 2 * nwarp]; nne = colptr[c + 2 * nwarp + 1]; }
+    if (nb < ne) prefetch_column_l2(rowval, val, nb, ne, lane);
     int64_t o = out_colptr[c];
-#pragma unroll 4
-    for (int64_t i0 = b; i0 < e; i0 += 32) {
-      const int64_t i = i0 + lane;
-      const int h = i < e ? __ldg(gene2h + __ldcs(rowval + i)) : -1;
-      const unsigned m = __ballot_sync(FULL, h >= 0);
-      if (h >= 0) {
-        const int64_t p = o + __popc(m & ((1u << lane) - 1u));
-        out_rowval[p] = h;
-        out_val[p] = __ldcs(val + i);
+    for (int64_t i0 = b; i0 < e; i0 += 32 * UN) {
+      int g[UN], h[UN];
+      float x[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t i = i0 + 32 * u + lane;
+        g[u] = i < e ? __ldcs(rowval + i) : -1;
+        x[u] = i < e ? __ldcs(val + i) : 0.f;
       }
-      o += __popc(m);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) h[u] = g[u] >= 0 ? __ldg(gene2h + g[u]) : -1;
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const unsigned m = __ballot_sync(FULL, h[u] >= 0);
+        if (h[u] >= 0) {
+          const int64_t p = o + __popc(m & ((1u << lane) - 1u));
+          out_rowval[p] = h[u];
+          out_val[p] = x[u];
+        }
+        o += __popc(m);
+      }
     }
+    b = nb; e = ne; nb = nnb; ne = nne;
   }
 }
 
@@ -870,7 +919,7 @@ extern "C" csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, 
   CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &counts, true));
   CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &r->colptr));
   if (m->n_cells > 0) {
-    k_select_count<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->cp(), m->rv(), (const int32_t*)map->p, m->n_cells,
+    k_select_count<<<ctx->sm_count * resident_ctas(k_select_count, 256, 0, 8), 256, 0, ctx->stream>>>(m->cp(), m->rv(), (const int32_t*)map->p, m->n_cells,
                                                                 (int64_t*)counts->p);
     CSC_LAUNCHED(ctx);
   }
@@ -891,7 +940,7 @@ extern "C" csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, 
   CSC_TRY(dev_alloc(ctx, (size_t)r->nnz * 4, &r->rowval));
   CSC_TRY(dev_alloc(ctx, (size_t)r->nnz * 4, &r->val));
   if (r->nnz > 0) {
-    k_select_fill<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->cp(), m->rv(), m->v(), (const int32_t*)map->p, m->n_cells,
+    k_select_fill<<<ctx->sm_count * resident_ctas(k_select_fill, 256, 0, 8), 256, 0, ctx->stream>>>(m->cp(), m->rv(), m->v(), (const int32_t*)map->p, m->n_cells,
                                                                r->cp(), (int32_t*)r->rowval->p, r->v());
     CSC_LAUNCHED(ctx);
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -912,9 +961,19 @@ extern "C" csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* no
   CSC_TRY(build_gene2h(ctx, norm->n_genes, features, n_feat, &map, &H));
   CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_partial: partial must be fp64[2*H], H=%lld",
               (long long)H);
-  if (norm->n_cells > 0) {
-    k_scale_stats<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p,
-                                                               norm->n_cells, (int32_t)H, partial->as<double>());
+  if (norm->n_cells > 0 && H > 0) {
+    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(k_scale_stats, 256, 0, 4),
+                                      ceil_div64(norm->n_cells, 8));
+    // the private tables stay below 256 MB (a whole-transcriptome call with every gene selected)
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)256 << 20) / (2 * H * 8)));
+    DevPtr priv;
+    CSC_TRY(dev_alloc(ctx, (size_t)grid * 2 * H * 8, &priv));
+    CSC_CUDA(ctx, cudaMemsetAsync(priv->p, 0, (size_t)grid * 2 * H * 8, ctx->stream));
+    k_scale_stats<<<grid, 256, 0, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, norm->n_cells,
+                                                 (int32_t)H, (double*)priv->p);
+    CSC_LAUNCHED(ctx);
+    k_scale_stats_reduce<<<(unsigned)ceil_div64(2 * H, 256), 256, 0, ctx->stream>>>((const double*)priv->p, grid,
+                                                                                   (int32_t)(2 * H), partial->as<double>());
     CSC_LAUNCHED(ctx);
   }
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
