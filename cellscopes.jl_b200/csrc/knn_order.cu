@@ -9,6 +9,7 @@
 // tiles before its own cluster.  Pure reordering: results are identical, ids are mapped back at the end.
 #include <cmath>
 #include <cub/cub.cuh>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -18,47 +19,49 @@ constexpr int KO_D = 64;          // prepared row length (floats)
 constexpr int KO_CHUNK = 128;     // centroids staged in shared memory at a time (32 KB)
 
 // label[i] = argmax_c <x_i, cent_c>; optionally accumulates the per-cluster sums of the assigned points
-// (sample stride `stride`: point i is row i * stride)
+// (sample stride `stride`: point i is row i * stride).  The scores run in packed fp16 (HFMA2: rows and centroids are
+// unit vectors, 16 products per accumulator half): the labels only steer the ORDER of the scan, which is exact in any
+// order, and half the instructions of the fp32 loop (0.63 -> 0.35 ms for the pass over 500k rows).
 __global__ void __launch_bounds__(128)
 k_km_assign(const float* __restrict__ x, int64_t n, int64_t stride, const float* __restrict__ cent, int K, int32_t* __restrict__ label,
             float* __restrict__ sums, int32_t* __restrict__ counts) {
-  __shared__ __align__(16) float sc[KO_CHUNK * KO_D];
+  __shared__ __align__(16) __half2 sc[KO_CHUNK * KO_D / 2];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
-  float xr[KO_D];
-  {
-    const float4* src = reinterpret_cast<const float4*>(x + (valid ? i * stride : 0) * KO_D);
+  const float4* src = reinterpret_cast<const float4*>(x + (valid ? i * stride : 0) * KO_D);
+  __half2 xh[KO_D / 2];
 #pragma unroll
-    for (int j = 0; j < KO_D / 4; ++j) {
-      const float4 v = __ldg(src + j);
-      xr[4 * j] = v.x;
-      xr[4 * j + 1] = v.y;
-      xr[4 * j + 2] = v.z;
-      xr[4 * j + 3] = v.w;
-    }
+  for (int j = 0; j < KO_D / 4; ++j) {
+    const float4 v = __ldg(src + j);
+    xh[2 * j] = __floats2half2_rn(v.x, v.y);
+    xh[2 * j + 1] = __floats2half2_rn(v.z, v.w);
   }
   float best = -2.f;
   int bi = 0;
   for (int c0 = 0; c0 < K; c0 += KO_CHUNK) {
     const int nc = min(KO_CHUNK, K - c0);
     __syncthreads();
-    for (int j = threadIdx.x; j < nc * KO_D / 4; j += blockDim.x)
-      reinterpret_cast<float4*>(sc)[j] = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)c0 * KO_D) + j);
+    for (int j = threadIdx.x; j < nc * KO_D / 4; j += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(cent + (int64_t)c0 * KO_D) + j);
+      sc[2 * j] = __floats2half2_rn(v.x, v.y);
+      sc[2 * j + 1] = __floats2half2_rn(v.z, v.w);
+    }
     __syncthreads();
     for (int c = 0; c < nc; ++c) {
-      const float4* cr = reinterpret_cast<const float4*>(sc + c * KO_D);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const uint4* cr = reinterpret_cast<const uint4*>(sc + c * (KO_D / 2));   // same address for the whole warp: broadcast
+      __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
-      for (int j = 0; j < KO_D / 4; ++j) {
-        const float4 v = cr[j];      // same address for the whole warp: broadcast
-        a0 = fmaf(xr[4 * j], v.x, a0);
-        a1 = fmaf(xr[4 * j + 1], v.y, a1);
-        a2 = fmaf(xr[4 * j + 2], v.z, a2);
-        a3 = fmaf(xr[4 * j + 3], v.w, a3);
+      for (int j = 0; j < KO_D / 8; ++j) {
+        const uint4 v = cr[j];
+        a0 = __hfma2(xh[4 * j], *reinterpret_cast<const __half2*>(&v.x), a0);
+        a1 = __hfma2(xh[4 * j + 1], *reinterpret_cast<const __half2*>(&v.y), a1);
+        a2 = __hfma2(xh[4 * j + 2], *reinterpret_cast<const __half2*>(&v.z), a2);
+        a3 = __hfma2(xh[4 * j + 3], *reinterpret_cast<const __half2*>(&v.w), a3);
       }
-      const float s = (a0 + a1) + (a2 + a3);
-      if (s > best) {
-        best = s;
+      const float2 f = __half22float2(__hadd2(__hadd2(a0, a1), __hadd2(a2, a3)));
+      const float sco = f.x + f.y;
+      if (sco > best) {
+        best = sco;
         bi = c0 + c;
       }
     }
@@ -68,7 +71,13 @@ k_km_assign(const float* __restrict__ x, int64_t n, int64_t stride, const float*
   if (sums) {
     float* dst = sums + (int64_t)bi * KO_D;
 #pragma unroll
-    for (int j = 0; j < KO_D; ++j) atomicAdd(dst + j, xr[j]);
+    for (int j = 0; j < KO_D / 4; ++j) {
+      const float4 v = __ldg(src + j);                     // the fp32 row again (L1/L2): the centroids stay fp32 means
+      atomicAdd(dst + 4 * j, v.x);
+      atomicAdd(dst + 4 * j + 1, v.y);
+      atomicAdd(dst + 4 * j + 2, v.z);
+      atomicAdd(dst + 4 * j + 3, v.w);
+    }
     atomicAdd(counts + bi, 1);
   }
 }
