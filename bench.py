@@ -265,6 +265,12 @@ def main():
             "lambda_1": float(info["principalvars"][0]), "lambda_k": float(info["principalvars"][-1]),
             "min_rel_gap": float(np.min(-np.diff(info["principalvars"]) / info["principalvars"][:-1])),
             "nnz_local": int(nnz_local)}
+    # margin at the HVG rank boundary (published with every benchmark): relative distance between the last
+    # selected and the first rejected variance_standardized
+    hv = last.get("hvg") if isinstance(last, dict) else None
+    if hv is not None and "order" in hv and hv["order"].size > n_features:
+        vs = hv["variance_standardized"][hv["order"]]
+        diag["hvg_boundary_rel_margin"] = float((vs[n_features - 1] - vs[n_features]) / max(abs(vs[n_features - 1]), 1e-300))
     # ---- roofline of the dominant kernel (kNN scan) -------------------------------------------
     peaks, peak_kind = measured_peaks()
     scan_ms = stage_ms["knn_scan"] / args.steps
