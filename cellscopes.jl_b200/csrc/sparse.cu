@@ -248,7 +248,7 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 // Integer sums are order-independent, so the result is deterministic; the raw moments are exact.
 // HBM traffic: 4 B value read + 4 B value written + 4 B row index per non-zero.
 // What bounds the pass (tools/micro/norm_bench.cu, C2 shape): without the table updates it streams at 0.76 of the
-// HBM rate; the 3.4 shared-memory atomics per entry run at ~7 lanes/clk/SM (bank conflicts of 32 random genes),
+// HBM rate; the 3.4 shared-memory atomics per entry run at ~7 lanes/clk/SM (with or without bank conflicts),
 // 0.22 ms on their own, and go through the same load/store unit as the global accesses.  The compiler does not move
 // a global load across an atomic, so a loop of load -> update -> load exposes one DRAM latency per entry group: the
 // loads of UN entries per lane are therefore issued first (0.74 -> 0.52 ms), the next cell's lines are prefetched

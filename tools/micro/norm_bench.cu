@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_norm_VP(const Args a) {
 }
 
 // ---- raw shared-memory atomic rate: NA atomics per lane per round on random table entries
-template <int NA>
+template <int NA, bool CONFLICT_FREE = false>
 __global__ void __launch_bounds__(768, 2) k_atoms(unsigned* sink, int G, int rounds) {
   extern __shared__ unsigned int stab[];
   for (int g = threadIdx.x; g < 4 * G; g += blockDim.x) stab[g] = 0u;
@@ -410,7 +410,9 @@ __global__ void __launch_bounds__(768, 2) k_atoms(unsigned* sink, int G, int rou
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
       h = h * 1664525u + 1013904223u;
-      atomicAdd(&stab[(h >> 8) % (unsigned)G + (k & 3) * G], h & 3u);
+      unsigned a = (h >> 8) % (unsigned)G;
+      if (CONFLICT_FREE) a = min((a & ~31u) | (threadIdx.x & 31u), (unsigned)G - 1u);   // lane = bank: no conflicts in a warp
+      atomicAdd(&stab[a + (k & 3) * G], h & 3u);
     }
   }
   __syncthreads();
@@ -507,24 +509,9 @@ int main(int argc, char** argv) {
   run("S all (shipped)", k_norm_S<ALL>, 768, 2);
   run("S no atomics", k_norm_S<F_WRITE>, 768, 2);
   constexpr int AF = ALL | F_FASTLOG;
-  run("SP un4 768x2 nopf", k_norm_SP<ALL, 4, 768, 2, false, false>, 768, 2);
-  run("SP un4 768x2 pfrow", k_norm_SP<ALL, 4, 768, 2, false, true>, 768, 2);
   run("SP un4 768x2 pf", k_norm_SP<ALL, 4, 768, 2, true, false>, 768, 2);
-  run("SP un8 768x2 pf", k_norm_SP<ALL, 8, 768, 2, true, false>, 768, 2);
-  run("SP un2 1024x2 pf", k_norm_SP<ALL, 2, 1024, 2, true, false>, 1024, 2);
-  run("SP un4 1024x2 pf", k_norm_SP<ALL, 4, 1024, 2, true, false>, 1024, 2);
   run("SP un4 768x2 pf fastlog", k_norm_SP<AF, 4, 768, 2, true, false>, 768, 2);
   run("SP un4 768x2 pf noatom", k_norm_SP<F_WRITE, 4, 768, 2, true, false>, 768, 2);
-  run("SP un4 768x2 pf raw only", k_norm_SP<F_WRITE | F_S1 | F_E, 4, 768, 2, true, false>, 768, 2);
-  run("SP un4 768x2 pf y only", k_norm_SP<F_WRITE | F_Y, 4, 768, 2, true, false>, 768, 2);
-  run("VP nit1 768x2 pf", k_norm_VP<ALL, 1, 768, 2, true>, 768, 2);
-  run("VP nit2 768x2 pf", k_norm_VP<ALL, 2, 768, 2, true>, 768, 2);
-  run("VP nit2 768x2 nopf", k_norm_VP<ALL, 2, 768, 2, false>, 768, 2);
-  run("VP nit1 1024x2 pf", k_norm_VP<ALL, 1, 1024, 2, true>, 1024, 2);
-  run("VP nit2 1024x2 pf", k_norm_VP<ALL, 2, 1024, 2, true>, 1024, 2);
-  run("VP nit2 512x2 pf", k_norm_VP<ALL, 2, 512, 2, true>, 512, 2);
-  run("VP nit2 768x2 pf fastlog", k_norm_VP<AF, 2, 768, 2, true>, 768, 2);
-  run("VP nit2 768x2 pf noatom", k_norm_VP<F_WRITE, 2, 768, 2, true>, 768, 2);
   // atomic rate
   unsigned* sink;
   CK(cudaMalloc(&sink, 4));
@@ -548,5 +535,6 @@ int main(int argc, char** argv) {
   atoms("ATOMS x1/round", k_atoms<1>, 1);
   atoms("ATOMS x4/round", k_atoms<4>, 4);
   atoms("ATOMS x16/round", k_atoms<16>, 16);
+  atoms("ATOMS x4 conflict-free", k_atoms<4, true>, 4);
   return 0;
 }
