@@ -125,6 +125,29 @@ def test_gene_moments_large_counts(cs, oracle, ctx):
     assert np.allclose(got[:50], s1, rtol=1e-12) and np.allclose(got[50:], s2, rtol=1e-12)
 
 
+@pytest.mark.parametrize("n_genes", [30000, 60000])
+def test_gene_moments_exact_when_tables_do_not_fit(cs, oracle, ctx, n_genes):
+    """Whole-transcriptome gene counts: with 30k genes only the sum table fits in shared memory (the squares go to
+    the fp64 table in global memory), with 60k genes nothing does.  Moments stay bit-exact, normalised values within
+    tolerance, and the fused pass equals the standalone one."""
+    rng = np.random.default_rng(n_genes)
+    n_cells = 400
+    m = sp.random(n_genes, n_cells, density=0.01, format="csc", random_state=rng,
+                  data_rvs=lambda k: rng.integers(1, 40, size=k).astype(np.float64))
+    m.data[::97] = 300.0                                   # beyond the one-byte fast path of the squares
+    raw = ctx.sparse_from_scipy(m)
+    st = ctx.vec(2 * n_genes)
+    ctx.gene_stats_partial(raw, st)
+    s1, s2, _, _ = oracle.gene_moments(m)
+    got = st.download()
+    assert np.array_equal(got[:n_genes], s1) and np.array_equal(got[n_genes:], s2)
+    st2 = ctx.vec(2 * n_genes)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0, False, st2)
+    assert np.array_equal(st2.download(), got)
+    want = oracle.normalize_object(m)
+    assert rel_close(norm.download(values_only=True), want.data, 1e-5)
+
+
 @pytest.mark.parametrize("nfeat", [200, 2000])
 def test_hvg_set_bit_exact(cs, oracle, ctx, medium_counts, nfeat):
     raw = ctx.sparse_from_scipy(medium_counts)
