@@ -64,13 +64,11 @@ SIGNATURES = {
     "csc_sparse_download": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32]),
     "csc_sparse_free": (_I32, [_P]),
     "csc_generate_counts": (_I32, [_P, _I64, _I64, _I64, _U64, _P, _P, _P, _P, _I32, _I32, _F32, _F32, _F32, _PP]),
-    "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _P, _PP]),
-    "csc_normalize_fuses_norm_stats": (_I32, [_I64]),
+    "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _PP]),
     "csc_gene_stats_partial": (_I32, [_P, _P, _P]),
     "csc_hvg_finish": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
     "csc_sparse_select_rows": (_I32, [_P, _P, _P, _I64, _PP]),
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
-    "csc_scale_stats_select": (_I32, [_P, _P, _I64, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
     "csc_scale_gram_partial": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _P, _P]),
     "csc_dense_alloc": (_I32, [_P, _I64, _I64, _PP]),
@@ -107,8 +105,8 @@ def csc_from_arrays(data, indices, indptr, shape):
 
 
 def _host_free(ctx, ptr):
-    if ctx.h is not None:
-        ctx.lib.csc_host_free(ctx.h, C.c_void_p(ptr))
+    # a block that outlives its context (Context.close() leaves live blocks alone) goes back with a NULL context
+    ctx.lib.csc_host_free(ctx.h if ctx.h is not None else None, C.c_void_p(ptr))
 
 
 def load_library(path: str | None = None):
@@ -126,7 +124,7 @@ def load_library(path: str | None = None):
         fn = getattr(lib, name)       # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.csc_abi_version() != 1:
+    if lib.csc_abi_version() != 2:
         raise CellScopesCudaError(-101, "ABI version mismatch")
     _lib = lib
     return lib
@@ -268,15 +266,12 @@ class Context:
 
     # ---- stages ----------------------------------------------------------------------------
     def normalize(self, raw, scale_factor=10000.0, norm_method=NORM_LOGARITHM, pseudocount=1.0, nan_to_zero=False,
-                  gene_stats=None, norm_stats=None):
+                  gene_stats=None):
         h = C.c_void_p()
         self.check(self.lib.csc_normalize(self.h, raw.h, float(scale_factor), int(norm_method), float(pseudocount),
                                           1 if nan_to_zero else 0, gene_stats.h if gene_stats is not None else None,
-                                          norm_stats.h if norm_stats is not None else None, C.byref(h)))
+                                          C.byref(h)))
         return Sparse(self, h)
-
-    def normalize_fuses_norm_stats(self, n_genes):
-        return bool(self.lib.csc_normalize_fuses_norm_stats(int(n_genes)))
 
     def gene_stats_partial(self, raw, gene_stats):
         self.check(self.lib.csc_gene_stats_partial(self.h, raw.h, gene_stats.h))
@@ -303,12 +298,6 @@ class Context:
     def scale_stats_partial(self, norm, features, partial):
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
         self.check(self.lib.csc_scale_stats_partial(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h))
-
-    def scale_stats_select(self, norm_stats, n_genes, features, partial):
-        """partial += the rows of the all-gene (sum y, sum y^2) table that csc_normalize filled"""
-        f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
-        self.check(self.lib.csc_scale_stats_select(self.h, norm_stats.h, int(n_genes), _ptr(f), 0 if f is None else f.size,
-                                                   partial.h))
 
     def scale_fill(self, norm, features, partial, n_cells_total, scale_max=10.0, do_scale=True, do_center=True):
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)

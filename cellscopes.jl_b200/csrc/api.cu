@@ -143,8 +143,12 @@ csc_status csc_host_alloc(csc_ctx* ctx, int64_t bytes, void** out) {
 }
 
 csc_status csc_host_free(csc_ctx* ctx, void* p) {
-  if (!ctx) return CSC_ERR_ARG;
   if (!p) return CSC_OK;
+  if (!ctx) {
+    // the context that handed the block out is gone (csc_destroy leaves blocks that are still live alone: they back
+    // result arrays the caller may still read): the block goes straight back to the driver
+    return cudaFreeHost(p) == cudaSuccess ? CSC_OK : csc_fail(nullptr, CSC_ERR_CUDA, "csc_host_free: cudaFreeHost failed");
+  }
   CSC_GUARD_BEGIN
   auto it = ctx->host_live.find(p);
   CSC_REQUIRE(ctx, it != ctx->host_live.end(), "csc_host_free: pointer was not allocated by csc_host_alloc of this context");
@@ -219,7 +223,8 @@ csc_status csc_destroy(csc_ctx* ctx) {
   ctx->cache.release_all();
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);
-  for (auto& kv : ctx->host_live) cudaFreeHost(kv.first);
+  // blocks still live belong to result arrays of the caller: they stay valid and are released by
+  // csc_host_free(NULL, p)
   for (int b = 0; b < 2; ++b) {
     if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
     if (ctx->ev_bounce[b]) cudaEventDestroy(ctx->ev_bounce[b]);

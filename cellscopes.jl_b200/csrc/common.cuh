@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <new>
 #include <string>
@@ -112,6 +113,9 @@ struct csc_sparse {
   DevPtr colptr;  // int64 [n_cells+1], 0-based
   DevPtr rowval;  // int32 [nnz], 0-based
   DevPtr val;     // float [nnz]
+  // upper bound on |value| when one is known (set by csc_normalize, inherited by csc_sparse_select_rows), else +inf:
+  // k_scale_stats_fx derives the scale of its fixed-point accumulators from it
+  double vmax_bound = std::numeric_limits<double>::infinity();
   const int64_t* cp() const { return (const int64_t*)colptr->p; }
   const int32_t* rv() const { return (const int32_t*)rowval->p; }
   float* v() const { return (float*)val->p; }

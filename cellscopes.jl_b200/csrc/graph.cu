@@ -22,11 +22,15 @@ __global__ void k_graph_keys(const int32_t* __restrict__ idx, int64_t n_total, i
   if (e < n_fwd) {
     const int64_t cell = lo + e / k;
     const int32_t nb = idx[cell * k + e % k];
-    key = ((unsigned long long)(cell - lo) << row_bits) | (unsigned int)nb;
+    // an id outside [0, n_total) (a table gathered from elsewhere, a placeholder of a failed kNN) would spill into the
+    // column bits of the key and index the SNN lists out of bounds: flag it, the host turns the flag into CSC_ERR_ARG
+    if (nb < 0 || nb >= n_total) n_valid[1] = 1ull;
+    else key = ((unsigned long long)(cell - lo) << row_bits) | (unsigned int)nb;
   } else if (e < n_all) {
     const int64_t r = e - n_fwd;
     const int64_t cell = r / k;
     const int32_t nb = idx[r];
+    if (nb < 0 || nb >= n_total) n_valid[1] = 1ull;
     if (nb >= lo && nb < hi) key = ((unsigned long long)(nb - lo) << row_bits) | (unsigned int)cell;
   }
   if (e < n_all) keys[e] = key;
@@ -174,7 +178,7 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   DevPtr keys_a, keys_b, counter;
   CSC_TRY(dev_alloc(ctx, (size_t)n_all * 8, &keys_a));
   CSC_TRY(dev_alloc(ctx, (size_t)n_all * 8, &keys_b));
-  CSC_TRY(dev_alloc(ctx, 8, &counter, true));
+  CSC_TRY(dev_alloc(ctx, 16, &counter, true));      // [0] valid keys, [1] bad-id flag
   CSC_TRACE(ctx, "graph: alloc keys");
   int row_bits = 1, col_bits = 1;
   while (((int64_t)1 << row_bits) < n_cells_total) ++row_bits;
@@ -196,10 +200,11 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
     ctx->launches += 1 + (key_bits + 7) / 8;
   }
   CSC_TRACE(ctx, "graph: keys+sort");
-  unsigned long long n_valid = 0;
-  CSC_CUDA(ctx, cudaMemcpyAsync(&n_valid, counter->p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long h_counter[2] = {0, 0};
+  CSC_CUDA(ctx, cudaMemcpyAsync(h_counter, counter->p, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int64_t nv = (int64_t)n_valid;
+  CSC_REQUIRE(ctx, h_counter[1] == 0, "csc_graph_build: a neighbour id is outside [0, n_cells_total)");
+  const int64_t nv = (int64_t)h_counter[0];
   const unsigned long long* skeys = (const unsigned long long*)keys_b->p;
   // run-length encode
   DevPtr head, pos;

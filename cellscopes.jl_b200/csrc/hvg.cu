@@ -316,8 +316,18 @@ csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, in
       ly[i] = std::log10(var[kept[i]]);
     }
   });
-  // The reference requires every gene to have variance > 0 (:143,:151 would mis-assign names otherwise);
-  // here such genes are kept out of the fit and rank last with variance_standardized = 0.
+  // The reference requires every gene to have variance > 0: it filters the data frame (:143) and then assigns the
+  // gene names of ALL genes to it (:151), which throws a DimensionMismatch when a row was dropped.  Same here (and in
+  // the oracle): selecting such a gene would put 0/0 = NaN rows into the scaled matrix and the Gram matrix.
+  if ((int64_t)kept.size() != n_genes) {
+    int64_t first_bad = 0;
+    while (first_bad < n_genes && var[first_bad] > 0.0) ++first_bad;
+    return csc_fail(ctx, CSC_ERR_ARG,
+                    "find_variable_genes: %lld of %lld genes have variance <= 0 (first: gene %lld); the reference requires "
+                    "every gene to vary (processing.jl:143,151) -- its object constructor drops all-zero genes first "
+                    "(subset_matrix, utils.jl:313-320)",
+                    (long long)(n_genes - (int64_t)kept.size()), (long long)n_genes, (long long)first_bad);
+  }
   if (!kept.empty()) {
     std::vector<double> pred;
     loess_fit_predict(lx, ly, span, pred);

@@ -1301,6 +1301,12 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double trace = 0.0;
   for (double d : diag) trace += d;
+  // a NaN anywhere in the scaled matrix (a selected gene with zero variance: 0/0 in scale_object) reaches
+  // the Gram diagonal; LAPACK's gesdd fails on such input in the reference, and the iteration below would never converge
+  for (int r = 0; r < H; ++r)
+    if (!std::isfinite(diag[r]) || !std::isfinite(hsum[r]))
+      return csc_fail(ctx, CSC_ERR_NUMERIC, "csc_pca_solve: the Gram matrix is not finite (feature row %d); a selected gene has "
+                      "zero variance or NaN values in the scaled matrix", r);
 
   std::vector<double> evals((size_t)k), U((size_t)H * k);
   int iters = 0;
@@ -1497,6 +1503,9 @@ extern "C" csc_status csc_pca_solve(csc_ctx* ctx, const csc_vec* colsum, const c
       stop_mult *= 0.1;
     }
     SolveProf::get().report(ctx->stream);
+    if (!(resid <= tol))      // also true for a NaN residual
+      return csc_fail(ctx, CSC_ERR_NUMERIC, "csc_pca_solve: the eigensolver did not converge: residual %.3e > tol %.3e after "
+                      "%d products (max_iter %d)", resid, tol, iters, max_iter);
     std::vector<double> hq((size_t)H * b);
     CSC_CUDA(ctx, cudaMemcpyAsync(hq.data(), Q, hq.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

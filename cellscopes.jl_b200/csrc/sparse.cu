@@ -18,6 +18,15 @@ __global__ void k_colptr_rebase(const T* __restrict__ in, int64_t* __restrict__ 
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = (int64_t)in[i] - base;
 }
+// 0 <= cp[i] <= cp[i+1] <= nnz for every column (every warp-per-column kernel trusts this)
+__global__ void k_colptr_check(const int64_t* __restrict__ cp, int64_t n_cells, int64_t nnz, int* __restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n_cells; i += stride) {
+    const int64_t b = cp[i], e = cp[i + 1];
+    if (b < 0 || e < b || e > nnz) atomicMax(bad, 2);
+  }
+}
 template <typename T>
 __global__ void k_narrow_idx(const T* __restrict__ in, int32_t* __restrict__ out, int64_t n, int64_t base,
                              int64_t n_rows, int* __restrict__ bad) {
@@ -25,7 +34,7 @@ __global__ void k_narrow_idx(const T* __restrict__ in, int32_t* __restrict__ out
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     int64_t r = (int64_t)in[i] - base;
-    if (r < 0 || r >= n_rows) *bad = 1;
+    if (r < 0 || r >= n_rows) atomicMax(bad, 1);
     out[i] = (int32_t)r;
   }
 }
@@ -134,6 +143,10 @@ extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n
     CSC_LAUNCHED(ctx);
     return (csc_status)CSC_OK;
   }));
+  if (n_cells > 0) {
+    k_colptr_check<<<grid_for(n_cells, sm), 256, 0, ctx->stream>>>(d_cp, n_cells, nnz, d_bad);
+    CSC_LAUNCHED(ctx);
+  }
   CSC_TRY(staged_upload(ctx, rowval, dt_size(idx_dtype), nnz, [&](void* src, int64_t o, int64_t cnt) {
     if (idx_dtype == CSC_DT_I64)
       k_narrow_idx<int64_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)src, d_rv + o, cnt, index_base, n_genes, d_bad);
@@ -155,6 +168,7 @@ extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n
   int h_bad = 0;
   CSC_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CSC_REQUIRE(ctx, h_bad != 2, "csc_sparse_upload: colptr is not monotone within [index_base, index_base + nnz]");
   CSC_REQUIRE(ctx, h_bad == 0, "csc_sparse_upload: a row index is outside [0, n_genes)");
   *out = m.release();
   return CSC_OK;
@@ -232,9 +246,11 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K1/K2  normalize_object (processing.jl:15-31) fused with the per-gene moments the next two stages need:
-//   raw counts   (sum x, sum x^2)  -> find_variable_genes (processing.jl:138-139)
-//   normalised   (sum y, sum y^2)  -> scale_object        (processing.jl:66-67)
+// K1/K2  normalize_object (processing.jl:15-31) fused with the per-gene moments of the RAW counts
+//   (sum x, sum x^2)  -> find_variable_genes (processing.jl:138-139)
+// (The moments of the normalised values that scale_object needs are NOT taken here any more: round 1 accumulated
+// them in 32-bit fixed point scaled by the theoretical range of y, which resolved y^2 to ~3e-5 only and to ~40 for
+// norm_method = "none".  k_scale_stats_fx takes them for the selected rows with 64-bit accumulators.)
 //
 // A CTA owns a contiguous range of cells; a warp owns one cell at a time.  Pass 1 over the column: fp64 column
 // sum (warp-shuffle reduction).  Pass 2 (the column is still in L1): y = log((x * inv) * sf + pc), written with
@@ -243,8 +259,6 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 // fp64 tables in global memory once per CTA:
 //   S1 = sum x            u32, exact (x integer <= 65535; anything else goes straight to the fp64 table)
 //   E  = sum (x^2 - x)    u32, exact (x <= 255)            -> sum x^2 = S1 + E
-//   Y1 = sum round(y s1)  i32, fixed point; s1 = 2^31 / (cells_per_cta * ymax): resolution ~ 4e-6 per entry
-//   Y2 = sum round(y^2 s2) u32, fixed point
 // Integer sums are order-independent, so the result is deterministic; the raw moments are exact.
 // HBM traffic: 4 B value read + 4 B value written + 4 B row index per non-zero.
 // What bounds the pass (tools/micro/norm_bench.cu, C2 shape): without the table updates it streams at 0.76 of the
@@ -274,15 +288,12 @@ struct NormArgs {
   double sf, pc;
   int method, nan_to_zero;
   double* gstats;     // fp64 [2G] raw moments (or null)
-  double* nstats;     // fp64 [2G] normalised moments (or null)
   int64_t cells_per_cta;
-  float ymax, s1, s2; // fixed-point range and scales of the normalised moments
-  double inv_s1, inv_s2;
 };
 
 // RAW: 0 = no raw moments, 1 = S1 table only (E goes to global memory), 2 = S1 and E tables,
 //      3 = no table fits: every update goes to the fp64 table in global memory
-template <bool WRITE_NORM, int RAW, bool NSTATS>
+template <bool WRITE_NORM, int RAW>
 __global__ void __launch_bounds__(768, 2)
 k_normalize(const NormArgs a) {
   extern __shared__ unsigned int stab[];
@@ -290,9 +301,7 @@ k_normalize(const NormArgs a) {
   unsigned int* s1tab = stab;
   constexpr int NRAW = RAW == 2 ? 2 : RAW == 1 ? 1 : 0;
   unsigned int* etab = stab + (NRAW >= 1 ? G : 0);
-  int* y1tab = reinterpret_cast<int*>(stab + NRAW * G);
-  unsigned int* y2tab = reinterpret_cast<unsigned int*>(y1tab) + G;
-  constexpr int NTAB = NRAW + (NSTATS ? 2 : 0);
+  constexpr int NTAB = NRAW;
   if (NTAB > 0) {
     for (int g = threadIdx.x; g < NTAB * G; g += blockDim.x) stab[g] = 0u;
     __syncthreads();
@@ -312,9 +321,9 @@ k_normalize(const NormArgs a) {
     // column bounds two cells ahead, the next cell's lines on their way into L2 while this one is processed
     int64_t nnb = 0, nne = 0;
     if (c + 2 * nwarp < c1) { nnb = a.colptr[c + 2 * nwarp]; nne = a.colptr[c + 2 * nwarp + 1]; }
-    if (nb < ne) prefetch_column_l2((RAW > 0 || NSTATS) ? a.rowval : nullptr, a.raw, nb, ne, lane);
+    if (nb < ne) prefetch_column_l2(RAW > 0 ? a.rowval : nullptr, a.raw, nb, ne, lane);
     float scale = 0.f;
-    if (WRITE_NORM || NSTATS) {
+    if (WRITE_NORM) {
       double s = 0.0;
 #pragma unroll 4
       for (int64_t i = b + lane; i < e; i += 32) s += (double)a.raw[i];
@@ -331,7 +340,7 @@ k_normalize(const NormArgs a) {
       for (int u = 0; u < UN; ++u) {
         const int64_t i = i0 + 32 * u;
         xs[u] = i < e ? a.raw[i] : 0.f;
-        gs[u] = ((RAW > 0 || NSTATS) && i < e) ? __ldcs(a.rowval + i) : 0;
+        gs[u] = (RAW > 0 && i < e) ? __ldcs(a.rowval + i) : 0;
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -339,7 +348,7 @@ k_normalize(const NormArgs a) {
         if (i >= e) break;
         const float x = xs[u];
         float y = 0.f;
-        if (WRITE_NORM || NSTATS) {
+        if (WRITE_NORM) {
           const float t = x * scale;
           if (a.method == CSC_NORM_LOGARITHM) {
             // log(1 + t): from t = 1 on, 1 + t is at least 2, where __logf is good to 3 ulp and the rounding of the
@@ -350,11 +359,11 @@ k_normalize(const NormArgs a) {
             y = t;
           }
           if (a.nan_to_zero && y != y) y = 0.f;
-          if (WRITE_NORM) __stcs(a.out + i, y);
+          __stcs(a.out + i, y);
         }
-        if (RAW > 0 || NSTATS) {
+        if (RAW > 0) {
           const int g = gs[u];
-          if (RAW > 0) {
+          {
             const float xr = rintf(x);
             if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
               const unsigned int xi = (unsigned int)x;
@@ -371,16 +380,6 @@ k_normalize(const NormArgs a) {
               atomicAdd(&a.gstats[(int64_t)G + g], xd * xd);
             }
           }
-          if (NSTATS) {
-            if (fabsf(y) <= a.ymax) {   // false for NaN / Inf / out-of-range values
-              atomicAdd(&y1tab[g], __float2int_rn(y * a.s1));
-              atomicAdd(&y2tab[g], __float2uint_rn(y * y * a.s2));
-            } else {
-              const double yd = (double)y;
-              atomicAdd(&a.nstats[g], yd);
-              atomicAdd(&a.nstats[(int64_t)G + g], yd * yd);
-            }
-          }
         }
       }
     }
@@ -395,49 +394,21 @@ k_normalize(const NormArgs a) {
         if (v) atomicAdd(&a.gstats[g], (double)v);
         if (v || ex) atomicAdd(&a.gstats[(int64_t)G + g], (double)v + (double)ex);  // sum x^2 = sum x + sum (x^2 - x)
       }
-      if (NSTATS) {
-        const int v1 = y1tab[g];
-        const unsigned int v2 = y2tab[g];
-        if (v1) atomicAdd(&a.nstats[g], (double)v1 * a.inv_s1);
-        if (v2) atomicAdd(&a.nstats[(int64_t)G + g], (double)v2 * a.inv_s2);
-      }
-    }
-  }
-}
-
-// norm_stats fallback (tables do not fit): per-gene sum y / sum y^2 over all genes straight from the normalised values
-__global__ void __launch_bounds__(256)
-k_norm_moments_global(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
-                      int64_t n_cells, int32_t n_genes, double* __restrict__ nstats) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t c = warp; c < n_cells; c += nwarp) {
-    const int64_t b = colptr[c], e = colptr[c + 1];
-#pragma unroll 4
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const int g = __ldcs(rowval + i);
-      const double y = (double)__ldcs(val + i);
-      atomicAdd(&nstats[g], y);
-      atomicAdd(&nstats[(int64_t)n_genes + g], y * y);
     }
   }
 }
 
 static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* out, double sf, double pc, int method,
-                                   int nan_to_zero, double* gstats, double* nstats) {
+                                   int nan_to_zero, double* gstats) {
   if (raw->n_cells == 0) return CSC_OK;
   const int threads = 768;
   const size_t G = (size_t)raw->n_genes;
   const size_t budget = (size_t)200 * 1024;
-  // which tables fit: raw S1 (+E), normalised Y1/Y2
+  // which tables fit: raw S1 (+E)
   int raw_mode = 0;
-  bool nst = false;
   if (gstats) raw_mode = (2 * G * 4 <= budget) ? 2 : (G * 4 <= budget ? 1 : 3);
   const int nraw = raw_mode == 2 ? 2 : raw_mode == 1 ? 1 : 0;
-  if (nstats && out && (size_t)(nraw + 2) * G * 4 <= budget) nst = true;
-  const int ntab = nraw + (nst ? 2 : 0);
-  const size_t smem = (size_t)ntab * G * 4;
+  const size_t smem = (size_t)nraw * G * 4;
   const int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(2, ((size_t)220 * 1024) / (smem + 1024))) : 2;
   int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
   // a CTA's u32 tables must not overflow: <= 65535 (S1) and <= 65025 (E) per entry * 65536 cells
@@ -456,19 +427,7 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   a.method = method;
   a.nan_to_zero = nan_to_zero;
   a.gstats = gstats;
-  a.nstats = nstats;
   a.cells_per_cta = cells_per_cta;
-  // range of y for non-negative counts: t = x/colsum*sf in [0, sf]
-  double ymax = method == CSC_NORM_LOGARITHM ? std::max(std::fabs(std::log(pc > 0 ? pc : 1e-300)), std::fabs(std::log(sf + pc)))
-                                              : std::fabs(sf);
-  if (!(ymax > 0.0) || !std::isfinite(ymax)) ymax = 1.0;
-  a.ymax = (float)(ymax * 1.0001);
-  const double s1 = 0.98 * 2147483648.0 / ((double)cells_per_cta * a.ymax);
-  const double s2 = 0.98 * 4294967296.0 / ((double)cells_per_cta * (double)a.ymax * a.ymax);
-  a.s1 = (float)s1;
-  a.s2 = (float)s2;
-  a.inv_s1 = 1.0 / (double)a.s1;
-  a.inv_s2 = 1.0 / (double)a.s2;
   auto launch = [&](auto kern) -> csc_status {
     if (smem > 48 * 1024)
       CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -478,32 +437,15 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   };
   const bool wn = out != nullptr;
   csc_status st = CSC_OK;
-#define NORM_CASE(W, R, N) if (wn == W && raw_mode == R && nst == N) st = launch(k_normalize<W, R, N>);
-  NORM_CASE(true, 0, false) NORM_CASE(true, 1, false) NORM_CASE(true, 2, false) NORM_CASE(true, 3, false)
-  NORM_CASE(true, 0, true) NORM_CASE(true, 1, true) NORM_CASE(true, 2, true) NORM_CASE(true, 3, true)
-  NORM_CASE(false, 1, false) NORM_CASE(false, 2, false) NORM_CASE(false, 3, false)
+#define NORM_CASE(W, R) if (wn == W && raw_mode == R) st = launch(k_normalize<W, R>);
+  NORM_CASE(true, 0) NORM_CASE(true, 1) NORM_CASE(true, 2) NORM_CASE(true, 3)
+  NORM_CASE(false, 1) NORM_CASE(false, 2) NORM_CASE(false, 3)
 #undef NORM_CASE
-  CSC_TRY(st);
-  if (nstats && !nst && out) {
-    // tables did not fit: one more pass over the normalised values
-    k_norm_moments_global<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(raw->cp(), raw->rv(), out, raw->n_cells,
-                                                                       (int32_t)raw->n_genes, nstats);
-    CSC_LAUNCHED(ctx);
-  }
-  return CSC_OK;
-}
-
-// 1 when csc_normalize can keep the all-gene normalised moments in per-CTA shared-memory tables (four 32-bit tables of
-// n_genes entries within 200 KB: n_genes <= 12800); otherwise its norm_stats output costs a pass of global fp64
-// atomics over every stored entry, and a caller that only needs the moments of the selected genes is better off
-// with csc_scale_stats_partial after the selection.
-extern "C" int32_t csc_normalize_fuses_norm_stats(int64_t n_genes) {
-  return (size_t)n_genes * 16 <= (size_t)200 * 1024 ? 1 : 0;
+  return st;
 }
 
 extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
-                                    double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
-                                    csc_sparse** out) {
+                                    double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out) {
   if (!ctx || !raw || !out) return CSC_ERR_ARG;
   CSC_GUARD_BEGIN
   // processing.jl:28: throw(ArgumentError("Unknown normalization method"))
@@ -511,8 +453,6 @@ extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double 
               "Unknown normalization method: %d", norm_method);
   CSC_REQUIRE(ctx, !gene_stats || (gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * raw->n_genes),
               "csc_normalize: gene_stats must be fp64[2*n_genes]");
-  CSC_REQUIRE(ctx, !norm_stats || (norm_stats->dtype == CSC_DT_F64 && norm_stats->n >= 2 * raw->n_genes),
-              "csc_normalize: norm_stats must be fp64[2*n_genes]");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_NORMALIZE);
   std::unique_ptr<csc_sparse> m(new csc_sparse());
@@ -524,7 +464,12 @@ extern "C" csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double 
   m->rowval = raw->rowval;
   CSC_TRY(dev_alloc(ctx, (size_t)raw->nnz * 4, &m->val));
   CSC_TRY(launch_normalize(ctx, raw, m->v(), scale_factor, pseudocount, norm_method, nan_to_zero,
-                           gene_stats ? gene_stats->as<double>() : nullptr, norm_stats ? norm_stats->as<double>() : nullptr));
+                           gene_stats ? gene_stats->as<double>() : nullptr));
+  // bound on |y| (k_scale_stats_fx scales its fixed-point accumulators by it): t = x / colsum * sf lies in [0, sf] for
+  // non-negative counts; entries outside the bound take the fp64 route there, so the bound only has to be usual
+  m->vmax_bound = norm_method == CSC_NORM_LOGARITHM
+                      ? std::max(std::fabs(std::log(pseudocount > 0 ? pseudocount : 1e-300)), std::fabs(std::log(scale_factor + pseudocount)))
+                      : std::fabs(scale_factor);
   *out = m.release();
   return CSC_OK;
   CSC_GUARD_END(ctx)
@@ -537,21 +482,9 @@ extern "C" csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw
               "csc_gene_stats_partial: gene_stats must be fp64[2*n_genes]");
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   StageTimer st(ctx, CSC_T_GENE_STATS);
-  CSC_TRY(launch_normalize(ctx, raw, nullptr, 1.0, 1.0, 0, 0, gene_stats->as<double>(), nullptr));
+  CSC_TRY(launch_normalize(ctx, raw, nullptr, 1.0, 1.0, 0, 0, gene_stats->as<double>()));
   return CSC_OK;
   CSC_GUARD_END(ctx)
-}
-
-// partial[0:H] = all_stats[rows], partial[H:2H] = all_stats[G + rows] for the selected rows in original gene order
-__global__ void k_stats_select(const double* __restrict__ all, int32_t n_genes, const int32_t* __restrict__ gene2h,
-                               int32_t n_feat, double* __restrict__ part) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_genes) return;
-  const int h = gene2h[g];
-  if (h >= 0) {
-    part[h] += all[g];
-    part[n_feat + h] += all[(int64_t)n_genes + g];
-  }
 }
 
 extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
@@ -576,11 +509,99 @@ extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, in
 // ------------------------------------------------------------------------------------------
 // K4  scale_object (processing.jl:65-93)
 // ------------------------------------------------------------------------------------------
-// per-gene sum y / sum y^2 of the normalised values of the selected rows, exact fp64 sums (a constant gene must come
-// out with variance exactly 0: processing.jl:66-67 then divides 0 by 0).  Every CTA adds into its OWN fp64 table in
-// global memory (`priv`, [gridDim.x][2 n_feat], zeroed by the caller): atomics of different CTAs never meet at an
-// address (the shared table serialised the whole grid on the popular genes: 6.5 ms at C3), k_scale_stats_reduce adds
-// the tables up.  Loads of four entries per lane are issued before the look-ups, the next column is prefetched.
+// per-gene sum y / sum y^2 of the normalised values of the selected rows (processing.jl:66-67 takes mean and var of
+// them).  Two kernels:
+//
+// k_scale_stats_fx -- the usual one.  64-bit fixed-point accumulators in SHARED memory, each as a (lo, hi) pair of u32
+// words because shared memory adds 32-bit integers natively (a 64-bit or fp64 shared add is a CAS loop): the low word
+// is added with atomicAdd, whose return value tells the adding thread whether ITS add wrapped the word, and only then
+// (or when the addend itself is >= 2^32) the high word is touched -- ~1.1 shared atomics per sum.  Scales: 2^e with
+// e = 32 - ceil(log2(bound on |y|)) for both sums, i.e. y is resolved to 2^-28 (3.7e-9) and y^2 to 2^-28 for the
+// logarithm method with the default scale factor: relative resolution < 4e-7 even for a y of 0.1 squared, against the
+// 1e-5 the path promises, and 10^4 times finer than the 32-bit tables of round 1 (which ADVICE r1 found to round
+// y^2 = 4 to 0 for norm_method "none").  Integer sums are order-independent -> deterministic.  Values outside the
+// bound, NaN and Inf go straight to the fp64 table in global memory.  A CTA flushes its tables once, as fp64 adds.
+//
+// k_scale_stats -- exact fp64 sums in per-CTA private tables in global memory (atomics of different CTAs never meet
+// at an address; k_scale_stats_reduce adds the tables up).  Used when no bound on |y| is known (an uploaded
+// normalised matrix), when the bound leaves fewer than 20 fractional bits (norm_method "none" with a large scale
+// factor), or when the tables of H rows do not fit in shared memory.
+// Loads of four entries per lane are issued before the look-ups, the next column is prefetched into L2.
+struct StatsFx {
+  float bound;        // |y| <= bound -> fixed-point route
+  float s1, s2;       // 2^e1, 2^e2
+  double inv_s1, inv_s2;
+};
+
+__device__ __forceinline__ void fx_add(unsigned int* lo, unsigned int* hi, long long v) {
+  const unsigned int l = (unsigned int)(unsigned long long)v;
+  unsigned int h = (unsigned int)((unsigned long long)v >> 32);
+  const unsigned int old = atomicAdd(lo, l);
+  h += (old + l < old) ? 1u : 0u;     // the carry of THIS add (64-bit two's complement arithmetic, word by word)
+  if (h) atomicAdd(hi, h);
+}
+
+template <bool IDENT>   // IDENT: the matrix is already the row subset (gene2h is the identity)
+__global__ void __launch_bounds__(512, 2)
+k_scale_stats_fx(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
+                 const int32_t* __restrict__ gene2h, int64_t n_cells, int32_t n_feat, const StatsFx fx,
+                 double* __restrict__ part) {
+  extern __shared__ unsigned int fxtab[];   // [4][n_feat]: y lo, y hi, y^2 lo, y^2 hi
+  unsigned int* y1lo = fxtab;
+  unsigned int* y1hi = fxtab + n_feat;
+  unsigned int* y2lo = fxtab + 2 * n_feat;
+  unsigned int* y2hi = fxtab + 3 * n_feat;
+  for (int i = threadIdx.x; i < 4 * n_feat; i += blockDim.x) fxtab[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int UN = 4;
+  int64_t b = 0, e = 0, nb = 0, ne = 0;
+  if (warp < n_cells) { b = colptr[warp]; e = colptr[warp + 1]; }
+  if (warp + nwarp < n_cells) { nb = colptr[warp + nwarp]; ne = colptr[warp + nwarp + 1]; }
+  for (int64_t c = warp; c < n_cells; c += nwarp) {
+    int64_t nnb = 0, nne = 0;
+    if (c + 2 * nwarp < n_cells) { nnb = colptr[c + 2 * nwarp]; nne = colptr[c + 2 * nwarp + 1]; }
+    if (nb < ne) prefetch_column_l2(rowval, val, nb, ne, lane);
+    for (int64_t i0 = b + lane; i0 < e; i0 += 32 * UN) {
+      int g[UN];
+      float x[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int64_t i = i0 + 32 * u;
+        g[u] = i < e ? __ldcs(rowval + i) : -1;
+        x[u] = i < e ? __ldcs(val + i) : 0.f;
+      }
+      int h[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) h[u] = IDENT ? g[u] : (g[u] >= 0 ? __ldg(gene2h + g[u]) : -1);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (h[u] >= 0) {
+          const float y = x[u];
+          if (fabsf(y) <= fx.bound) {     // false for NaN / Inf / out-of-range values
+            fx_add(&y1lo[h[u]], &y1hi[h[u]], __float2ll_rn(y * fx.s1));        // y * 2^e1 is exact in fp32
+            fx_add(&y2lo[h[u]], &y2hi[h[u]], __double2ll_rn((double)y * (double)y * (double)fx.s2));
+          } else {
+            const double yd = (double)y;
+            atomicAdd(&part[h[u]], yd);
+            atomicAdd(&part[n_feat + h[u]], yd * yd);
+          }
+        }
+      }
+    }
+    b = nb; e = ne; nb = nnb; ne = nne;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < n_feat; h += blockDim.x) {
+    const long long v1 = (long long)(((unsigned long long)y1hi[h] << 32) | y1lo[h]);
+    const long long v2 = (long long)(((unsigned long long)y2hi[h] << 32) | y2lo[h]);
+    if (v1) atomicAdd(&part[h], (double)v1 * fx.inv_s1);
+    if (v2) atomicAdd(&part[n_feat + h], (double)v2 * fx.inv_s2);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_scale_stats(const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, const float* __restrict__ val,
               const int32_t* __restrict__ gene2h, int64_t n_cells, int32_t n_feat, double* __restrict__ priv) {
@@ -916,6 +937,7 @@ extern "C" csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, 
   r->n_genes = H;
   r->n_cells = m->n_cells;
   r->nnz = 0;
+  r->vmax_bound = m->vmax_bound;
   CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &counts, true));
   CSC_TRY(dev_alloc(ctx, (size_t)(m->n_cells + 1) * 8, &r->colptr));
   if (m->n_cells > 0) {
@@ -962,19 +984,47 @@ extern "C" csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* no
   CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_partial: partial must be fp64[2*H], H=%lld",
               (long long)H);
   if (norm->n_cells > 0 && H > 0) {
-    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(k_scale_stats, 256, 0, 4),
-                                      ceil_div64(norm->n_cells, 8));
-    // the private tables stay below 256 MB (a whole-transcriptome call with every gene selected)
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)256 << 20) / (2 * H * 8)));
-    DevPtr priv;
-    CSC_TRY(dev_alloc(ctx, (size_t)grid * 2 * H * 8, &priv));
-    CSC_CUDA(ctx, cudaMemsetAsync(priv->p, 0, (size_t)grid * 2 * H * 8, ctx->stream));
-    k_scale_stats<<<grid, 256, 0, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, norm->n_cells,
-                                                 (int32_t)H, (double*)priv->p);
-    CSC_LAUNCHED(ctx);
-    k_scale_stats_reduce<<<(unsigned)ceil_div64(2 * H, 256), 256, 0, ctx->stream>>>((const double*)priv->p, grid,
-                                                                                   (int32_t)(2 * H), partial->as<double>());
-    CSC_LAUNCHED(ctx);
+    // fixed-point route: a bound on |y| is known, it leaves >= 20 fractional bits, and four u32 tables of H rows fit
+    const double bound = norm->vmax_bound * 1.0001;
+    int e1 = -1;
+    if (std::isfinite(bound) && bound > 0.0) e1 = 32 - (int)std::ceil(std::log2(bound));
+    const size_t smem = (size_t)4 * H * 4;
+    const char* impl = getenv("CSC_SCALE_STATS_IMPL");
+    const bool force_exact = impl && strcmp(impl, "fp64") == 0;
+    if (e1 >= 20 && smem <= (size_t)96 * 1024 && !force_exact) {
+      if (e1 > 40) e1 = 40;
+      StatsFx fx;
+      fx.bound = (float)bound;
+      fx.s1 = (float)std::ldexp(1.0, e1);
+      const bool ident = features == nullptr;
+      auto kern = ident ? k_scale_stats_fx<true> : k_scale_stats_fx<false>;
+      if (smem > 48 * 1024) CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(kern, 512, smem, 2),
+                                                                   ceil_div64(norm->n_cells, 16)));
+      // the y^2 accumulator of a CTA must stay below 2^62: bound^2 * 2^e2 * (cells of the CTA)
+      const double cells_per_cta = (double)ceil_div64(norm->n_cells, grid) + 16.0;
+      const int e2 = std::min(e1, 62 - (int)std::ceil(std::log2(bound * bound)) - (int)std::ceil(std::log2(cells_per_cta)));
+      fx.s2 = (float)std::ldexp(1.0, e2);
+      fx.inv_s1 = std::ldexp(1.0, -e1);
+      fx.inv_s2 = std::ldexp(1.0, -e2);
+      kern<<<grid, 512, smem, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, norm->n_cells, (int32_t)H,
+                                             fx, partial->as<double>());
+      CSC_LAUNCHED(ctx);
+    } else {
+      int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(k_scale_stats, 256, 0, 4),
+                                        ceil_div64(norm->n_cells, 8));
+      // the private tables stay below 256 MB (a whole-transcriptome call with every gene selected)
+      grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)256 << 20) / (2 * H * 8)));
+      DevPtr priv;
+      CSC_TRY(dev_alloc(ctx, (size_t)grid * 2 * H * 8, &priv));
+      CSC_CUDA(ctx, cudaMemsetAsync(priv->p, 0, (size_t)grid * 2 * H * 8, ctx->stream));
+      k_scale_stats<<<grid, 256, 0, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, norm->n_cells,
+                                                   (int32_t)H, (double*)priv->p);
+      CSC_LAUNCHED(ctx);
+      k_scale_stats_reduce<<<(unsigned)ceil_div64(2 * H, 256), 256, 0, ctx->stream>>>((const double*)priv->p, grid,
+                                                                                     (int32_t)(2 * H), partial->as<double>());
+      CSC_LAUNCHED(ctx);
+    }
   }
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CSC_OK;
@@ -1108,28 +1158,6 @@ extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* nor
   StageTimer st2(ctx, CSC_T_PCA_GRAM);
   return gram_tc_split(ctx, (const __half*)hi16->p, (const __half*)lo16->p, norm->n_cells, (int)H, pitch, gram->as<double>(),
                        colsum->as<double>());
-  CSC_GUARD_END(ctx)
-}
-
-extern "C" csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_stats, int64_t n_genes, const int64_t* features,
-                                             int64_t n_feat, csc_vec* partial) {
-  if (!ctx || !norm_stats || !partial) return CSC_ERR_ARG;
-  CSC_GUARD_BEGIN
-  CSC_REQUIRE(ctx, norm_stats->dtype == CSC_DT_F64 && norm_stats->n >= 2 * n_genes && n_genes > 0,
-              "csc_scale_stats_select: norm_stats must be fp64[2*n_genes]");
-  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageTimer st(ctx, CSC_T_SCALE_STATS);
-  DevPtr map;
-  int64_t H = 0;
-  CSC_TRY(build_gene2h(ctx, n_genes, features, n_feat, &map, &H));
-  CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_select: partial must be fp64[2*H], H=%lld",
-              (long long)H);
-  k_stats_select<<<(unsigned)ceil_div64(n_genes, 256), 256, 0, ctx->stream>>>(norm_stats->as<double>(), (int32_t)n_genes,
-                                                                              (const int32_t*)map->p, (int32_t)H,
-                                                                              partial->as<double>());
-  CSC_LAUNCHED(ctx);
-  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return CSC_OK;
   CSC_GUARD_END(ctx)
 }
 

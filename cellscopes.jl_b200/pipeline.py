@@ -6,8 +6,7 @@ point) and to a *communicator* (``LocalComm`` for one GPU, ``TorchComm`` for one
 ``torch.distributed``).  The collectives are exactly the natural ones:
 
   all-reduce  fp64 [2G]      per-gene sum x, sum x^2            (find_variable_genes)
-  all-reduce  fp64 [2H]      per-HVG sum y, sum y^2             (scale_object; selected from the all-gene
-                             table that the normalise pass filled)
+  all-reduce  fp64 [2H]      per-HVG sum y, sum y^2             (scale_object)
   all-reduce  fp64 [H], [H*H] column sums and Gram of Z         (run_pca)
   all-gather  fp32 [N x k_pc] embedding                          (kNN keys)
   all-gather  int32 [N x k]   neighbour table                    (adjacency / SNN)
@@ -163,13 +162,9 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     G, n_loc = raw.shape
     if offsets is None:
         offsets = np.array([0, n_cells_total], dtype=np.int64)
-    # a1 + the raw moments of a2 + the normalised moments of a3, one pass over the counts
+    # a1 + the raw moments of a2, one pass over the counts
     stats = be.vec(2 * G, np.float64)
-    # the normalised moments of ALL genes ride along only while their tables fit in shared memory (<= 12800 genes);
-    # a whole-transcriptome matrix takes the moments of the selected genes in a pass of its own after the selection
-    fused_nstats = be.normalize_fuses_norm_stats(G) if hasattr(be, "normalize_fuses_norm_stats") else True
-    nstats = be.vec(2 * G, np.float64) if fused_nstats else None
-    norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats, nstats)
+    norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats)
     comm.allreduce_sum(stats)
     # a2
     hvg = be.hvg_finish(stats, G, n_cells_total, p.n_features, p.span)
@@ -179,13 +174,11 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     # a3
     part = be.vec(2 * H, np.float64)
     src, src_feats = norm, feats                  # what the scale / Gram / transform passes read
-    if not fused_nstats and hasattr(be, "select_rows") and G >= 4 * H:
+    if hasattr(be, "select_rows") and G >= 4 * H:
         # whole-transcriptome matrix: subset_count first (few of the rows are kept), everything after reads the subset
         src, src_feats = be.select_rows(norm, feats), None
-    if fused_nstats:
-        be.scale_stats_select(nstats, G, feats, part)
-    else:
-        be.scale_stats_partial(src, src_feats, part)
+    # the normalised moments of the selected rows (64-bit fixed-point accumulators on the device)
+    be.scale_stats_partial(src, src_feats, part)
     comm.allreduce_sum(part)
     colsum = be.vec(H, np.float64)
     gram = be.vec(H * H, np.float64)
@@ -205,6 +198,7 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
         emb = be.pca_transform_sparse(src, src_feats, part, n_cells_total, pca, p.scale_max, p.do_scale, p.do_center)
     else:
         emb = be.pca_transform(scaled, pca)
+    nnz_selected = src.nnz if hasattr(src, "nnz") else None
     if src is not norm:
         src.free()
     if not p.keep_norm:
@@ -217,4 +211,7 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     graph = be.graph_build(idx_all, n_cells_total, p.k, cell_offset, cell_offset + n_loc, _GRAPH[p.graph_mode],
                            p.snn_prune)
     return {"norm": norm, "hvg": hvg, "rows": rows, "scaled": scaled, "pca": pca, "embedding": emb,
-            "knn_idx": idx, "knn_dist": dist, "graph": graph, "gene_stats": stats}
+            "knn_idx": idx, "knn_dist": dist, "graph": graph, "gene_stats": stats,
+            # the all-gathered tables (the local ones again when world == 1) and the size of what the scale / Gram /
+            # transform passes read (the row subset of a whole-transcriptome matrix)
+            "keys": keys, "knn_idx_all": idx_all, "nnz_selected": nnz_selected}

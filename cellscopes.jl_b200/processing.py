@@ -41,11 +41,8 @@ class _Session:
         self.raw = None          # Sparse
         self.raw_key = None
         self.gene_stats = None   # Vec fp64[2G] raw moments
-        self.norm_stats = None   # Vec fp64[2G] normalised moments (filled by normalize_object)
         self.norm = None         # Sparse
-        self.scaled = None       # Dense
-        self.scaled_rows = None  # gene ids (original order) of the scaled matrix
-        self.scale_args = None   # (feature_idx, partial Vec, scale_max, do_scale, do_center) that define `scaled`
+        self.scaled = None       # _ScaledSource
         self.pca = None
         self.emb = None
         self.knn = None
@@ -84,10 +81,8 @@ def normalize_object(x, scale_factor=10000, norm_method="logarithm", pseudocount
         raw = _ensure_raw(x, s)
         g = raw.shape[0]
         s.gene_stats = s.ctx.vec(2 * g, np.float64)
-        s.norm_stats = s.ctx.vec(2 * g, np.float64)
         # processing.jl:44-46: imaging objects replace NaN by 0
-        s.norm = s.ctx.normalize(raw, scale_factor, code, pseudocount, bool(getattr(x, "imaging", False)), s.gene_stats,
-                                 s.norm_stats)
+        s.norm = s.ctx.normalize(raw, scale_factor, code, pseudocount, bool(getattr(x, "imaging", False)), s.gene_stats)
         pattern = x.rawCount._mtx if sp.issparse(x.rawCount._mtx) else None
         lazy = LazyDeviceMatrix(s.norm, "sparse", raw.shape, pattern)
         x.normCount = NormCountObject(lazy, x.rawCount.cell_name, x.rawCount.gene_name, scale_factor, norm_method,
@@ -150,16 +145,43 @@ def find_variable_genes(x, nFeatures: int = 2000, span: float = 0.3, ctx=None):
 # ---------------------------------------------------------------------------------------------
 # scale_object  (processing.jl:65-93)
 # ---------------------------------------------------------------------------------------------
-def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, do_center, norm_stats=None):
+class _ScaledSource:
+    """What defines a scaled matrix on the device: the normalised rows it is taken from (``src``: the normalised
+    matrix itself with ``feats`` naming the rows, or the row subset made by csc_sparse_select_rows with
+    ``feats = None``), the all-reduced moments ``part`` and the scale arguments.  The dense matrix (4 H bytes per cell)
+    is only built when somebody reads it (``dense()``): run_pca takes the Gram straight from ``src``
+    (csc_scale_gram_partial) and the embedding from the sparse rows (csc_pca_transform_sparse)."""
+
+    def __init__(self, c, src, feats, part, rows, n_cells_total, scale_max, do_scale, do_center):
+        self.c, self.src, self.feats, self.part, self.rows = c, src, feats, part, rows
+        self.n_cells_total, self.scale_max, self.do_scale, self.do_center = n_cells_total, scale_max, do_scale, do_center
+        self._dense = None
+
+    @property
+    def shape(self):
+        return self.src.shape[1], int(self.rows.size)      # cells x selected genes (device layout)
+
+    def dense(self):
+        if self._dense is None:
+            self._dense = self.c.scale_fill(self.src, self.feats, self.part, self.n_cells_total, self.scale_max,
+                                            self.do_scale, self.do_center)
+        return self._dense
+
+    def download(self, dtype=np.float64, row_lo=0, row_hi=None):      # LazyDeviceMatrix("dense_t") reads through this
+        return self.dense().download(dtype, row_lo, row_hi)
+
+
+def _scale_device(c, norm_dev, feature_idx, n_cells_total, scale_max, do_scale, do_center):
     g = norm_dev.shape[0]
     rows = np.arange(g, dtype=np.int64) if feature_idx is None else np.unique(np.asarray(feature_idx, dtype=np.int64))
     part = c.vec(2 * rows.size, np.float64)
-    if norm_stats is not None:
-        c.scale_stats_select(norm_stats, g, feature_idx, part)     # moments already taken by the normalise pass
-    else:
-        c.scale_stats_partial(norm_dev, feature_idx, part)
-    dense = c.scale_fill(norm_dev, feature_idx, part, n_cells_total, scale_max, do_scale, do_center)
-    return dense, rows, (feature_idx, part, scale_max, do_scale, do_center)
+    src, feats = norm_dev, feature_idx
+    if feature_idx is not None and g >= 4 * rows.size:
+        # subset_count on the device (utils.jl:59-87): a whole-transcriptome matrix keeps ~6 % of its rows, every later
+        # pass reads the subset
+        src, feats = c.select_rows(norm_dev, feature_idx), None
+    c.scale_stats_partial(src, feats, part)
+    return _ScaledSource(c, src, feats, part, rows, n_cells_total, scale_max, do_scale, do_center)
 
 
 def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_center: bool = True, ctx=None, **kwargs):
@@ -169,7 +191,6 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
         s = _session(x, ctx)
         if s.norm is None:
             s.norm = s.ctx.sparse_from_scipy(x.normCount.count_mtx)
-            s.norm_stats = None
         genes = x.normCount.gene_name
         fidx = None
         if features is not None:
@@ -180,10 +201,11 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
         eff_max = kwargs.get("scale_max", 10.0)
         eff_scale = kwargs.get("do_scale", True)
         eff_center = kwargs.get("do_center", True)
-        dense, rows, sargs = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center, s.norm_stats)
-        s.scaled, s.scaled_rows, s.scale_args = dense, rows, sargs
-        lazy = LazyDeviceMatrix(dense, "dense_t", (rows.size, s.norm.shape[1]))
-        x.scaleCount = ScaleCountObject(lazy, x.normCount.cell_name, [genes[i] for i in rows], do_scale, do_center,
+        sc = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], eff_max, eff_scale, eff_center)
+        s.scaled = sc
+        # scaleCount stays on the device, and is not even built there until it is read (count_mtx) or run_pca needs it
+        lazy = LazyDeviceMatrix(sc, "dense_t", (sc.rows.size, s.norm.shape[1]))
+        x.scaleCount = ScaleCountObject(lazy, x.normCount.cell_name, [genes[i] for i in sc.rows], do_scale, do_center,
                                         scale_max)
         return x
     # matrix method (processing.jl:65-76): genes x cells in, same shape out (dense)
@@ -191,8 +213,7 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
     m = x.count_mtx if isinstance(x, NormCountObject) else x
     m = sp.csc_matrix(m) if not sp.issparse(m) else m.tocsc()
     dev = c.sparse_from_scipy(m)
-    dense, _, _ = _scale_device(c, dev, None, m.shape[1], scale_max, do_scale, do_center)
-    out = dense.download(np.float64).T
+    out = _scale_device(c, dev, None, m.shape[1], scale_max, do_scale, do_center).download(np.float64).T
     if isinstance(x, NormCountObject):
         return ScaleCountObject(out, x.cell_name, x.gene_name, do_scale, do_center, scale_max)
     return out
@@ -201,20 +222,28 @@ def scale_object(x, features=None, scale_max=10.0, do_scale: bool = True, do_cen
 # ---------------------------------------------------------------------------------------------
 # run_pca  (processing.jl:164-193)
 # ---------------------------------------------------------------------------------------------
-def _pca_device(c, dense, n_cells_total, maxoutdim, tol=1e-9, max_iter=500, sparse_src=None):
-    """``sparse_src = (norm, (feature_idx, partial, scale_max, do_scale, do_center))``: the normalised device matrix and
-    the scale arguments that produced ``dense``; the embedding is then taken from the sparse matrix (far less work)."""
-    h = dense.shape[1]
+def _pca_device(c, scaled, n_cells_total, maxoutdim, tol=1e-9, max_iter=500):
+    """``scaled``: a ``_ScaledSource`` (Gram straight from the sparse normalised rows, embedding from them too: the dense
+    matrix is never built) or a dense device matrix (uploaded scaleCount)."""
+    if isinstance(scaled, _ScaledSource):
+        h = int(scaled.rows.size)
+        colsum = c.vec(h, np.float64)
+        gram = c.vec(h * h, np.float64)
+        if scaled._dense is not None:
+            c.pca_partial(scaled._dense, colsum, gram)
+        else:
+            c.scale_gram_partial(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, colsum, gram,
+                                 scaled.scale_max, scaled.do_scale, scaled.do_center)
+        model = c.pca_solve(colsum, gram, h, n_cells_total, maxoutdim, tol, max_iter)
+        emb = c.pca_transform_sparse(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, model, scaled.scale_max,
+                                     scaled.do_scale, scaled.do_center)
+        return model, emb
+    h = scaled.shape[1]
     colsum = c.vec(h, np.float64)
     gram = c.vec(h * h, np.float64)
-    c.pca_partial(dense, colsum, gram)
+    c.pca_partial(scaled, colsum, gram)
     model = c.pca_solve(colsum, gram, h, n_cells_total, maxoutdim, tol, max_iter)
-    if sparse_src is not None:
-        norm, (fidx, part, smax, dsc, dct) = sparse_src
-        emb = c.pca_transform_sparse(norm, fidx, part, n_cells_total, model, smax, dsc, dct)
-    else:
-        emb = c.pca_transform(dense, model)
-    return model, emb
+    return model, c.pca_transform(scaled, model)
 
 
 def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=None):
@@ -230,19 +259,15 @@ def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=Non
         # Re-scaling the subset from normCount gives the same rows (scaling is per gene).
         if s.norm is None:
             s.norm = s.ctx.sparse_from_scipy(sc_obj.normCount.count_mtx)
-            s.norm_stats = None
         pos = {g: i for i, g in enumerate(sc_obj.normCount.gene_name)}
         fidx = np.array([pos[f] for f in features], dtype=np.int64)
-        dense, rows, sargs = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True, s.norm_stats)
-        sparse_src = (s.norm, sargs)
+        scaled = _scale_device(s.ctx, s.norm, fidx, s.norm.shape[1], 10.0, True, True)
     elif s.scaled is not None:
-        dense = s.scaled
-        sparse_src = (s.norm, s.scale_args) if (s.norm is not None and s.scale_args is not None) else None
+        scaled = s.scaled
     else:
-        sparse_src = None
-        dense = s.ctx.dense_upload(np.ascontiguousarray(np.asarray(sc_obj.scaleCount.count_mtx).T))
-    n = dense.shape[0]
-    model, emb = _pca_device(s.ctx, dense, n, maxoutdim, sparse_src=sparse_src)
+        scaled = s.ctx.dense_upload(np.ascontiguousarray(np.asarray(sc_obj.scaleCount.count_mtx).T))
+    n = scaled.shape[0]
+    model, emb = _pca_device(s.ctx, scaled, n, maxoutdim)
     s.pca, s.emb = model, emb
     info = model.info()
     proj = emb.download(np.float64)                     # N x k Float64 (utils.jl:108-117, int_objects.jl:153)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CSC_ABI_VERSION 1
+#define CSC_ABI_VERSION 2
 
 typedef int32_t csc_status;
 enum {
@@ -97,7 +97,9 @@ csc_status csc_flush_l2(csc_ctx* ctx);
 /* ---- pinned host memory (optional) -------------------------------------------------------
  * Results copied into pageable memory move at ~5 GB/s (staging + first-touch page faults); into page-locked
  * memory they move at PCIe rate.  A caller that wants that allocates its result arrays here; blocks are cached
- * per context and handed back by csc_host_free.  Every download entry point accepts either kind of memory. */
+ * per context and handed back by csc_host_free.  Every download entry point accepts either kind of memory.
+ * Lifetime: csc_destroy does NOT free blocks that are still live (they back result arrays the caller may still
+ * read); release those with csc_host_free(NULL, p) once the context is gone. */
 csc_status csc_host_alloc(csc_ctx* ctx, int64_t bytes, void** out);
 csc_status csc_host_free(csc_ctx* ctx, void* p);
 
@@ -138,15 +140,10 @@ csc_status csc_generate_counts(csc_ctx* ctx, int64_t n_genes, int64_t cell_lo, i
 /* out shares the sparsity pattern of raw.  nan_to_zero = the replace!(NaN=>0) of :44-46.
  * gene_stats (optional, fp64[2*n_genes]) receives += per-gene (sum x, sum x^2) of the RAW counts of this
  * shard, fused into the same pass (find_variable_genes :138-139 needs them; exact for integer counts).
- * norm_stats (optional, fp64[2*n_genes]) receives += per-gene (sum y, sum y^2) of the NORMALISED values of
- * this shard (scale_object :66-67 needs them for its rows), accumulated in 32-bit fixed point per CTA
- * (resolution ~1e-6 of the value range; deterministic). */
+ * (ABI 1 also took a norm_stats table here, filled in 32-bit fixed point; it was too coarse -- see
+ * csc_scale_stats_partial, which now takes the normalised moments of the selected rows with 64-bit accumulators.) */
 csc_status csc_normalize(csc_ctx* ctx, const csc_sparse* raw, double scale_factor, int32_t norm_method,
-                         double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_vec* norm_stats,
-                         csc_sparse** out);
-/* 1 when csc_normalize fills norm_stats from shared-memory tables in the same pass (n_genes <= 12800); with more genes
- * norm_stats costs a pass of global atomics and csc_scale_stats_partial on the selected genes is the cheaper route. */
-int32_t csc_normalize_fuses_norm_stats(int64_t n_genes);
+                         double pseudocount, int32_t nan_to_zero, csc_vec* gene_stats, csc_sparse** out);
 
 /* ---- a2: find_variable_genes src/scrna/processing.jl:133-155 ---------------------------- */
 /* per-gene (sum x, sum x^2) of this shard, += into gene_stats fp64[2*n_genes] (standalone K2) */
@@ -168,13 +165,11 @@ csc_status csc_sparse_select_rows(csc_ctx* ctx, const csc_sparse* m, const int64
 /* ---- a3: scale_object src/scrna/processing.jl:65-93 ------------------------------------- */
 /* features[n_feat]: 0-based gene ids in any order; rows are taken in ORIGINAL gene order like
  * subset_count (src/scrna/utils.jl:72-76).  features == NULL -> all genes.
- * partial: fp64[2*H] += (sum y, sum y^2) of the normalised values of this shard. */
+ * partial: fp64[2*H] += (sum y, sum y^2) of the normalised values of this shard: 64-bit fixed-point accumulators
+ * (resolution 2^-28 of y and of y^2 for the logarithm method; deterministic) when the matrix came out of
+ * csc_normalize / csc_sparse_select_rows with a usable bound on |y|, exact fp64 sums otherwise. */
 csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                                    csc_vec* partial);
-/* the same partial taken from the all-gene table that csc_normalize filled (norm_stats, fp64[2*n_genes]):
- * partial[0:H] += sum y, partial[H:2H] += sum y^2 of the selected rows in original gene order */
-csc_status csc_scale_stats_select(csc_ctx* ctx, const csc_vec* norm_stats, int64_t n_genes, const int64_t* features,
-                                  int64_t n_feat, csc_vec* partial);
 /* partial already summed over ranks; out = dense fp32 [n_cells_local x H], cell-major, which is the
  * memory layout of Julia's genes x cells column-major Matrix: min((y-mean)/sd, scale_max) (:69-74). */
 csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,

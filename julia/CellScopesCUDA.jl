@@ -44,7 +44,7 @@ function sym(name::Symbol)
     if _lib[] == C_NULL
         _lib[] = Libdl.dlopen(libpath())       # throws if the library is missing: no CPU path
         v = ccall(Libdl.dlsym(_lib[], :csc_abi_version), Int32, ())
-        v == 1 || error("libcellscopes_cuda ABI version $v, this shim binds version 1")
+        v == 2 || error("libcellscopes_cuda ABI version $v, this shim binds version 2")
     end
     get!(_sym, name) do
         Libdl.dlsym(_lib[], name)
@@ -136,13 +136,11 @@ norm_code(m::AbstractString) = m == "logarithm" ? Int32(0) : m == "none" ? Int32
 
 function dev_normalize(ctx, raw::Handle, n_genes; scale_factor, norm_method, pseudocount, nan_to_zero::Bool)
     gstats = vec_alloc(ctx, 2 * n_genes)        # sum x, sum x^2 per gene   (find_variable_genes)
-    nstats = vec_alloc(ctx, 2 * n_genes)        # sum y, sum y^2 per gene   (scale_object)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx, ccall(sym(:csc_normalize), Int32,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Int32, Float64, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
-        ctx.h, raw.h, Float64(scale_factor), norm_code(norm_method), Float64(pseudocount), Int32(nan_to_zero), gstats.h,
-        nstats.h, r))
-    Handle(r[], :csc_sparse_free, ctx), gstats, nstats
+        (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Int32, Float64, Int32, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+        ctx.h, raw.h, Float64(scale_factor), norm_code(norm_method), Float64(pseudocount), Int32(nan_to_zero), gstats.h, r))
+    Handle(r[], :csc_sparse_free, ctx), gstats
 end
 
 function dev_hvg(ctx, gstats::Handle, n_genes, n_cells, nFeatures, span)
@@ -164,14 +162,13 @@ mutable struct Session
     raw_id::UInt
     gstats::Union{Handle,Nothing}
     norm::Union{Handle,Nothing}
-    nstats::Union{Handle,Nothing}
     scaled::Union{Handle,Nothing}       # dense, cell-major [N x H]
     emb::Union{Handle,Nothing}          # dense [N x k]
 end
 const _sessions = WeakKeyDict{Any,Session}()
 function session(obj; ctx=nothing)
     get!(_sessions, obj) do
-        Session(ctx === nothing ? default_context() : ctx, nothing, UInt(0), nothing, nothing, nothing, nothing, nothing)
+        Session(ctx === nothing ? default_context() : ctx, nothing, UInt(0), nothing, nothing, nothing, nothing)
     end
 end
 function ensure_raw!(s::Session, obj)
@@ -179,7 +176,7 @@ function ensure_raw!(s::Session, obj)
     if s.raw === nothing || s.raw_id != objectid(m)
         s.raw = upload(s.ctx, m)
         s.raw_id = objectid(m)
-        s.gstats = nothing; s.norm = nothing; s.nstats = nothing
+        s.gstats = nothing; s.norm = nothing
     end
     s.raw
 end
@@ -206,7 +203,7 @@ function normalize_object(sc_obj::cs.get_object_group("All"); scale_factor=10000
     m = sc_obj.rawCount.count_mtx
     # processing.jl:44-46: imaging objects replace NaN (zero-sum cells) by 0
     imaging = isa(sc_obj, Union{cs.MerfishObject,cs.CartanaObject,cs.XeniumObject})
-    s.norm, s.gstats, s.nstats = dev_normalize(s.ctx, raw, size(m, 1); scale_factor, norm_method, pseudocount, nan_to_zero=imaging)
+    s.norm, s.gstats = dev_normalize(s.ctx, raw, size(m, 1); scale_factor, norm_method, pseudocount, nan_to_zero=imaging)
     pattern = m isa SparseMatrixCSC ? m : sparse(m)
     sc_obj.normCount = cs.NormCountObject(download_like(s.ctx, s.norm, pattern), sc_obj.rawCount.cell_name,
                                           sc_obj.rawCount.gene_name, scale_factor, norm_method, pseudocount)
@@ -247,20 +244,15 @@ end
 # a3  scale_object (processing.jl:65-93)
 # ------------------------------------------------------------------------------------------------
 "rows `fidx` (1-based gene ids, any order; nothing = all) of the normalised device matrix -> dense device matrix + host copy"
-function dev_scale(ctx, norm::Handle, nstats, n_genes, n_cells, fidx; scale_max=10.0, do_scale=true, do_center=true, want_host=true)
+function dev_scale(ctx, norm::Handle, n_genes, n_cells, fidx; scale_max=10.0, do_scale=true, do_center=true, want_host=true)
     rows = fidx === nothing ? collect(1:n_genes) : sort(unique(fidx))        # subset_count keeps original order (utils.jl:72-76)
     H = length(rows)
     f0 = fidx === nothing ? Int64[] : Int64.(fidx .- 1)
     fptr = fidx === nothing ? Ptr{Int64}(C_NULL) : pointer(f0)
     part = vec_alloc(ctx, 2H)
     GC.@preserve f0 begin
-        if nstats !== nothing
-            check(ctx, ccall(sym(:csc_scale_stats_select), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Int64, Ptr{Cvoid}),
-                             ctx.h, nstats.h, n_genes, fptr, length(f0), part.h))
-        else
-            check(ctx, ccall(sym(:csc_scale_stats_partial), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}),
-                             ctx.h, norm.h, fptr, length(f0), part.h))
-        end
+        check(ctx, ccall(sym(:csc_scale_stats_partial), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}),
+                         ctx.h, norm.h, fptr, length(f0), part.h))
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ctx, ccall(sym(:csc_scale_fill), Int32,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}, Int64, Float64, Int32, Int32, Ptr{Ptr{Cvoid}}),
@@ -289,14 +281,14 @@ function scale_object(sc_obj::cs.get_object_group("All"); features::Union{Vector
     s = session(sc_obj; ctx)
     nc = sc_obj.normCount
     if s.norm === nothing
-        s.norm = upload(s.ctx, nc.count_mtx); s.nstats = nothing
+        s.norm = upload(s.ctx, nc.count_mtx)
     end
     fidx = features === nothing ? nothing : Int64.(filter(!isnothing, indexin(features, nc.gene_name)))
     g, n = size(nc.count_mtx)
     # processing.jl:78-83 forwards only kwargs... to the matrix method: the effective values are always the
     # defaults (10.0, true, true) while the user's values are recorded in the object.  Mirrored, not fixed.
     eff = (scale_max=get(kwargs, :scale_max, 10.0), do_scale=get(kwargs, :do_scale, true), do_center=get(kwargs, :do_center, true))
-    s.scaled, host, rows = dev_scale(s.ctx, s.norm, s.nstats, g, n, fidx; eff...)
+    s.scaled, host, rows = dev_scale(s.ctx, s.norm, g, n, fidx; eff...)
     sc_obj.scaleCount = cs.ScaleCountObject(host, nc.cell_name, nc.gene_name[rows], do_scale, do_center, scale_max)
     sc_obj
 end
@@ -329,9 +321,9 @@ function run_pca(sc_obj::cs.get_object_group("All"); method=:svd, pratio=1, maxo
     if length(sgenes) == length(sc_obj.rawCount.gene_name) && length(features) != length(sgenes)
         # processing.jl:166-167: scaleCount still has all genes -> take the variable genes (rows are scaled per gene,
         # so re-scaling the subset from normCount gives the same rows)
-        s.norm === nothing && (s.norm = upload(s.ctx, sc_obj.normCount.count_mtx); s.nstats = nothing)
+        s.norm === nothing && (s.norm = upload(s.ctx, sc_obj.normCount.count_mtx))
         fidx = Int64.(indexin(features, sc_obj.normCount.gene_name))
-        dense, _, _ = dev_scale(s.ctx, s.norm, s.nstats, length(sc_obj.normCount.gene_name), n, fidx; want_host=false)
+        dense, _, _ = dev_scale(s.ctx, s.norm, length(sc_obj.normCount.gene_name), n, fidx; want_host=false)
     elseif s.scaled !== nothing
         dense = s.scaled
     else

@@ -77,7 +77,7 @@ class NumpyBackend:
     def vec(self, n, dtype=np.float64):
         return NpVec(np.zeros(int(n), dtype=dtype))
 
-    def normalize(self, raw, scale_factor, norm_method, pseudocount, nan_to_zero, gene_stats, norm_stats=None):
+    def normalize(self, raw, scale_factor, norm_method, pseudocount, nan_to_zero, gene_stats):
         m = raw.m
         g = m.shape[0]
         if gene_stats is not None:
@@ -86,10 +86,6 @@ class NumpyBackend:
             gene_stats.a[g:2 * g] += s2
         out = oracle.normalize_object(m, scale_factor, "logarithm" if norm_method == 0 else "none", pseudocount,
                                       nan_to_zero)
-        if norm_stats is not None:
-            r = out.tocsr()
-            norm_stats.a[:g] += np.asarray(r.sum(axis=1)).ravel()
-            norm_stats.a[g:2 * g] += np.asarray(r.multiply(r).sum(axis=1)).ravel()
         return NpSparse(out)
 
     def hvg_finish(self, gene_stats, n_genes, n_cells_total, n_features, span):
@@ -104,12 +100,6 @@ class NumpyBackend:
         order = np.lexsort((np.arange(n_genes), -vs))
         return {"mean": mean, "variance": var, "variance_expected": ve, "variance_standardized": vs,
                 "order": order, "features": order[:min(n_features, n_genes)].copy()}
-
-    def scale_stats_select(self, norm_stats, n_genes, features, partial):
-        rows = np.arange(n_genes) if features is None else np.unique(features)
-        h = rows.size
-        partial.a[:h] += norm_stats.a[rows]
-        partial.a[h:2 * h] += norm_stats.a[n_genes + rows]
 
     def scale_stats_partial(self, norm, features, partial):
         rows = np.unique(features)

@@ -78,6 +78,15 @@ def test_upload_rejects_bad_rows(cs, ctx):
         ctx.sparse_upload(3, 2, np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0]))
 
 
+def test_upload_rejects_bad_colptr(cs, ctx):
+    """interior column pointers must be monotone and within [0, nnz]"""
+    rows, vals = np.array([0, 1, 2, 0]), np.ones(4)
+    for cp in ([0, 3, 2, 4], [0, 5, 4, 4], [0, -1, 2, 4]):
+        with pytest.raises(cs.CellScopesCudaError) as ei:
+            ctx.sparse_upload(3, 3, np.array(cp), rows, vals)
+        assert ei.value.code == -1
+
+
 def test_empty_and_ragged_columns(cs, oracle, ctx):
     """Empty columns, a single-entry column and a full column."""
     rng = np.random.default_rng(0)
@@ -176,6 +185,20 @@ def test_hvg_nfeatures_clamped(cs, ctx, small_counts):
     assert np.array_equal(np.sort(got["features"]), np.arange(g))
 
 
+def test_hvg_rejects_zero_variance_gene(cs, oracle, ctx):
+    """processing.jl:143,151: the reference throws when a gene does not vary; so do the oracle and the library."""
+    d = np.array([[1, 0, 2, 0, 3], [2, 2, 2, 2, 2], [0, 1, 0, 4, 0]], dtype=np.int64)
+    m = sp.csc_matrix(d)
+    with pytest.raises(ValueError):
+        oracle.find_variable_genes(m, 2)
+    raw = ctx.sparse_from_scipy(m)
+    st = ctx.vec(6)
+    ctx.gene_stats_partial(raw, st)
+    with pytest.raises(cs.CellScopesCudaError) as ei:
+        ctx.hvg_finish(st, 3, 5, 2, 0.3)
+    assert ei.value.code == -1 and "variance" in str(ei.value)
+
+
 # ---- a3 scale -------------------------------------------------------------------------------
 def _scaled_pair(cs, oracle, ctx, counts, nfeat, **kw):
     norm_o = oracle.normalize_object(counts)
@@ -203,31 +226,66 @@ def test_scale_matches_oracle(cs, oracle, ctx, medium_counts, kw):
         assert (want >= 10.0).any(), "the clip must actually be exercised"
 
 
-def test_fused_normalised_moments_match_standalone(cs, oracle, ctx, medium_counts):
-    """csc_normalize's fixed-point (sum y, sum y^2) table agrees with the fp64 pass over the normalised values, and
-    the scaled matrix built from it meets the same tolerance."""
-    raw = ctx.sparse_from_scipy(medium_counts)
+@pytest.mark.parametrize("method,sf", [("logarithm", 1e4), ("none", 1e4), ("none", 1.0), ("logarithm", 1e6)])
+def test_scale_moments_match_oracle(cs, oracle, ctx, medium_counts, method, sf, monkeypatch):
+    """(sum y, sum y^2) of the selected rows -- 64-bit fixed-point accumulators for the logarithm method, fp64 sums when
+    the value range leaves too few fractional bits ("none" with a large scale factor) -- against float64 sums of the
+    oracle's normalised matrix, and the scaled matrix built from them (the 32-bit tables of round 1 resolved
+    y^2 to ~40 for "none" and to 3e-5 for the logarithm)."""
     g, n = medium_counts.shape
-    nst = ctx.vec(2 * g)
-    norm = ctx.normalize(raw, 1e4, 0, 1.0, False, None, nst)
-    got = nst.download()
-    want = oracle.normalize_object(medium_counts).tocsr()
-    s1 = np.asarray(want.sum(axis=1)).ravel()
-    s2 = np.asarray(want.multiply(want).sum(axis=1)).ravel()
-    assert np.allclose(got[:g], s1, rtol=2e-6, atol=1e-4)
-    assert np.allclose(got[g:], s2, rtol=2e-6, atol=1e-3)
+    raw = ctx.sparse_from_scipy(medium_counts)
+    norm = ctx.normalize(raw, sf, cs.pipeline.norm_code(method), 1.0)
+    want = oracle.normalize_object(medium_counts, sf, method, 1.0).tocsr()
     feats = np.arange(0, g, 3)
+    s1 = np.asarray(want[feats].sum(axis=1)).ravel()
+    s2 = np.asarray(want[feats].multiply(want[feats]).sum(axis=1)).ravel()
+    got = {}
+    for impl in ("", "fp64"):
+        monkeypatch.setenv("CSC_SCALE_STATS_IMPL", impl)
+        part = ctx.vec(2 * feats.size)
+        ctx.scale_stats_partial(norm, feats, part)
+        got[impl] = part.download()
+        # the device values are fp32 (relative 6e-8 each): sums agree to ~1e-6 relative
+        assert np.allclose(got[impl][:feats.size], s1, rtol=2e-6, atol=1e-9 * sf)
+        assert np.allclose(got[impl][feats.size:], s2, rtol=4e-6, atol=1e-9 * sf * sf)
+    # the two device routes see the SAME fp32 values: they differ by the fixed-point resolution only
+    assert np.allclose(got[""], got["fp64"], rtol=1e-9, atol=1e-6)
+    monkeypatch.setenv("CSC_SCALE_STATS_IMPL", "")
     part = ctx.vec(2 * feats.size)
-    ctx.scale_stats_select(nst, g, feats, part)
+    ctx.scale_stats_partial(norm, feats, part)
     z = ctx.scale_fill(norm, feats, part, n).download(np.float64).T
-    wz = oracle.scale_object(oracle.normalize_object(medium_counts)[feats])
+    wz = oracle.scale_object(want[feats].tocsc())
     assert rel_close(z, wz, 1e-5, atol=2e-6)
     # sharding invariance: two cell ranges add up to the whole
     a, b = ctx.sparse_from_scipy(medium_counts[:, :n // 3]), ctx.sparse_from_scipy(medium_counts[:, n // 3:])
-    nst2 = ctx.vec(2 * g)
-    ctx.normalize(a, 1e4, 0, 1.0, False, None, nst2)
-    ctx.normalize(b, 1e4, 0, 1.0, False, None, nst2)
-    assert np.allclose(nst2.download(), got, rtol=1e-6, atol=1e-3)
+    p2 = ctx.vec(2 * feats.size)
+    for shard in (a, b):
+        ctx.scale_stats_partial(ctx.normalize(shard, sf, cs.pipeline.norm_code(method), 1.0), feats, p2)
+    assert np.allclose(p2.download(), got[""], rtol=1e-12, atol=1e-7)
+
+
+def test_scale_moments_rare_gene_in_deep_cells(cs, oracle, ctx):
+    """A gene seen in three very deep cells only (y ~ 0.1): its sd must still come out to 1e-6 (the case ADVICE r1
+    computed a 1e-4..1e-3 relative sd error for)."""
+    rng = np.random.default_rng(5)
+    n, g = 3000, 40
+    d = rng.poisson(0.3, size=(g, n)).astype(np.int64)
+    d[:, :3] += rng.poisson(3000, size=(g, 3))          # three deep cells (~1.2e5 counts each)
+    d[7] = 0
+    d[7, :3] = 1                                          # y = log1p(1e4 / 1.2e5) ~ 0.08
+    m = sp.csc_matrix(d)
+    raw = ctx.sparse_from_scipy(m)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0)
+    part = ctx.vec(2 * g)
+    ctx.scale_stats_partial(norm, None, part)
+    got = part.download()
+    y = oracle.normalize_object(m).toarray()
+    assert np.allclose(got[:g], y.sum(axis=1), rtol=1e-6)
+    assert np.allclose(got[g:], (y * y).sum(axis=1), rtol=1e-6)
+    sd_got = np.sqrt((got[g:] - got[:g] ** 2 / n) / (n - 1))
+    assert np.allclose(sd_got, y.std(axis=1, ddof=1), rtol=2e-6)
+    z = ctx.scale_fill(norm, None, part, n).download(np.float64).T
+    assert rel_close(z, oracle.scale_object(sp.csc_matrix(y)), 1e-5, atol=2e-6)
 
 
 def test_scale_rows_in_original_gene_order(cs, oracle, ctx, small_counts):
@@ -311,6 +369,27 @@ def test_pca_block_solver(cs, oracle, ctx):
     print("eigensolver iters", model.iters, "resid", model.resid)
     assert model.resid < 1e-7
     _check_pca(emb.download(np.float64), model.info(), want, k)
+
+
+def test_pca_solve_reports_non_finite_gram_and_non_convergence(cs, ctx):
+    """CSC_ERR_NUMERIC (-5) instead of NaN loadings returned as OK."""
+    rng = np.random.default_rng(2)
+    h, n = 300, 500
+    z = rng.standard_normal((n, h))
+    gram = z.T @ z
+    colsum = z.sum(axis=0)
+    bad = gram.copy()
+    bad[17, :] = np.nan
+    bad[:, 17] = np.nan
+    with pytest.raises(cs.CellScopesCudaError) as ei:
+        ctx.pca_solve(ctx.vec_from(colsum), ctx.vec_from(bad.ravel()), h, n, 10)
+    assert ei.value.code == -5
+    # a flat noise spectrum cannot be resolved to 1e-13 in two products
+    with pytest.raises(cs.CellScopesCudaError) as ei:
+        ctx.pca_solve(ctx.vec_from(colsum), ctx.vec_from(gram.ravel()), h, n, 10, tol=1e-13, max_iter=2)
+    assert ei.value.code == -5
+    ok = ctx.pca_solve(ctx.vec_from(colsum), ctx.vec_from(gram.ravel()), h, n, 10)
+    assert ok.resid <= 1e-9
 
 
 def test_pca_on_pipeline_data(cs, oracle, ctx, medium_counts):
@@ -550,6 +629,25 @@ def test_graphs_identical_to_oracle(cs, oracle, ctx, n, k):
     pruned = ctx.graph_build(tab, n, k, mode=cs._capi.GRAPH_SNN_JACCARD, snn_prune=1 / 15).to_scipy()
     wantp = oracle.snn_jaccard(widx, prune=1 / 15)
     assert np.array_equal(pruned.indices, wantp.indices) and np.array_equal(pruned.data, wantp.data)
+
+
+def test_graph_rejects_ids_out_of_range(cs, ctx):
+    idx = np.array([[1, 2], [0, 2], [0, 7]], dtype=np.int32)       # 7 >= n
+    for mode in (cs._capi.GRAPH_SUM, cs._capi.GRAPH_SNN_JACCARD):
+        with pytest.raises(cs.CellScopesCudaError) as ei:
+            ctx.graph_build(ctx.vec_from(idx.ravel()), 3, 2, 0, 3, mode)
+        assert ei.value.code == -1
+
+
+def test_pinned_results_outlive_their_context(cs):
+    """arrays returned in page-locked blocks stay valid after Context.close()"""
+    c = cs.Context(0)
+    v = c.vec_from(np.arange(1 << 18, dtype=np.float64))      # 2 MiB -> pinned download
+    out = v.download()
+    v.free()
+    c.close()
+    assert out[12345] == 12345.0 and out.sum() == (1 << 18) * ((1 << 18) - 1) / 2
+    del out
 
 
 def test_graph_column_shards_concatenate(cs, oracle, ctx):

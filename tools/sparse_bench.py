@@ -24,16 +24,13 @@ for r in range(reps):
     ctx.flush_l2()
     ctx.stage_times(reset=True)
     stats = ctx.vec(2 * G, np.float64)
-    nstats = ctx.vec(2 * G, np.float64)
-    norm = ctx.normalize(raw, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, stats, nstats)
+    norm = ctx.normalize(raw, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, stats)
     hv = ctx.hvg_finish(stats, G, N, H, 0.3)
     feats = hv["features"]
     rows = np.unique(feats)
     part = ctx.vec(2 * rows.size, np.float64)
     ctx.flush_l2()
-    ctx.scale_stats_select(nstats, G, feats, part)
-    part2 = ctx.vec(2 * rows.size, np.float64)
-    ctx.scale_stats_partial(norm, feats, part2)       # the standalone pass, for comparison
+    ctx.scale_stats_partial(norm, feats, part)
     ctx.flush_l2()
     scaled = ctx.scale_fill(norm, feats, part, N)
     ctx.synchronize()
