@@ -31,8 +31,7 @@ def test_moment_tables_add_up_over_cell_shards(cs, ctx, full):
     for lo, hi in [(0, 123_457), (123_457, 400_001), (400_001, N)]:
         shard = ctx.generate_counts(full["p"], lo, hi)
         st = ctx.vec(2 * G, np.float64)
-        ns = ctx.vec(2 * G, np.float64)
-        ctx.normalize(shard, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, st, ns)
+        ctx.normalize(shard, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, st)
         acc += st.download()
         nnz += shard.nnz
     assert nnz == full["raw"].nnz

@@ -407,11 +407,10 @@ def test_sparse_transform_equals_dense_transform(cs, oracle, ctx, medium_counts)
     component count that is not a multiple of 32 and with clipping active."""
     raw = ctx.sparse_from_scipy(medium_counts)
     g, n = medium_counts.shape
-    nst = ctx.vec(2 * g)
-    norm = ctx.normalize(raw, 1e4, 0, 1.0, False, None, nst)
+    norm = ctx.normalize(raw, 1e4, 0, 1.0)
     feats = np.arange(1, g, 2)
     part = ctx.vec(2 * feats.size)
-    ctx.scale_stats_select(nst, g, feats, part)
+    ctx.scale_stats_partial(norm, feats, part)
     for k, smax in ((20, 10.0), (50, 10.0), (33, 1.5)):
         dense = ctx.scale_fill(norm, feats, part, n, smax)
         colsum, gram = ctx.vec(feats.size), ctx.vec(feats.size ** 2)
@@ -453,12 +452,12 @@ def test_fused_scale_gram_equals_fill_then_gram(cs, oracle, ctx, medium_counts, 
     the oracle's scaled matrix.  333 features exercise the fallback (H not a multiple of 4), 1200 the zero-padded atom."""
     raw = ctx.sparse_from_scipy(medium_counts)
     G, N = medium_counts.shape
-    st, ns = ctx.vec(2 * G), ctx.vec(2 * G)
-    norm = ctx.normalize(raw, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, st, ns)
+    st = ctx.vec(2 * G)
+    norm = ctx.normalize(raw, 1e4, cs.pipeline.norm_code("logarithm"), 1.0, False, st)
     feats = ctx.hvg_finish(st, G, N, nfeat, 0.3)["features"]
     H = np.unique(feats).size
     part = ctx.vec(2 * H)
-    ctx.scale_stats_select(ns, G, feats, part)
+    ctx.scale_stats_partial(norm, feats, part)
     args = dict(scale_max=10.0, do_scale=True, do_center=True)
     args.update(kw)
     c1, g1 = ctx.vec(H), ctx.vec(H * H)
