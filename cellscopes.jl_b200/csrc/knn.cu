@@ -205,11 +205,11 @@ extern "C" csc_status csc_knn(csc_ctx* ctx, const csc_dense* queries, const csc_
               "csc_knn: queries [%lld,+%lld) are not a row range of the keys", (long long)query_offset,
               (long long)queries->n_rows);
   const int d = dim_hi - dim_lo + (metric == CSC_METRIC_EUCLIDEAN ? 1 : 0);
-  // v3 (fp16 filter on tcgen05 + proof + exact refine) serves cosine with k <= 24; v2 (3xTF32 on tcgen05) k <= 32
+  // v3 (fp16 filter on tcgen05 + proof + exact refine) serves cosine with k <= 32; v2 (3xTF32 on tcgen05) k <= 32
   // and up to 64 dimensions; the CUDA-core kernel the rest.  CSC_KNN_IMPL = simt | tf32 forces an older path.
   const char* impl = getenv("CSC_KNN_IMPL");
   const bool use_tc = d <= 64 && k <= 32 && !(impl && strcmp(impl, "simt") == 0);
-  const bool use_f16 = use_tc && metric == CSC_METRIC_COSINE && k <= 24 && !(impl && strcmp(impl, "tf32") == 0);
+  const bool use_f16 = use_tc && metric == CSC_METRIC_COSINE && !(impl && strcmp(impl, "tf32") == 0);
   const int DP = use_tc ? 64 : pad_dim(d);
   CSC_REQUIRE(ctx, DP > 0, "csc_knn: %d dimensions not supported (max 64, 63 for euclidean)", dim_hi - dim_lo);
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -51,8 +51,8 @@ constexpr int F_ACC = 3;                  // TMEM accumulators of 128 columns, u
 constexpr int F_TILE_BYTES = F_BN * 128;  // 16 KB
 constexpr int F_PAIRS = 8;                // (block, TMEM lane quarter): 32 query rows each
 constexpr int F_THREADS = 64 + 2 * F_PAIRS * 32;   // producer, MMA issuer, 8 drain warps, 8 insert warps
-constexpr int F_L = 32;                   // candidates kept per row
-constexpr int F_QS = 4;                   // parked chunks per pair (slots of 32 keys x 32 rows x 4 bytes)
+constexpr int F_LP = 64;                  // pitch of a row's candidate list in global memory (FL = 32 or 48 of them used)
+constexpr int F_QS = 5;                   // parked chunks per pair (slots of 32 keys x 32 rows x 4 bytes)
 constexpr int F_TMEM_A = F_ACC * F_BN;    // first column of the query operands (2 blocks x 32 columns)
 constexpr float F_SCALE = 256.f;          // operands are scaled so that small components stay normal in fp16
 constexpr float F_EPS = 1.0e-3f;          // bound on |approx - exact| for unit rows (see the header)
@@ -83,7 +83,7 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
 
 // Candidate sets.  A pair of warps serves 32 query rows, thread = row in both.  The DRAIN warp empties the accumulators
 // and only asks "does any row of mine have a score above its threshold in these 32 keys?"; if so it PARKS the 32 x 32
-// chunk in the pair's queue in shared memory (8 x STS.128 per lane) and returns to the accumulator stream at once.  The INSERT warp works the queue off concurrently and owns the sets: F_L = 32
+// chunk in the pair's queue in shared memory (8 x STS.128 per lane) and returns to the accumulator stream at once.  The INSERT warp works the queue off concurrently and owns the sets: FL = 32 or 48
 // slots per row -- scores in REGISTERS of the row's thread, key ids in shared memory --, unsorted (the refine kernel orders by exact score
 // anyway).  Each score carries its slot number in the 5 low mantissa bits, so the set's minimum -- the threshold tau --
 // and the slot it sits in come out of one FMNMX3 tree; a new candidate overwrites that slot by predicated moves and the
@@ -94,32 +94,45 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
 //   only after all warps of its block have let go of it, one such warp per unit -- 69 % of the units have one -- held up
 //   the tensor pipe for everybody: the scan ran at the pace of the slowest warp.  A warp-cooperative insert (lane = slot,
 //   shuffles and warp reductions) is worse still: ~600 cycles per insertion, its collectives form one long dependent chain.)
-constexpr float F_PACK_SLACK = 1.0e-5f;   // cosine units; |score| <= 1 so 64 ulp < 7.7e-6
+constexpr float F_PACK_SLACK = 2.0e-5f;   // cosine units; |score| <= 1, 6 slot bits: 64 ulp per value, 128 ulp accumulated < 1.6e-5
 constexpr float F_EMPTY = -3.0e38f;       // empty slot (finite: -inf with slot bits would be a NaN)
+constexpr uint32_t F_SLOT_MASK = 63u;     // slot number in the 6 low mantissa bits (FL <= 64)
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ float set_min(const float (&x)[F_L]) {
-  static_assert(F_L == 32, "tree written for 32 slots");
-  float m[11];
+// minimum of FL values by a tree of 3-input minima
+template <int N>
+__device__ __forceinline__ float min_tree(const float (&x)[N]) {
+  if constexpr (N == 1) {
+    return x[0];
+  } else if constexpr (N == 2) {
+    return fminf(x[0], x[1]);
+  } else {
+    constexpr int M = (N + 2) / 3;
+    float m[M];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) m[i] = fmin3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
-  m[10] = fminf(x[30], x[31]);
-  const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
-  return fmin3(fmin3(a, b, c), m[9], m[10]);
+    for (int i = 0; i < M; ++i) {
+      if (3 * i + 2 < N) m[i] = fmin3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+      else if (3 * i + 1 < N) m[i] = fminf(x[3 * i], x[3 * i + 1]);
+      else m[i] = x[3 * i];
+    }
+    return min_tree<M>(m);
+  }
 }
-// v beats tau: it replaces the set's minimum.  ids = the row's column of the [slot][256 rows] id array in shared memory
-// (one store with a run-time slot instead of 32 predicated register moves).
-__device__ __forceinline__ void set_insert(float (&x)[F_L], int* ids, float& tau, float v, int id) {
-  const uint32_t slot = __float_as_uint(tau) & (F_L - 1);
-  const float vp = __uint_as_float((__float_as_uint(v) & ~(uint32_t)(F_L - 1)) | slot);
+// v beats tau: it replaces the set's minimum.  ids = the row's candidate list in GLOBAL memory ([F_LP] ints, written
+// through on every insertion: a fire-and-forget 4-byte store that stays in L2 -- round 1 kept the ids in 32 KB of
+// shared memory, which now holds a deeper park queue and lets the set grow to 48 slots).
+template <int FL>
+__device__ __forceinline__ void set_insert(float (&x)[FL], int32_t* ids, float& tau, float v, int id) {
+  const uint32_t slot = __float_as_uint(tau) & F_SLOT_MASK;
+  const float vp = __uint_as_float((__float_as_uint(v) & ~F_SLOT_MASK) | slot);
 #pragma unroll
-  for (int q = 0; q < F_L; ++q) x[q] = (slot == (uint32_t)q) ? vp : x[q];
-  ids[slot * F_TQ] = id;
-  tau = set_min(x);
+  for (int q = 0; q < FL; ++q) x[q] = (slot == (uint32_t)q) ? vp : x[q];
+  ids[slot] = id;
+  tau = min_tree<FL>(x);
 }
 
 // slot layout: [8 column quads][32 lanes] float4
@@ -132,7 +145,7 @@ __device__ __forceinline__ void park_chunk(const uint32_t (&r)[32], unsigned cha
                                     __uint_as_float(r[4 * i + 3]));
 }
 
-template <int KS>   // k-steps of 16 halves: ceil(d / 16)
+template <int KS, int FL>   // k-steps of 16 halves: ceil(d / 16); candidates kept per row
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restrict__ q16, int64_t n_q, int64_t n_keys,
                int64_t query_offset, const int32_t* __restrict__ self_pos, const int32_t* __restrict__ start_tile,
@@ -142,8 +155,7 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
   // 1024-byte alignment for the swizzled tiles, as an offset so that the pointers stay in the shared window
   unsigned char* sB = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // F_STAGES x 16 KB
   unsigned char* q_slots = sB + F_STAGES * F_TILE_BYTES;                            // [8 pairs][F_QS] parked chunks
-  int* l_id = reinterpret_cast<int*>(q_slots + F_PAIRS * F_QS * F_SLOT_BYTES);        // [32 slots][256 rows] candidate key ids
-  float* s_tau = reinterpret_cast<float*>(l_id + F_L * F_TQ);                         // [256 rows] thresholds, insert -> drain
+  float* s_tau = reinterpret_cast<float*>(q_slots + F_PAIRS * F_QS * F_SLOT_BYTES);    // [256 rows] thresholds, insert -> drain
   int* q_key = reinterpret_cast<int*>(s_tau + F_TQ);                                  // [8 pairs][F_QS] first key of a parked chunk
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_key + F_PAIRS * F_QS);
   const uint32_t bar_full = smem_u32(bars + 0);        // [F_STAGES]
@@ -372,14 +384,20 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
     const bool qvalid = qrow < n_q;
     // the key that is this row itself (excluded): a row range of the keys, or an explicit position per row
     const int self_i = self_pos ? (qvalid ? self_pos[qrow] : -1) : (int)(query_offset + qrow);
-    float x[F_L];
-    int* ids = l_id + row;                              // [slot * F_TQ]
+    float x[FL];
+    // the row's candidate list in global memory: list 0 at the row's place; list p >= 1 of a split block at
+    // [(p - 1) * split rows + row within the split blocks]
+    const int64_t split_rows = ((int64_t)gridDim.x - n_whole) / max(n_parts, 1) * F_TQ;
+    const int64_t xrow = (int64_t)(part - 1) * split_rows + (qrow - (int64_t)n_whole * F_TQ);
+    int32_t* ids = part == 0 ? out_idx + (qvalid ? qrow : 0) * F_LP : xtr_idx + (qvalid ? xrow : 0) * F_LP;
 #pragma unroll
-    for (int j = 0; j < F_L; ++j) {
-      x[j] = __uint_as_float((__float_as_uint(F_EMPTY) & ~(uint32_t)(F_L - 1)) | (uint32_t)j);
-      ids[j * F_TQ] = INT_MAX;
+    for (int j = 0; j < FL; ++j) x[j] = __uint_as_float((__float_as_uint(F_EMPTY) & ~F_SLOT_MASK) | (uint32_t)j);
+    if (qvalid) {
+      int4* i4 = reinterpret_cast<int4*>(ids);
+#pragma unroll
+      for (int j = 0; j < F_LP / 4; ++j) i4[j] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
     }
-    float tau = set_min(x);
+    float tau = min_tree<FL>(x);
     const unsigned char* my_slots = q_slots + pair * (F_QS * F_SLOT_BYTES);
     int qs = 0;
     uint32_t qpar = 0u;
@@ -406,8 +424,8 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
         cm &= cm - 1;
         const int id = key_base + j;
         const float v = sv[((j >> 2) * 32 + lane) * 4 + (j & 3)];
-        if (v > tau && id != self_i && id < (int)n_keys) {
-          set_insert(x, ids, tau, v, id);
+        if (v > tau && id != self_i && id < (int)n_keys && qvalid) {
+          set_insert<FL>(x, ids, tau, v, id);
           ++n_ins;
         }
       }
@@ -426,17 +444,10 @@ k_knn_scan_f16(const __grid_constant__ CUtensorMap kmap, const __half* __restric
         qpar ^= 1u;
       }
     }
-    // the row's 32 candidates (unsorted) and the bound on every score outside the set
-    if (qvalid) {
-      // list 0 at the row's place; list p >= 1 of a split block at [(p - 1) * split rows + row within the split blocks]
-      const int64_t split_rows = ((int64_t)gridDim.x - n_whole) / max(n_parts, 1) * F_TQ;
-      const int64_t xrow = (int64_t)(part - 1) * split_rows + (qrow - (int64_t)n_whole * F_TQ);
-      int32_t* oi = part == 0 ? out_idx + qrow * F_L : xtr_idx + xrow * F_L;
-#pragma unroll
-      for (int j = 0; j < F_L; ++j) oi[j] = ids[j * F_TQ];
-      // a set that never filled up reports -inf: it holds every key (of the part's range)
+    // the candidate ids are in place (written through on insertion); the bound on every score outside the set.
+    // A set that never filled up reports -inf: it holds every key (of the part's range)
+    if (qvalid)
       (part == 0 ? out_thr + qrow : xtr_thr + xrow)[0] = tau < -1.0e37f ? -INFINITY : tau * (1.f / (F_SCALE * F_SCALE)) + F_PACK_SLACK;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -455,11 +466,11 @@ __global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restr
 
 // Exact re-scoring of the 32 candidates (fp64 accumulation over the fp32 operands), final ordering (descending
 // score, ties by ascending id) and the completeness proof: rows whose exact k-th score does not clear
-// a_L + eps are appended to the fallback list.  One WARP per query row, one lane per candidate (F_L = 32): the
-// candidate list is read coalesced, the 32 key rows are gathered side by side, and the order comes from a bitonic
-// network over the lanes.  (One thread per row with an insertion sort kept its 32-entry lists in local memory and
+// a_L + eps are appended to the fallback list.  One WARP per query row, one lane per candidate, 32 candidates at a
+// time (a list of FL = 48 is two sub-lists, the second half empty; the running best 32 are merged like the lists of
+// the key-range parts -- k <= 32, so nothing below rank 32 matters): the candidate list is read coalesced, the 32 key
+// rows are gathered side by side, and the order comes from a bitonic network over the lanes.  (One thread per row with an insertion sort kept its 32-entry lists in local memory and
 // read the candidate table with a 128-byte stride: 2.6 ms at 500k rows.)
-static_assert(F_L == 32, "k_knn_refine_prove maps one candidate to one lane");
 __device__ __forceinline__ bool ranks_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
 // sorts (v, id) over the 32 lanes: afterwards lane j holds the j-th best
@@ -488,7 +499,7 @@ __device__ __forceinline__ void bitonic_sort32(float& v, int& id, int lane, int 
 __global__ void __launch_bounds__(256)
 k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_q, int32_t k, int32_t d,
                    const float* __restrict__ thr, const int32_t* __restrict__ in_idx, int64_t split_row0, int64_t split_rows,
-                   int32_t n_lists, const float* __restrict__ xtr_thr, const int32_t* __restrict__ xtr_idx,
+                   int32_t n_lists, int32_t n_sub, const float* __restrict__ xtr_thr, const int32_t* __restrict__ xtr_idx,
                    const int32_t* __restrict__ perm_k, const int32_t* __restrict__ perm_q, float* __restrict__ out_score,
                    int32_t* __restrict__ out_idx, int32_t* __restrict__ fallback_rows, int32_t* __restrict__ n_fallback) {
   const unsigned FULL = 0xffffffffu;
@@ -501,9 +512,10 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
   int id = INT_MAX;                                       // original key id: what is reported and what breaks ties
   int cnt = 0;
   float a_l = -INFINITY;
-  for (int l = 0; l < lists; ++l) {
+  for (int ls = 0; ls < lists * n_sub; ++ls) {
+    const int l = ls / n_sub, sub = ls - l * n_sub;
     const int64_t xrow = (int64_t)(l - 1) * split_rows + (row - split_row0);
-    const int pos = l == 0 ? in_idx[row * F_L + lane] : xtr_idx[xrow * F_L + lane];
+    const int pos = l == 0 ? in_idx[row * F_LP + sub * 32 + lane] : xtr_idx[xrow * F_LP + sub * 32 + lane];
     a_l = fmaxf(a_l, l == 0 ? thr[row] : xtr_thr[xrow]);
     const bool valid = pos != INT_MAX;
     cnt += __popc(__ballot_sync(FULL, valid));
@@ -520,7 +532,7 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
       cv = (float)acc;
     }
     bitonic_sort32(cv, cid, lane, 2);
-    if (l == 0) {
+    if (ls == 0) {
       v = cv;
       id = cid;
     } else {
@@ -643,7 +655,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
     CSC_LAUNCHED(ctx);
   }
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &thr));
-  CSC_TRY(dev_alloc(ctx, (size_t)n_q * F_L * 4, &cand));
+  CSC_TRY(dev_alloc(ctx, (size_t)n_q * F_LP * 4, &cand));
   // The scan runs one CTA per SM.  When the number of 256-row blocks is not a multiple of the SM count, the last wave
   // is thin (1954 blocks on 148 SMs: 13 full waves and 30 CTAs that take as long as a full wave).  Those blocks are
   // cut into n_parts CTAs over the key range instead (see the kernel); CSC_KNN_SPLIT=0 disables.
@@ -664,7 +676,7 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   DevPtr xthr, xcand;
   if (n_parts > 1) {
     CSC_TRY(dev_alloc(ctx, (size_t)(n_parts - 1) * split_rows * 4, &xthr));
-    CSC_TRY(dev_alloc(ctx, (size_t)(n_parts - 1) * split_rows * F_L * 4, &xcand));
+    CSC_TRY(dev_alloc(ctx, (size_t)(n_parts - 1) * split_rows * F_LP * 4, &xcand));
   }
   CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &fb_rows));
   CSC_TRY(dev_alloc(ctx, 4, &fb_count, true));
@@ -672,13 +684,23 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
   if (getenv("CSC_KNN_CNT")) CSC_TRY(dev_alloc(ctx, 128, &dbg_cnt, true));
   CUtensorMap kmap;
   CSC_TRY(make_map_f16(ctx, encode, &kmap, (const __half*)k16->p, n_keys));
-  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_PAIRS * F_QS * F_SLOT_BYTES + (size_t)F_L * F_TQ * 4 + (size_t)F_TQ * 4 + 128 + (24 + 2 * F_PAIRS * F_QS) * 8 + 64;
+  const size_t smem = 1024 + (size_t)F_TILE_BYTES * F_STAGES + (size_t)F_PAIRS * F_QS * F_SLOT_BYTES + (size_t)F_TQ * 4 + 128 + (24 + 2 * F_PAIRS * F_QS) * 8 + 64;
   const int dbg_mode = getenv("CSC_KNN_DBG") ? atoi(getenv("CSC_KNN_DBG")) : 0;
   cudaEventRecord(ctx->ev_k0, ctx->stream);
+  // candidates kept per row: the proof needs e_k (exact k-th best) to clear a_L (approximate L-th best) by eps = 1e-3.
+  // L = 32 does that for k <= 24 on all but ~0.05 % of the rows; k = 25..32 (run_clustering's default is 30,
+  // processing.jl:309) takes L = 48.  CSC_KNN_L = 32 | 48 forces one.
+  int fl = k <= 24 ? 32 : 48;
+  if (const char* fe = getenv("CSC_KNN_L")) fl = atoi(fe) >= 48 ? 48 : 32;
 #define F_LAUNCH(KS)                                                                                                     \
   do {                                                                                                                   \
-    CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_knn_scan_f16<KS><<<(unsigned)(n_whole + n_split_blocks * n_parts), F_THREADS, smem, ctx->stream>>>(                 \
+    if (fl == 32) F_LAUNCH2(KS, 32);                                                                                     \
+    else F_LAUNCH2(KS, 48);                                                                                              \
+  } while (0)
+#define F_LAUNCH2(KS, FL)                                                                                                \
+  do {                                                                                                                   \
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_knn_scan_f16<KS, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k_knn_scan_f16<KS, FL><<<(unsigned)(n_whole + n_split_blocks * n_parts), F_THREADS, smem, ctx->stream>>>(             \
         kmap, (const __half*)q16->p, n_q, n_keys, query_offset, d_self, d_start, (float*)thr->p, (int32_t*)cand->p,       \
         (int)n_whole, n_parts, xthr ? (float*)xthr->p : nullptr, xcand ? (int32_t*)xcand->p : nullptr, dbg_mode,          \
         dbg_cnt ? (unsigned long long*)dbg_cnt->p : nullptr);                                                             \
@@ -690,11 +712,12 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
     default: F_LAUNCH(4); break;
   }
 #undef F_LAUNCH
+#undef F_LAUNCH2
   CSC_LAUNCHED(ctx);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   k_knn_refine_prove<<<(unsigned)ceil_div64(n_q, 8), 256, 0, ctx->stream>>>(
       q_prep, k_prep, n_q, k, d_eff, (const float*)thr->p, (const int32_t*)cand->p, n_whole * F_TQ, split_rows, n_parts,
-      xthr ? (const float*)xthr->p : nullptr, xcand ? (const int32_t*)xcand->p : nullptr, d_perm_k, d_perm_q, out_score, out_idx,
+      fl / 32 + (fl % 32 ? 1 : 0), xthr ? (const float*)xthr->p : nullptr, xcand ? (const int32_t*)xcand->p : nullptr, d_perm_k, d_perm_q, out_score, out_idx,
       (int32_t*)fb_rows->p, (int32_t*)fb_count->p);
   CSC_LAUNCHED(ctx);
   int32_t n_fb = 0;

@@ -20,7 +20,7 @@ import scipy.sparse as sp
 
 from . import _capi
 from .objects import (ClusteringObject, LazyDeviceMatrix, NormCountObject, PCAObject, RawCountObject,
-                      ReductionObject, ScaleCountObject, VariableGeneObject, scRNAObject)
+                      ReductionObject, ScaleCountObject, UMAPObject, VariableGeneObject, scRNAObject)
 from .pipeline import metric_code, norm_code
 
 _default_ctx = None
@@ -330,4 +330,14 @@ def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1
     cl.knn_distances = dist.download_as(np.float64).reshape(n, n_neighbors).T
     cl.device_graph = gdev
     sc_obj.clustData = cl
+    # hand-off to run_umap / run_clustering_atlas: the reference's atlas branch takes its neighbour table from
+    # `dimReduction.umap.knn_data` when a UMAP object exists (processing.jl:196-197; filled by run_umap at :334-346 with
+    # the k x n index matrix of UMAP's own NN-descent).  The exact table is put there, so a later run_umap-less
+    # run_clustering of the reference (or anything else that reads knn_data) consumes the exact kNN.
+    um = sc_obj.dimReduction.umap
+    if um is None:
+        sc_obj.dimReduction.umap = UMAPObject(None, "UMAP", None, emb.shape[1], int(n_neighbors), str(metric), None,
+                                              cl.knn_indices)
+    else:
+        um.knn_data, um.n_neighbors, um.metric = cl.knn_indices, int(n_neighbors), str(metric)
     return sc_obj

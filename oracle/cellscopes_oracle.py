@@ -115,13 +115,23 @@ def gene_moments(mtx):
     return s1, s2, mean, var
 
 
-def _kd_vertices(x, leaf_size_cutoff):
+# The two points of Loess.jl 0.6.3 that SURVEY A.3 could only recall, not verify (the package is not vendored in
+# /root/reference and Julia is absent).  The oracle's DEFAULT is ("middle", True); the other settings exist so that
+# tests can show whether the HVG set depends on them (tests/test_oracle.py, tests/test_gpu_configs.py):
+#   odd_median  "middle": an odd-length node splits at its true median, the (k+1)-th of 2k+1 order statistics;
+#               "lower" : at the k-th (`mid = length(perm) ÷ 2` read with 1-based indexing), left child = k points.
+#   centred     True : the local quadratic is fitted in (x - v), so the intercept is the value at the vertex;
+#               False: in raw x like `us[i, 1+l] = w * x^l`, value = b0 + b1 v + b2 v^2, slope = b1 + 2 b2 v
+#                      (the same polynomial, different rounding).
+LOESS_VARIANTS = [("middle", True), ("lower", True), ("middle", False), ("lower", False)]
+
+
+def _kd_vertices(x, leaf_size_cutoff, odd_median="middle"):
     """Loess.jl 0.6.3 src/kd.jl [3P]: 1-D kd-tree.  Vertices = {min, max} plus every
     split median.  A node with <= leaf_size_cutoff points is a leaf.  Split at the
     median: even length -> mean of the two middle order statistics, left/right get
-    n/2 each; odd length -> the middle order statistic, left gets floor(n/2) points
-    and right the rest (median included).  (The odd-length convention is recalled,
-    not verified: see SURVEY A.3.)"""
+    n/2 each; odd length -> see ``odd_median`` above (default: the middle order
+    statistic, left gets floor(n/2) points and right the rest, median included)."""
     xs = np.sort(np.asarray(x, dtype=np.float64), kind="stable")
     verts = {float(xs[0]), float(xs[-1])}
     stack = [(0, xs.size)]
@@ -132,7 +142,7 @@ def _kd_vertices(x, leaf_size_cutoff):
             continue
         mid = n // 2
         if n % 2 == 1:
-            med = float(xs[lo + mid])
+            med = float(xs[lo + mid]) if odd_median == "middle" else float(xs[lo + mid - 1])
         else:
             med = float((xs[lo + mid - 1] + xs[lo + mid]) / 2)
         verts.add(med)
@@ -183,7 +193,7 @@ def _pivoted_qr_solve3(us, vs):
     return coef
 
 
-def loess_fit(x, y, span=0.75, degree=2, cell=0.2):
+def loess_fit(x, y, span=0.75, degree=2, cell=0.2, odd_median="middle", centred=True):
     """Loess.jl 0.6.3 ``loess(xs, ys; span, degree=2, cell=0.2)`` for one predictor [3P].
 
     q = max(1, floor(span*n)); kd-tree leaf cutoff = ceil(cell*span*n).  At every
@@ -203,7 +213,7 @@ def loess_fit(x, y, span=0.75, degree=2, cell=0.2):
         raise ValueError("span must be in the range (0, 1].")
     q = max(1, int(math.floor(span * n)))
     cutoff = int(math.ceil(cell * span * n))
-    verts = _kd_vertices(x, cutoff)
+    verts = _kd_vertices(x, cutoff, odd_median)
     val = np.empty(verts.size)
     slope = np.empty(verts.size)
     for vi, v in enumerate(verts):
@@ -215,12 +225,16 @@ def loess_fit(x, y, span=0.75, degree=2, cell=0.2):
             dmax = 1.0
         u = dq / dmax
         w = np.sqrt((1.0 - u ** 3) ** 3)
-        xc = x[order] - v
+        xc = x[order] - v if centred else x[order]
         us = np.stack([w, w * xc, w * xc * xc], axis=1)
         vs = y[order] * w
         coef = _pivoted_qr_solve3(us, vs)
-        val[vi] = coef[0]
-        slope[vi] = coef[1]
+        if centred:
+            val[vi] = coef[0]
+            slope[vi] = coef[1]
+        else:
+            val[vi] = coef[0] + coef[1] * v + coef[2] * v * v
+            slope[vi] = coef[1] + 2.0 * coef[2] * v
     return verts, val, slope
 
 
@@ -252,25 +266,23 @@ def loess_predict(model, z):
     return out
 
 
-def find_variable_genes(mtx, nFeatures=2000, span=0.3):
-    """processing.jl:133-155.
-
-    mean/var of RAW counts per gene over all cells (:138-139, exact-moment rule of
-    SURVEY A.3-7), loess of log10(var) on log10(mean) with span (:144),
-    variance_expected = 10^predict (:145), variance_standardized =
-    var((x - mean)/sqrt(variance_expected)) (:146-150) = var/variance_expected,
-    stable descending sort (:152), first nFeatures (:153).
-    The reference requires every gene to have variance > 0 (:143,:151)."""
-    m = sp.csc_matrix(mtx)
-    n_genes = m.shape[0]
+def hvg_from_moments(s1, s2, n_cells, nFeatures=2000, span=0.3, odd_median="middle", centred=True):
+    """processing.jl:140-155 from the exact integer moments (S1 = sum x, S2 = sum x^2 per gene): everything of
+    find_variable_genes after :138-139.  Separate so that the Loess variants can be run on the moment tables of the
+    full-size benchmark matrices (33k points) without the matrices themselves."""
+    s1 = np.asarray(s1, dtype=np.float64)
+    s2 = np.asarray(s2, dtype=np.float64)
+    n_genes = s1.size
+    n = float(n_cells)
     nFeatures = min(int(nFeatures), n_genes)               # :134-137
-    s1, s2, mean, var = gene_moments(m)
+    mean = s1 / n
+    var = (s2 - s1 * s1 / n) / (n - 1)
     if np.any(~(var > 0.0)):
         raise ValueError("find_variable_genes: a gene has variance <= 0 "
                          "(reference precondition, processing.jl:143,151)")
     lx = np.log10(mean)
     ly = np.log10(var)
-    model = loess_fit(lx, ly, span=span)
+    model = loess_fit(lx, ly, span=span, odd_median=odd_median, centred=centred)
     var_exp = 10.0 ** loess_predict(model, lx)
     var_std = var / var_exp
     # sort(..., rev=true) is stable: ties keep ascending gene order (:152)
@@ -281,6 +293,20 @@ def find_variable_genes(mtx, nFeatures=2000, span=0.3):
         "features": order[:nFeatures].copy(), "S1": s1, "S2": s2,
         "loess": model,
     }
+
+
+def find_variable_genes(mtx, nFeatures=2000, span=0.3, odd_median="middle", centred=True):
+    """processing.jl:133-155.
+
+    mean/var of RAW counts per gene over all cells (:138-139, exact-moment rule of
+    SURVEY A.3-7), loess of log10(var) on log10(mean) with span (:144),
+    variance_expected = 10^predict (:145), variance_standardized =
+    var((x - mean)/sqrt(variance_expected)) (:146-150) = var/variance_expected,
+    stable descending sort (:152), first nFeatures (:153).
+    The reference requires every gene to have variance > 0 (:143,:151)."""
+    m = sp.csc_matrix(mtx)
+    s1, s2, _, _ = gene_moments(m)
+    return hvg_from_moments(s1, s2, m.shape[1], nFeatures, span, odd_median, centred)
 
 
 # ----------------------------------------------------------------------------
