@@ -241,10 +241,14 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        comm = cs.TorchComm(device=torch.device("cuda", local_rank))
+    ctx = cs.Context(local_rank)
+    if world > 1:
+        # the data-path collectives are NCCL calls inside libcellscopes_cuda.so on the context's stream
+        # (CSC_BENCH_COMM=torch: the round-1 route through torch.distributed, for comparison)
+        comm = cs.TorchComm(device=torch.device("cuda", local_rank)) if os.environ.get("CSC_BENCH_COMM") == "torch" \
+            else cs.NcclComm.from_torch(ctx)
     else:
         comm = cs.LocalComm()
-    ctx = cs.Context(local_rank)
     offsets = cs.partition_cells(n_cells, world)
     lo, hi = int(offsets[rank]), int(offsets[rank + 1])
     params = cs.PathParams(n_features=n_features, n_pcs=n_pcs, k=k, graph_mode=args.graph)

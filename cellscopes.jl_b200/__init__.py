@@ -12,8 +12,9 @@ from . import _capi, objects, pipeline, processing, synth  # noqa: F401
 from ._capi import CellScopesCudaError, Context, load_library  # noqa: F401
 from .objects import (ClusteringObject, NormCountObject, PCAObject, RawCountObject, ReductionObject,  # noqa: F401
                       ScaleCountObject, UMAPObject, VariableGeneObject, scRNAObject, subset_count, subset_matrix)
-from .pipeline import LocalComm, PathParams, TorchComm, partition_cells, run_path  # noqa: F401
-from .processing import (find_variable_genes, normalize_object, run_clustering, run_pca, scale_object)  # noqa: F401
+from .pipeline import LocalComm, NcclComm, PathParams, TorchComm, partition_cells, run_path  # noqa: F401
+from .processing import (find_all_markers, find_markers, find_variable_genes, normalize_object, run_clustering, run_pca,
+                         scale_object)  # noqa: F401
 
 __version__ = "0.1.0"
 from ._capi import csc_from_arrays  # noqa: E402,F401

@@ -20,7 +20,7 @@ NORM_LOGARITHM, NORM_NONE = 0, 1
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
 STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
-          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host"]
+          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host", "markers"]
 T_COUNT = len(STAGES)
 
 _NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,
@@ -89,6 +89,14 @@ SIGNATURES = {
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32, _I32]),
     "csc_graph_free": (_I32, [_P]),
+    "csc_marker_stats": (_I32, [_P, _P, _P, _I32, _F64, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_I64)]),
+    "csc_comm_unique_id": (_I32, [_P, _I64]),
+    "csc_comm_init": (_I32, [_P, _P, _I64, _I32, _I32]),
+    "csc_comm_info": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
+    "csc_comm_destroy": (_I32, [_P]),
+    "csc_comm_allreduce_sum": (_I32, [_P, _P]),
+    "csc_comm_allgather_rows": (_I32, [_P, _P, _P, _PP]),
+    "csc_comm_allgather_i32": (_I32, [_P, _P, _P, _I32, _PP]),
 }
 
 _lib = None
@@ -204,6 +212,55 @@ class Context:
 
     def flush_l2(self):
         self.check(self.lib.csc_flush_l2(self.h))
+
+    def marker_stats(self, norm, labels, n_groups, expr_cutoff=0.0):
+        """csc_marker_stats: the per-(gene, group) tables of the Mann-Whitney tests and of the result columns."""
+        g = norm.shape[0]
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        tabs = {k: np.zeros((g, n_groups), dtype=np.float64) for k in ("rank_sum", "sum_expm1", "n_expr", "nnz", "sum_x")}
+        per_gene = {k: np.zeros(g, dtype=np.float64) for k in ("tie_adj", "n_neg", "n_zero_stored")}
+        n_incl = _I64()
+        self.check(self.lib.csc_marker_stats(self.h, norm.h, _ptr(lab), int(n_groups), float(expr_cutoff),
+                                             _ptr(tabs["rank_sum"]), _ptr(tabs["sum_expm1"]), _ptr(tabs["n_expr"]),
+                                             _ptr(tabs["nnz"]), _ptr(tabs["sum_x"]), _ptr(per_gene["tie_adj"]),
+                                             _ptr(per_gene["n_neg"]), _ptr(per_gene["n_zero_stored"]), C.byref(n_incl)))
+        tabs.update(per_gene)
+        tabs["n_included"] = n_incl.value
+        return tabs
+
+    # ---- multi-GPU: NCCL inside the library ------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """128-byte NCCL unique id (rank 0 makes it; the host moves it to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        rc = self.lib.csc_comm_unique_id(buf, 128)
+        if rc != 0:
+            raise CellScopesCudaError(rc, (self.lib.csc_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.csc_comm_init(self.h, buf, 128, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, v = _I32(), _I32(), _I32()
+        self.check(self.lib.csc_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def comm_allreduce_sum(self, vec):
+        self.check(self.lib.csc_comm_allreduce_sum(self.h, vec.h))
+        return vec
+
+    def comm_allgather_rows(self, dense, offsets):
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_comm_allgather_rows(self.h, dense.h, _ptr(o), C.byref(h)))
+        return Dense(self, h)
+
+    def comm_allgather_i32(self, vec, offsets, width):
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_comm_allgather_i32(self.h, vec.h, _ptr(o), int(width), C.byref(h)))
+        return Vec(self, h)
 
     # ---- vectors ---------------------------------------------------------------------------
     def vec(self, n, dtype=np.float64):

@@ -219,6 +219,7 @@ csc_status csc_destroy(csc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->alive) *ctx->alive = false;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
   ctx->gemm_ws.reset();
   ctx->cache.release_all();
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);

@@ -73,10 +73,14 @@ struct csc_ctx {
   cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   std::shared_ptr<DevMem> gemm_ws;   // split-K partials of the fp64 GEMM (grow-only)
   int64_t knn_fallback_rows = 0;   // rows of the last csc_knn call that needed the exact re-scan
+  // multi-GPU (comm.cu): the NCCL communicator of this context's rank, collectives run on `stream`
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   int trace = 0;                // CSC_LOG_LEVEL >= 2: print host-side checkpoints of the stages
   double trace_t0 = 0.0;
 };
 void csc_trace(csc_ctx* ctx, const char* label);
+void comm_release(csc_ctx* ctx);   // comm.cu
 #define CSC_TRACE(ctx, label)                 \
   do {                                        \
     if ((ctx)->trace) csc_trace((ctx), label); \

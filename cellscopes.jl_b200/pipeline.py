@@ -98,6 +98,40 @@ class LocalComm:
         pass
 
 
+class NcclComm:
+    """One process per GPU; every collective is a csc_comm_* call: NCCL inside libcellscopes_cuda.so, enqueued on the
+    context's own stream, no host synchronisation around it.  ``bootstrap`` moves the 128-byte unique id from rank 0
+    to the others (any callable ``bytes|None -> bytes``; ``from_torch`` uses a torch.distributed broadcast, a Julia
+    host would use MPI.jl / Distributed.jl)."""
+
+    def __init__(self, be, rank, world, bootstrap):
+        self.be, self.rank, self.world = be, int(rank), int(world)
+        uid = bootstrap(be.comm_unique_id() if self.rank == 0 else None)
+        be.comm_init(uid, self.rank, self.world)
+
+    @classmethod
+    def from_torch(cls, be):
+        import torch.distributed as dist
+
+        def bootstrap(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        return cls(be, dist.get_rank(), dist.get_world_size(), bootstrap)
+
+    def allreduce_sum(self, vec):
+        return self.be.comm_allreduce_sum(vec)
+
+    def allgather_rows(self, be, dense, offsets):
+        return be.comm_allgather_rows(dense, offsets)
+
+    def allgather_i32(self, be, vec, offsets, k):
+        return be.comm_allgather_i32(vec, offsets, k)
+
+    def barrier(self):
+        self.be.synchronize()
+
+
 class TorchComm:
     """One process per GPU; collectives through torch.distributed on tensors that alias the
     library's device buffers (``__cuda_array_interface__``), so no staging copy is made for the

@@ -341,3 +341,148 @@ def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1
     else:
         um.knn_data, um.n_neighbors, um.metric = cl.knn_indices, int(n_neighbors), str(metric)
     return sc_obj
+
+
+# ---------------------------------------------------------------------------------------------
+# find_markers / find_all_markers  (processing.jl:350-414)
+# ---------------------------------------------------------------------------------------------
+def _normal_two_sided(z):
+    """2 * ccdf(Normal(), z) = erfc(z / sqrt 2), vectorised, without leaving numpy."""
+    from scipy.special import erfc
+    return erfc(np.asarray(z, dtype=np.float64) / np.sqrt(2.0))
+
+
+def _exact_small_pvalues(c, norm_dev, cells_1, cells_2, genes):
+    """The exact branch of HypothesisTests.MannWhitneyUTest (n1 + n2 <= 10, or <= 50 without ties): at most 50 cells,
+    so the rows come to the host and the permutation distribution is counted there."""
+    import itertools
+    import scipy.stats
+    cols = np.concatenate([cells_1, cells_2])
+    sub = sp.hstack([norm_dev.to_scipy(int(j), int(j) + 1) for j in cols]).tocsr()[genes].toarray()
+    nx, ny = len(cells_1), len(cells_2)
+    out = np.full(len(genes), np.nan)
+    for r, row in enumerate(sub):
+        ranks = scipy.stats.rankdata(row)
+        if nx + ny > 10 and np.unique(row).size < row.size:
+            continue                                     # ties and more than 10 cells: the approximate test applies
+        u = ranks[:nx].sum() - nx * (nx + 1) / 2
+        if nx + ny <= 10:
+            us = np.array([ranks[list(cb)].sum() - nx * (nx + 1) / 2 for cb in itertools.combinations(range(nx + ny), nx)])
+        else:
+            us = None
+        mid = nx * ny / 2
+        if us is not None:
+            p = np.mean(us <= u) if u < mid else np.mean(us >= u)
+        else:
+            p = scipy.stats.mannwhitneyu(row[:nx], row[nx:], alternative="less" if u < mid else "greater", method="exact").pvalue
+        out[r] = min(1.0, 2 * p)
+    return out
+
+
+def _marker_frame(genes, tabs, g1, n1, n2, rest, expr_cutoff, min_pct, p_cutoff, only_pos, exact_fn=None):
+    """Result columns of find_markers from the per-(gene, group) tables.  ``g1``: column of cluster_1; cluster_2 is
+    column ``rest`` (an int) or everything else (``rest is None``: the totals minus cluster_1)."""
+    R, S, P, Z, X = (tabs[k] for k in ("rank_sum", "sum_expm1", "n_expr", "nnz", "sum_x"))
+    n = float(n1 + n2)
+
+    def col(t, j):
+        return t[:, j] if j is not None else t.sum(axis=1) - t[:, g1]
+    nnz_all = Z.sum(axis=1)
+    n_zero_all = tabs["n_included"] - nnz_all + tabs["n_zero_stored"]              # the zero tie group of every gene
+    zero_rank = tabs["n_neg"] + 0.5 * (n_zero_all + 1.0)
+    r1 = R[:, g1] + (n1 - Z[:, g1]) * zero_rank                                    # + the implicit zeros of cluster_1
+    tieadj = tabs["tie_adj"] + n_zero_all ** 3 - n_zero_all
+    u = r1 - n1 * (n1 + 1) / 2.0
+    mu = u - n1 * n2 / 2.0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sigma = np.sqrt(n1 * n2 * (n + 1.0 - tieadj / (n * (n - 1.0))) / 12.0)
+        p = _normal_two_sided(np.abs(mu - 0.5 * np.sign(mu)) / sigma)
+    p = np.where((mu == 0) & (sigma == 0), 1.0, p)
+    sx1, sx2 = X[:, g1], col(X, rest)
+    tested = np.flatnonzero((sx1 > 0.0) & (sx2 > 0.0))                             # :364-367
+    if exact_fn is not None and tested.size:
+        pe = exact_fn(tested)
+        p = p.copy()
+        p[tested] = np.where(np.isnan(pe), p[tested], pe)
+    mean1 = np.log(S[:, g1] / n1 + 1.0)
+    mean2 = np.log(col(S, rest) / n2 + 1.0)
+    zero_counts = expr_cutoff < 0                                                   # an implicit zero exceeds a negative cut-off
+    pct1 = (P[:, g1] + ((n1 - Z[:, g1]) if zero_counts else 0.0)) / n1
+    pct2 = (col(P, rest) + ((n2 - col(Z, rest)) if zero_counts else 0.0)) / n2
+    logfc = mean1 - mean2
+    p_adj = np.minimum(p * tested.size, 1.0)                                        # Bonferroni over the tested genes (:384)
+    sel = np.zeros(len(genes), dtype=bool)
+    sel[tested] = True
+    sel &= (pct1 > min_pct) & (p < p_cutoff)
+    if only_pos:
+        sel &= logfc > 0.0
+    idx = np.flatnonzero(sel)
+    idx = idx[np.argsort(-logfc[idx], kind="stable")]                               # sort!(:avg_logFC, rev=true) (:389)
+    return pd.DataFrame({"gene": [genes[i] for i in idx], "p_val": p[idx], "avg_logFC": logfc[idx], "pct_1": pct1[idx],
+                         "pct_2": pct2[idx], "p_val_adj": p_adj[idx]})
+
+
+def _marker_inputs(sc_obj, anno, ctx):
+    if sc_obj.clustData is None or sc_obj.clustData.clustering is None:
+        raise ValueError("Clustering has not been done. Please complete the \"RunClustering\" first!")
+    if sc_obj.normCount is None:
+        raise ValueError("find_markers: normCount is missing; run normalize_object first")
+    s = _session(sc_obj, ctx)
+    if s.norm is None:
+        s.norm = s.ctx.sparse_from_scipy(sc_obj.normCount.count_mtx)
+    df = sc_obj.clustData.clustering
+    pos = {c: i for i, c in enumerate(sc_obj.normCount.cell_name)}
+    lab = np.empty(len(pos), dtype=object)
+    lab[:] = None
+    lab[[pos[c] for c in df["cell_id"]]] = df[str(anno)].to_numpy()               # extract_cluster_count (utils.jl:89-106)
+    return s, lab
+
+
+def find_markers(sc_obj, cluster_1=None, cluster_2=None, anno="cluster", expr_cutoff=0.0, min_pct=0.1, p_cutoff=0.05,
+                 only_pos=True, ctx=None):
+    if cluster_1 is None:
+        raise ValueError("Please provide the name of the cell cluster for which you wish to obtain the differential genes. "
+                         "The \"cluster_1\" parameter cannot be left blank.")
+    if cluster_2 is None:
+        raise ValueError("Please enter the name of the cell cluster you wish to compare against. The \"cluster_2\" parameter "
+                         "cannot be left blank.")
+    s, lab = _marker_inputs(sc_obj, anno, ctx)
+    labels = np.where(lab == cluster_1, 0, np.where(lab == cluster_2, 1, -1)).astype(np.int32)
+    n1, n2 = int((labels == 0).sum()), int((labels == 1).sum())
+    if n1 == 0 or n2 == 0:
+        raise ValueError(f"find_markers: cluster {cluster_1!r} has {n1} cells, cluster {cluster_2!r} has {n2}")
+    tabs = s.ctx.marker_stats(s.norm, labels, 2, expr_cutoff)
+    exact_fn = None
+    if n1 + n2 <= 50:
+        c1, c2 = np.flatnonzero(labels == 0), np.flatnonzero(labels == 1)
+        exact_fn = lambda genes: _exact_small_pvalues(s.ctx, s.norm, c1, c2, genes)   # noqa: E731
+    return _marker_frame(sc_obj.normCount.gene_name, tabs, 0, n1, n2, 1, expr_cutoff, min_pct, p_cutoff, only_pos, exact_fn)
+
+
+def find_all_markers(sc_obj, anno="cluster", expr_cutoff=0.0, min_pct=0.1, p_cutoff=0.05, only_pos=True, ctx=None):
+    """Every cluster (in order of first appearance) against all other cells.  Like the reference, the thresholds given
+    here are NOT forwarded: find_markers runs with its defaults (processing.jl:408).  One device pass serves all
+    clusters: with every cell taking part the ranks do not depend on the cluster, only the rank sums do."""
+    s, lab = _marker_inputs(sc_obj, anno, ctx)
+    if any(v is None for v in lab):
+        raise ValueError("find_all_markers: a cell has no cluster label")
+    clusters = list(pd.unique(sc_obj.clustData.clustering[str(anno)]))
+    code = {c: i for i, c in enumerate(clusters)}
+    labels = np.fromiter((code[v] for v in lab), dtype=np.int32, count=lab.size)
+    sizes = np.bincount(labels, minlength=len(clusters))
+    tabs = s.ctx.marker_stats(s.norm, labels, len(clusters), 0.0)
+    frames = []
+    n = int(labels.size)
+    for c in clusters:
+        j = code[c]
+        if n <= 50:
+            relab = np.where(labels == j, 0, 1).astype(np.int32)
+            t2 = s.ctx.marker_stats(s.norm, relab, 2, 0.0)
+            c1, c2 = np.flatnonzero(relab == 0), np.flatnonzero(relab == 1)
+            f = _marker_frame(sc_obj.normCount.gene_name, t2, 0, len(c1), len(c2), 1, 0.0, 0.1, 0.05, True,
+                              lambda genes: _exact_small_pvalues(s.ctx, s.norm, c1, c2, genes))
+        else:
+            f = _marker_frame(sc_obj.normCount.gene_name, tabs, j, int(sizes[j]), n - int(sizes[j]), None, 0.0, 0.1, 0.05, True)
+        f["cluster"] = c
+        frames.append(f)
+    return pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()

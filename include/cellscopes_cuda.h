@@ -21,10 +21,10 @@
  *     the library and released with the matching *_free or with csc_destroy.
  *   - A context owns one GPU, one stream.  It is not thread-safe; distinct contexts are
  *     independent.  Multi-GPU = one context per process per GPU (cells sharded in
- *     contiguous column ranges); the few exchange steps are exposed as device-resident
- *     "partials" that the host all-reduces / all-gathers (torch.distributed / NCCL)
- *     between the *_partial and the *_finish call.  With one GPU the host simply skips
- *     the collective.
+ *     contiguous column ranges); the few exchange steps are device-resident "partials"
+ *     that are all-reduced / all-gathered between the *_partial and the *_finish call
+ *     with the csc_comm_* entry points (NCCL inside the library, on the context's
+ *     stream).  With one GPU the host simply skips the collective.
  *   - Matrices are genes x cells, compressed sparse COLUMN: a column is a cell
  *     (src/scrna/objects.jl:10-24).  Indices at the ABI are int64 with an explicit
  *     index_base (1 for Julia, 0 for C/Python).  On the device they are narrowed to
@@ -74,6 +74,7 @@ enum {
   CSC_T_KNN_SCAN, /* the all-pairs scan kernel alone (inside CSC_T_KNN): the dominant kernel of the path */
   CSC_T_GRAM_MMA, /* the tcgen05 Gram kernel alone (inside CSC_T_PCA_GRAM) */
   CSC_T_ALLOC_HOST, /* HOST milliseconds spent inside the device allocator (pool growth shows up here) */
+  CSC_T_MARKERS,    /* csc_marker_stats */
   CSC_T_COUNT
 };
 
@@ -236,6 +237,44 @@ csc_status csc_graph_info(const csc_graph* g, int64_t* n_rows, int64_t* n_cols, 
 csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, void* nzval, int32_t val_dtype,
                               int32_t index_base);
 csc_status csc_graph_free(csc_graph* g);
+
+/* ---- f3: find_markers / find_all_markers src/scrna/processing.jl:350-414 --------------------------------------
+ * Sufficient statistics of the per-gene Mann-Whitney U tests (HypothesisTests.MannWhitneyUTest, :376) and of the
+ * columns of the result frame (:378-382) for EVERY group of cells at once, from one sort of the stored entries of the
+ * normalised matrix.  labels: host int32[n_cells]; -1 = the cell takes no part (find_markers: cluster_1 -> 0,
+ * cluster_2 -> 1; find_all_markers: label = cluster, "cluster c against all other cells" then needs only c's rank sum).
+ * Outputs, host fp64, [n_genes x n_groups] row-major: rank_sum = sum of the (tie-averaged, 1-based) ranks of the
+ * STORED entries of the group among all participating cells; sum_expm1 = sum expm1(x) (:378-379); n_expr = #(x >
+ * expr_cutoff) (:381-382); nnz = #stored; sum_x = sum x (the rowSum > 0 filter of :364-366).  Per gene [n_genes]:
+ * tie_adj = sum (t^3 - t) over the tie groups of the non-zero values; n_neg = #negative values; n_zero_stored = #stored
+ * zeros.  The implicit zeros of a gene are one more tie group, ranked n_neg + (n0 + 1) / 2 with n0 = *n_included - (all
+ * stored entries of the gene) + n_zero_stored: the caller adds (n_label - nnz) of them per group and n0^3 - n0 to the
+ * tie term.  Limits: n_genes <= 65535, n_groups <= 65535 (16 bits each in the sort key). */
+csc_status csc_marker_stats(csc_ctx* ctx, const csc_sparse* norm, const int32_t* labels, int32_t n_groups,
+                            double expr_cutoff, double* rank_sum, double* sum_expm1, double* n_expr, double* nnz,
+                            double* sum_x, double* tie_adj, double* n_neg, double* n_zero_stored, int64_t* n_included);
+
+/* ---- multi-GPU: the exchange steps of the path, NCCL over NVLink inside the library ----------------
+ * One process per GPU, one context each; cells sharded in contiguous column ranges.  The reference is single-process
+ * Julia (no counterpart to cite); these are the collectives BASELINE.json's north_star names: all-reduce of the per-gene
+ * statistics (processing.jl:138-139, :66-67 taken per shard) and of the Gram / column sums (run_pca :164-193), all-gather
+ * of the embedding before the kNN query pass and of the k x N neighbour table before the adjacency (:218-232).
+ * NCCL is dlopen'ed on first use (libnccl.so.2; CSC_NCCL_LIB overrides); without it these return CSC_ERR_UNSUPPORTED.
+ * Rendezvous: rank 0 calls csc_comm_unique_id, the HOST moves the 128 bytes to every rank (MPI.jl, Distributed.jl,
+ * a shared file, torch.distributed ...), every rank calls csc_comm_init with the same id.
+ * All collectives are enqueued on the context's stream and return without waiting: the kernels of the next stage are
+ * ordered behind them on the same stream. */
+csc_status csc_comm_unique_id(void* id_out /*[128]*/, int64_t id_bytes);
+csc_status csc_comm_init(csc_ctx* ctx, const void* unique_id, int64_t id_bytes, int32_t rank, int32_t world);
+csc_status csc_comm_info(const csc_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
+csc_status csc_comm_destroy(csc_ctx* ctx); /* also done by csc_destroy */
+/* v <- sum over ranks of v, in place (fp64 / fp32 / int32 / int64) */
+csc_status csc_comm_allreduce_sum(csc_ctx* ctx, csc_vec* v);
+/* rows of every rank, concatenated in rank order; row_offsets[world + 1] = global row ranges of the ranks (ragged
+ * shards need no padding).  out: dense [row_offsets[world] x n_cols] / int32 [row_offsets[world] * width]. */
+csc_status csc_comm_allgather_rows(csc_ctx* ctx, const csc_dense* local, const int64_t* row_offsets, csc_dense** out);
+csc_status csc_comm_allgather_i32(csc_ctx* ctx, const csc_vec* local, const int64_t* row_offsets, int32_t width,
+                                  csc_vec** out);
 
 #ifdef __cplusplus
 }

@@ -493,3 +493,107 @@ def run_pipeline(counts, nFeatures=2000, span=0.3, scale_max=10.0, n_pcs=50, k=2
     adj = adjacency_atlas(idx) if graph == "atlas" else adjacency_small(idx)
     return {"norm": norm, "hvg": hvg, "rows": rows, "scaled": scaled, "pca": pca,
             "knn_idx": idx, "knn_dist": dist, "adj": adj}
+
+
+# ----------------------------------------------------------------------------
+# f3  find_markers / find_all_markers (processing.jl:350-414)
+# ----------------------------------------------------------------------------
+def _mwu_exact_pvalue(x, y):
+    """HypothesisTests.ExactMannWhitneyUTest [3P]: the permutation distribution of U (two-sided: twice the smaller
+    tail, capped at 1).  Only reached for nx + ny <= 10, or <= 50 without ties (HypothesisTests' MannWhitneyUTest
+    dispatch); enumerates the C(n, nx) assignments for n <= 10 and uses the tie-free counting recursion otherwise."""
+    import itertools
+    import scipy.stats
+    nx, ny = len(x), len(y)
+    allv = np.concatenate([x, y])
+    ranks = scipy.stats.rankdata(allv)
+    u = ranks[:nx].sum() - nx * (nx + 1) / 2
+    if nx + ny <= 10:
+        us = np.array([ranks[list(c)].sum() - nx * (nx + 1) / 2 for c in itertools.combinations(range(nx + ny), nx)])
+        mid = nx * ny / 2
+        p = np.mean(us <= u) if u < mid else np.mean(us >= u)
+        return float(min(1.0, 2 * p))
+    # no ties: number of arrangements with statistic u (Mann & Whitney's recursion)
+    cnt = np.zeros((nx + 1, ny + 1, nx * ny + 1))
+    cnt[0, :, 0] = 1
+    cnt[:, 0, 0] = 1
+    for i in range(1, nx + 1):
+        for j in range(1, ny + 1):
+            for k in range(i * j + 1):
+                cnt[i, j, k] = (cnt[i - 1, j, k - j] if k >= j else 0) + cnt[i, j - 1, k]
+    pmf = cnt[nx, ny] / cnt[nx, ny].sum()
+    ui = int(round(u))
+    p = pmf[:ui + 1].sum() if u < nx * ny / 2 else pmf[ui:].sum()
+    return float(min(1.0, 2 * p))
+
+
+def mann_whitney_pvalue(x, y):
+    """HypothesisTests.MannWhitneyUTest(x, y) -> pvalue (two-sided) [3P, HypothesisTests 0.11]:
+    exact for nx + ny <= 10 or (nx + ny <= 50 and no ties), else the normal approximation with tie and continuity
+    correction:  U = sum ranks(x) - nx (nx + 1) / 2;  mu = U - nx ny / 2;
+    sigma = sqrt(nx ny (n + 1 - tieadj / (n (n - 1))) / 12),  tieadj = sum (t^3 - t);
+    p = 2 ccdf(Normal, |mu - 0.5 sign(mu)| / sigma), and 1 when mu == sigma == 0."""
+    import scipy.stats
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    nx, ny = x.size, y.size
+    n = nx + ny
+    ranks = scipy.stats.rankdata(np.concatenate([x, y]))
+    _, t = np.unique(np.concatenate([x, y]), return_counts=True)
+    tieadj = float(((t.astype(np.float64) ** 3) - t).sum())
+    if n <= 10 or (n <= 50 and tieadj == 0):
+        return _mwu_exact_pvalue(x, y)
+    u = ranks[:nx].sum() - nx * (nx + 1) / 2
+    mu = u - nx * ny / 2
+    sigma = math.sqrt(nx * ny * (n + 1 - tieadj / (n * (n - 1))) / 12)
+    if mu == 0 and sigma == 0:
+        return 1.0
+    z = abs(mu - 0.5 * np.sign(mu)) / sigma
+    return float(2 * scipy.stats.norm.sf(z))
+
+
+def find_markers(norm, cluster_of_cell, cluster_1, cluster_2, gene_name=None, expr_cutoff=0.0, min_pct=0.1,
+                 p_cutoff=0.05, only_pos=True):
+    """processing.jl:350-391 on a genes x cells NORMALISED matrix and a per-cell cluster label.
+
+    genes with rowSum > 0 in BOTH clusters (:364-367); per gene MannWhitneyUTest(x, y) on the dense rows (:376-377);
+    mean_i = log(mean(expm1(x)) + 1) (:378-379); avg_logFC = mean1 - mean2; pct_i = #(x > expr_cutoff)/n_i (:381-382);
+    Bonferroni over the tested genes (:384); keep pct_1 > min_pct and p_val < p_cutoff (:385), avg_logFC > 0 if
+    only_pos (:386-388); sorted by avg_logFC, descending (:389).  Returns a dict of columns."""
+    m = sp.csr_matrix(norm)
+    lab = np.asarray(cluster_of_cell)
+    c1 = np.flatnonzero(lab == cluster_1)
+    c2 = np.flatnonzero(lab == cluster_2)
+    a = m[:, c1].toarray()
+    b = m[:, c2].toarray()
+    keep = np.flatnonzero((a.sum(axis=1) > 0.0) & (b.sum(axis=1) > 0.0))
+    a, b = a[keep], b[keep]
+    p = np.array([mann_whitney_pvalue(x, y) for x, y in zip(a, b)])
+    mean1 = np.log(np.expm1(a).mean(axis=1) + 1)
+    mean2 = np.log(np.expm1(b).mean(axis=1) + 1)
+    logfc = mean1 - mean2
+    pct1 = (a > expr_cutoff).mean(axis=1)
+    pct2 = (b > expr_cutoff).mean(axis=1)
+    p_adj = np.minimum(p * keep.size, 1.0)
+    sel = (pct1 > min_pct) & (p < p_cutoff)
+    if only_pos:
+        sel &= logfc > 0.0
+    idx = np.flatnonzero(sel)
+    idx = idx[np.argsort(-logfc[idx], kind="stable")]
+    genes = keep if gene_name is None else np.asarray(gene_name, dtype=object)[keep]
+    return {"gene": genes[idx], "p_val": p[idx], "avg_logFC": logfc[idx], "pct_1": pct1[idx], "pct_2": pct2[idx],
+            "p_val_adj": p_adj[idx], "tested": keep, "p_all": p, "logfc_all": logfc}
+
+
+def find_all_markers(norm, cluster_of_cell, gene_name=None):
+    """processing.jl:393-414: every cluster, in order of first appearance, against all other cells ("nonself");
+    find_markers is called with its DEFAULT thresholds (the arguments of find_all_markers are not forwarded, :408)."""
+    lab = np.asarray(cluster_of_cell)
+    _, first = np.unique(lab, return_index=True)
+    out = []
+    for c in lab[np.sort(first)]:
+        relab = np.where(lab == c, c, "nonself")
+        r = find_markers(norm, relab, c, "nonself", gene_name)
+        r["cluster"] = np.full(r["gene"].size, c, dtype=object)
+        out.append(r)
+    return out

@@ -715,3 +715,28 @@ def test_vec_download_as_converts_on_the_device(cs, ctx):
         assert np.array_equal(vf.download_as(np.float32), f32)
     with pytest.raises(Exception):
         ctx.vec_from(np.zeros(4, np.float32)).download_as(np.int64)
+
+
+# ---- multi-GPU plumbing on one GPU ------------------------------------------------------------
+def test_nccl_collectives_inside_the_library_single_rank(cs, ctx):
+    """csc_comm_*: NCCL is dlopen'ed by the library and the collectives run on the context's stream.  One rank is all
+    a 1-GPU box can offer (the N > 1 equality is checked by bench.py's `one_vs_n` diag and tools/multigpu_check.py):
+    a world of one must leave an all-reduce unchanged and an all-gather equal to its input, through the real NCCL calls."""
+    c = cs.Context(0)
+    comm = cs.NcclComm(c, 0, 1, lambda uid: uid)
+    info = c.comm_info()
+    assert info["world"] == 1 and info["rank"] == 0 and info["nccl_version"] >= 21800
+    v = c.vec_from(np.arange(1000, dtype=np.float64))
+    comm.allreduce_sum(v)
+    assert np.array_equal(v.download(), np.arange(1000.0))
+    d = c.dense_upload(np.arange(600, dtype=np.float32).reshape(200, 3))
+    g = comm.allgather_rows(c, d, np.array([0, 200]))
+    assert g.shape == (200, 3) and np.array_equal(g.download(np.float32), np.arange(600, dtype=np.float32).reshape(200, 3))
+    t = c.vec_from(np.arange(80, dtype=np.int32))
+    gi = comm.allgather_i32(c, t, np.array([0, 20]), 4)
+    assert np.array_equal(gi.download(), np.arange(80, dtype=np.int32))
+    with pytest.raises(cs.CellScopesCudaError):
+        comm.allgather_rows(c, d, np.array([0, 199]))          # offsets disagree with the local row count
+    with pytest.raises(cs.CellScopesCudaError):
+        c.comm_init(c.comm_unique_id(), 0, 1)                   # a context has one communicator
+    c.close()

@@ -184,3 +184,33 @@ def test_golden_vectors(oracle):
     assert np.allclose(np.abs(res["pca"]["embedding"]), np.abs(np.array(g["embedding"])), rtol=1e-7, atol=1e-9)
     assert res["knn_idx"].tolist() == g["knn_idx"]
     assert res["adj"].toarray().tolist() == g["adj"]
+
+
+def test_mann_whitney_matches_scipy(oracle):
+    """f3 oracle: the normal approximation (ties + continuity) equals scipy's asymptotic method; the tie-free exact
+    branch equals scipy's exact method; n <= 10 with ties enumerates the permutations."""
+    import scipy.stats
+    rng = np.random.default_rng(0)
+    for nx, ny in [(30, 40), (20, 45), (60, 200)]:
+        x = np.round(rng.exponential(1, nx), 1) * (rng.random(nx) < 0.6)
+        y = np.round(rng.exponential(1.3, ny), 1) * (rng.random(ny) < 0.7)
+        want = scipy.stats.mannwhitneyu(x, y, alternative="two-sided", method="asymptotic", use_continuity=True).pvalue
+        assert np.isclose(oracle.mann_whitney_pvalue(x, y), want, rtol=1e-12)
+    x, y = rng.random(12), rng.random(14) + 0.3
+    assert np.isclose(oracle.mann_whitney_pvalue(x, y), scipy.stats.mannwhitneyu(x, y, method="exact").pvalue, rtol=1e-12)
+    # 3 vs 3 without ties: U = 0 has probability 1/20 per tail
+    assert np.isclose(oracle.mann_whitney_pvalue([1, 2, 3], [4, 5, 6]), 0.1)
+    assert oracle.mann_whitney_pvalue([0, 0, 1], [0, 1, 1]) <= 1.0
+
+
+def test_find_markers_oracle_columns(oracle):
+    rng = np.random.default_rng(2)
+    dense = rng.poisson(0.8, size=(40, 120)).astype(float)
+    dense[:10, :60] += rng.poisson(3.0, size=(10, 60))              # markers of cluster "a"
+    norm = oracle.normalize_object(sp.csc_matrix(dense))
+    lab = np.array(["a"] * 60 + ["b"] * 60, dtype=object)
+    r = oracle.find_markers(norm, lab, "a", "b")
+    assert set(range(10)) <= set(r["gene"]) and np.all(r["avg_logFC"] > 0) and np.all(np.diff(r["avg_logFC"]) <= 0)
+    assert np.all(r["p_val_adj"] >= r["p_val"]) and np.all(r["pct_1"] > 0.1)
+    allm = oracle.find_all_markers(norm, lab)
+    assert [m["cluster"][0] for m in allm if m["gene"].size][0] == "a"

@@ -18,7 +18,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = cs.Context(local)
-comm = cs.TorchComm(device=torch.device("cuda", local))
+comm = cs.TorchComm(device=torch.device("cuda", local)) if os.environ.get("CSC_BENCH_COMM") == "torch" else cs.NcclComm.from_torch(ctx)
 offsets = cs.partition_cells(N, world)
 lo, hi = int(offsets[rank]), int(offsets[rank + 1])
 p = cs.synth.make_params(G, N, density=0.06, seed=11)
