@@ -89,6 +89,11 @@ SIGNATURES = {
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32, _I32]),
     "csc_graph_free": (_I32, [_P]),
+    "csc_read_mtx": (_I32, [_P, C.c_char_p, _PP]),
+    "csc_sparse_col_sums": (_I32, [_P, _P]),
+    "csc_sparse_select_cols": (_I32, [_P, _P, _P, _I64, _PP]),
+    "csc_sparse_merge": (_I32, [_P, _P, _P, _I32, _I64, _PP]),
+    "csc_tf_idf": (_I32, [_P, _P, _P, _I64, _F64, _PP]),
     "csc_marker_stats": (_I32, [_P, _P, _P, _I32, _F64, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_I64)]),
     "csc_comm_unique_id": (_I32, [_P, _I64]),
     "csc_comm_init": (_I32, [_P, _P, _I64, _I32, _I32]),
@@ -212,6 +217,34 @@ class Context:
 
     def flush_l2(self):
         self.check(self.lib.csc_flush_l2(self.h))
+
+    def read_mtx(self, path):
+        """MatrixMarket coordinate file (plain or .gz) -> device CSC (rows = genes, columns = cells)."""
+        h = C.c_void_p()
+        self.check(self.lib.csc_read_mtx(self.h, os.fsencode(path), C.byref(h)))
+        return Sparse(self, h)
+
+    def select_cols(self, m, cols):
+        """the columns ``cols`` (0-based) of a device matrix as a new device matrix"""
+        c = np.ascontiguousarray(cols, dtype=np.int64)
+        h = C.c_void_p()
+        self.check(self.lib.csc_sparse_select_cols(self.h, m.h, _ptr(c), c.size, C.byref(h)))
+        return Sparse(self, h)
+
+    def sparse_merge(self, mats, row_maps, n_rows_merged):
+        """merge_matrices: ``mats`` side by side; row r of mats[i] becomes row row_maps[i][r] of the result."""
+        n = len(mats)
+        maps = [np.ascontiguousarray(m, dtype=np.int64) for m in row_maps]
+        hp = (C.c_void_p * n)(*[m.h for m in mats])
+        mp = (C.c_void_p * n)(*[m.ctypes.data for m in maps])
+        h = C.c_void_p()
+        self.check(self.lib.csc_sparse_merge(self.h, hp, mp, n, int(n_rows_merged), C.byref(h)))
+        return Sparse(self, h)
+
+    def tf_idf(self, raw, gene_stats, n_cells_total, scale_factor=10000.0):
+        h = C.c_void_p()
+        self.check(self.lib.csc_tf_idf(self.h, raw.h, gene_stats.h, int(n_cells_total), float(scale_factor), C.byref(h)))
+        return Sparse(self, h)
 
     def marker_stats(self, norm, labels, n_groups, expr_cutoff=0.0):
         """csc_marker_stats: the per-(gene, group) tables of the Mann-Whitney tests and of the result columns."""
@@ -520,6 +553,12 @@ class Sparse(_Handle):
     @property
     def nnz(self):
         return self.info()[2]
+
+    def column_sums(self):
+        """colSum (utils.jl:1-2), fp64 on the host"""
+        out = np.zeros(self.shape[1], dtype=np.float64)
+        self.ctx.check(self.ctx.lib.csc_sparse_col_sums(self.h, _ptr(out)))
+        return out
 
     def range_nnz(self, lo, hi):
         z = _I64()

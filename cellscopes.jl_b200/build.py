@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError(f"nvcc failed on {src}")
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-               "-Xlinker", "--exclude-libs,ALL"]
+               "-Xlinker", "--exclude-libs,ALL", "-lz"]      # zlib: gzip'ed MatrixMarket files (csc_read_mtx)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -515,11 +515,11 @@ extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, in
 // k_scale_stats_fx -- the usual one.  64-bit fixed-point accumulators in SHARED memory, each as a (lo, hi) pair of u32
 // words because shared memory adds 32-bit integers natively (a 64-bit or fp64 shared add is a CAS loop): the low word
 // is added with atomicAdd, whose return value tells the adding thread whether ITS add wrapped the word, and only then
-// (or when the addend itself is >= 2^32) the high word is touched -- ~1.1 shared atomics per sum.  Scales: 2^e with
-// e = 32 - ceil(log2(bound on |y|)) for both sums, i.e. y is resolved to 2^-28 (3.7e-9) and y^2 to 2^-28 for the
-// logarithm method with the default scale factor: relative resolution < 4e-7 even for a y of 0.1 squared, against the
-// 1e-5 the path promises, and 10^4 times finer than the 32-bit tables of round 1 (which ADVICE r1 found to round
-// y^2 = 4 to 0 for norm_method "none").  Integer sums are order-independent -> deterministic.  Values outside the
+// (or when the addend itself is >= 2^32) the high word is touched -- two shared atomics per sum at the scales in use.
+// Scales: the largest powers of two that keep a CTA's sums inside 61 bits (see csc_scale_stats_partial): 2^44 for y and
+// 2^42 for y^2 with the logarithm method and the default scale factor, i.e. y^2 is resolved to 2e-13 -- fp64-grade, and
+// 10^8 times finer than the 32-bit tables of round 1 (which ADVICE r1 found to round y^2 = 4 to 0 for norm_method
+// "none").  Integer sums are order-independent -> deterministic.  Values outside the
 // bound, NaN and Inf go straight to the fp64 table in global memory.  A CTA flushes its tables once, as fp64 adds.
 //
 // k_scale_stats -- exact fp64 sums in per-CTA private tables in global memory (atomics of different CTAs never meet
@@ -984,29 +984,35 @@ extern "C" csc_status csc_scale_stats_partial(csc_ctx* ctx, const csc_sparse* no
   CSC_REQUIRE(ctx, partial->dtype == CSC_DT_F64 && partial->n >= 2 * H, "csc_scale_stats_partial: partial must be fp64[2*H], H=%lld",
               (long long)H);
   if (norm->n_cells > 0 && H > 0) {
-    // fixed-point route: a bound on |y| is known, it leaves >= 20 fractional bits, and four u32 tables of H rows fit
+    // fixed-point route: a bound on |y| is known, four u32 tables of H rows fit, and the 64-bit accumulators leave
+    // enough fractional bits: the scales are the largest powers of two for which a CTA's sums stay below 2^61
+    // (|y| 2^e1 cells < 2^61, y^2 2^e2 cells < 2^61), capped at 2^-44 / 2^-52 resolution.  Logarithm method, default
+    // scale factor, 3400 cells per CTA: e1 = 44, e2 = 42 (y^2 resolved to 2e-13); "none" with scale factor 1e4 leaves
+    // e2 = 22 only and takes the fp64 route.
     const double bound = norm->vmax_bound * 1.0001;
-    int e1 = -1;
-    if (std::isfinite(bound) && bound > 0.0) e1 = 32 - (int)std::ceil(std::log2(bound));
+    const bool bounded = std::isfinite(bound) && bound > 0.0;
     const size_t smem = (size_t)4 * H * 4;
     const char* impl = getenv("CSC_SCALE_STATS_IMPL");
     const bool force_exact = impl && strcmp(impl, "fp64") == 0;
-    if (e1 >= 20 && smem <= (size_t)96 * 1024 && !force_exact) {
-      if (e1 > 40) e1 = 40;
+    const bool ident = features == nullptr;
+    auto kern = ident ? k_scale_stats_fx<true> : k_scale_stats_fx<false>;
+    int grid_fx = 1, e1 = -1, e2 = -1;
+    if (bounded && smem <= (size_t)96 * 1024 && !force_exact) {
+      if (smem > 48 * 1024) CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      grid_fx = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(kern, 512, smem, 2),
+                                                           ceil_div64(norm->n_cells, 16)));
+      const int cell_bits = (int)std::ceil(std::log2((double)ceil_div64(norm->n_cells, grid_fx) + 16.0));
+      e1 = std::min(44, 61 - (int)std::ceil(std::log2(bound)) - cell_bits);
+      e2 = std::min(52, 61 - (int)std::ceil(std::log2(bound * bound)) - cell_bits);
+    }
+    if (e1 >= 28 && e2 >= 32) {
       StatsFx fx;
       fx.bound = (float)bound;
       fx.s1 = (float)std::ldexp(1.0, e1);
-      const bool ident = features == nullptr;
-      auto kern = ident ? k_scale_stats_fx<true> : k_scale_stats_fx<false>;
-      if (smem > 48 * 1024) CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * resident_ctas(kern, 512, smem, 2),
-                                                                   ceil_div64(norm->n_cells, 16)));
-      // the y^2 accumulator of a CTA must stay below 2^62: bound^2 * 2^e2 * (cells of the CTA)
-      const double cells_per_cta = (double)ceil_div64(norm->n_cells, grid) + 16.0;
-      const int e2 = std::min(e1, 62 - (int)std::ceil(std::log2(bound * bound)) - (int)std::ceil(std::log2(cells_per_cta)));
       fx.s2 = (float)std::ldexp(1.0, e2);
       fx.inv_s1 = std::ldexp(1.0, -e1);
       fx.inv_s2 = std::ldexp(1.0, -e2);
+      const int grid = grid_fx;
       kern<<<grid, 512, smem, ctx->stream>>>(norm->cp(), norm->rv(), norm->v(), (const int32_t*)map->p, norm->n_cells, (int32_t)H,
                                              fx, partial->as<double>());
       CSC_LAUNCHED(ctx);

@@ -238,6 +238,26 @@ csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowv
                               int32_t index_base);
 csc_status csc_graph_free(csc_graph* g);
 
+/* ---- f4: data formats on the way into the path -----------------------------------------------------------------
+ * csc_read_mtx: the MatrixMarket.mmread of read_10x (src/fileio.jl:7,16): a "coordinate integer|real|pattern general"
+ * file, plain or gzip (matrix.mtx / matrix.mtx.gz), parsed on the host threads and assembled on the device like
+ * sparse(I, J, V) (duplicates summed, explicit zeros kept).  rows = genes, columns = cells.
+ * csc_sparse_merge: merge_matrices (src/integration/int_utils.jl:1-23): the matrices side by side, rows mapped onto
+ * the sorted union of the row names by row_maps[i][r] (0-based row of the merged matrix for row r of matrix i; the
+ * host owns the names); zero values are dropped (`if val != 0`, :11).
+ * csc_tf_idf: run_tf_idf (src/scatac/atac_processing.jl:1-13): log1p(idf_g * (x / colsum_c) * scale_factor) with
+ * idf_g = n_cells_total / rowsum_g on the stored pattern; gene_stats[0:n_genes] = the row sums, already summed over the
+ * ranks (csc_gene_stats_partial fills them). */
+csc_status csc_read_mtx(csc_ctx* ctx, const char* path, csc_sparse** out);
+/* colSum (src/scrna/utils.jl:1-2): host fp64[n_cells]; and the column half of subset_matrix / subset_count
+ * (utils.jl:59-87, 313-327): the columns cols[n_sel] (0-based, any order, repeats allowed) as a new matrix */
+csc_status csc_sparse_col_sums(const csc_sparse* m, double* out);
+csc_status csc_sparse_select_cols(csc_ctx* ctx, const csc_sparse* m, const int64_t* cols, int64_t n_sel, csc_sparse** out);
+csc_status csc_sparse_merge(csc_ctx* ctx, const csc_sparse* const* mats, const int64_t* const* row_maps, int32_t n_mats,
+                            int64_t n_rows_merged, csc_sparse** out);
+csc_status csc_tf_idf(csc_ctx* ctx, const csc_sparse* raw, const csc_vec* gene_stats, int64_t n_cells_total,
+                      double scale_factor, csc_sparse** out);
+
 /* ---- f3: find_markers / find_all_markers src/scrna/processing.jl:350-414 --------------------------------------
  * Sufficient statistics of the per-gene Mann-Whitney U tests (HypothesisTests.MannWhitneyUTest, :376) and of the
  * columns of the result frame (:378-382) for EVERY group of cells at once, from one sort of the stored entries of the

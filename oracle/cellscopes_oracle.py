@@ -597,3 +597,48 @@ def find_all_markers(norm, cluster_of_cell, gene_name=None):
         r["cluster"] = np.full(r["gene"].size, c, dtype=object)
         out.append(r)
     return out
+
+
+# ----------------------------------------------------------------------------
+# f4  ingest: merge_matrices (int_utils.jl:1-23), run_tf_idf (atac_processing.jl:1-13), check_duplicates (utils.jl:31-46)
+# ----------------------------------------------------------------------------
+def merge_matrices(matrices, row_names):
+    """int_utils.jl:1-23: the matrices side by side on the SORTED union of their row names; every non-zero value
+    (`if val != 0`, :11) is pushed as Float64; rows a matrix does not have stay empty in its columns."""
+    all_rows = sorted(set(n for names in row_names for n in names))
+    pos = {n: i for i, n in enumerate(all_rows)}
+    blocks = []
+    for m, names in zip(matrices, row_names):
+        m = sp.coo_matrix(m)
+        keep = m.data != 0
+        rows = np.array([pos[names[r]] for r in m.row[keep]], dtype=np.int64)
+        blocks.append(sp.coo_matrix((m.data[keep].astype(np.float64), (rows, m.col[keep])), shape=(len(all_rows), m.shape[1])))
+    out = sp.hstack(blocks).tocsc()
+    out.sort_indices()
+    return out, all_rows
+
+
+def run_tf_idf(mtx, scale_factor=10000):
+    """atac_processing.jl:1-13: tf = x / colsum (:3-4); idf = n_cells / rowsum (:7-8); log1p(idf * tf * scale_factor)
+    (:11-12), on the stored pattern."""
+    m = sp.csc_matrix(mtx).astype(np.float64)
+    m.sort_indices()
+    npeaks = np.asarray(m.sum(axis=0)).ravel()
+    rsums = np.asarray(m.sum(axis=1)).ravel()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tf = m.data * np.repeat(1.0 / npeaks, np.diff(m.indptr))
+        idf = m.shape[1] / rsums
+        v = np.log1p((idf[m.indices] * tf) * float(scale_factor))
+    return sp.csc_matrix((v, m.indices.copy(), m.indptr.copy()), shape=m.shape)
+
+
+def check_duplicates(arr):
+    """utils.jl:31-46: (names in order of first appearance, {name: position of its SECOND occurrence})."""
+    seen, uniq, removed = set(), [], {}
+    for i, v in enumerate(arr):
+        if v not in seen:
+            seen.add(v)
+            uniq.append(v)
+        elif v not in removed:
+            removed[v] = i
+    return uniq, removed
