@@ -8,7 +8,8 @@ Layout: ``csrc/`` CUDA kernels + the C ABI (include/cellscopes_cuda.h), ``_capi`
 ``processing``/``objects`` the host-side mirror of the reference's operator interface,
 ``pipeline`` the device-resident, cell-sharded orchestration, ``synth`` the synthetic workloads.
 """
-from . import _capi, ingest, objects, pipeline, processing, synth  # noqa: F401
+from . import _capi, ingest, integration, objects, pipeline, processing, synth  # noqa: F401
+from .integration import harmony_matrix, run_harmony  # noqa: F401
 from .ingest import merge_matrices, read_10x, run_tf_idf  # noqa: F401
 from ._capi import CellScopesCudaError, Context, load_library  # noqa: F401
 from .objects import (ClusteringObject, NormCountObject, PCAObject, RawCountObject, ReductionObject,  # noqa: F401

@@ -20,7 +20,7 @@ NORM_LOGARITHM, NORM_NONE = 0, 1
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
 STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
-          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host", "markers"]
+          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host", "markers", "harmony"]
 T_COUNT = len(STAGES)
 
 _NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,
@@ -89,6 +89,9 @@ SIGNATURES = {
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32, _I32]),
     "csc_graph_free": (_I32, [_P]),
+    "csc_harmony": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P, _F64, _I32, _I32, _F64, _F64, _U64, _P, _P,
+                           C.POINTER(_I32), _P, C.POINTER(_I32), _P]),
+    "csc_kmeans": (_I32, [_P, _P, _I64, _I32, _I32, _P, _I32, _F64, _I32, _P, _P, C.POINTER(_F64), C.POINTER(_I32)]),
     "csc_read_mtx": (_I32, [_P, C.c_char_p, _PP]),
     "csc_sparse_col_sums": (_I32, [_P, _P]),
     "csc_sparse_select_cols": (_I32, [_P, _P, _P, _I64, _PP]),
@@ -217,6 +220,40 @@ class Context:
 
     def flush_l2(self):
         self.check(self.lib.csc_flush_l2(self.h))
+
+    def kmeans(self, x, k, init_idx, max_iter=100, tol=1e-4, unit_rows=False):
+        """csc_kmeans: (centres [k x d], labels [n], objective, iterations)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        idx = np.ascontiguousarray(init_idx, dtype=np.int64)
+        cen = np.empty((int(k), x.shape[1]), dtype=np.float64)
+        lab = np.empty(x.shape[0], dtype=np.int32)
+        obj, it = _F64(), _I32()
+        self.check(self.lib.csc_kmeans(self.h, _ptr(x), x.shape[0], x.shape[1], int(k), _ptr(idx), int(max_iter), float(tol),
+                                       1 if unit_rows else 0, _ptr(cen), _ptr(lab), C.byref(obj), C.byref(it)))
+        return cen, lab, obj.value, it.value
+
+    def harmony(self, z, batch, n_batch, y0, theta, lamb, sigma, block_size=0.05, max_iter_harmony=10, max_iter_kmeans=20,
+                eps_kmeans=1e-5, eps_harmony=1e-4, seed=123, want_r=False):
+        """csc_harmony: dict(Z_corr [n x d], objective_harmony, kmeans_rounds, R [n x K] if asked)"""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        n, d = z.shape
+        b = np.ascontiguousarray(batch, dtype=np.int32)
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        k = y0.shape[0]
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lm = np.ascontiguousarray(lamb, dtype=np.float64)
+        sg = np.ascontiguousarray(sigma, dtype=np.float64)
+        out = np.empty_like(z)
+        obj = np.zeros(int(max_iter_harmony) + 2, dtype=np.float64)
+        rounds = np.zeros(int(max_iter_harmony) + 1, dtype=np.int32)
+        n_obj, n_rounds = _I32(obj.size), _I32(rounds.size)
+        r = np.empty((n, k), dtype=np.float64) if want_r else None
+        self.check(self.lib.csc_harmony(self.h, _ptr(z), n, d, _ptr(b), int(n_batch), _ptr(y0), k, _ptr(th), _ptr(lm), _ptr(sg),
+                                        float(block_size), int(max_iter_harmony), int(max_iter_kmeans), float(eps_kmeans),
+                                        float(eps_harmony), int(seed), _ptr(out), _ptr(obj), C.byref(n_obj), _ptr(rounds),
+                                        C.byref(n_rounds), _ptr(r)))
+        return {"Z_corr": out, "objective_harmony": obj[:n_obj.value].copy(), "kmeans_rounds": rounds[:n_rounds.value].copy(),
+                "R": r}
 
     def read_mtx(self, path):
         """MatrixMarket coordinate file (plain or .gz) -> device CSC (rows = genes, columns = cells)."""

@@ -75,6 +75,7 @@ enum {
   CSC_T_GRAM_MMA, /* the tcgen05 Gram kernel alone (inside CSC_T_PCA_GRAM) */
   CSC_T_ALLOC_HOST, /* HOST milliseconds spent inside the device allocator (pool growth shows up here) */
   CSC_T_MARKERS,    /* csc_marker_stats */
+  CSC_T_HARMONY,    /* csc_harmony, csc_kmeans */
   CSC_T_COUNT
 };
 
@@ -237,6 +238,28 @@ csc_status csc_graph_info(const csc_graph* g, int64_t* n_rows, int64_t* n_cols, 
 csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, void* nzval, int32_t val_dtype,
                               int32_t index_base);
 csc_status csc_graph_free(csc_graph* g);
+
+/* ---- f2: run_harmony src/integration/int_processing.jl:1-12 -> HarmonyObject src/integration/int_objects.jl:115-236,
+ *      init_cluster! / cluster! / update_R! / compute_objective! / moe_correct_ridge src/integration/int_utils.jl:49-199
+ * z_orig: host fp64 [n x d], cell-major (the memory of the reference's d x N data_mat); batch[n] in [0, n_batch) = the
+ * level of the batch column in sorted order (get_dummies, int_utils.jl:202-211); y0: host fp64 [K x d], the k-means
+ * centres of the unit-length cells (cluster_kmeans :49-56: csc_kmeans below, or the caller's own); theta[n_batch],
+ * lamb[n_batch] (the ridge diagonal without its leading 0), sigma[K]; the remaining arguments as the keywords of
+ * HarmonyObject (:153-166).  seed drives the update order of update_R! (the stable argsort of a counter-based hash
+ * of (seed, round, cell): Julia's randperm cannot be reproduced).  Outputs: z_corr_out host fp64 [n x d] (Z_corr, what
+ * run_harmony stores as the new cell_embedding, :9-10); objective_harmony[*n_objective] (in: capacity); kmeans_rounds
+ * [*n_rounds] (in: capacity); r_out (optional) host fp64 [n x K], the final soft assignment.  fp64 throughout. */
+csc_status csc_harmony(csc_ctx* ctx, const double* z_orig, int64_t n, int32_t d, const int32_t* batch, int32_t n_batch,
+                       const double* y0, int32_t K, const double* theta, const double* lamb, const double* sigma,
+                       double block_size, int32_t max_iter_harmony, int32_t max_iter_kmeans, double eps_kmeans,
+                       double eps_harmony, uint64_t seed, double* z_corr_out, double* objective_harmony,
+                       int32_t* n_objective, int32_t* kmeans_rounds, int32_t* n_rounds, double* r_out);
+/* Lloyd's k-means in fp64 from the rows init_idx[K] of x (host fp64 [n x d]); unit_rows != 0 applies csc_harmony's
+ * Z_cos transform to the rows first.  Stops when the objective changes by less than tol (Clustering.jl's rule) or after
+ * max_iter assignments.  centers_out host fp64 [K x d]; labels_out (optional) int32[n]. */
+csc_status csc_kmeans(csc_ctx* ctx, const double* x, int64_t n, int32_t d, int32_t K, const int64_t* init_idx,
+                      int32_t max_iter, double tol, int32_t unit_rows, double* centers_out, int32_t* labels_out,
+                      double* objective_out, int32_t* iters_out);
 
 /* ---- f4: data formats on the way into the path -----------------------------------------------------------------
  * csc_read_mtx: the MatrixMarket.mmread of read_10x (src/fileio.jl:7,16): a "coordinate integer|real|pattern general"

@@ -642,3 +642,154 @@ def check_duplicates(arr):
         elif v not in removed:
             removed[v] = i
     return uniq, removed
+
+
+# ----------------------------------------------------------------------------
+# f2  run_harmony (int_processing.jl:1-12; HarmonyObject int_objects.jl:115-236; int_utils.jl:49-199)
+# ----------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def hash_order(seed, rnd, n):
+    """The update order that replaces Julia's randperm (not reproducible): stable argsort of a counter-based hash of
+    (seed, round, cell) -- the same three splitmix64 steps as the library (harmony.cu: k_hm_perm_keys)."""
+    with np.errstate(over="ignore"):
+        h = _splitmix64(np.uint64(seed) ^ np.uint64(0xD1B54A32D192ED03))
+        h = _splitmix64(h ^ np.uint64(rnd))
+        h = _splitmix64(h ^ ((np.arange(n, dtype=np.uint64) * np.uint64(0x2545F4914F6CDD1D)) & _M64))
+    return np.argsort(h, kind="stable")
+
+
+def harmony_zcos(z):
+    """int_objects.jl:201-203: every cell divided by its LARGEST coordinate, then scaled to unit L2 length."""
+    z = np.asarray(z, dtype=np.float64)
+    v = z / z.max(axis=1, keepdims=True)
+    return v / np.sqrt((v * v).sum(axis=1, keepdims=True))
+
+
+def kmeans_lloyd(x, k, init_idx, max_iter=100, tol=1e-4):
+    """cluster_kmeans (int_utils.jl:49-56) restated as Lloyd's iteration from the rows ``init_idx`` (Clustering.jl's
+    k-means++ seeding depends on Julia's RNG): stop when the objective changes by less than ``tol`` or after
+    ``max_iter`` assignments; an empty cluster keeps its centre; ties go to the lower cluster id."""
+    x = np.asarray(x, dtype=np.float64)
+    cen = x[np.asarray(init_idx)].copy()
+    prev = np.inf
+    lab = None
+    for it in range(1, max(1, max_iter) + 1):
+        d2 = ((x[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2) if x.shape[0] * k <= 2_000_000 else \
+            (x * x).sum(1)[:, None] - 2 * x @ cen.T + (cen * cen).sum(1)[None, :]
+        lab = d2.argmin(axis=1)
+        obj = float(d2[np.arange(x.shape[0]), lab].sum())
+        if abs(obj - prev) < tol:
+            break
+        prev = obj
+        for c in range(k):
+            m = lab == c
+            if m.any():
+                cen[c] = x[m].mean(axis=0)
+    return cen, lab, obj, it
+
+
+def run_harmony(z_orig, batch, y0, theta=None, lamb=None, sigma=0.1, block_size=0.05, max_iter_harmony=10,
+                max_iter_kmeans=20, epsilon_cluster=1e-5, epsilon_harmony=1e-4, seed=123):
+    """HarmonyObject(...) + harmonize! on a cells x d matrix (the reference's data_mat is its transpose) and an integer
+    batch label per cell (level index in sorted order).  ``y0`` [K x d]: the k-means centres of harmony_zcos(z_orig).
+    Follows the reference line by line, INCLUDING its departures from harmonypy: optimized_norm is the L1 norm
+    (int_utils.jl:32-41), the convergence window of cluster! lags one iteration (:160-166), Z_cos after a correction is
+    Z_corr with dimension j divided by the L1 norm of the old Z_cos of cell j (:197), the tail of the update order beyond
+    n_blocks * floor(N / n_blocks) is skipped (:141).  Returns dict(Z_corr, R, objective_harmony, kmeans_rounds)."""
+    zo = np.asarray(z_orig, dtype=np.float64).T.copy()           # d x N
+    d, n = zo.shape
+    batch = np.asarray(batch)
+    nb = int(batch.max()) + 1
+    phi = np.zeros((nb, n))
+    phi[batch, np.arange(n)] = 1.0
+    k = y0.shape[0]
+    theta = np.full(nb, 2.0 if theta is None else theta, dtype=np.float64) if np.ndim(theta) == 0 else np.asarray(theta, float)
+    lamb = np.full(nb, 1.0 if lamb is None else lamb, dtype=np.float64) if np.ndim(lamb) == 0 else np.asarray(lamb, float)
+    sigma = np.full(k, sigma, dtype=np.float64) if np.ndim(sigma) == 0 else np.asarray(sigma, float)
+    pr_b = phi.sum(axis=1) / n
+    lamb_mat = np.diag(np.concatenate([[0.0], lamb]))
+    phi_moe = np.vstack([np.ones((1, n)), phi])
+    z_cos = harmony_zcos(zo.T).T
+    z_corr = zo.copy()
+
+    def l1(m, cols):
+        return np.abs(m[:, cols]).sum(axis=0)
+
+    # init_cluster! (:58-71)
+    y = np.asarray(y0, dtype=np.float64).T.copy()                # d x K
+    y = y / l1(y, np.arange(k))[None, :]
+    dist = 2 * (1 - y.T @ z_cos)
+    r = -dist / sigma[:, None]
+    r -= r.max(axis=0, keepdims=True)
+    r = np.exp(r)
+    r /= r.sum(axis=0, keepdims=True)
+    e = np.outer(r.sum(axis=1), pr_b)
+    o = r @ phi.T
+    obj_k, obj_h, rounds = [], [], []
+
+    def objective():
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ent = r * np.log(r)
+        ent = np.where(np.isfinite(ent), ent, 0.0)
+        w = (theta[None, :] * np.log((o + 1) / (e + 1))) @ phi
+        obj_k.append(float((r * dist).sum() + (ent * sigma[:, None]).sum() + ((r * sigma[:, None]) * w).sum()))
+    objective()
+    obj_h.append(obj_k[-1])
+    rnd = 0
+    n_blocks = int(math.ceil(1 / block_size))
+    per = n // n_blocks
+    window = 3
+    for _ in range(max_iter_harmony):
+        j = 0
+        for i in range(1, max_iter_kmeans + 1):
+            y = z_cos @ r.T
+            y = y / l1(y, np.arange(k))[None, :]
+            dist = 2 * (1 - y.T @ z_cos)
+            sd = -dist / sigma[:, None]
+            sd -= sd.max(axis=0, keepdims=True)
+            sd = np.exp(sd)
+            order = hash_order(seed, rnd, n)
+            rnd += 1
+            for b in range(n_blocks):
+                cells = order[per * b:min(per * (b + 1), n)]
+                if cells.size == 0:
+                    continue
+                e -= np.outer(r[:, cells].sum(axis=1), pr_b)
+                o -= r[:, cells] @ phi[:, cells].T
+                rb = sd[:, cells] * (((e + 1) / (o + 1)) ** theta[None, :] @ phi[:, cells])
+                rb = rb / np.abs(rb).sum(axis=0, keepdims=True)
+                r[:, cells] = rb
+                e += np.outer(rb.sum(axis=1), pr_b)
+                o += rb @ phi[:, cells].T
+            objective()
+            if i > window:
+                okl = len(obj_k)
+                o_old = sum(obj_k[okl - 3 - w] for w in range(1, window))
+                o_new = sum(obj_k[okl - 2 - w] for w in range(1, window))
+                if abs(o_old - o_new) / abs(o_old) < epsilon_cluster:
+                    break
+            j = i
+        rounds.append(j)
+        obj_h.append(obj_k[-1])
+        # moe_correct_ridge (:188-199)
+        z_corr = zo.copy()
+        for c in range(k):
+            phi_rk = phi_moe * r[c][None, :]
+            x = phi_rk @ phi_moe.T + lamb_mat
+            w = np.linalg.inv(x) @ phi_rk @ zo.T
+            w[0, :] = 0.0
+            z_corr -= w.T @ phi_rk
+        z_cos = z_corr / l1(z_cos, np.arange(d))[:, None]
+        if (obj_h[-2] - obj_h[-1]) / abs(obj_h[-2]) < epsilon_harmony:
+            break
+    return {"Z_corr": z_corr.T.copy(), "R": r.T.copy(), "objective_harmony": np.array(obj_h), "kmeans_rounds": np.array(rounds)}
