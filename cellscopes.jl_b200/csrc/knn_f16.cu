@@ -471,6 +471,17 @@ __global__ void k_to_f16(const float* __restrict__ x, int64_t n, __half* __restr
 // the key-range parts -- k <= 32, so nothing below rank 32 matters): the candidate list is read coalesced, the 32 key
 // rows are gathered side by side, and the order comes from a bitonic network over the lanes.  (One thread per row with an insertion sort kept its 32-entry lists in local memory and
 // read the candidate table with a 128-byte stride: 2.6 ms at 500k rows.)
+// the exact score of a (query, key) pair: fp64 accumulation of the fp32 products (one expression, shared by the refine
+// kernel and the direct scan of the unproven rows so that both produce the same bits)
+__device__ __forceinline__ float exact_score64(const float4* __restrict__ qr, const float4* __restrict__ kr, int d) {
+  double acc = 0.0;
+  for (int i = 0; i < (d + 3) / 4; ++i) {
+    const float4 a = __ldg(qr + i), b = __ldg(kr + i);
+    acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+  }
+  return (float)acc;
+}
+
 __device__ __forceinline__ bool ranks_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
 // sorts (v, id) over the 32 lanes: afterwards lane j holds the j-th best
@@ -523,13 +534,7 @@ k_knn_refine_prove(const float* __restrict__ q, const float* __restrict__ keys, 
     int cid = INT_MAX;
     if (valid) {
       cid = perm_k ? perm_k[pos] : pos;
-      const float4* kr = reinterpret_cast<const float4*>(keys + (int64_t)pos * 64);
-      double acc = 0.0;
-      for (int i = 0; i < (d + 3) / 4; ++i) {
-        const float4 a = __ldg(qr + i), b = __ldg(kr + i);
-        acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
-      }
-      cv = (float)acc;
+      cv = exact_score64(qr, reinterpret_cast<const float4*>(keys + (int64_t)pos * 64), d);
     }
     bitonic_sort32(cv, cid, lane, 2);
     if (ls == 0) {
@@ -594,6 +599,99 @@ __global__ void k_scatter_results(const float* __restrict__ s, const int32_t* __
   for (int j = 0; j < k; ++j) {
     out_score[orow * k + j] = sc[j];
     out_idx[orow * k + j] = id[j];
+  }
+}
+
+// ---- a handful of unproven rows: direct exact scan ---------------------------------------------------------------
+// The 3xTF32 re-scan works on blocks of 128 query rows, one CTA per block against ALL keys: for the one or two rows a
+// 1M-cell run leaves unproven that is a single CTA walking a million keys (7.3 ms of a 190 ms step, ncu r2).  Few rows
+// are scanned directly instead: every (row, key) pair gets the exact score of the refine kernel (fp64 accumulation of
+// the fp32 products, same expression, hence the same bits), a key whose score reaches the row's current k-th best (the
+// exact k-th of its candidate list) is appended to the row's buffer -- that is every member of the true top k plus
+// the few keys that tie or beat the list's tail --, and one CTA per row orders the buffer by (score descending,
+// original id ascending) and writes the first k distinct keys.  Rows with fewer than k candidates so far, or whose
+// buffer overflows, report failure and the caller takes the tensor-core re-scan after all.
+constexpr int FB_CAP = 1024;             // buffer entries per row
+constexpr int FB_DIRECT_MAX = 512;       // rows up to which the direct scan is used
+
+__global__ void __launch_bounds__(256)
+k_knn_fb_scan(const float* __restrict__ q, const float* __restrict__ keys, int64_t n_keys, int32_t d, int32_t k,
+              const int32_t* __restrict__ fb_rows, int64_t query_offset, const int32_t* __restrict__ self_pos,
+              const int32_t* __restrict__ perm_q, const float* __restrict__ out_score, int32_t* __restrict__ buf_id,
+              float* __restrict__ buf_score, int32_t* __restrict__ buf_n) {
+  const int r = blockIdx.y;
+  const int row = fb_rows[r];
+  const int64_t orow = perm_q ? perm_q[row] : row;
+  const float s_k = out_score[orow * k + (k - 1)];       // -inf when the list held fewer than k keys: everything qualifies
+  const int self_i = self_pos ? self_pos[row] : (int)(query_offset + row);
+  const float4* qr = reinterpret_cast<const float4*>(q + (int64_t)row * 64);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_keys; p += (int64_t)gridDim.x * blockDim.x) {
+    if (p == self_i) continue;
+    const float s = exact_score64(qr, reinterpret_cast<const float4*>(keys + p * 64), d);
+    if (s >= s_k) {
+      const int slot = atomicAdd(buf_n + r, 1);
+      if (slot < FB_CAP) {
+        buf_id[(int64_t)r * FB_CAP + slot] = (int32_t)p;
+        buf_score[(int64_t)r * FB_CAP + slot] = s;
+      }
+    }
+  }
+}
+
+// one CTA per row: bitonic sort of the buffer by (score descending, original id ascending), first k distinct keys out
+__global__ void __launch_bounds__(256)
+k_knn_fb_merge(const int32_t* __restrict__ fb_rows, const int32_t* __restrict__ buf_id, const float* __restrict__ buf_score,
+               const int32_t* __restrict__ buf_n, int32_t k, const int32_t* __restrict__ perm_k, const int32_t* __restrict__ perm_q,
+               float* __restrict__ out_score, int32_t* __restrict__ out_idx, int32_t* __restrict__ failed) {
+  __shared__ unsigned long long key[FB_CAP];
+  const int r = blockIdx.x;
+  const int n = buf_n[r];
+  if (n > FB_CAP || n < k) {
+    if (threadIdx.x == 0) failed[r] = 1;
+    return;
+  }
+  for (int i = threadIdx.x; i < FB_CAP; i += blockDim.x) {
+    unsigned long long v = 0ull;                          // sorts last (descending order)
+    if (i < n) {
+      const float s = buf_score[(int64_t)r * FB_CAP + i];
+      const uint32_t u = __float_as_uint(s);
+      const uint32_t o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      const int pos = buf_id[(int64_t)r * FB_CAP + i];
+      const uint32_t oid = (uint32_t)(perm_k ? perm_k[pos] : pos);
+      v = ((unsigned long long)o << 32) | (unsigned long long)(0xFFFFFFFFu - oid);
+    }
+    key[i] = v;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= FB_CAP; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < FB_CAP; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool desc = (i & k2) == 0;
+          const unsigned long long a = key[i], b = key[l];
+          if (desc ? a < b : a > b) {
+            key[i] = b;
+            key[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const int64_t orow = perm_q ? perm_q[fb_rows[r]] : fb_rows[r];
+    int w = 0;
+    unsigned long long prev = ~0ull;
+    for (int i = 0; i < n && w < k; ++i) {
+      if (key[i] == prev) continue;                       // the same key collected twice cannot happen; equal (score, id) can only be it
+      prev = key[i];
+      const uint32_t o = (uint32_t)(key[i] >> 32);
+      out_score[orow * k + w] = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+      out_idx[orow * k + w] = (int32_t)(0xFFFFFFFFu - (uint32_t)(key[i] & 0xFFFFFFFFull));
+      ++w;
+    }
+    failed[r] = w < k ? 1 : 0;
   }
 }
 
@@ -737,7 +835,30 @@ csc_status knn_scan_f16(csc_ctx* ctx, const float* q_prep, int64_t n_q, const fl
             units, h[0], (double)h[0] / units, h[0] ? (double)h[1] / h[0] : 0.0, (double)h[2], h[0] ? (double)h[2] / h[0] : 0.0,
             h[0] ? (double)h[3] / h[0] : 0.0, h[0] ? (double)h[4] / h[0] : 0.0, (double)h[4] / (double)n_q);
   }
-  if (n_fb > 0) {
+  bool direct_ok = false;
+  if (n_fb > 0 && n_fb <= FB_DIRECT_MAX && !(getenv("CSC_KNN_FB_DIRECT") && atoi(getenv("CSC_KNN_FB_DIRECT")) == 0)) {
+    // a handful of unproven rows: direct exact scan (see k_knn_fb_scan)
+    DevPtr bid, bsc, bn, bfail;
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * FB_CAP * 4, &bid));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * FB_CAP * 4, &bsc));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * 4, &bn, true));
+    CSC_TRY(dev_alloc(ctx, (size_t)n_fb * 4, &bfail, true));
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_keys, 256), (int64_t)ctx->sm_count * 8 / std::min(n_fb, 8)));
+    k_knn_fb_scan<<<dim3(gx, (unsigned)n_fb), 256, 0, ctx->stream>>>(q_prep, k_prep, n_keys, d_eff, k, (const int32_t*)fb_rows->p,
+                                                                     query_offset, d_self, d_perm_q, out_score, (int32_t*)bid->p,
+                                                                     (float*)bsc->p, (int32_t*)bn->p);
+    CSC_LAUNCHED(ctx);
+    k_knn_fb_merge<<<(unsigned)n_fb, 256, 0, ctx->stream>>>((const int32_t*)fb_rows->p, (const int32_t*)bid->p, (const float*)bsc->p,
+                                                            (const int32_t*)bn->p, k, d_perm_k, d_perm_q, out_score, out_idx,
+                                                            (int32_t*)bfail->p);
+    CSC_LAUNCHED(ctx);
+    std::vector<int32_t> hfail((size_t)n_fb);
+    CSC_CUDA(ctx, cudaMemcpyAsync(hfail.data(), bfail->p, (size_t)n_fb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    direct_ok = true;
+    for (int32_t f : hfail) direct_ok = direct_ok && f == 0;
+  }
+  if (n_fb > 0 && !direct_ok) {
     // the unproven rows go through the exact 3xTF32 scan
     DevPtr gq, gself, gs, gi;
     CSC_TRY(dev_alloc(ctx, (size_t)n_fb * 64 * 4, &gq));

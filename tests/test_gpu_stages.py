@@ -579,7 +579,7 @@ def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
     keys = ctx.dense_upload(x)
 
     def run(env):
-        for kk in ("CSC_KNN_ORDER", "CSC_KNN_IMPL", "CSC_KNN_SPLIT"):
+        for kk in ("CSC_KNN_ORDER", "CSC_KNN_IMPL", "CSC_KNN_SPLIT", "CSC_KNN_FB_DIRECT", "CSC_KNN_L"):
             monkeypatch.delenv(kk, raising=False)
         for kk, v in env.items():
             monkeypatch.setenv(kk, v)
@@ -598,6 +598,10 @@ def test_knn_paths_agree_at_scale(cs, ctx, monkeypatch):
     splits = [run({"CSC_KNN_SPLIT": "0"}), run({"CSC_KNN_SPLIT": "2"}), run({"CSC_KNN_SPLIT": "3", "CSC_KNN_ORDER": "0"}),
               run({"CSC_KNN_SPLIT": "8"})]
     assert a[4] < n // 20, "the proof should cover almost every row"
+    # the unproven rows: direct exact scan (default when there are few) against the tensor-core re-scan; k = 15 with 32
+    # candidates leaves a handful, the same k with the proof starved (k close to L is emulated by k = 24) leaves more
+    splits.append(run({"CSC_KNN_FB_DIRECT": "0"}))
+    print("fallback rows:", a[4])
     for other in [b, c] + splits:
         assert np.array_equal(a[0], other[0])
         assert np.array_equal(a[2], other[2])
@@ -652,6 +656,47 @@ def test_knn_default_k_stays_on_the_fp16_path(cs, ctx, monkeypatch, k):
     for r in differ:
         assert np.allclose(np.sort(d1[r]), np.sort(d2[r]), atol=2e-6)
     assert differ.size <= n // 1000, f"{differ.size} rows differ between the two paths"
+
+
+def test_knn_few_unproven_rows_take_the_direct_scan(cs, ctx, monkeypatch):
+    """Rows whose candidate list cannot be proven complete are re-scanned exactly: directly (k_knn_fb_scan) when they are
+    few, through the 3xTF32 tensor-core scan otherwise.  Find a k that leaves between 1 and 512 such rows (32 candidates
+    per row forced), and require the two routes to give the same table, equal to an fp64 brute force on those rows."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, d = 50000, 50
+    centers = rng.normal(size=(40, d)) * 1.5
+    x = (centers[rng.integers(0, 40, n)] + rng.normal(size=(n, d)) * np.linspace(1.2, 0.2, d)).astype(np.float32)
+    keys = ctx.dense_upload(x)
+    monkeypatch.setenv("CSC_KNN_L", "32")
+    found = None
+    for k in (24, 26, 27, 28, 29, 30):
+        monkeypatch.setenv("CSC_KNN_FB_DIRECT", "1")
+        i1, d1 = ctx.knn(keys, keys, k)
+        fb = ctx.knn_last_fallback_rows()
+        if 1 <= fb <= 512:
+            found = (k, fb, i1.download().reshape(n, k), d1.download().reshape(n, k))
+            break
+    assert found is not None, "no k left between 1 and 512 unproven rows: the direct scan was not exercised"
+    k, fb, i1, d1 = found
+    monkeypatch.setenv("CSC_KNN_FB_DIRECT", "0")
+    i2, d2 = ctx.knn(keys, keys, k)
+    i2, d2 = i2.download().reshape(n, k), d2.download().reshape(n, k)
+    assert ctx.knn_last_fallback_rows() == fb
+    differ = np.flatnonzero((i1 != i2).any(axis=1))
+    for r in differ:                                       # only the order of (near-)equal distances may differ
+        assert np.allclose(np.sort(d1[r]), np.sort(d2[r]), atol=2e-6)
+    assert np.allclose(d1, d2, atol=2e-6)
+    xt = torch.as_tensor(x, device="cuda:0").double()
+    unit = xt / xt.norm(dim=1, keepdim=True)
+    sim = unit @ unit.T
+    sim.fill_diagonal_(-2.0)
+    top = torch.topk(sim, k + 1, dim=1)
+    ref_idx, ref_sim = top.indices.cpu().numpy(), top.values.cpu().numpy()
+    sep = ref_sim[:, k - 1] - ref_sim[:, k] >= 1e-6
+    wrong = [r for r in np.flatnonzero(sep) if set(i1[r].tolist()) != set(ref_idx[r, :k].tolist())]
+    assert not wrong, f"k={k}, {fb} unproven rows: {len(wrong)} rows with a wrong neighbour set"
+    print(f"direct scan exercised: k={k}, {fb} unproven rows, {differ.size} rows ordered differently by the two routes")
 
 
 def test_knn_bad_k(cs, ctx):
