@@ -70,7 +70,9 @@ SIGNATURES = {
     "csc_sparse_select_rows": (_I32, [_P, _P, _P, _I64, _PP]),
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
-    "csc_scale_gram_partial": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _P, _P]),
+    "csc_scale_gram_partial": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _P, _P, _PP]),
+    "csc_split_free": (_I32, [_P]),
+    "csc_pca_transform_split": (_I32, [_P, _P, _P, _PP]),
     "csc_dense_alloc": (_I32, [_P, _I64, _I64, _PP]),
     "csc_dense_upload": (_I32, [_P, _P, _I32, _I64, _I64, _PP]),
     "csc_dense_download": (_I32, [_P, _P, _I32, _I64, _I64]),
@@ -435,12 +437,22 @@ class Context:
         return Dense(self, h)
 
     def scale_gram_partial(self, norm, features, partial, n_cells_total, colsum, gram, scale_max=10.0, do_scale=True,
-                           do_center=True):
-        """scale_fill + pca_partial without the dense scaled matrix: colsum += column sums, gram += Z'Z of this shard."""
+                           do_center=True, keep_operands=False):
+        """scale_fill + pca_partial without the dense scaled matrix: colsum += column sums, gram += Z'Z of this shard.
+        ``keep_operands``: returns the fp16 hi/lo split of the scaled matrix (a ``Split``, or None when the fallback ran)
+        for pca_transform_split."""
         f = None if features is None else np.ascontiguousarray(features, dtype=np.int64)
+        h = C.c_void_p()
         self.check(self.lib.csc_scale_gram_partial(self.h, norm.h, _ptr(f), 0 if f is None else f.size, partial.h,
                                                    int(n_cells_total), float(scale_max), 1 if do_scale else 0,
-                                                   1 if do_center else 0, colsum.h, gram.h))
+                                                   1 if do_center else 0, colsum.h, gram.h,
+                                                   C.byref(h) if keep_operands else None))
+        return Split(self, h) if (keep_operands and h.value) else None
+
+    def pca_transform_split(self, split, pca):
+        h = C.c_void_p()
+        self.check(self.lib.csc_pca_transform_split(self.h, split.h, pca.h, C.byref(h)))
+        return Dense(self, h)
 
     def dense_upload(self, arr):
         arr = np.ascontiguousarray(arr)
@@ -653,6 +665,10 @@ class Dense(_Handle):
     def __cuda_array_interface__(self):
         r, c, p = self.info()
         return {"shape": (r, c), "typestr": "<f4", "data": (p or 0, False), "version": 3, "strides": None}
+
+
+class Split(_Handle):
+    _free = "csc_split_free"
 
 
 class Pca(_Handle):

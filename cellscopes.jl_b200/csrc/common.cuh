@@ -152,6 +152,15 @@ struct csc_pca {
   int32_t kpad;
 };
 
+// split-precision operands of the scaled matrix (written by csc_scale_gram_partial): hi = fp16(Z), lo = fp16(Z - hi),
+// both [n_rows][pitch] with column n_feat = 1 and zeros up to the pitch
+struct csc_split {
+  csc_ctx* ctx;
+  int64_t n_rows, n_feat;
+  int32_t pitch;
+  DevPtr hi, lo;
+};
+
 struct csc_graph {
   csc_ctx* ctx;
   int64_t n_rows, n_cols, nnz;

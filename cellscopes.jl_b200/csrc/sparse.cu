@@ -1100,9 +1100,10 @@ csc_status gram_tc_split(csc_ctx* ctx, const __half* hi16, const __half* lo16, i
 // a multiple of 4 or exceeds what one CTA's column table holds.
 extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                                              const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
-                                             int32_t do_center, csc_vec* colsum, csc_vec* gram) {
+                                             int32_t do_center, csc_vec* colsum, csc_vec* gram, csc_split** operands) {
   if (!ctx || !norm || !partial || !colsum || !gram) return CSC_ERR_ARG;
   CSC_GUARD_BEGIN
+  if (operands) *operands = nullptr;
   CSC_CUDA(ctx, cudaSetDevice(ctx->device));
   DevPtr map;
   int64_t H = 0;
@@ -1162,8 +1163,20 @@ extern "C" csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* nor
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   StageTimer st2(ctx, CSC_T_PCA_GRAM);
-  return gram_tc_split(ctx, (const __half*)hi16->p, (const __half*)lo16->p, norm->n_cells, (int)H, pitch, gram->as<double>(),
-                       colsum->as<double>());
+  CSC_TRY(gram_tc_split(ctx, (const __half*)hi16->p, (const __half*)lo16->p, norm->n_cells, (int)H, pitch, gram->as<double>(),
+                        colsum->as<double>()));
+  if (operands) {
+    // the caller keeps the split operands: csc_pca_transform_split takes the embedding from them as a tensor-core GEMM
+    std::unique_ptr<csc_split> sp(new csc_split());
+    sp->ctx = ctx;
+    sp->n_rows = norm->n_cells;
+    sp->n_feat = H;
+    sp->pitch = pitch;
+    sp->hi = hi16;
+    sp->lo = lo16;
+    *operands = sp.release();
+  }
+  return CSC_OK;
   CSC_GUARD_END(ctx)
 }
 

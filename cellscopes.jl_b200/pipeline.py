@@ -216,6 +216,7 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     comm.allreduce_sum(part)
     colsum = be.vec(H, np.float64)
     gram = be.vec(H * H, np.float64)
+    split = None
     if p.keep_scaled or not hasattr(be, "scale_gram_partial"):
         scaled = be.scale_fill(src, src_feats, part, n_cells_total, p.scale_max, p.do_scale, p.do_center)
         # a4
@@ -223,12 +224,17 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     else:
         # a3 + a4 fused: nothing after the Gram reads the dense scaled matrix (the embedding comes from the sparse one)
         scaled = None
-        be.scale_gram_partial(src, src_feats, part, n_cells_total, colsum, gram, p.scale_max, p.do_scale, p.do_center)
+        split = be.scale_gram_partial(src, src_feats, part, n_cells_total, colsum, gram, p.scale_max, p.do_scale, p.do_center,
+                                      keep_operands=p.n_pcs <= 64 and hasattr(be, "pca_transform_split"))
     comm.allreduce_sum(colsum)
     comm.allreduce_sum(gram)
     pca = be.pca_solve(colsum, gram, H, n_cells_total, p.n_pcs, p.pca_tol, p.pca_max_iter)
     # the embedding comes straight from the sparse normalised matrix (Z = S + 1 z0' is sparse-plus-rank-one)
-    if hasattr(be, "pca_transform_sparse"):
+    if split is not None:
+        # the fp16 hi/lo operands the Gram kernel consumed are still in HBM: the embedding is one tensor-core GEMM over them
+        emb = be.pca_transform_split(split, pca)
+        split.free()
+    elif hasattr(be, "pca_transform_sparse"):
         emb = be.pca_transform_sparse(src, src_feats, part, n_cells_total, pca, p.scale_max, p.do_scale, p.do_center)
     else:
         emb = be.pca_transform(scaled, pca)

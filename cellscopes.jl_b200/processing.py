@@ -229,14 +229,19 @@ def _pca_device(c, scaled, n_cells_total, maxoutdim, tol=1e-9, max_iter=500):
         h = int(scaled.rows.size)
         colsum = c.vec(h, np.float64)
         gram = c.vec(h * h, np.float64)
+        split = None
         if scaled._dense is not None:
             c.pca_partial(scaled._dense, colsum, gram)
         else:
-            c.scale_gram_partial(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, colsum, gram,
-                                 scaled.scale_max, scaled.do_scale, scaled.do_center)
+            split = c.scale_gram_partial(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, colsum, gram,
+                                         scaled.scale_max, scaled.do_scale, scaled.do_center, keep_operands=maxoutdim <= 64)
         model = c.pca_solve(colsum, gram, h, n_cells_total, maxoutdim, tol, max_iter)
-        emb = c.pca_transform_sparse(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, model, scaled.scale_max,
-                                     scaled.do_scale, scaled.do_center)
+        if split is not None:
+            emb = c.pca_transform_split(split, model)
+            split.free()
+        else:
+            emb = c.pca_transform_sparse(scaled.src, scaled.feats, scaled.part, scaled.n_cells_total, model, scaled.scale_max,
+                                         scaled.do_scale, scaled.do_center)
         return model, emb
     h = scaled.shape[1]
     colsum = c.vec(h, np.float64)

@@ -58,6 +58,7 @@ typedef struct csc_dense csc_dense;   /* device dense fp32, cell-major: rows = c
 typedef struct csc_vec csc_vec;       /* device buffer of fp64/fp32/int32 (partials, tables) */
 typedef struct csc_pca csc_pca;       /* PCA model: loadings, variances */
 typedef struct csc_graph csc_graph;   /* device CSC graph: cells x local cells */
+typedef struct csc_split csc_split;   /* fp16 hi/lo operands of the scaled matrix (Gram / transform GEMMs) */
 
 enum { CSC_DT_F32 = 0, CSC_DT_F64 = 1, CSC_DT_I32 = 2, CSC_DT_I64 = 3 };
 enum { CSC_NORM_LOGARITHM = 0, CSC_NORM_NONE = 1 };       /* processing.jl:23-29 */
@@ -183,7 +184,10 @@ csc_status csc_scale_fill(csc_ctx* ctx, const csc_sparse* norm, const int64_t* f
  * only, ready for the all-reduce) without materialising the dense matrix.  Same arguments as csc_scale_fill. */
 csc_status csc_scale_gram_partial(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                                   const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
-                                  int32_t do_center, csc_vec* colsum, csc_vec* gram);
+                                  int32_t do_center, csc_vec* colsum, csc_vec* gram, csc_split** operands);
+/* operands (optional): the fp16 hi/lo split of this shard's scaled matrix that the Gram kernel consumed, kept for
+ * csc_pca_transform_split (4 H bytes per cell of device memory until csc_split_free). */
+csc_status csc_split_free(csc_split* s);
 
 
 /* ---- dense cell-major matrices: scaleCount.count_mtx', pca.cell_embedding ---------------- */
@@ -215,6 +219,9 @@ csc_status csc_pca_transform(csc_ctx* ctx, const csc_dense* scaled, const csc_pc
 csc_status csc_pca_transform_sparse(csc_ctx* ctx, const csc_sparse* norm, const int64_t* features, int64_t n_feat,
                                     const csc_vec* partial, int64_t n_cells_total, double scale_max, int32_t do_scale,
                                     int32_t do_center, const csc_pca* p, csc_dense** out);
+/* the same embedding as a tensor-core GEMM over the split operands kept by csc_scale_gram_partial: E = Z U - 1 (m'U),
+ * three tcgen05 kind::f16 passes (hi Uhi', hi Ulo', lo Uhi'), HBM-bound (4 H bytes per cell read once); k <= 64 */
+csc_status csc_pca_transform_split(csc_ctx* ctx, const csc_split* operands, const csc_pca* p, csc_dense** out);
 csc_status csc_pca_free(csc_pca* p);
 
 /* ---- a5/a6: kNN inside run_clustering src/scrna/processing.jl:195-201, 263-266 ----------- */

@@ -307,9 +307,9 @@ without a dense scaled matrix in device memory.  `features0` are 0-based gene id
 function scale_gram_partial!(ctx, norm, features0::Vector{Int64}, part, n_cells::Integer, colsum, gram;
                              scale_max::Real=10.0, do_scale::Bool=true, do_center::Bool=true)
     GC.@preserve features0 check(ctx, ccall(sym(:csc_scale_gram_partial), Int32,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}, Int64, Float64, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}),
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cvoid}, Int64, Float64, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
         ctx.h, norm.h, pointer(features0), length(features0), part.h, n_cells, Float64(scale_max), Int32(do_scale),
-        Int32(do_center), colsum.h, gram.h))
+        Int32(do_center), colsum.h, gram.h, C_NULL))          # C_NULL: the fp16 operands are not kept (csc_pca_transform_split)
     return nothing
 end
 

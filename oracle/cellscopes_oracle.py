@@ -793,3 +793,150 @@ def run_harmony(z_orig, batch, y0, theta=None, lamb=None, sigma=0.1, block_size=
         if (obj_h[-2] - obj_h[-1]) / abs(obj_h[-2]) < epsilon_harmony:
             break
     return {"Z_corr": z_corr.T.copy(), "R": r.T.copy(), "objective_harmony": np.array(obj_h), "kmeans_rounds": np.array(rounds)}
+
+
+# ----------------------------------------------------------------------------
+# f1  Leiden (processing.jl:233-234, 279-280: Leiden.leiden(adj_mat, resolution = res)) -- Traag, Waltman & van Eck 2019,
+#     Constant Potts Model quality (what Leiden.jl optimises):  H = sum_c [ e_c - gamma * n_c (n_c - 1) / 2 ]
+#     with e_c the total weight of the edges inside c and n_c its number of cells.
+# ----------------------------------------------------------------------------
+def cpm_quality(adj, labels, gamma):
+    """CPM quality of a partition of a symmetric weighted graph (every undirected edge stored twice)."""
+    a = sp.coo_matrix(adj)
+    labels = np.asarray(labels)
+    inside = labels[a.row] == labels[a.col]
+    off = a.row != a.col
+    e_in = a.data[inside & off].sum() / 2.0 + a.data[inside & ~off].sum()
+    _, n_c = np.unique(labels, return_counts=True)
+    return float(e_in - gamma * (n_c * (n_c - 1) / 2.0).sum())
+
+
+def communities_connected(adj, labels):
+    """True when every community induces a connected subgraph (the guarantee Leiden adds to Louvain)."""
+    import scipy.sparse.csgraph as csg
+    a = sp.csr_matrix(adj)
+    labels = np.asarray(labels)
+    coo = a.tocoo()
+    keep = labels[coo.row] == labels[coo.col]
+    sub = sp.csr_matrix((np.ones(keep.sum()), (coo.row[keep], coo.col[keep])), shape=a.shape)
+    n_comp, comp = csg.connected_components(sub, directed=False)
+    return n_comp == np.unique(labels).size
+
+
+def leiden_cpm(adj, gamma, seed=1234, theta=0.01, max_levels=50):
+    """Sequential Leiden with the CPM quality function: fast local moving (queue), refinement (random merges of
+    well-connected singletons, temperature ``theta``), aggregation on the refined partition with the non-refined one as
+    the initial assignment; repeated until nothing moves.  Returns (labels per node, quality)."""
+    rng = np.random.default_rng(seed)
+    a = sp.csr_matrix(adj).astype(np.float64)
+    a.setdiag(0)
+    a.eliminate_zeros()
+    n0 = a.shape[0]
+    node_of = np.arange(n0)                      # original node -> current aggregate node
+    size = np.ones(n0)
+    part = np.arange(n0)                          # aggregate node -> community
+    g = a
+    for _ in range(max_levels):
+        n = g.shape[0]
+        indptr, indices, data = g.indptr, g.indices, g.data
+        csize = np.bincount(part, weights=size, minlength=n).astype(np.float64)
+        # ---- fast local moving ----
+        queue = list(rng.permutation(n))
+        inq = np.ones(n, dtype=bool)
+        moved_any = False
+        while queue:
+            v = queue.pop(0)
+            inq[v] = False
+            nb, w = indices[indptr[v]:indptr[v + 1]], data[indptr[v]:indptr[v + 1]]
+            own = part[v]
+            kvc = {}
+            for u, ww in zip(nb, w):
+                if u != v:
+                    kvc[part[u]] = kvc.get(part[u], 0.0) + ww
+            csize[own] -= size[v]
+            best, best_gain = own, kvc.get(own, 0.0) - gamma * size[v] * csize[own]
+            for c, k in kvc.items():
+                gain = k - gamma * size[v] * csize[c]
+                if gain > best_gain + 1e-12:
+                    best, best_gain = c, gain
+            if 0.0 > best_gain + 1e-12:              # an empty community
+                empty = np.flatnonzero(csize == 0)
+                if empty.size:
+                    best, best_gain = int(empty[0]), 0.0
+            csize[best] += size[v]
+            if best != own:
+                part[v] = best
+                moved_any = True
+                for u in nb:
+                    if part[u] != best and not inq[u]:
+                        queue.append(u)
+                        inq[u] = True
+        # ---- refinement ----
+        ref = np.arange(n)
+        rsize = size.copy()
+        for c in np.unique(part):
+            members = np.flatnonzero(part == c)
+            if members.size == 1:
+                continue
+            nc = size[members].sum()
+            in_c = np.zeros(n, dtype=bool)
+            in_c[members] = True
+            # weight from v to the rest of its community
+            kin = np.array([data[indptr[v]:indptr[v + 1]][in_c[indices[indptr[v]:indptr[v + 1]]] & (indices[indptr[v]:indptr[v + 1]] != v)].sum() for v in members])
+            well = kin >= gamma * size[members] * (nc - size[members])
+            ext = {}                                  # refined community -> weight to the rest of c
+            for v, k in zip(members, kin):
+                ext[v] = k
+            singleton = {v: True for v in members}
+            for v in rng.permutation(members[well]):
+                if not singleton[v]:
+                    continue
+                nb, w = indices[indptr[v]:indptr[v + 1]], data[indptr[v]:indptr[v + 1]]
+                kvr = {}
+                for u, ww in zip(nb, w):
+                    if u != v and in_c[u]:
+                        kvr[ref[u]] = kvr.get(ref[u], 0.0) + ww
+                cands, gains = [], []
+                for r, k in kvr.items():
+                    if r == ref[v]:
+                        continue
+                    if ext[r] >= gamma * rsize[r] * (nc - rsize[r]):        # the target is well connected within c
+                        gain = k - gamma * size[v] * rsize[r]
+                        if gain >= 0:
+                            cands.append(r)
+                            gains.append(gain)
+                if not cands:
+                    continue
+                p = np.exp((np.array(gains) - max(gains)) / theta)
+                r = cands[int(rng.choice(len(cands), p=p / p.sum()))]
+                # merge v into r
+                k_vr = kvr[r]
+                ext[r] = ext[r] + ext[v] - 2 * k_vr
+                rsize[r] += size[v]
+                singleton[r] = False if r in singleton else False
+                for u in members:
+                    pass
+                ref[v] = r
+                singleton[v] = False
+                # the members of r are no longer singletons
+                for u in np.flatnonzero(ref == r):
+                    singleton[u] = False
+        # ---- aggregate on the refined partition ----
+        uniq, new_id = np.unique(ref, return_inverse=True)
+        if uniq.size == n and not moved_any:
+            break
+        m = uniq.size
+        coo = g.tocoo()
+        ng = sp.coo_matrix((coo.data, (new_id[coo.row], new_id[coo.col])), shape=(m, m)).tocsr()
+        ng.sum_duplicates()
+        new_size = np.bincount(new_id, weights=size, minlength=m)
+        new_part = np.zeros(m, dtype=np.int64)
+        new_part[new_id] = part
+        _, new_part = np.unique(new_part, return_inverse=True)
+        node_of = new_id[node_of]
+        g, size, part = ng, new_size, new_part
+        if uniq.size == n:
+            break
+    labels = part[node_of]
+    _, labels = np.unique(labels, return_inverse=True)
+    return labels, cpm_quality(adj, labels, gamma)
