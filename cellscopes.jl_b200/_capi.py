@@ -20,7 +20,7 @@ NORM_LOGARITHM, NORM_NONE = 0, 1
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 GRAPH_BINARY, GRAPH_SUM, GRAPH_SNN_JACCARD = 0, 1, 2
 STAGES = ["upload", "normalize", "gene_stats", "hvg", "scale_stats", "scale_fill", "pca_gram", "pca_solve",
-          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host", "markers", "harmony"]
+          "pca_transform", "knn", "graph", "generate", "knn_scan", "gram_mma", "alloc_host", "markers", "harmony", "leiden"]
 T_COUNT = len(STAGES)
 
 _NP_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float64): DT_F64,
@@ -91,6 +91,7 @@ SIGNATURES = {
     "csc_graph_info": (_I32, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "csc_graph_download": (_I32, [_P, _P, _P, _P, _I32, _I32]),
     "csc_graph_free": (_I32, [_P]),
+    "csc_leiden": (_I32, [_P, _P, _F64, _I32, _I32, _P, C.POINTER(_I32), C.POINTER(_F64), C.POINTER(_I32)]),
     "csc_harmony": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P, _F64, _I32, _I32, _F64, _F64, _U64, _P, _P,
                            C.POINTER(_I32), _P, C.POINTER(_I32), _P]),
     "csc_kmeans": (_I32, [_P, _P, _I64, _I32, _I32, _P, _I32, _F64, _I32, _P, _P, C.POINTER(_F64), C.POINTER(_I32)]),
@@ -222,6 +223,15 @@ class Context:
 
     def flush_l2(self):
         self.check(self.lib.csc_flush_l2(self.h))
+
+    def leiden(self, graph, resolution=0.06, max_levels=0, max_sweeps=0):
+        """csc_leiden: dict(labels int32[n], n_communities, quality, levels)"""
+        n = graph.info()[0]
+        lab = np.empty(n, dtype=np.int32)
+        nc, lv, q = _I32(), _I32(), _F64()
+        self.check(self.lib.csc_leiden(self.h, graph.h, float(resolution), int(max_levels), int(max_sweeps), _ptr(lab), C.byref(nc),
+                                       C.byref(q), C.byref(lv)))
+        return {"labels": lab, "n_communities": nc.value, "quality": q.value, "levels": lv.value}
 
     def kmeans(self, x, k, init_idx, max_iter=100, tol=1e-4, unit_rows=False):
         """csc_kmeans: (centres [k x d], labels [n], objective, iterations)"""

@@ -293,13 +293,14 @@ def run_pca(sc_obj, method="svd", pratio=1, maxoutdim=10, package="MLJ", ctx=Non
 # run_clustering  (processing.jl:195-318): kNN + adjacency.  Leiden (:233-234, :279-280) is out of scope.
 # ---------------------------------------------------------------------------------------------
 def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1234, graph=None, snn_prune=0.0,
-                   partition_fn=None, ctx=None):
+                   partition_fn=None, leiden=True, ctx=None):
     """Builds the graph the reference hands to Leiden.
 
     n < 10000 cells -> the "small" binary union adjacency (:268-278); otherwise the "atlas" COO-summed
     adjacency where mutual pairs carry 2 (:218-232).  ``graph="snn"`` gives the Jaccard-weighted SNN graph.
-    The kNN is exact (the reference's NN-descent is approximate and unseeded).  ``partition_fn(adj, res,
-    seed)`` may supply a community-detection step; without it ``clustData.clustering`` stays None.
+    The kNN is exact (the reference's NN-descent is approximate and unseeded).  The communities come from the device
+    Leiden (csc_leiden: CPM quality with resolution ``res``, like Leiden.jl; deterministic, ``seed_use`` is not needed);
+    ``leiden=False`` stops after the graph, ``partition_fn(adj, res, seed)`` substitutes another community detection.
     """
     if sc_obj.dimReduction is None or sc_obj.dimReduction.pca is None:
         raise ValueError("run_clustering: run_pca first")
@@ -318,7 +319,19 @@ def run_clustering(sc_obj, n_neighbors=30, metric="cosine", res=0.06, seed_use=1
     s.knn = (idx, dist)
     clustering = None
     result = None
-    if partition_fn is not None:
+    if partition_fn is None and leiden:
+        # Leiden.leiden(adj_mat, resolution = res) (processing.jl:233-234, 279-280) on the device graph
+        ld = s.ctx.leiden(gdev, res)
+        order = np.argsort(-np.bincount(ld["labels"], minlength=ld["n_communities"]), kind="stable")   # largest first
+        members = [np.flatnonzero(ld["labels"] == c) for c in order]
+        result = {"partition": members, "quality": ld["quality"], "levels": ld["levels"]}
+        labels = np.empty(n, dtype=object)
+        for i, mem in enumerate(members):
+            labels[mem] = str(i + 1)
+        clustering = pd.DataFrame({"cluster": labels, "cell_id": sc_obj.rawCount.cell_name})   # ordered like colnames(obj), :241
+        if sc_obj.metaData is not None:
+            sc_obj.metaData["cluster"] = labels
+    elif partition_fn is not None:
         result = partition_fn(adj, res, seed_use)
         labels = np.empty(n, dtype=object)
         for i, members in enumerate(result["partition"]):

@@ -77,6 +77,7 @@ enum {
   CSC_T_ALLOC_HOST, /* HOST milliseconds spent inside the device allocator (pool growth shows up here) */
   CSC_T_MARKERS,    /* csc_marker_stats */
   CSC_T_HARMONY,    /* csc_harmony, csc_kmeans */
+  CSC_T_LEIDEN,     /* csc_leiden */
   CSC_T_COUNT
 };
 
@@ -245,6 +246,15 @@ csc_status csc_graph_info(const csc_graph* g, int64_t* n_rows, int64_t* n_cols, 
 csc_status csc_graph_download(const csc_graph* g, int64_t* colptr, int64_t* rowval, void* nzval, int32_t val_dtype,
                               int32_t index_base);
 csc_status csc_graph_free(csc_graph* g);
+
+/* ---- f1: community detection on the graph src/scrna/processing.jl:233-234, 279-280 (Leiden.leiden(adj_mat, resolution)) --
+ * Leiden scheme (local moving, refinement inside the communities, aggregation on the refined partition) for the
+ * Constant Potts Model quality H = sum_c [e_c - resolution * n_c (n_c - 1) / 2] on a graph built by csc_graph_build
+ * with all columns on this device (cell_lo = 0, cell_hi = n).  Parallel and deterministic (the reference's is
+ * sequential and seeded from Julia's RNG: partitions are comparable by quality, not label by label).
+ * labels_out: host int32[n], communities numbered 0.. in order of first appearance; quality = H of the result. */
+csc_status csc_leiden(csc_ctx* ctx, const csc_graph* g, double resolution, int32_t max_levels, int32_t max_sweeps,
+                      int32_t* labels_out, int32_t* n_communities, double* quality, int32_t* levels_out);
 
 /* ---- f2: run_harmony src/integration/int_processing.jl:1-12 -> HarmonyObject src/integration/int_objects.jl:115-236,
  *      init_cluster! / cluster! / update_R! / compute_objective! / moe_correct_ridge src/integration/int_utils.jl:49-199
