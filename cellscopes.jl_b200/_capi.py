@@ -67,6 +67,7 @@ SIGNATURES = {
     "csc_normalize": (_I32, [_P, _P, _F64, _I32, _F64, _I32, _P, _PP]),
     "csc_gene_stats_partial": (_I32, [_P, _P, _P]),
     "csc_hvg_finish": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
+    "csc_hvg_finish_collective": (_I32, [_P, _P, _I64, _I64, _I64, _F64, _P, _P, _P, _P, _P]),
     "csc_sparse_select_rows": (_I32, [_P, _P, _P, _I64, _PP]),
     "csc_scale_stats_partial": (_I32, [_P, _P, _P, _I64, _P]),
     "csc_scale_fill": (_I32, [_P, _P, _P, _I64, _P, _I64, _F64, _I32, _I32, _PP]),
@@ -415,12 +416,14 @@ class Context:
     def gene_stats_partial(self, raw, gene_stats):
         self.check(self.lib.csc_gene_stats_partial(self.h, raw.h, gene_stats.h))
 
-    def hvg_finish(self, gene_stats, n_genes, n_cells_total, n_features=2000, span=0.3):
+    def hvg_finish(self, gene_stats, n_genes, n_cells_total, n_features=2000, span=0.3, collective=False):
+        """``collective``: every rank of the context's communicator makes this call (csc_hvg_finish_collective)."""
         g = int(n_genes)
         out = {k: np.empty(g, dtype=np.float64) for k in
                ("mean", "variance", "variance_expected", "variance_standardized")}
         order = np.empty(g, dtype=np.int64)
-        self.check(self.lib.csc_hvg_finish(self.h, gene_stats.h, g, int(n_cells_total), int(n_features), float(span),
+        fn = self.lib.csc_hvg_finish_collective if collective else self.lib.csc_hvg_finish
+        self.check(fn(self.h, gene_stats.h, g, int(n_cells_total), int(n_features), float(span),
                                            _ptr(out["mean"]), _ptr(out["variance"]), _ptr(out["variance_expected"]),
                                            _ptr(out["variance_standardized"]), _ptr(order)))
         out["order"] = order

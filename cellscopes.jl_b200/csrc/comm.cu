@@ -134,6 +134,18 @@ csc_status check_offsets(csc_ctx* ctx, const int64_t* offsets, int64_t local_row
 
 }  // namespace
 
+// host fp64 vector summed over the ranks (small tables: the Loess vertex fits dealt out by csc_hvg_finish)
+csc_status comm_allreduce_f64(csc_ctx* ctx, double* host_inout, size_t n) {
+  if (!ctx->comm || ctx->comm_world <= 1 || n == 0) return CSC_OK;
+  DevPtr d;
+  CSC_TRY(dev_alloc(ctx, n * 8, &d));
+  CSC_CUDA(ctx, cudaMemcpyAsync(d->p, host_inout, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CSC_NCCL(ctx, nccl_api()->AllReduce(d->p, d->p, n, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  CSC_CUDA(ctx, cudaMemcpyAsync(host_inout, d->p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CSC_OK;
+}
+
 void comm_release(csc_ctx* ctx) {
   if (ctx->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;

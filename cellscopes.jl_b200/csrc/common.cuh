@@ -258,4 +258,4 @@ __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 // stage launchers implemented in the other translation units ------------------------------------
 csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, int64_t n_cells_total,
                            int64_t n_features, double span, double* mean, double* variance, double* var_exp,
-                           double* var_std, int64_t* order);
+                           double* var_std, int64_t* order, bool collective = false);

@@ -162,8 +162,14 @@ void kd_vertices(const std::vector<double>& xs_sorted, int64_t cutoff, std::vect
 }  // namespace
 
 // x, y: the points (genes with variance > 0).  out[i] = loess prediction at x[i].
-static void loess_fit_predict(const std::vector<double>& x, const std::vector<double>& y, double span,
-                              std::vector<double>& out) {
+// With a communicator on the context (one process per GPU) the vertex fits -- the expensive part, ~15 ms of one host
+// thread for 33 k genes -- are dealt out over the ranks (vertex i to rank i mod world) and their (value, slope) pairs are
+// all-reduced: every rank adds zeros for the vertices it did not fit, so all ranks end with bit-identical tables, and
+// eight ranks no longer run eight copies of the same 8-thread job on the same host cores.
+csc_status comm_allreduce_f64(csc_ctx* ctx, double* host_inout, size_t n);   // comm.cu
+
+static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::vector<double>& x, const std::vector<double>& y,
+                                    double span, std::vector<double>& out) {
   const int64_t n = (int64_t)x.size();
   const double cell = 0.2;
   const int64_t q = std::max<int64_t>(1, (int64_t)std::floor(span * (double)n));
@@ -235,15 +241,22 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
       slope[vi] = coef[1];
     }
   };
-  const size_t n_thr = (n >= 2000 && nv >= 8) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  const size_t world = (collective && ctx && ctx->comm && ctx->comm_world > 1 && nv >= 8) ? (size_t)ctx->comm_world : 1;
+  const size_t rank = world > 1 ? (size_t)ctx->comm_rank : 0;
+  if (world > 1) {
+    std::fill(val.begin(), val.end(), 0.0);
+    std::fill(slope.begin(), slope.end(), 0.0);
+  }
+  const size_t my_nv = (nv + world - 1 - rank) / world;                 // vertices rank, rank + world, ...
+  const size_t n_thr = (n >= 2000 && my_nv >= 2) ? std::min<size_t>(std::min<size_t>(8, my_nv), std::max(1u, std::thread::hardware_concurrency())) : 1;
   if (n_thr <= 1) {
-    fit_range(0, 1);
+    fit_range(rank, world);
   } else {
     // no exception may leave a thread (it would terminate the process): record it and rethrow after the join
     std::vector<int> failed(n_thr, 0);
     auto guarded = [&](size_t tix) {
       try {
-        fit_range(tix, n_thr);
+        fit_range(rank + world * tix, world * n_thr);
       } catch (...) {
         failed[tix] = 1;
       }
@@ -260,6 +273,14 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
     for (size_t tix = started; tix < n_thr; ++tix) guarded(tix);
     for (size_t tix = 0; tix < n_thr; ++tix)
       if (failed[tix]) throw std::bad_alloc();
+  }
+  if (world > 1) {
+    std::vector<double> both(2 * nv);
+    std::copy(val.begin(), val.end(), both.begin());
+    std::copy(slope.begin(), slope.end(), both.begin() + nv);
+    CSC_TRY(comm_allreduce_f64(ctx, both.data(), both.size()));
+    std::copy(both.begin(), both.begin() + nv, val.begin());
+    std::copy(both.begin() + nv, both.end(), slope.begin());
   }
   out.resize((size_t)n);
   parallel_for(n, [&](int64_t i_lo, int64_t i_hi) {
@@ -292,11 +313,12 @@ static void loess_fit_predict(const std::vector<double>& x, const std::vector<do
     out[i] = h00 * val[lo] + h10 * h * slope[lo] + h01 * val[hi] + h11 * h * slope[hi];
   }
   });
+  return CSC_OK;
 }
 
 csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, int64_t n_cells_total,
                            int64_t n_features, double span, double* mean, double* variance, double* var_exp,
-                           double* var_std, int64_t* order) {
+                           double* var_std, int64_t* order, bool collective) {
   (void)n_features;  // the caller takes order[0:n_features]; clamping is :134-137
   const double N = (double)n_cells_total;
   std::vector<double> mu((size_t)n_genes), var((size_t)n_genes), ve((size_t)n_genes, 0.0), vs((size_t)n_genes, 0.0);
@@ -330,7 +352,7 @@ csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, in
   }
   if (!kept.empty()) {
     std::vector<double> pred;
-    loess_fit_predict(lx, ly, span, pred);
+    CSC_TRY(loess_fit_predict(ctx, collective, lx, ly, span, pred));
     parallel_for((int64_t)kept.size(), [&](int64_t lo, int64_t hi) {
       for (int64_t i = lo; i < hi; ++i) {
         const int64_t g = kept[i];

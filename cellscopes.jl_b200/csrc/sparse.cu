@@ -502,7 +502,28 @@ extern "C" csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, in
   CSC_CUDA(ctx, cudaMemcpyAsync(h.data(), gene_stats->mem->p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return launch_hvg_host(ctx, h.data(), n_genes, n_cells_total, n_features, span, mean, variance, variance_expected,
-                         variance_standardized, order);
+                         variance_standardized, order, false);
+  CSC_GUARD_END(ctx)
+}
+
+// the same, called by EVERY rank of the context's communicator with the all-reduced table: the Loess vertex fits are
+// dealt out over the ranks and their results all-reduced (identical outputs on every rank)
+extern "C" csc_status csc_hvg_finish_collective(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
+                                                int64_t n_features, double span, double* mean, double* variance,
+                                                double* variance_expected, double* variance_standardized, int64_t* order) {
+  if (!ctx || !gene_stats) return CSC_ERR_ARG;
+  CSC_GUARD_BEGIN
+  CSC_REQUIRE(ctx, gene_stats->dtype == CSC_DT_F64 && gene_stats->n >= 2 * n_genes && n_genes > 0,
+              "csc_hvg_finish_collective: gene_stats must be fp64[2*n_genes]");
+  CSC_REQUIRE(ctx, n_cells_total >= 2, "csc_hvg_finish_collective: need at least 2 cells");
+  CSC_REQUIRE(ctx, span > 0.0 && span <= 1.0, "span must be in the range (0, 1].");
+  CSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageTimer st(ctx, CSC_T_HVG);
+  std::vector<double> h((size_t)2 * n_genes);
+  CSC_CUDA(ctx, cudaMemcpyAsync(h.data(), gene_stats->mem->p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return launch_hvg_host(ctx, h.data(), n_genes, n_cells_total, n_features, span, mean, variance, variance_expected,
+                         variance_standardized, order, true);
   CSC_GUARD_END(ctx)
 }
 

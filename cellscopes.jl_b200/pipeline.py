@@ -201,7 +201,10 @@ def run_path(be, comm, raw, n_cells_total, cell_offset, p: PathParams, offsets=N
     norm = be.normalize(raw, p.scale_factor, norm_code(p.norm_method), p.pseudocount, False, stats)
     comm.allreduce_sum(stats)
     # a2
-    hvg = be.hvg_finish(stats, G, n_cells_total, p.n_features, p.span)
+    if isinstance(comm, NcclComm) and comm.world > 1:
+        hvg = be.hvg_finish(stats, G, n_cells_total, p.n_features, p.span, collective=True)   # Loess fits dealt over the ranks
+    else:
+        hvg = be.hvg_finish(stats, G, n_cells_total, p.n_features, p.span)
     feats = hvg["features"]
     rows = np.unique(feats)                       # subset_count keeps original gene order
     H = int(rows.size)

@@ -160,6 +160,13 @@ csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_gen
                           int64_t n_features, double span, double* mean, double* variance,
                           double* variance_expected, double* variance_standardized, int64_t* order);
 
+/* The same for one process per GPU: called by EVERY rank of the context's communicator (csc_comm_init) with the
+ * all-reduced table; the Loess vertex fits are dealt out over the ranks and their (value, slope) pairs all-reduced, so
+ * every rank returns bit-identical outputs without N copies of the same host job competing for the host cores. */
+csc_status csc_hvg_finish_collective(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
+                                     int64_t n_features, double span, double* mean, double* variance,
+                                     double* variance_expected, double* variance_standardized, int64_t* order);
+
 /* subset_count (src/scrna/utils.jl:59-87): the rows features[n_feat] (0-based, any order) of m in ORIGINAL gene order,
  * renumbered 0..H-1, as a new matrix with the same cells.  scale_object works on this subset in the reference; here it
  * pays off when few of the genes are kept (whole-transcriptome matrices): the passes after it take features == NULL. */
