@@ -168,14 +168,17 @@ __global__ void k_ld_propose(const u64* __restrict__ ukeys, const double* __rest
   prop[v] = best;
 }
 __global__ void k_ld_merge(const int32_t* __restrict__ prop, int32_t* __restrict__ ref, const double* __restrict__ size,
-                           double* __restrict__ rsize, int32_t* __restrict__ members, int64_t n, int* __restrict__ merged) {
+                           double* __restrict__ rsize, const int32_t* __restrict__ members_before, int32_t* __restrict__ members,
+                           int64_t n, int* __restrict__ merged) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   const int r = prop[v];
   if (r < 0) return;
   // a singleton target must stay where it is in this round: it has no proposal of its own, or the two singletons chose
   // each other (the usual case), and then the one with the larger id moves
-  const bool target_single = members[r] == 1;
+  // (decided on the member counts as they were when the round started: the result does not depend on the order in
+  // which the threads of this kernel run)
+  const bool target_single = members_before[r] == 1;
   if (target_single && (r > (int)v || (prop[r] >= 0 && prop[r] != (int)v))) return;
   ref[v] = r;
   atomicAdd(rsize + r, size[v]);
@@ -361,10 +364,11 @@ extern "C" csc_status csc_leiden(csc_ctx* ctx, const csc_graph* g, double resolu
       if (quiet >= 2) break;                       // both halves had their turn and nothing moved
     }
     // ---------------- refinement ----------------
-    DevPtr ref, rsize, members, ext, prop;
+    DevPtr ref, rsize, members, members_before, ext, prop;
     CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &ref));
     CSC_TRY(dev_alloc(ctx, (size_t)n * 8, &rsize));
     CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &members));
+    CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &members_before));
     CSC_TRY(dev_alloc(ctx, (size_t)n * 8, &ext));
     CSC_TRY(dev_alloc(ctx, (size_t)n * 4, &prop));
     k_ld_iota_ones<<<lb(n), 256, 0, s>>>((int32_t*)ref->p, nullptr, n);
@@ -392,8 +396,9 @@ extern "C" csc_status csc_leiden(csc_ctx* ctx, const csc_graph* g, double resolu
                                          (int32_t*)prop->p);
       CSC_LAUNCHED(ctx);
       CSC_CUDA(ctx, cudaMemsetAsync(flag->p, 0, 8, s));
-      k_ld_merge<<<lb(n), 256, 0, s>>>((const int32_t*)prop->p, (int32_t*)ref->p, size, (double*)rsize->p, (int32_t*)members->p, n,
-                                       (int*)flag->p);
+      CSC_CUDA(ctx, cudaMemcpyAsync(members_before->p, members->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+      k_ld_merge<<<lb(n), 256, 0, s>>>((const int32_t*)prop->p, (int32_t*)ref->p, size, (double*)rsize->p,
+                                       (const int32_t*)members_before->p, (int32_t*)members->p, n, (int*)flag->p);
       CSC_LAUNCHED(ctx);
       int merged = 0;
       CSC_CUDA(ctx, cudaMemcpyAsync(&merged, flag->p, 4, cudaMemcpyDeviceToHost, s));

@@ -841,9 +841,9 @@ def test_split_transform_equals_sparse_and_dense_transform(cs, oracle, ctx, medi
     z = dense.download(np.float64)
     want = (z - info["mean"][None, :]) @ info["loadings"]
     scale = np.sqrt((want ** 2).mean(axis=0))
-    # the tensor core accumulates the whole gene axis in its fp32 accumulator (truncating adds): measured 2.5e-5 of the
-    # component's rms for 2000 genes, against 1e-5 for the CUDA-core versions; the 1e-4 of the embedding check holds
-    for name, got, tol in (("split", a, 5e-5), ("sparse", b, 2e-5), ("dense", c, 2e-5)):
+    # the tensor core's adds into its fp32 accumulator truncate: one accumulator over 2000 genes cost 6.8e-5 of the
+    # component's rms (measured); the gene axis is therefore cut into four accumulators that are added round-to-nearest
+    for name, got, tol in (("split", a, 3e-5), ("sparse", b, 2e-5), ("dense", c, 2e-5)):
         err = np.abs(got - want).max(axis=0) / scale
         assert err.max() < tol, (name, err.max())
     assert a.shape == (N, k)
