@@ -376,8 +376,11 @@ def main():
         hbm_entry("scale_moments", 8.0 * nnz_local + 8.0 * n_loc, per_step["scale_stats"])
     # scale -> fp16 hi/lo operands of the Gram: 8 B per entry of the matrix it reads, 4 B per (cell, selected gene) written
     hbm_entry("scale_split", 8.0 * nnz_sel + 4.0 * params.n_features * n_loc, per_step["scale_fill"])
-    hbm_entry("pca_transform_sparse", 8.0 * nnz_sel + 4.0 * params.n_pcs * n_loc, per_step["pca_transform"],
-              note="bound by the L2 gathers of the loading rows, not by HBM")
+    # embedding = tensor-core GEMM over the fp16 hi/lo operands kept from the Gram pass: 2 x 2 B per (cell, padded gene)
+    # read once, 4 B per (cell, component) written
+    pitch = ((params.n_features + 1 + 63) // 64) * 64
+    hbm_entry("pca_transform_split_gemm", 4.0 * pitch * n_loc + 4.0 * params.n_pcs * n_loc, per_step["pca_transform"],
+              note="k_transform_tc (tcgen05 kind::f16, three passes): HBM-bound by design")
 
     # ---- e2e: host buffers through the reference-facing API -----------------------------------
     e2e = None
