@@ -38,7 +38,8 @@ def _nvcc() -> str:
 
 
 def _sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    # .cu through nvcc; .cpp (host-only code with CPU intrinsics) through nvcc's host compiler pass-through
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _headers_mtime() -> float:
@@ -48,9 +49,13 @@ def _headers_mtime() -> float:
 
 
 def _compile(nvcc, src, obj, verbose):
-    cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    if src.endswith(".cpp"):
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-fvisibility=default", "-I", os.path.join(ROOT, "include"),
+               "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+    else:
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, r.returncode, r.stdout + r.stderr
 
@@ -62,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hm = _headers_mtime()
     jobs, objs = [], []
     for src in _sources():
-        obj = os.path.join(OBJ, src[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(
             os.path.getmtime(os.path.join(CSRC, src)), hm)

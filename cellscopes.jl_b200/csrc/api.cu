@@ -226,6 +226,7 @@ csc_status csc_destroy(csc_ctx* ctx) {
   for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);
   // blocks still live belong to result arrays of the caller: they stay valid and are released by
   // csc_host_free(NULL, p)
+  if (ctx->up_stage) cudaFreeHost(ctx->up_stage);
   for (int b = 0; b < 2; ++b) {
     if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
     if (ctx->ev_bounce[b]) cudaEventDestroy(ctx->ev_bounce[b]);

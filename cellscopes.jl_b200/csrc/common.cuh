@@ -70,6 +70,9 @@ struct csc_ctx {
   std::multimap<size_t, void*> host_free;
   // pinned bounce buffers for device->host copies into pageable memory (see d2h_copy)
   void* bounce[2] = {nullptr, nullptr};
+  // page-locked slots of the host lane of the two-lane upload (csc_sparse_upload), grown on demand
+  void* up_stage = nullptr;
+  size_t up_stage_bytes = 0;
   cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   std::shared_ptr<DevMem> gemm_ws;   // split-K partials of the fp64 GEMM (grow-only)
   int64_t knn_fallback_rows = 0;   // rows of the last csc_knn call that needed the exact re-scan

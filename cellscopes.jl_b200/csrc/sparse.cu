@@ -1,7 +1,12 @@
 // Sparse stages: ingest (narrowing), normalize_object, raw gene moments, scale_object.
 // All kernels stream the cell-major CSC once, a warp per cell (column), coalesced along the
 // non-zeros of the column, with warp-shuffle reductions for the per-cell sums.
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include <cuda_fp16.h>
 
@@ -94,6 +99,230 @@ static csc_status staged_upload(csc_ctx* ctx, const void* host, size_t elem, int
   return CSC_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-lane upload of a large 64-bit array.  The reference's matrices arrive as Int64 row indices and Int64 / Float64
+// values (16 B per stored entry); the device keeps int32 / fp32 (8 B).  Copying the wide arrays and narrowing on the
+// device is bound by PCIe at 16 B per entry (26.4 GB = 490 ms of a 692 ms end-to-end pass at C3).  Here the array is
+// eaten from both ends at once:
+//   * host lane: worker threads claim 2 M-element pieces from the FRONT, narrow them into page-locked slots (row
+//     indices to uint16 when n_genes <= 65536, values to uint16 when every value of the piece is an integer in
+//     [0, 65535] -- raw counts are -- else to int32 / fp32) and hand them to the bus; a uint16 piece is widened to its
+//     final place by a small kernel (2 B instead of 8 B on the bus);
+//   * bus lane: whenever no narrowed piece is waiting and fewer than two copies are queued, the main thread claims a
+//     16 M-element piece from the BACK and copies it wide, narrowed by the device kernels as before.
+// The split point is wherever the two lanes meet, so the host cores take exactly the share they can convert while the
+// bus is busy, on any mix of core count, memory bandwidth and link speed.  Everything is enqueued on the context's stream.
+// ------------------------------------------------------------------------------------------
+enum UpKind { UP_IDX_I64 = 0, UP_VAL_F64 = 1, UP_VAL_I64 = 2 };
+static const int64_t UP_SLOT_MAX = (int64_t)2 << 20;   // elements per host-lane piece (bus-lane pieces: 8 of these)
+
+__global__ void k_widen16_idx(const uint16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (int32_t)in[i];
+}
+__global__ void k_widen16_val(const uint16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)in[i];
+}
+
+// host_narrow.cpp (g++: AVX-512 behind a run-time CPU check): narrow `cnt` elements at `src` into `stage`; returns the
+// element size written (2 or 4); row indices outside [0, n_rows) set *bad
+int host_narrow_piece(int kind, const void* src, int64_t cnt, void* stage, bool idx16, int64_t base, int64_t n_rows, int* bad);
+
+static csc_status two_lane_upload(csc_ctx* ctx, int kind, const void* host, void* dev, int64_t n, int64_t base,
+                                  int64_t n_rows, int* d_bad, int* host_bad) {
+  if (n == 0) return CSC_OK;
+  int64_t UP_SLOT = UP_SLOT_MAX;               // CSC_UPLOAD_PIECE: smaller pieces, so that tests reach every branch on small inputs
+  if (const char* e = getenv("CSC_UPLOAD_PIECE")) UP_SLOT = std::max<int64_t>(16, std::min<int64_t>(UP_SLOT_MAX, atoll(e)));
+  const int64_t UP_WIDE = 8 * UP_SLOT;
+  unsigned hw = std::thread::hardware_concurrency();
+  int n_workers = (int)std::max(1u, std::min(31u, hw > 1 ? hw - 1 : 1u));
+  if (const char* e = getenv("CSC_UPLOAD_THREADS")) n_workers = std::max(1, std::min(64, atoi(e)));
+  const int n_slots = 2 * n_workers;
+  const size_t slot_bytes = (size_t)UP_SLOT * 4;
+  if (ctx->up_stage_bytes < slot_bytes * n_slots) {
+    if (ctx->up_stage) cudaFreeHost(ctx->up_stage);
+    ctx->up_stage = nullptr;
+    ctx->up_stage_bytes = 0;
+    CSC_CUDA(ctx, cudaHostAlloc(&ctx->up_stage, slot_bytes * n_slots, cudaHostAllocDefault));
+    ctx->up_stage_bytes = slot_bytes * n_slots;
+  }
+  const bool idx16 = kind == UP_IDX_I64 && n_rows <= 65536;
+  DevPtr d16, dwide[2];
+  CSC_TRY(dev_alloc(ctx, (size_t)UP_SLOT * 2 * n_slots, &d16));
+  for (int b = 0; b < 2; ++b) CSC_TRY(dev_alloc(ctx, (size_t)std::min(n, UP_WIDE) * 8, &dwide[b]));
+  struct Events {
+    std::vector<cudaEvent_t> ev;
+    ~Events() {
+      for (auto e : ev) cudaEventDestroy(e);
+    }
+  } events;
+  events.ev.resize(n_slots + 2);
+  for (auto& e : events.ev) {
+    e = nullptr;
+    CSC_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+
+  struct Piece {
+    int slot;
+    int64_t off, cnt;
+    int elem;
+  };
+  std::mutex mu;
+  std::condition_variable cv_workers, cv_main;
+  int64_t front = 0, back = n;                 // [front, back) is unclaimed
+  std::deque<Piece> ready;
+  std::vector<char> slot_free(n_slots, 1);
+  int active = n_workers;
+  bool abort = false;
+  int bad_local = 0;
+
+  auto worker = [&](int w) {
+    for (;;) {
+      Piece pc;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        if (abort || front >= back) break;
+        pc.off = front;
+        pc.cnt = std::min(UP_SLOT, back - front);
+        front += pc.cnt;
+        cv_workers.wait(lk, [&] { return abort || slot_free[2 * w] || slot_free[2 * w + 1]; });
+        if (abort) break;
+        pc.slot = slot_free[2 * w] ? 2 * w : 2 * w + 1;
+        slot_free[pc.slot] = 0;
+      }
+      int bad = 0;
+      pc.elem = host_narrow_piece(kind, (const char*)host + (size_t)pc.off * 8, pc.cnt,
+                                (char*)ctx->up_stage + slot_bytes * pc.slot, idx16, base, n_rows, &bad);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (bad) bad_local = 1;
+        ready.push_back(pc);
+      }
+      cv_main.notify_one();
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      --active;
+    }
+    cv_main.notify_one();
+  };
+  std::vector<std::thread> pool;
+  struct Joiner {                              // on every way out: stop the workers and wait for them
+    std::vector<std::thread>& pool;
+    std::mutex& mu;
+    std::condition_variable& cv;
+    bool& abort;
+    ~Joiner() {
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        abort = true;
+      }
+      cv.notify_all();
+      for (auto& t : pool) t.join();
+    }
+  } joiner{pool, mu, cv_workers, abort};
+  for (int w = 0; w < n_workers; ++w) {
+    try {
+      pool.emplace_back(worker, w);
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(mu);
+      --active;                                // the bus lane (and the workers that did start) take its share
+    }
+  }
+
+  struct Flight {
+    cudaEvent_t ev;
+    int slot;                                  // host slot to release on completion, -1 for a bus-lane piece
+  };
+  std::deque<Flight> flight;
+  const int sm = ctx->sm_count;
+  int wide_b = 0;
+  auto retire = [&](bool block) -> cudaError_t {
+    while (!flight.empty()) {
+      cudaError_t e = block ? cudaEventSynchronize(flight.front().ev) : cudaEventQuery(flight.front().ev);
+      if (e == cudaErrorNotReady) return cudaSuccess;
+      if (e != cudaSuccess) return e;
+      if (flight.front().slot >= 0) {
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          slot_free[flight.front().slot] = 1;
+        }
+        cv_workers.notify_all();
+      }
+      flight.pop_front();
+      block = false;
+    }
+    return cudaSuccess;
+  };
+  for (;;) {
+    CSC_CUDA(ctx, retire(false));
+    Piece pc{-1, 0, 0, 0};
+    bool wide = false, done = false;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      if (!ready.empty()) {
+        pc = ready.front();
+        ready.pop_front();
+      } else if (front < back && flight.size() < 2) {
+        pc.cnt = std::min(UP_WIDE, back - front);
+        back -= pc.cnt;
+        pc.off = back;
+        wide = true;
+      } else if (active == 0 && front >= back) {
+        done = true;
+      } else if (flight.empty()) {
+        cv_main.wait_for(lk, std::chrono::microseconds(200));
+        continue;
+      }
+    }
+    if (done) break;
+    if (pc.cnt == 0) {                         // nothing to issue: wait for the oldest queued copy
+      CSC_CUDA(ctx, retire(true));
+      continue;
+    }
+    if (wide) {
+      void* st = dwide[wide_b]->p;
+      CSC_CUDA(ctx, cudaMemcpyAsync(st, (const char*)host + (size_t)pc.off * 8, (size_t)pc.cnt * 8, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+      if (kind == UP_IDX_I64)
+        k_narrow_idx<int64_t><<<grid_for(pc.cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)st, (int32_t*)dev + pc.off, pc.cnt,
+                                                                           base, n_rows, d_bad);
+      else if (kind == UP_VAL_F64)
+        k_narrow_val<double><<<grid_for(pc.cnt, sm), 256, 0, ctx->stream>>>((const double*)st, (float*)dev + pc.off, pc.cnt);
+      else
+        k_narrow_val<int64_t><<<grid_for(pc.cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)st, (float*)dev + pc.off, pc.cnt);
+      CSC_LAUNCHED(ctx);
+      cudaEvent_t ev = events.ev[n_slots + wide_b];
+      CSC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+      flight.push_back({ev, -1});
+      wide_b ^= 1;
+    } else {
+      const char* st = (const char*)ctx->up_stage + slot_bytes * pc.slot;
+      if (pc.elem == 4) {
+        CSC_CUDA(ctx, cudaMemcpyAsync((char*)dev + (size_t)pc.off * 4, st, (size_t)pc.cnt * 4, cudaMemcpyHostToDevice,
+                                      ctx->stream));
+      } else {
+        uint16_t* d = (uint16_t*)d16->p + (size_t)UP_SLOT * pc.slot;
+        CSC_CUDA(ctx, cudaMemcpyAsync(d, st, (size_t)pc.cnt * 2, cudaMemcpyHostToDevice, ctx->stream));
+        if (kind == UP_IDX_I64)
+          k_widen16_idx<<<grid_for(pc.cnt, sm), 256, 0, ctx->stream>>>(d, (int32_t*)dev + pc.off, pc.cnt);
+        else
+          k_widen16_val<<<grid_for(pc.cnt, sm), 256, 0, ctx->stream>>>(d, (float*)dev + pc.off, pc.cnt);
+        CSC_LAUNCHED(ctx);
+      }
+      cudaEvent_t ev = events.ev[pc.slot];
+      CSC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+      flight.push_back({ev, pc.slot});
+    }
+  }
+  CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bad_local) *host_bad = 1;
+  return CSC_OK;
+}
+
 extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n_cells, const void* colptr,
                                         const void* rowval, int32_t idx_dtype, const void* nzval, int32_t val_dtype,
                                         int32_t index_base, csc_sparse** out) {
@@ -147,6 +376,14 @@ extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n
     k_colptr_check<<<grid_for(n_cells, sm), 256, 0, ctx->stream>>>(d_cp, n_cells, nnz, d_bad);
     CSC_LAUNCHED(ctx);
   }
+  // 64-bit inputs of at least 32 M entries take the two-lane upload (see two_lane_upload); CSC_UPLOAD_HOST_NARROW=0 keeps
+  // the plain wide copy + device narrowing, =2 takes the two lanes at any size
+  const char* hn = getenv("CSC_UPLOAD_HOST_NARROW");
+  const bool two_lane = hn ? atoi(hn) == 2 || (atoi(hn) != 0 && nnz >= ((int64_t)32 << 20)) : nnz >= ((int64_t)32 << 20);
+  int host_bad = 0;
+  if (two_lane && idx_dtype == CSC_DT_I64) {
+    CSC_TRY(two_lane_upload(ctx, UP_IDX_I64, rowval, d_rv, nnz, index_base, n_genes, d_bad, &host_bad));
+  } else
   CSC_TRY(staged_upload(ctx, rowval, dt_size(idx_dtype), nnz, [&](void* src, int64_t o, int64_t cnt) {
     if (idx_dtype == CSC_DT_I64)
       k_narrow_idx<int64_t><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const int64_t*)src, d_rv + o, cnt, index_base, n_genes, d_bad);
@@ -155,6 +392,9 @@ extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n
     CSC_LAUNCHED(ctx);
     return (csc_status)CSC_OK;
   }));
+  if (two_lane && (val_dtype == CSC_DT_F64 || val_dtype == CSC_DT_I64)) {
+    CSC_TRY(two_lane_upload(ctx, val_dtype == CSC_DT_F64 ? UP_VAL_F64 : UP_VAL_I64, nzval, d_v, nnz, 0, 0, d_bad, &host_bad));
+  } else
   CSC_TRY(staged_upload(ctx, nzval, dt_size(val_dtype), nnz, [&](void* src, int64_t o, int64_t cnt) {
     switch (val_dtype) {
       case CSC_DT_F32: k_narrow_val<float><<<grid_for(cnt, sm), 256, 0, ctx->stream>>>((const float*)src, d_v + o, cnt); break;
@@ -169,7 +409,7 @@ extern "C" csc_status csc_sparse_upload(csc_ctx* ctx, int64_t n_genes, int64_t n
   CSC_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   CSC_REQUIRE(ctx, h_bad != 2, "csc_sparse_upload: colptr is not monotone within [index_base, index_base + nnz]");
-  CSC_REQUIRE(ctx, h_bad == 0, "csc_sparse_upload: a row index is outside [0, n_genes)");
+  CSC_REQUIRE(ctx, h_bad == 0 && host_bad == 0, "csc_sparse_upload: a row index is outside [0, n_genes)");
   *out = m.release();
   return CSC_OK;
   CSC_GUARD_END(ctx)

@@ -73,6 +73,36 @@ def test_upload_int64_one_based_and_float_values(cs, ctx, small_counts):
     assert np.array_equal(cp - 1, sub.indptr) and np.array_equal(rv - 1, sub.indices)
 
 
+@pytest.mark.parametrize("piece", ["777", "100000"])
+def test_upload_two_lanes_equals_plain_upload(cs, ctx, medium_counts, monkeypatch, piece):
+    """csc_sparse_upload's two-lane route for large Int64 / Float64 inputs (host cores narrow pieces from the front --
+    to uint16 where lossless -- while the bus carries wide pieces from the back): forced at test sizes with small pieces,
+    it must leave exactly what the plain route leaves."""
+    m = medium_counts
+    monkeypatch.setenv("CSC_UPLOAD_HOST_NARROW", "2")
+    monkeypatch.setenv("CSC_UPLOAD_PIECE", piece)
+    cp, rv = m.indptr.astype(np.int64) + 1, m.indices.astype(np.int64) + 1
+    frac = m.data.astype(np.float64) * 0.37          # not integers: the fp32 branch
+    mixed = m.data.astype(np.float64)
+    mixed[::1500] = 70000.5                          # a few pieces fail the uint16 test, the others pass
+    for vals in (m.data.astype(np.int64), m.data.astype(np.float64), frac, mixed):
+        h = ctx.sparse_upload(m.shape[0], m.shape[1], cp, rv, vals, index_base=1)
+        gcp, grv, gv = h.download(0, m.shape[1], index_base=1)
+        assert np.array_equal(gcp, cp) and np.array_equal(grv, rv)
+        assert np.array_equal(gv.astype(np.float32), vals.astype(np.float32))
+    # more than 65536 genes: indices travel as int32
+    rng = np.random.default_rng(3)
+    big = sp.random(70000, 300, density=0.01, format="csc", random_state=rng, data_rvs=lambda n: rng.integers(1, 9, n))
+    h = ctx.sparse_upload(70000, 300, big.indptr.astype(np.int64), big.indices.astype(np.int64), big.data.astype(np.float64))
+    assert (h.to_scipy() != big).nnz == 0
+    # a row index out of range is caught in whichever lane it lands
+    for pos in (5, rv.size // 2, rv.size - 3):
+        bad = rv.copy()
+        bad[pos] = m.shape[0] + 1
+        with pytest.raises(cs.CellScopesCudaError):
+            ctx.sparse_upload(m.shape[0], m.shape[1], cp, bad, mixed, index_base=1)
+
+
 def test_upload_rejects_bad_rows(cs, ctx):
     with pytest.raises(cs.CellScopesCudaError):
         ctx.sparse_upload(3, 2, np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0]))

@@ -85,3 +85,64 @@ def test_lazy_matrix_is_not_touched_by_shape(cs):
     lz = cs.objects.LazyDeviceMatrix(Boom(), "dense_t", (5, 7))
     n = cs.ScaleCountObject(lz, list("abcdefg"), list("vwxyz"), True, True, 10.0)
     assert n.shape == (5, 7) and n.device is lz.handle
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_upload_host_lane_narrowing(cs, variant):
+    """Host lane of csc_sparse_upload (csrc/host_narrow.cpp): Int64 / Float64 pieces narrowed to uint16 when that is
+    lossless, else to int32 / fp32; range violations of row indices flagged.  Variant 0 = generic loops, 1 = AVX-512 when the
+    CPU has it.  Expected values are NumPy casts (the device-side narrowing kernels do the same casts)."""
+    import ctypes
+    lib = ctypes.CDLL(cs._capi.LIB_PATH)
+    fn = lib.csc_test_host_narrow
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int,
+                   ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(5)
+
+    def run(kind, src, idx16=0, base=0, n_rows=0):
+        stage = np.zeros(src.size * 4 + 64, np.uint8)
+        bad = ctypes.c_int(0)
+        elem = fn(variant, kind, src.ctypes.data, src.size, stage.ctypes.data, idx16, base, n_rows, ctypes.byref(bad))
+        assert not stage[src.size * elem:].any()           # nothing written past the piece
+        return elem, stage[:src.size * elem], bad.value
+
+    for n in (0, 1, 15, 16, 17, 1000, 4099):
+        # row indices, 1-based, 33k genes -> uint16
+        idx = rng.integers(1, 33001, n).astype(np.int64)
+        elem, out, bad = run(0, idx, idx16=1, base=1, n_rows=33000)
+        assert (elem, bad) == (2, 0) and np.array_equal(out.view(np.uint16), (idx - 1).astype(np.uint16))
+        # 100k genes -> int32
+        idx = rng.integers(0, 100000, n).astype(np.int64)
+        elem, out, bad = run(0, idx, idx16=0, base=0, n_rows=100000)
+        assert (elem, bad) == (4, 0) and np.array_equal(out.view(np.int32), idx.astype(np.int32))
+        if n:
+            for wrong in (-1, 100000, 1 << 40):
+                idx2 = idx.copy()
+                idx2[n // 2] = wrong
+                assert run(0, idx2, idx16=0, base=0, n_rows=100000)[2] == 1
+                assert run(0, idx2 + 1, idx16=1, base=1, n_rows=100000)[2] == 1
+        # counts as Float64 -> uint16; one non-integer / large / negative / -0.0 / NaN value sends the piece to fp32
+        val = rng.integers(0, 65536, n).astype(np.float64)
+        elem, out, _ = run(1, val)
+        assert elem == 2 and np.array_equal(out.view(np.uint16), val.astype(np.uint16))
+        for odd in (0.5, 65536.0, -3.0, -0.0, np.nan, np.inf, 1e300):
+            if not n:
+                break
+            v2 = val.copy()
+            v2[n - 1 - n // 3] = odd
+            elem, out, _ = run(1, v2)
+            with np.errstate(over="ignore"):
+                want = v2.astype(np.float32)
+            assert elem == 4 and np.array_equal(out.view(np.uint32), want.view(np.uint32)), odd
+        # counts as Int64
+        vi = rng.integers(0, 65536, n).astype(np.int64)
+        elem, out, _ = run(2, vi)
+        assert elem == 2 and np.array_equal(out.view(np.uint16), vi.astype(np.uint16))
+        for odd in (-1, 65536, (1 << 53) + 1):
+            if not n:
+                break
+            v2 = vi.copy()
+            v2[n // 2] = odd
+            elem, out, _ = run(2, v2)
+            assert elem == 4 and np.array_equal(out.view(np.float32), v2.astype(np.float32)), odd
