@@ -510,11 +510,16 @@ extern "C" csc_status csc_sparse_download(const csc_sparse* m, int64_t cell_lo, 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// lanes 0-15: the 128-byte lines of val[b, e); lanes 16-31: those of rowval[b, e)
+// lanes 0-15: the 128-byte lines of val[b, e); lanes 16-31: those of rowval[b, e).  Only the HEAD of the column (the
+// first PF_CAP entries) is prefetched: it hides the DRAM latency of a warp's first loads after a column switch, the
+// rest of a long column streams behind it anyway.  Prefetching whole columns of a whole-transcriptome matrix (1650
+// entries, 13 KB per column and array pair, x 3500-6000 resident warps) pushed the columns being worked on out of L2:
+// ncu at C3 showed k_normalize reading 23.5 GB for 13.2 GB of input and k_select_fill 24.5 GB.
+constexpr int64_t PF_CAP = 512;
 __device__ __forceinline__ void prefetch_column_l2(const int32_t* rowval, const float* val, int64_t b, int64_t e, int lane) {
   const char* base = lane < 16 ? reinterpret_cast<const char*>(val) : reinterpret_cast<const char*>(rowval);
   if (base == nullptr) return;
-  const int64_t hi = e * 4;
+  const int64_t hi = min(e, b + PF_CAP) * 4;
   for (int64_t off = ((b * 4) & ~(int64_t)127) + 128 * (lane & 15); off < hi; off += 128 * 16) prefetch_l2(base + off);
 }
 
@@ -529,12 +534,17 @@ struct NormArgs {
   int method, nan_to_zero;
   double* gstats;     // fp64 [2G] raw moments (or null)
   int64_t cells_per_cta;
+  int32_t n_e;        // RAW = 1: genes [0, n_e) also have an E slot in shared memory (what is left of it beside the S1 table)
 };
 
-// RAW: 0 = no raw moments, 1 = S1 table only (E goes to global memory), 2 = S1 and E tables,
+// RAW: 0 = no raw moments, 1 = S1 table + E slots for the first n_e genes (E of the others goes to global memory:
+//      13.6 % of the C3 entries are counts >= 2, 225 M fp64 atomics per pass when no gene had a slot), 2 = S1 and E tables,
 //      3 = no table fits: every update goes to the fp64 table in global memory
-template <bool WRITE_NORM, int RAW>
-__global__ void __launch_bounds__(768, 2)
+// BIG: the tables leave room for one CTA per SM only (whole-transcriptome matrices): 1024 threads and 8 entries per
+// lane in flight instead of 768 x 2 CTAs and 4 -- with 24 warps per SM and 1 KB of loads per warp in flight the pass sat
+// at 0.37 of the HBM rate with no unit busier than 48 % (ncu): latency, not throughput
+template <bool WRITE_NORM, int RAW, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 768, BIG ? 1 : 2)
 k_normalize(const NormArgs a) {
   extern __shared__ unsigned int stab[];
   const int G = a.n_genes;
@@ -542,8 +552,9 @@ k_normalize(const NormArgs a) {
   constexpr int NRAW = RAW == 2 ? 2 : RAW == 1 ? 1 : 0;
   unsigned int* etab = stab + (NRAW >= 1 ? G : 0);
   constexpr int NTAB = NRAW;
+  const int n_e = RAW == 2 ? G : RAW == 1 ? a.n_e : 0;
   if (NTAB > 0) {
-    for (int g = threadIdx.x; g < NTAB * G; g += blockDim.x) stab[g] = 0u;
+    for (int g = threadIdx.x; g < G + n_e; g += blockDim.x) stab[g] = 0u;
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
@@ -553,7 +564,7 @@ k_normalize(const NormArgs a) {
   const int64_t c1 = min(c0 + a.cells_per_cta, a.n_cells);
   const bool pc_is_one = (a.pc == 1.0);
   const float pcf = (float)a.pc;
-  constexpr int UN = 4;   // entries per lane whose loads are issued before the first update (see the header comment)
+  constexpr int UN = BIG ? 8 : 4;   // entries per lane whose loads are issued before the first update (see the header comment)
   int64_t b = 0, e = 0, nb = 0, ne = 0;
   if (c0 + warp < c1) { b = a.colptr[c0 + warp]; e = a.colptr[c0 + warp + 1]; }
   if (c0 + warp + nwarp < c1) { nb = a.colptr[c0 + warp + nwarp]; ne = a.colptr[c0 + warp + nwarp + 1]; }
@@ -565,7 +576,7 @@ k_normalize(const NormArgs a) {
     float scale = 0.f;
     if (WRITE_NORM) {
       double s = 0.0;
-#pragma unroll 4
+#pragma unroll (BIG ? 8 : 4)
       for (int64_t i = b + lane; i < e; i += 32) s += (double)a.raw[i];
       s = warp_sum(s);
       // (x * (1/s)) * sf of processing.jl:24 with the two cell constants folded in fp64 and applied in fp32: the
@@ -608,7 +619,7 @@ k_normalize(const NormArgs a) {
             if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
               const unsigned int xi = (unsigned int)x;
               atomicAdd(&s1tab[g], xi);
-              if (RAW == 2 && xi <= 255u) {
+              if ((RAW == 2 || (RAW == 1 && g < n_e)) && xi <= 255u) {
                 if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
               } else if (xi >= 2u) {
                 const double xd = (double)x;
@@ -630,7 +641,7 @@ k_normalize(const NormArgs a) {
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
       if (NRAW > 0) {
         const unsigned int v = s1tab[g];
-        const unsigned int ex = RAW == 2 ? etab[g] : 0u;
+        const unsigned int ex = g < n_e ? etab[g] : 0u;
         if (v) atomicAdd(&a.gstats[g], (double)v);
         if (v || ex) atomicAdd(&a.gstats[(int64_t)G + g], (double)v + (double)ex);  // sum x^2 = sum x + sum (x^2 - x)
       }
@@ -641,15 +652,16 @@ k_normalize(const NormArgs a) {
 static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* out, double sf, double pc, int method,
                                    int nan_to_zero, double* gstats) {
   if (raw->n_cells == 0) return CSC_OK;
-  const int threads = 768;
   const size_t G = (size_t)raw->n_genes;
   const size_t budget = (size_t)200 * 1024;
   // which tables fit: raw S1 (+E)
   int raw_mode = 0;
   if (gstats) raw_mode = (2 * G * 4 <= budget) ? 2 : (G * 4 <= budget ? 1 : 3);
-  const int nraw = raw_mode == 2 ? 2 : raw_mode == 1 ? 1 : 0;
-  const size_t smem = (size_t)nraw * G * 4;
+  const size_t n_e = raw_mode == 2 ? G : raw_mode == 1 ? std::min(G, (budget - G * 4) / 4) : 0;
+  const size_t smem = raw_mode == 1 || raw_mode == 2 ? (G + n_e) * 4 : 0;
   const int ctas_per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(2, ((size_t)220 * 1024) / (smem + 1024))) : 2;
+  const bool big = ctas_per_sm == 1;
+  const int threads = big ? 1024 : 768;
   int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
   // a CTA's u32 tables must not overflow: <= 65535 (S1) and <= 65025 (E) per entry * 65536 cells
   int64_t cells_per_cta = std::max<int64_t>(16, ceil_div64(raw->n_cells, grid));
@@ -668,6 +680,7 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   a.nan_to_zero = nan_to_zero;
   a.gstats = gstats;
   a.cells_per_cta = cells_per_cta;
+  a.n_e = (int32_t)n_e;
   auto launch = [&](auto kern) -> csc_status {
     if (smem > 48 * 1024)
       CSC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -677,7 +690,8 @@ static csc_status launch_normalize(csc_ctx* ctx, const csc_sparse* raw, float* o
   };
   const bool wn = out != nullptr;
   csc_status st = CSC_OK;
-#define NORM_CASE(W, R) if (wn == W && raw_mode == R) st = launch(k_normalize<W, R>);
+#define NORM_CASE(W, R)                                                      \
+  if (wn == W && raw_mode == R) st = big ? launch(k_normalize<W, R, true>) : launch(k_normalize<W, R, false>);
   NORM_CASE(true, 0) NORM_CASE(true, 1) NORM_CASE(true, 2) NORM_CASE(true, 3)
   NORM_CASE(false, 1) NORM_CASE(false, 2) NORM_CASE(false, 3)
 #undef NORM_CASE
@@ -1156,7 +1170,7 @@ k_select_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
   for (int64_t c = warp; c < n_cells; c += nwarp) {
     int64_t nnb = 0, nne = 0;
     if (c + 2 * nwarp < n_cells) { nnb = colptr[c + 2 * nwarp]; nne = colptr[c + 2 * nwarp + 1]; }
-    if (nb < ne) prefetch_column_l2(rowval, val, nb, ne, lane);
+    if (nb < ne) prefetch_column_l2(rowval, nullptr, nb, ne, lane);
     int64_t o = out_colptr[c];
     for (int64_t i0 = b; i0 < e; i0 += 32 * UN) {
       int g[UN], h[UN];
@@ -1165,10 +1179,13 @@ k_select_fill(const int64_t* __restrict__ colptr, const int32_t* __restrict__ ro
       for (int u = 0; u < UN; ++u) {
         const int64_t i = i0 + 32 * u + lane;
         g[u] = i < e ? __ldcs(rowval + i) : -1;
-        x[u] = i < e ? __ldcs(val + i) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) h[u] = g[u] >= 0 ? __ldg(gene2h + g[u]) : -1;
+      // the value is fetched for kept entries only: with 6 % of the rows kept ~40 % of the 32-byte sectors of val are
+      // touched instead of all of them
+#pragma unroll
+      for (int u = 0; u < UN; ++u) x[u] = h[u] >= 0 ? __ldcs(val + i0 + 32 * u + lane) : 0.f;
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const unsigned m = __ballot_sync(FULL, h[u] >= 0);
