@@ -14,45 +14,67 @@
 namespace {
 
 // idx[] = the permutation of a stable ascending sort by key (ties, -0.0 == +0.0 included, keep the lower index): what
-// std::sort over (key, index) pairs gives, as an LSD radix sort over the order-preserving integer image of the
-// doubles (six 11-bit passes; the pair sort cost 2 x 1.7 ms of the 8 ms that 33k genes take).  No NaN keys.
+// std::sort over (key, index) pairs gives.  The order-preserving integer image of the doubles is LSD-radix-sorted on
+// its upper 32 bits only -- 8-byte records (key prefix, index), three passes of 11 / 11 / 10 bits, a pass whose digit
+// is the same for all keys is skipped --, which leaves groups of keys that agree in sign, exponent and 20 mantissa
+// bits (a handful among 33 k genes, unless values repeat) in index order; those groups are then ordered by the full
+// key.  (Six passes over all 64 bits with separate key and index arrays cost 2 x 1.2 ms of the 4.6 ms that 33k genes
+// took; the pair sort before that 2 x 1.7 ms.)  No NaN keys.
 void stable_argsort(const std::vector<double>& key, std::vector<int64_t>& idx) {
   const size_t n = key.size();
   idx.resize(n);
-  if (n < 4096) {
-    std::vector<std::pair<double, int64_t>> pk(n);
-    for (size_t i = 0; i < n; ++i) pk[i] = std::make_pair(key[i], (int64_t)i);
+  auto image = [](double d) {
+    d += 0.0;                                             // -0.0 -> +0.0: they compare equal
+    uint64_t u;
+    memcpy(&u, &d, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  };
+  if (n < 4096 || n > 0xffffffffull) {
+    std::vector<std::pair<uint64_t, int64_t>> pk(n);
+    for (size_t i = 0; i < n; ++i) pk[i] = std::make_pair(image(key[i]), (int64_t)i);
     std::sort(pk.begin(), pk.end());
     for (size_t i = 0; i < n; ++i) idx[i] = pk[i].second;
     return;
   }
-  std::vector<uint64_t> k0(n), k1(n);
-  std::vector<int64_t> i1(n);
+  struct Rec {
+    uint32_t k, i;
+  };
+  std::vector<Rec> r0(n), r1(n);
   for (size_t i = 0; i < n; ++i) {
-    const double d = key[i] + 0.0;                        // -0.0 -> +0.0: they compare equal
-    uint64_t u;
-    memcpy(&u, &d, 8);
-    k0[i] = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-    idx[i] = (int64_t)i;
+    r0[i].k = (uint32_t)(image(key[i]) >> 32);
+    r0[i].i = (uint32_t)i;
   }
-  uint64_t* ka = k0.data();
-  uint64_t* kb = k1.data();
-  int64_t* ia = idx.data();
-  int64_t* ib = i1.data();
-  for (int pass = 0; pass < 6; ++pass) {
-    const int shift = 11 * pass;
+  Rec* ra = r0.data();
+  Rec* rb = r1.data();
+  const int shifts[3] = {0, 11, 22}, bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass];
+    const uint32_t mask = (1u << bits[pass]) - 1u;
     size_t cnt[2049] = {0};
-    for (size_t i = 0; i < n; ++i) ++cnt[((ka[i] >> shift) & 2047u) + 1];
-    for (int bkt = 0; bkt < 2048; ++bkt) cnt[bkt + 1] += cnt[bkt];
-    for (size_t i = 0; i < n; ++i) {
-      const size_t o = cnt[(ka[i] >> shift) & 2047u]++;
-      kb[o] = ka[i];
-      ib[o] = ia[i];
+    for (size_t i = 0; i < n; ++i) ++cnt[((ra[i].k >> shift) & mask) + 1];
+    bool single = false;
+    for (int bkt = 0; bkt < 2048; ++bkt) {
+      single |= cnt[bkt + 1] == n;
+      cnt[bkt + 1] += cnt[bkt];
     }
-    std::swap(ka, kb);
-    std::swap(ia, ib);
+    if (single) continue;
+    for (size_t i = 0; i < n; ++i) rb[cnt[(ra[i].k >> shift) & mask]++] = ra[i];
+    std::swap(ra, rb);
   }
-  // six passes: the result is back in the first pair of buffers (idx)
+  // groups of equal prefix: by (full key, index)
+  std::vector<std::pair<uint64_t, uint32_t>> grp;
+  for (size_t g0 = 0; g0 < n;) {
+    size_t g1 = g0 + 1;
+    while (g1 < n && ra[g1].k == ra[g0].k) ++g1;
+    if (g1 - g0 > 1) {
+      grp.clear();
+      for (size_t i = g0; i < g1; ++i) grp.emplace_back(image(key[ra[i].i]), ra[i].i);
+      std::sort(grp.begin(), grp.end());
+      for (size_t i = g0; i < g1; ++i) ra[i].i = grp[i - g0].second;
+    }
+    g0 = g1;
+  }
+  for (size_t i = 0; i < n; ++i) idx[i] = (int64_t)ra[i].i;
 }
 
 // fn(begin, end) over [0, n) on a few host threads (the per-gene loops of 33k transcendental calls); the pieces are
@@ -79,61 +101,84 @@ void parallel_for(int64_t n, F fn) {
   if (next < n) fn(next, n);                              // the pieces whose thread did not start
 }
 
-// Householder QR with column pivoting on a q x 3 system (Julia: qr(us, ColumnNorm()) \ vs)
-void pivoted_qr_solve3(std::vector<double>& a /* q x 3 column-major */, std::vector<double>& b, int64_t q,
+// Householder QR with column pivoting on a q x 3 system (Julia: qr(us, ColumnNorm()) \ vs).  The columns are swapped
+// by pointer; every step makes two fused passes over the rows (all dot products with the reflector, then all updates);
+// the sums run in four interleaved accumulators (a single fp64 accumulator retires one add per 4 cycles: the eleven
+// dependent sums over ~10 k rows were most of the 0.4 ms a vertex cost).  `vbuf`: scratch of q doubles.
+void pivoted_qr_solve3(double* a /* q x 3 column-major, destroyed */, double* b /* q, destroyed */, double* vbuf, int64_t q,
                        double coef[3]) {
   const int ncol = 3;
   int perm[3] = {0, 1, 2};
-  auto col = [&](int j) { return a.data() + (size_t)j * q; };
+  double* col[3] = {a, a + q, a + 2 * q};
+  auto sum4 = [](const double (&s)[4]) { return (s[0] + s[1]) + (s[2] + s[3]); };
   for (int k = 0; k < ncol; ++k) {
+    // squared norms of the remaining columns below row k, one pass
+    double nrm[3][4] = {{0}};
+    {
+      int64_t i = k;
+      for (; i + 4 <= q; i += 4)
+        for (int j = k; j < ncol; ++j)
+          for (int u = 0; u < 4; ++u) nrm[j][u] += col[j][i + u] * col[j][i + u];
+      for (; i < q; ++i)
+        for (int j = k; j < ncol; ++j) nrm[j][0] += col[j][i] * col[j][i];
+    }
     int p = k;
     double best = -1.0;
     for (int j = k; j < ncol; ++j) {
-      double s = 0.0;
-      const double* c = col(j);
-      for (int64_t i = k; i < q; ++i) s += c[i] * c[i];
-      if (s > best) {
-        best = s;
+      const double t = sum4(nrm[j]);
+      if (t > best) {
+        best = t;
         p = j;
       }
     }
     if (p != k) {
-      double* ck = col(k);
-      double* cp = col(p);
-      for (int64_t i = 0; i < q; ++i) std::swap(ck[i], cp[i]);
+      std::swap(col[k], col[p]);
       std::swap(perm[k], perm[p]);
     }
-    double* x = col(k);
-    double nrm2 = 0.0;
-    for (int64_t i = k; i < q; ++i) nrm2 += x[i] * x[i];
-    double alpha = std::sqrt(nrm2);
+    double* x = col[k];
+    double alpha = std::sqrt(best);
     if (alpha == 0.0) continue;
     if (x[k] > 0) alpha = -alpha;
-    // v = x - alpha e1 (stored in place of x below the diagonal after use)
-    std::vector<double> v((size_t)(q - k));
-    for (int64_t i = k; i < q; ++i) v[i - k] = x[i];
-    v[0] -= alpha;
-    double vnorm2 = 0.0;
-    for (double t : v) vnorm2 += t * t;
-    if (vnorm2 == 0.0) continue;
-    for (int j = k; j < ncol; ++j) {
-      double* c = col(j);
-      double s = 0.0;
-      for (int64_t i = k; i < q; ++i) s += v[i - k] * c[i];
-      s = 2.0 * s / vnorm2;
-      for (int64_t i = k; i < q; ++i) c[i] -= s * v[i - k];
+    // v = x - alpha e1
+    double* v = vbuf;
+    for (int64_t i = k; i < q; ++i) v[i] = x[i];
+    v[k] -= alpha;
+    // pass 1: v.v, v.col_j (j >= k), v.b
+    double dv[4] = {0}, dc[3][4] = {{0}}, db[4] = {0};
+    {
+      int64_t i = k;
+      for (; i + 4 <= q; i += 4)
+        for (int u = 0; u < 4; ++u) {
+          const double t = v[i + u];
+          dv[u] += t * t;
+          for (int j = k; j < ncol; ++j) dc[j][u] += t * col[j][i + u];
+          db[u] += t * b[i + u];
+        }
+      for (; i < q; ++i) {
+        const double t = v[i];
+        dv[0] += t * t;
+        for (int j = k; j < ncol; ++j) dc[j][0] += t * col[j][i];
+        db[0] += t * b[i];
+      }
     }
-    double s = 0.0;
-    for (int64_t i = k; i < q; ++i) s += v[i - k] * b[i];
-    s = 2.0 * s / vnorm2;
-    for (int64_t i = k; i < q; ++i) b[i] -= s * v[i - k];
+    const double vnorm2 = sum4(dv);
+    if (vnorm2 == 0.0) continue;
+    double sc[3] = {0, 0, 0};
+    for (int j = k; j < ncol; ++j) sc[j] = 2.0 * sum4(dc[j]) / vnorm2;
+    const double sb = 2.0 * sum4(db) / vnorm2;
+    // pass 2: the reflections
+    for (int64_t i = k; i < q; ++i) {
+      const double t = v[i];
+      for (int j = k; j < ncol; ++j) col[j][i] -= sc[j] * t;
+      b[i] -= sb * t;
+    }
   }
   double cp[3] = {0, 0, 0};
   for (int k = ncol - 1; k >= 0; --k) {
-    double s = b[k];
-    for (int j = k + 1; j < ncol; ++j) s -= col(j)[k] * cp[j];
-    double d = col(k)[k];
-    cp[k] = d != 0.0 ? s / d : 0.0;
+    double t = b[k];
+    for (int j = k + 1; j < ncol; ++j) t -= col[j][k] * cp[j];
+    const double d = col[k][k];
+    cp[k] = d != 0.0 ? t / d : 0.0;
   }
   for (int k = 0; k < ncol; ++k) coef[perm[k]] = cp[k];
 }
@@ -161,15 +206,17 @@ void kd_vertices(const std::vector<double>& xs_sorted, int64_t cutoff, std::vect
 
 }  // namespace
 
-// x, y: the points (genes with variance > 0).  out[i] = loess prediction at x[i].
+// x, y: the points (genes with variance > 0).  out[i] = finish(i, loess prediction at x[i]).
 // With a communicator on the context (one process per GPU) the vertex fits -- the expensive part, ~15 ms of one host
 // thread for 33 k genes -- are dealt out over the ranks (vertex i to rank i mod world) and their (value, slope) pairs are
 // all-reduced: every rank adds zeros for the vertices it did not fit, so all ranks end with bit-identical tables, and
 // eight ranks no longer run eight copies of the same 8-thread job on the same host cores.
 csc_status comm_allreduce_f64(csc_ctx* ctx, double* host_inout, size_t n);   // comm.cu
 
+// finish(i, prediction at x[i]) -> out[i]
+template <typename Finish>
 static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::vector<double>& x, const std::vector<double>& y,
-                                    double span, std::vector<double>& out) {
+                                    double span, std::vector<double>& out, Finish finish) {
   const int64_t n = (int64_t)x.size();
   const double cell = 0.2;
   const int64_t q = std::max<int64_t>(1, (int64_t)std::floor(span * (double)n));
@@ -177,66 +224,82 @@ static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::ve
   // the points sorted by (x, index): the q nearest to a vertex are a window around it, so they come out of a
   // two-pointer walk in O(q) instead of a selection over all n points per vertex
   std::vector<int64_t> sidx;
-  stable_argsort(x, sidx);                               // by (x, index) == a stable sort by x
+  stable_argsort(x, sidx);
+  if (ctx) CSC_TRACE(ctx, "hvg: argsort of log10 mean");                               // by (x, index) == a stable sort by x
   std::vector<double> xs((size_t)n);
   for (int64_t i = 0; i < n; ++i) xs[i] = x[sidx[i]];
   std::vector<double> verts;
   kd_vertices(xs, cutoff, verts);
   const size_t nv = verts.size();
   std::vector<double> val(nv), slope(nv);
+  std::vector<double> ys((size_t)n);
+  for (int64_t i = 0; i < n; ++i) ys[i] = y[sidx[i]];
   const double inf = std::numeric_limits<double>::infinity();
-  // the local fits are independent: a few host threads take the vertices round-robin (33 k genes give 33 fits over
-  // 10 k points each; one thread needs ~15 ms for them)
+  // The local fits are independent: host threads take the vertices round-robin (33 k genes give 33 fits over 9.9 k
+  // points each).  The q points nearest to a vertex -- ties of the q-th distance resolved towards the lower gene index,
+  // like the stable argsort of |x - v| in the oracle -- are a window of the sorted points plus, at most, a few tied
+  // points at its rim: the window comes from a binary search over "how many from the left", the rows of the weighted
+  // system are then built from contiguous slices of the sorted arrays.  (The least-squares solution does not depend on
+  // the order of the rows; the round-1 code walked outwards from the vertex point by point to visit them nearest-first.)
   auto fit_range = [&](size_t v_begin, size_t v_step) {
-    std::vector<int64_t> order;
-    std::vector<double> d;
-    order.reserve((size_t)q + 64);
-    d.reserve((size_t)q + 64);
-    std::vector<double> a((size_t)q * 3), b((size_t)q);
+    std::vector<double> a((size_t)q * 3), b((size_t)q), vbuf((size_t)q);
+    std::vector<std::pair<int64_t, int64_t>> tied;                     // (gene index, sorted position)
     for (size_t vi = v_begin; vi < nv; vi += v_step) {
       const double v = verts[vi];
-      // nearest first, ties by lower index: exactly the order of a stable sort of |x - v| (the oracle's argsort)
-      int64_t R = (int64_t)(std::lower_bound(xs.begin(), xs.end(), v) - xs.begin()), L = R - 1;
-      order.clear();
-      d.clear();
-      while (true) {
-        const double dl = L >= 0 ? std::fabs(xs[L] - v) : inf;
-        const double dr = R < n ? std::fabs(xs[R] - v) : inf;
-        const double dn = std::min(dl, dr);
-        if (dn == inf) break;
-        if ((int64_t)order.size() >= q && dn > d.back()) break;     // keep every tie of the q-th distance for now
-        if (dl <= dr) {
-          order.push_back(sidx[L--]);
-          d.push_back(dl);
-        } else {
-          order.push_back(sidx[R++]);
-          d.push_back(dr);
+      const int64_t R0 = (int64_t)(std::lower_bound(xs.begin(), xs.end(), v) - xs.begin());
+      const int64_t nL = R0, nR = n - R0;
+      auto dl = [&](int64_t i) { return i >= 1 && i <= nL ? std::fabs(xs[R0 - i] - v) : (i < 1 ? -inf : inf); };       // i-th to the left
+      auto dr = [&](int64_t j) { return j >= 1 && j <= nR ? std::fabs(xs[R0 + j - 1] - v) : (j < 1 ? -inf : inf); };   // j-th to the right
+      // smallest count from the left such that the next left point is not strictly closer than the last right one taken
+      int64_t lo_a = std::max<int64_t>(0, q - nR), hi_a = std::min(q, nL);
+      while (lo_a < hi_a) {
+        const int64_t m = (lo_a + hi_a) / 2;
+        if (dl(m + 1) < dr(q - m)) lo_a = m + 1;
+        else hi_a = m;
+      }
+      const double dq = std::max(dl(lo_a), dr(q - lo_a));               // the q-th smallest distance
+      // points strictly closer than dq (taken for sure) and points at exactly dq (taken by ascending gene index)
+      auto count_below = [&](auto dist, int64_t cnt, bool strict) {
+        int64_t lo = 0, hi = cnt;                                       // number of points with dist < dq (or <= dq)
+        while (lo < hi) {
+          const int64_t m = (lo + hi) / 2;
+          const double d = dist(m + 1);
+          if (strict ? d < dq : d <= dq) lo = m + 1;
+          else hi = m;
         }
+        return lo;
+      };
+      const int64_t aL = count_below(dl, nL, true), aLe = count_below(dl, nL, false);
+      const int64_t bR = count_below(dr, nR, true), bRe = count_below(dr, nR, false);
+      const int64_t need = q - aL - bR;                                 // >= 1 points of the tied rim
+      tied.clear();
+      for (int64_t i = aL + 1; i <= aLe; ++i) tied.emplace_back(sidx[R0 - i], R0 - i);
+      for (int64_t j = bR + 1; j <= bRe; ++j) tied.emplace_back(sidx[R0 + j - 1], R0 + j - 1);
+      if ((int64_t)tied.size() > need) {
+        std::nth_element(tied.begin(), tied.begin() + need, tied.end());
+        tied.resize((size_t)need);
       }
-      // equal distances: ascending index
-      for (size_t i0 = 0; i0 < order.size();) {
-        size_t i1 = i0 + 1;
-        while (i1 < order.size() && d[i1] == d[i0]) ++i1;
-        if (i1 - i0 > 1) std::sort(order.begin() + i0, order.begin() + i1);
-        i0 = i1;
-      }
-      double dmax = 0.0;
-      for (int64_t i = 0; i < q; ++i) dmax = std::max(dmax, d[i]);
-      if (dmax == 0.0) dmax = 1.0;
-      for (int64_t i = 0; i < q; ++i) {
-        const int64_t p = order[i];
-        const double u = d[i] / dmax;
+      const double dmax = dq == 0.0 ? 1.0 : dq;
+      double* a0 = a.data();
+      double* a1 = a0 + q;
+      double* a2 = a1 + q;
+      int64_t r = 0;
+      auto row = [&](int64_t pos) {
+        const double xc = xs[pos] - v;
+        const double u = std::fabs(xc) / dmax;
         const double u3 = u * u * u;
         const double t = 1.0 - u3;
         const double w = std::sqrt(t * t * t);
-        const double xc = x[p] - v;
-        a[i] = w;
-        a[(size_t)q + i] = w * xc;
-        a[(size_t)2 * q + i] = w * xc * xc;
-        b[i] = y[p] * w;
-      }
+        a0[r] = w;
+        a1[r] = w * xc;
+        a2[r] = w * xc * xc;
+        b[r] = ys[pos] * w;
+        ++r;
+      };
+      for (int64_t pos = R0 - aL; pos < R0 + bR; ++pos) row(pos);
+      for (const auto& tp : tied) row(tp.second);
       double coef[3];
-      pivoted_qr_solve3(a, b, q, coef);
+      pivoted_qr_solve3(a.data(), b.data(), vbuf.data(), q, coef);
       val[vi] = coef[0];
       slope[vi] = coef[1];
     }
@@ -248,7 +311,7 @@ static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::ve
     std::fill(slope.begin(), slope.end(), 0.0);
   }
   const size_t my_nv = (nv + world - 1 - rank) / world;                 // vertices rank, rank + world, ...
-  const size_t n_thr = (n >= 2000 && my_nv >= 2) ? std::min<size_t>(std::min<size_t>(8, my_nv), std::max(1u, std::thread::hardware_concurrency())) : 1;
+  const size_t n_thr = (n >= 2000 && my_nv >= 2) ? std::min<size_t>(std::min<size_t>(16, my_nv), std::max(1u, std::thread::hardware_concurrency())) : 1;
   if (n_thr <= 1) {
     fit_range(rank, world);
   } else {
@@ -274,6 +337,7 @@ static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::ve
     for (size_t tix = 0; tix < n_thr; ++tix)
       if (failed[tix]) throw std::bad_alloc();
   }
+  if (ctx) CSC_TRACE(ctx, "hvg: vertex fits");
   if (world > 1) {
     std::vector<double> both(2 * nv);
     std::copy(val.begin(), val.end(), both.begin());
@@ -284,34 +348,34 @@ static csc_status loess_fit_predict(csc_ctx* ctx, bool collective, const std::ve
   }
   out.resize((size_t)n);
   parallel_for(n, [&](int64_t i_lo, int64_t i_hi) {
-  for (int64_t i = i_lo; i < i_hi; ++i) {
-    const double z = x[i];
-    size_t hi = (size_t)(std::lower_bound(verts.begin(), verts.end(), z) - verts.begin());
-    if (hi < 1) hi = 1;
-    if (hi > nv - 1) hi = nv - 1;
-    if (nv == 1) {
-      out[i] = val[0];
-      continue;
+    for (int64_t i = i_lo; i < i_hi; ++i) {
+      const double z = x[i];
+      size_t hi = (size_t)(std::lower_bound(verts.begin(), verts.end(), z) - verts.begin());
+      if (hi < 1) hi = 1;
+      if (hi > nv - 1) hi = nv - 1;
+      double pred;
+      if (nv == 1) {
+        pred = val[0];
+      } else {
+        const size_t lo = hi - 1;
+        const double v1 = verts[lo], v2 = verts[hi];
+        if (z == v1) {
+          pred = val[lo];
+        } else if (z == v2) {
+          pred = val[hi];
+        } else {
+          const double h = v2 - v1;
+          const double t = (z - v1) / h;
+          const double omt = 1.0 - t;
+          const double h00 = (1 + 2 * t) * omt * omt;
+          const double h10 = t * omt * omt;
+          const double h01 = t * t * (3 - 2 * t);
+          const double h11 = t * t * (t - 1);
+          pred = h00 * val[lo] + h10 * h * slope[lo] + h01 * val[hi] + h11 * h * slope[hi];
+        }
+      }
+      out[i] = finish(i, pred);
     }
-    const size_t lo = hi - 1;
-    const double v1 = verts[lo], v2 = verts[hi];
-    if (z == v1) {
-      out[i] = val[lo];
-      continue;
-    }
-    if (z == v2) {
-      out[i] = val[hi];
-      continue;
-    }
-    const double h = v2 - v1;
-    const double t = (z - v1) / h;
-    const double omt = 1.0 - t;
-    const double h00 = (1 + 2 * t) * omt * omt;
-    const double h10 = t * omt * omt;
-    const double h01 = t * t * (3 - 2 * t);
-    const double h11 = t * t * (t - 1);
-    out[i] = h00 * val[lo] + h10 * h * slope[lo] + h01 * val[hi] + h11 * h * slope[hi];
-  }
   });
   return CSC_OK;
 }
@@ -321,46 +385,44 @@ csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, in
                            double* var_std, int64_t* order, bool collective) {
   (void)n_features;  // the caller takes order[0:n_features]; clamping is :134-137
   const double N = (double)n_cells_total;
-  std::vector<double> mu((size_t)n_genes), var((size_t)n_genes), ve((size_t)n_genes, 0.0), vs((size_t)n_genes, 0.0);
-  std::vector<double> lx, ly;
-  std::vector<int64_t> kept;
-  for (int64_t g = 0; g < n_genes; ++g) {
-    const double s1 = s1s2[g], s2 = s1s2[n_genes + g];
-    mu[g] = s1 / N;                            // exact-moment rule, SURVEY A.3-7
-    var[g] = (s2 - s1 * s1 / N) / (N - 1.0);
-    if (var[g] > 0.0) kept.push_back(g);       // filter(:variance => >(0.0)) processing.jl:143
-  }
-  lx.resize(kept.size());
-  ly.resize(kept.size());
-  parallel_for((int64_t)kept.size(), [&](int64_t lo, int64_t hi) {
-    for (int64_t i = lo; i < hi; ++i) {
-      lx[i] = std::log10(mu[kept[i]]);
-      ly[i] = std::log10(var[kept[i]]);
+  std::vector<double> mu((size_t)n_genes), var((size_t)n_genes), vs((size_t)n_genes, 0.0);
+  std::vector<double> lx((size_t)n_genes), ly((size_t)n_genes);
+  // one pass per gene: moments and their logarithms (a gene without variance gets NaN there and is reported below)
+  parallel_for(n_genes, [&](int64_t lo, int64_t hi) {
+    for (int64_t g = lo; g < hi; ++g) {
+      const double s1 = s1s2[g], s2 = s1s2[n_genes + g];
+      mu[g] = s1 / N;                          // exact-moment rule, SURVEY A.3-7
+      var[g] = (s2 - s1 * s1 / N) / (N - 1.0);
+      const bool keep = var[g] > 0.0;          // filter(:variance => >(0.0)) processing.jl:143
+      lx[g] = keep ? std::log10(mu[g]) : std::numeric_limits<double>::quiet_NaN();
+      ly[g] = keep ? std::log10(var[g]) : std::numeric_limits<double>::quiet_NaN();
     }
   });
+  int64_t n_kept = 0, first_bad = -1;
+  for (int64_t g = 0; g < n_genes; ++g) {
+    if (var[g] > 0.0) ++n_kept;
+    else if (first_bad < 0) first_bad = g;
+  }
+  CSC_TRACE(ctx, "hvg: moments, log10");
   // The reference requires every gene to have variance > 0: it filters the data frame (:143) and then assigns the
   // gene names of ALL genes to it (:151), which throws a DimensionMismatch when a row was dropped.  Same here (and in
   // the oracle): selecting such a gene would put 0/0 = NaN rows into the scaled matrix and the Gram matrix.
-  if ((int64_t)kept.size() != n_genes) {
-    int64_t first_bad = 0;
-    while (first_bad < n_genes && var[first_bad] > 0.0) ++first_bad;
+  if (n_kept != n_genes)
     return csc_fail(ctx, CSC_ERR_ARG,
                     "find_variable_genes: %lld of %lld genes have variance <= 0 (first: gene %lld); the reference requires "
                     "every gene to vary (processing.jl:143,151) -- its object constructor drops all-zero genes first "
                     "(subset_matrix, utils.jl:313-320)",
-                    (long long)(n_genes - (int64_t)kept.size()), (long long)n_genes, (long long)first_bad);
+                    (long long)(n_genes - n_kept), (long long)n_genes, (long long)first_bad);
+  std::vector<double> ve;
+  if (n_genes > 0) {
+    // the Loess prediction, 10^pred and the ratio in one pass over the genes
+    CSC_TRY(loess_fit_predict(ctx, collective, lx, ly, span, ve, [&](int64_t g, double pred) {
+      const double e = std::pow(10.0, pred);
+      vs[g] = var[g] / e;
+      return e;
+    }));
   }
-  if (!kept.empty()) {
-    std::vector<double> pred;
-    CSC_TRY(loess_fit_predict(ctx, collective, lx, ly, span, pred));
-    parallel_for((int64_t)kept.size(), [&](int64_t lo, int64_t hi) {
-      for (int64_t i = lo; i < hi; ++i) {
-        const int64_t g = kept[i];
-        ve[g] = std::pow(10.0, pred[i]);
-        vs[g] = var[g] / ve[g];
-      }
-    });
-  }
+  CSC_TRACE(ctx, "hvg: interpolation, pow, ratio");
   if (mean) std::copy(mu.begin(), mu.end(), mean);
   if (variance) std::copy(var.begin(), var.end(), variance);
   if (var_exp) std::copy(ve.begin(), ve.end(), var_exp);
@@ -373,6 +435,6 @@ csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, in
     stable_argsort(neg, ord);
     std::copy(ord.begin(), ord.end(), order);
   }
-  (void)ctx;
+  CSC_TRACE(ctx, "hvg: final order");
   return CSC_OK;
 }

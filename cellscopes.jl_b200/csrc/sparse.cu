@@ -137,7 +137,8 @@ static csc_status two_lane_upload(csc_ctx* ctx, int kind, const void* host, void
   int64_t UP_SLOT = UP_SLOT_MAX;               // CSC_UPLOAD_PIECE: smaller pieces, so that tests reach every branch on small inputs
   if (const char* e = getenv("CSC_UPLOAD_PIECE")) UP_SLOT = std::max<int64_t>(16, std::min<int64_t>(UP_SLOT_MAX, atoll(e)));
   const int64_t UP_WIDE = 8 * UP_SLOT;
-  unsigned hw = std::thread::hardware_concurrency();
+  // the host cores are shared by the ranks of the box (one process per GPU): each takes its share, minus the bus thread
+  unsigned hw = std::thread::hardware_concurrency() / (unsigned)std::max(1, ctx->comm_world);
   int n_workers = (int)std::max(1u, std::min(31u, hw > 1 ? hw - 1 : 1u));
   if (const char* e = getenv("CSC_UPLOAD_THREADS")) n_workers = std::max(1, std::min(64, atoi(e)));
   const int n_slots = 2 * n_workers;

@@ -30,9 +30,12 @@ for r in range(reps):
     rows = np.unique(feats)
     part = ctx.vec(2 * rows.size, np.float64)
     ctx.flush_l2()
-    ctx.scale_stats_partial(norm, feats, part)
+    src, src_feats = norm, feats
+    if G >= 4 * rows.size:                      # whole-transcriptome route of pipeline.run_path: subset_count first
+        src, src_feats = ctx.select_rows(norm, feats), None
+    ctx.scale_stats_partial(src, src_feats, part)
     ctx.flush_l2()
-    scaled = ctx.scale_fill(norm, feats, part, N)
+    scaled = ctx.scale_fill(src, src_feats, part, N)
     ctx.synchronize()
     ms, _ = ctx.stage_times()
     hn = rows.size
@@ -43,4 +46,4 @@ for r in range(reps):
           f"scale_stats {ms['scale_stats']:.3f} ms {b_stats / ms['scale_stats'] / 1e6:.0f} GB/s ({b_stats / ms['scale_stats'] / 1e6 / peak:.2f}) | "
           f"scale_fill {ms['scale_fill']:.3f} ms {b_fill / ms['scale_fill'] / 1e6:.0f} GB/s ({b_fill / ms['scale_fill'] / 1e6 / peak:.2f}) | hvg {ms['hvg']:.2f} ms",
           flush=True)
-    del norm, scaled
+    del norm, scaled, src
