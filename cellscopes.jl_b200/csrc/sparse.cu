@@ -538,9 +538,51 @@ struct NormArgs {
   int32_t n_e;        // RAW = 1: genes [0, n_e) also have an E slot in shared memory (what is left of it beside the S1 table)
 };
 
+// y of one stored entry (processing.jl:24-27): t = x * scale, log(t + pc) or t
+__device__ __forceinline__ float norm_value(float x, float scale, int method, bool pc_is_one, float pcf, int nan_to_zero) {
+  const float t = x * scale;
+  float y;
+  if (method == CSC_NORM_LOGARITHM) {
+    // log(1 + t): from t = 1 on, 1 + t is at least 2, where __logf is good to 3 ulp and the rounding of the
+    // sum costs 2^-24 / log 2 relative (4.5e-7 together, against the 1e-5 the path promises); below, and
+    // for any other pseudocount, the library functions
+    y = pc_is_one ? (t >= 1.f ? __logf(1.f + t) : log1pf(t)) : logf(t + pcf);
+  } else {
+    y = t;
+  }
+  if (nan_to_zero && y != y) y = 0.f;
+  return y;
+}
+
+// raw moments of one stored entry (x, gene g) into the CTA's tables / the fp64 table in global memory (RAW: see k_normalize).
+// (A formulation with two predicated shared-memory adds and one rare branch was not faster: 6.0 vs 5.9 ms at C3.)
+template <int RAW>
+__device__ __forceinline__ void raw_moment_update(float x, int g, unsigned int* s1tab, unsigned int* etab, int n_e, double* gstats,
+                                                  int G) {
+  const float xr = rintf(x);
+  if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
+    const unsigned int xi = (unsigned int)x;
+    atomicAdd(&s1tab[g], xi);
+    if ((RAW == 2 || (RAW == 1 && g < n_e)) && xi <= 255u) {
+      if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
+    } else if (xi >= 2u) {
+      const double xd = (double)x;
+      atomicAdd(&gstats[(int64_t)G + g], xd * xd - xd);
+    }
+  } else {
+    const double xd = (double)x;
+    atomicAdd(&gstats[g], xd);
+    atomicAdd(&gstats[(int64_t)G + g], xd * xd);
+  }
+}
+
 // RAW: 0 = no raw moments, 1 = S1 table + E slots for the first n_e genes (E of the others goes to global memory:
 //      13.6 % of the C3 entries are counts >= 2, 225 M fp64 atomics per pass when no gene had a slot), 2 = S1 and E tables,
 //      3 = no table fits: every update goes to the fp64 table in global memory
+// (Measured dead end, round 2: a group of 128 or 256 threads holding a whole 1650-entry column in registers, one read of
+// the column instead of two.  DRAM reads fell to the algorithmic 13.5 GB, but what a warp pays once per column -- bounds,
+// fp64 reduction, named barrier, reciprocal -- is then paid by 4-8 warps per column and the few resident warps cannot
+// hide the latencies: 8.2 ms with 256-thread groups, 15.7 ms with 128-thread groups, against 5.6 ms here.)
 // BIG: the tables leave room for one CTA per SM only (whole-transcriptome matrices): 1024 threads and 8 entries per
 // lane in flight instead of 768 x 2 CTAs and 4 -- with 24 warps per SM and 1 KB of loads per warp in flight the pass sat
 // at 0.37 of the HBM rate with no unit busier than 48 % (ncu): latency, not throughput
@@ -599,40 +641,8 @@ k_normalize(const NormArgs a) {
         const int64_t i = i0 + 32 * u;
         if (i >= e) break;
         const float x = xs[u];
-        float y = 0.f;
-        if (WRITE_NORM) {
-          const float t = x * scale;
-          if (a.method == CSC_NORM_LOGARITHM) {
-            // log(1 + t): from t = 1 on, 1 + t is at least 2, where __logf is good to 3 ulp and the rounding of the
-            // sum costs 2^-24 / log 2 relative (4.5e-7 together, against the 1e-5 the path promises); below, and
-            // for any other pseudocount, the library functions
-            y = pc_is_one ? (t >= 1.f ? __logf(1.f + t) : log1pf(t)) : logf(t + pcf);
-          } else {
-            y = t;
-          }
-          if (a.nan_to_zero && y != y) y = 0.f;
-          __stcs(a.out + i, y);
-        }
-        if (RAW > 0) {
-          const int g = gs[u];
-          {
-            const float xr = rintf(x);
-            if (RAW != 3 && xr == x && x >= 0.f && x <= 65535.f) {
-              const unsigned int xi = (unsigned int)x;
-              atomicAdd(&s1tab[g], xi);
-              if ((RAW == 2 || (RAW == 1 && g < n_e)) && xi <= 255u) {
-                if (xi >= 2u) atomicAdd(&etab[g], xi * xi - xi);
-              } else if (xi >= 2u) {
-                const double xd = (double)x;
-                atomicAdd(&a.gstats[(int64_t)G + g], xd * xd - xd);
-              }
-            } else {
-              const double xd = (double)x;
-              atomicAdd(&a.gstats[g], xd);
-              atomicAdd(&a.gstats[(int64_t)G + g], xd * xd);
-            }
-          }
-        }
+        if (WRITE_NORM) __stcs(a.out + i, norm_value(x, scale, a.method, pc_is_one, pcf, a.nan_to_zero));
+        if (RAW > 0) raw_moment_update<RAW>(x, gs[u], s1tab, etab, n_e, a.gstats, G);
       }
     }
     b = nb; e = ne; nb = nnb; ne = nne;

@@ -106,11 +106,13 @@ def normalize_object(x, scale_factor=10000, norm_method="logarithm", pseudocount
 # ---------------------------------------------------------------------------------------------
 def _vst_frame(res, gene_name):
     order = res["order"]
+    # one fancy-indexing pass per column (a Python loop over 33k gene names cost more than the device part of the call)
+    genes = gene_name if isinstance(gene_name, np.ndarray) else np.asarray(gene_name, dtype=object)
     df = pd.DataFrame({
         "mean": res["mean"][order], "variance": res["variance"][order],
         "variance_expected": res["variance_expected"][order],
         "variance_standardized": res["variance_standardized"][order],
-        "gene": [gene_name[i] for i in order],
+        "gene": genes[order],
     })
     return df
 

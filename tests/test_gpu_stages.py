@@ -164,6 +164,37 @@ def test_gene_moments_large_counts(cs, oracle, ctx):
     assert np.allclose(got[:50], s1, rtol=1e-12) and np.allclose(got[50:], s2, rtol=1e-12)
 
 
+@pytest.mark.parametrize("n_genes", [1500, 30000, 60000])
+def test_gene_moments_mixed_values_in_every_table_mode(cs, ctx, n_genes):
+    """The per-entry moment update (raw_moment_update in csrc/sparse.cu) in its three table modes (both tables / the sum
+    table + E slots for part of the genes / no table in shared memory) on values of every class it distinguishes: counts
+    of 1, small counts, counts above 255 (x^2 - x leaves the E table), above 65535, non-integers, stored zeros, -0.0 and
+    negative values.  All sums here are exactly representable, so the tables must equal the dense sums bit for bit, and
+    the pass fused into normalize must equal the standalone one."""
+    rng = np.random.default_rng(n_genes)
+    n_cells = 64
+    nnz_per = min(n_genes, 900)
+    rows = np.concatenate([np.sort(rng.choice(n_genes, size=nnz_per, replace=False)) for _ in range(n_cells)])
+    vals = rng.integers(1, 6, rows.size).astype(np.float64)
+    pick = rng.random(rows.size)
+    vals[pick < 0.02] = 300.0
+    vals[(pick >= 0.02) & (pick < 0.03)] = 2.5
+    vals[(pick >= 0.03) & (pick < 0.035)] = 70000.0
+    vals[(pick >= 0.035) & (pick < 0.04)] = 0.0
+    vals[(pick >= 0.04) & (pick < 0.045)] = -3.0
+    vals[(pick >= 0.045) & (pick < 0.05)] = -0.0
+    m = sp.csc_matrix((vals, rows, np.arange(n_cells + 1) * nnz_per), shape=(n_genes, n_cells))
+    raw = ctx.sparse_upload(n_genes, n_cells, m.indptr, m.indices, m.data)
+    st = ctx.vec(2 * n_genes)
+    ctx.gene_stats_partial(raw, st)
+    d = m.toarray()
+    want = np.r_[d.sum(axis=1), (d * d).sum(axis=1)]
+    assert np.array_equal(st.download(), want)
+    st2 = ctx.vec(2 * n_genes)
+    ctx.normalize(raw, 1e4, 1, 1.0, False, st2)
+    assert np.array_equal(st2.download(), want)
+
+
 @pytest.mark.parametrize("n_genes", [30000, 60000])
 def test_gene_moments_exact_when_tables_do_not_fit(cs, oracle, ctx, n_genes):
     """Whole-transcriptome gene counts: with 30k genes only the sum table fits in shared memory (the squares go to
