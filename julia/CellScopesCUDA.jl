@@ -448,12 +448,15 @@ end
 # ------------------------------------------------------------------------------------------------
 "Overwrite CellScopes' object-level methods of the five hot-path functions with the GPU path."
 function enable!()
+    # the methods are defined inside CellScopes and call back into THIS module, wherever it was loaded (the module object
+    # itself is spliced into the expression: no assumption that it lives in Main)
+    shim = @__MODULE__
     @eval CellScopes begin
-        normalize_object(sc_obj::get_object_group("All"); kw...) = Main.CellScopesCUDA.normalize_object(sc_obj; kw...)
-        find_variable_genes(sc_obj::get_object_group("All"); kw...) = Main.CellScopesCUDA.find_variable_genes(sc_obj; kw...)
-        scale_object(sc_obj::get_object_group("All"); kw...) = Main.CellScopesCUDA.scale_object(sc_obj; kw...)
-        run_pca(sc_obj::get_object_group("All"); kw...) = Main.CellScopesCUDA.run_pca(sc_obj; kw...)
-        run_clustering(sc_obj::get_object_group("All"); kw...) = Main.CellScopesCUDA.run_clustering(sc_obj; kw...)
+        normalize_object(sc_obj::get_object_group("All"); kw...) = $shim.normalize_object(sc_obj; kw...)
+        find_variable_genes(sc_obj::get_object_group("All"); kw...) = $shim.find_variable_genes(sc_obj; kw...)
+        scale_object(sc_obj::get_object_group("All"); kw...) = $shim.scale_object(sc_obj; kw...)
+        run_pca(sc_obj::get_object_group("All"); kw...) = $shim.run_pca(sc_obj; kw...)
+        run_clustering(sc_obj::get_object_group("All"); kw...) = $shim.run_clustering(sc_obj; kw...)
     end
     nothing
 end
