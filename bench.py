@@ -523,6 +523,10 @@ def run_e2e(cs, ctx, comm, dist, raw, n_genes, n_cells, lo, hi, params, offsets,
                             "the adjacency (Int64 CSC).  normCount.count_mtx and scaleCount.count_mtx stay on the device "
                             "as lazy matrices (downloaded only when read): the reference's consumers on this path never "
                             "read them",
+            "h2d_note": "h2d_bytes_per_step counts the host arrays handed to the API (Int64 colptr / rowval, Float64 values: 16 B per "
+                        "stored entry).  csc_sparse_upload moves them through two lanes: host threads narrow pieces from the front "
+                        "(to uint16 where lossless, else int32 / fp32) and copy 2-4 B per entry, the copy engine carries wide pieces "
+                        "from the back; fewer bytes than counted cross the bus, all of them inside the timed region",
             "timer": "host wall clock around synchronised calls (includes H2D, D2H and host marshalling)"}
 
 
