@@ -38,6 +38,30 @@ def test_moment_tables_add_up_over_cell_shards(cs, ctx, full):
     assert np.array_equal(acc, whole)
 
 
+def test_two_lane_upload_round_trip_at_full_size(cs, ctx, full):
+    """The 125 M stored entries of this matrix as the reference holds them (Int64 indices 1-based, Float64 values: 2 GB) go
+    through csc_sparse_upload's two-lane route (taken from 32 M entries on: host threads narrow from the front, the copy
+    engine carries wide pieces from the back) and must come back exactly: encode -> decode round trip over the whole
+    matrix, wherever the two lanes met; then the same with Int64 values and with a value no uint16 can hold in every
+    few-millionth place (pieces falling back to fp32)."""
+    raw = full["raw"]
+    cp, rv, val = raw.download(0, N, 1)                       # Int64 colptr / rowval (1-based), Float64 values
+    assert cp.dtype == np.int64 and rv.dtype == np.int64 and val.dtype == np.float64 and raw.nnz >= (32 << 20)
+    for values in (val, val.astype(np.int64)):
+        up = ctx.sparse_upload(G, N, cp, rv, values, index_base=1)
+        cp2, rv2, val2 = up.download(0, N, 1)
+        assert np.array_equal(cp2, cp) and np.array_equal(rv2, rv) and np.array_equal(val2, val)
+        del up, cp2, rv2, val2
+    odd = val.copy()
+    odd[::3_000_017] = 70000.5
+    up = ctx.sparse_upload(G, N, cp, rv, odd, index_base=1)
+    assert np.array_equal(up.download(0, N, 1, values_only=True), odd.astype(np.float32).astype(np.float64))
+    del up
+    rv[rv.size // 3] = G + 1                                  # one row index out of range, somewhere in the middle
+    with pytest.raises(cs.CellScopesCudaError):
+        ctx.sparse_upload(G, N, cp, rv, odd, index_base=1)
+
+
 def test_normalisation_round_trip(cs, ctx, full):
     """expm1(norm) / sf * colsum recovers the integer counts on a slice of cells in the middle of the matrix."""
     lo, hi = 250_000, 252_000
