@@ -49,7 +49,8 @@ NcclApi* nccl_api() {
     if (!n || !*n) continue;
     api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (api.handle) break;
-    api.error = dlerror() ? dlerror() : "dlopen failed";
+    const char* why = dlerror();                          // one call: dlerror() clears the message it returns
+    api.error = why ? why : "dlopen failed";
   }
   if (!api.handle) return &api;
 #define NCCL_SYM(field, name)                                        \
