@@ -82,6 +82,97 @@ k_km_assign(const float* __restrict__ x, int64_t n, int64_t stride, const float*
   }
 }
 
+// The label pass over ALL rows on the tensor cores (mma.sync m16n8k16, fp16 operands like k_km_assign, fp32 accumulation):
+// 1M rows x 512 centroids x 64 dimensions is a 6.6e10-flop GEMM with an argmax epilogue -- 1.6 ms in the HFMA2 loop above
+// (a quarter of the packed-fp16 FMA peak), replicated on every rank of a multi-GPU run because each rank orders all keys.
+// A CTA stages every centroid once (fp16, rows padded to 72 halves: the 8 x 4 fragment loads of a warp hit 32 different
+// banks) and its 8 warps walk over tiles of 32 rows: two m16 tiles share each B fragment, a lane keeps the running best of
+// the four rows it sees (strictly greater in increasing centroid order, lower index on a tie across the quad: the rule of
+// the scalar kernel).  Labels only steer the ORDER of the exact scan.
+constexpr int KA_PITCH = 72;      // halves per staged centroid
+constexpr int KA_MAXK = 1024;     // centroids that fit (144 KB); more clusters (> 2M keys) take the scalar kernel
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256)
+k_km_assign_mma(const float* __restrict__ x, int64_t n, const float* __restrict__ cent, int K, int32_t* __restrict__ label) {
+  extern __shared__ __align__(16) unsigned char ka_smem[];
+  __half* sc = reinterpret_cast<__half*>(ka_smem);
+  for (int j = threadIdx.x; j < K * (KO_D / 4); j += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(cent) + j);
+    const int r = j >> 4, c4 = j & 15;
+    *reinterpret_cast<uint2*>(sc + r * KA_PITCH + c4 * 4) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t n_tiles = ceil_div64(n, 32);
+  for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+    const int64_t row0 = tile * 32;
+    // A fragments of the two m16 tiles, four k-steps of 16: a0 (row g, k 2q..), a1 (row g+8, k 2q..), a2 / a3 the same at k + 8
+    uint32_t a[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int64_t r_lo = row0 + mt * 16 + g, r_hi = r_lo + 8;
+      const float2* p_lo = reinterpret_cast<const float2*>(x + (r_lo < n ? r_lo : 0) * KO_D);
+      const float2* p_hi = reinterpret_cast<const float2*>(x + (r_hi < n ? r_hi : 0) * KO_D);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 l0 = __ldg(p_lo + ks * 8 + q), l1 = __ldg(p_lo + ks * 8 + 4 + q);
+        const float2 h0 = __ldg(p_hi + ks * 8 + q), h1 = __ldg(p_hi + ks * 8 + 4 + q);
+        a[mt][ks][0] = pack_h2(l0.x, l0.y);
+        a[mt][ks][1] = pack_h2(h0.x, h0.y);
+        a[mt][ks][2] = pack_h2(l1.x, l1.y);
+        a[mt][ks][3] = pack_h2(h1.x, h1.y);
+      }
+    }
+    float best[2][2] = {{-3.0e38f, -3.0e38f}, {-3.0e38f, -3.0e38f}};
+    int bi[2][2] = {{0, 0}, {0, 0}};
+    for (int t = 0; t < K / 8; ++t) {
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const __half* bp = sc + (t * 8 + g) * KA_PITCH + q * 2;      // B fragment: centroid t*8+g, k = 2q.. and 2q+8..
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(bp + ks * 16 + 8);
+        mma_16816(c[0], a[0][ks], b0, b1);
+        mma_16816(c[1], a[1][ks], b0, b1);
+      }
+      const int n0 = t * 8 + q * 2;                               // c0, c1: row g, centroids n0, n0+1; c2, c3: row g+8
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (c[mt][0] > best[mt][0]) { best[mt][0] = c[mt][0]; bi[mt][0] = n0; }
+        if (c[mt][1] > best[mt][0]) { best[mt][0] = c[mt][1]; bi[mt][0] = n0 + 1; }
+        if (c[mt][2] > best[mt][1]) { best[mt][1] = c[mt][2]; bi[mt][1] = n0; }
+        if (c[mt][3] > best[mt][1]) { best[mt][1] = c[mt][3]; bi[mt][1] = n0 + 1; }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          const float os = __shfl_xor_sync(0xffffffffu, best[mt][h], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi[mt][h], o);
+          if (os > best[mt][h] || (os == best[mt][h] && oi < bi[mt][h])) {
+            best[mt][h] = os;
+            bi[mt][h] = oi;
+          }
+        }
+        const int64_t r = row0 + mt * 16 + h * 8 + g;
+        if (q == 0 && r < n) label[r] = bi[mt][h];
+      }
+    }
+  }
+}
+
 // centroid = normalised mean of its points; an empty cluster keeps its previous centroid
 __global__ void k_km_update(const float* __restrict__ sums, const int32_t* __restrict__ counts, int K, float* __restrict__ cent) {
   const int c = blockIdx.x;
@@ -140,6 +231,22 @@ __global__ void k_self_pos(const int32_t* __restrict__ perm_q, const int32_t* __
 __global__ void k_relabel(int32_t* __restrict__ label, int64_t n, const int32_t* __restrict__ rank) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) label[i] = __ldg(rank + label[i]);
+}
+
+// label pass over all rows: tensor-core kernel when the centroids fit in shared memory (CSC_KNN_KM_MMA=0: scalar kernel)
+static csc_status km_label_all(csc_ctx* ctx, const float* x, int64_t n, const float* cent, int K, int32_t* label) {
+  static const bool use_mma = !(getenv("CSC_KNN_KM_MMA") && atoi(getenv("CSC_KNN_KM_MMA")) == 0);
+  if (use_mma && K <= KA_MAXK && K % 8 == 0) {
+    const size_t smem = (size_t)K * KA_PITCH * 2;
+    CSC_CUDA(ctx, cudaFuncSetAttribute(k_km_assign_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = ceil_div64(n, 32);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_tiles, 8), (int64_t)ctx->sm_count));
+    k_km_assign_mma<<<grid, 256, smem, ctx->stream>>>(x, n, cent, K, label);
+  } else {
+    k_km_assign<<<(unsigned)ceil_div64(n, 128), 128, 0, ctx->stream>>>(x, n, 1, cent, K, label, nullptr, nullptr);
+  }
+  CSC_LAUNCHED(ctx);
+  return CSC_OK;
 }
 
 static csc_status sort_by_label(csc_ctx* ctx, const int32_t* labels, int64_t n, int K, DevPtr* perm, DevPtr* labels_sorted) {
@@ -210,9 +317,7 @@ csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const
     CSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   CSC_TRY(dev_alloc(ctx, (size_t)n_keys * 4, &lab_k));
-  k_km_assign<<<(unsigned)ceil_div64(n_keys, 128), 128, 0, ctx->stream>>>(k_prep, n_keys, 1, (const float*)cent->p, K,
-                                                                       (int32_t*)lab_k->p, nullptr, nullptr);
-  CSC_LAUNCHED(ctx);
+  CSC_TRY(km_label_all(ctx, k_prep, n_keys, (const float*)cent->p, K, (int32_t*)lab_k->p));
   k_relabel<<<(unsigned)ceil_div64(n_keys, 256), 256, 0, ctx->stream>>>((int32_t*)lab_k->p, n_keys, (const int32_t*)rank->p);
   CSC_LAUNCHED(ctx);
   CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_k->p, n_keys, K, perm_k, &labs_k));
@@ -231,9 +336,7 @@ csc_status knn_build_order(csc_ctx* ctx, const float* q_prep, int64_t n_q, const
     labs_q_ptr = (const int32_t*)labs_k->p;
   } else {
     CSC_TRY(dev_alloc(ctx, (size_t)n_q * 4, &lab_q));
-    k_km_assign<<<(unsigned)ceil_div64(n_q, 128), 128, 0, ctx->stream>>>(q_prep, n_q, 1, (const float*)cent->p, K, (int32_t*)lab_q->p,
-                                                                      nullptr, nullptr);
-    CSC_LAUNCHED(ctx);
+    CSC_TRY(km_label_all(ctx, q_prep, n_q, (const float*)cent->p, K, (int32_t*)lab_q->p));
     k_relabel<<<(unsigned)ceil_div64(n_q, 256), 256, 0, ctx->stream>>>((int32_t*)lab_q->p, n_q, (const int32_t*)rank->p);
     CSC_LAUNCHED(ctx);
     CSC_TRY(sort_by_label(ctx, (const int32_t*)lab_q->p, n_q, K, perm_q, &labs_q));
