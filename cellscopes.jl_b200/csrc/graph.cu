@@ -183,12 +183,16 @@ extern "C" csc_status csc_graph_build(csc_ctx* ctx, const csc_vec* knn_idx, int6
   int row_bits = 1, col_bits = 1;
   while (((int64_t)1 << row_bits) < n_cells_total) ++row_bits;
   while (((int64_t)1 << col_bits) < n_loc) ++col_bits;
-  const unsigned long long sentinel = 1ull << (row_bits + col_bits);
+  // "no entry" key: sorts after every valid key.  The all-ones pattern of the key's own bits is free unless the largest
+  // valid key (column n_loc - 1, row n_cells_total - 1) is all ones itself, i.e. both sizes are powers of two; only then
+  // does the sentinel need a bit of its own (at 1M cells that bit was a sixth radix pass over 40 M keys).
+  const bool free_top = (((int64_t)1 << row_bits) != n_cells_total) || (((int64_t)1 << col_bits) != n_loc);
+  const unsigned long long sentinel = free_top ? (1ull << (row_bits + col_bits)) - 1ull : 1ull << (row_bits + col_bits);
   k_graph_keys<<<nblk(n_all), 256, 0, ctx->stream>>>(idx, n_cells_total, k, cell_lo, cell_hi, row_bits, sentinel,
                                                       (unsigned long long*)keys_a->p, (unsigned long long*)counter->p);
   CSC_LAUNCHED(ctx);
   {
-    const int key_bits = row_bits + col_bits + 1;      // the sentinel owns the top bit
+    const int key_bits = row_bits + col_bits + (free_top ? 0 : 1);
     size_t tmp_bytes = 0;
     CSC_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)keys_a->p,
                                                  (unsigned long long*)keys_b->p, n_all, 0, key_bits, ctx->stream));
