@@ -259,6 +259,10 @@ __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 #endif
 
 // stage launchers implemented in the other translation units ------------------------------------
+// hvg_dev.cu: the same finish on the device (default for >= 1024 genes; CSC_HVG_HOST=1 keeps the host version)
+bool hvg_device_applies(int64_t n_genes, double span);
+csc_status launch_hvg_device(csc_ctx* ctx, const double* d_s1s2, int64_t n_genes, int64_t n_cells_total, double span, double* mean,
+                             double* variance, double* var_exp, double* var_std, int64_t* order);
 csc_status launch_hvg_host(csc_ctx* ctx, const double* s1s2, int64_t n_genes, int64_t n_cells_total,
                            int64_t n_features, double span, double* mean, double* variance, double* var_exp,
                            double* var_std, int64_t* order, bool collective = false);
