@@ -356,7 +356,8 @@ csc_status sort_pairs(csc_ctx* ctx, const unsigned long long* k_in, unsigned lon
 
 // true: the device path applies to this problem (else the caller takes launch_hvg_host)
 bool hvg_device_applies(int64_t n_genes, double span) {
-  static const bool off = getenv("CSC_HVG_HOST") && atoi(getenv("CSC_HVG_HOST")) != 0;
+  const char* e = getenv("CSC_HVG_HOST");                 // read per call: a test switches between the two versions
+  const bool off = e && atoi(e) != 0;
   if (off || n_genes < 1024 || n_genes >= ((int64_t)1 << 31)) return false;
   // vertices: both ends + one median per internal node of the halving down to ceil(0.2 span n) points
   const double leaves = 2.0 / (0.2 * span);

@@ -155,14 +155,18 @@ csc_status csc_gene_stats_partial(csc_ctx* ctx, const csc_sparse* raw, csc_vec* 
 /* gene_stats already summed over ranks.  Outputs (host, any may be NULL): mean/variance/
  * variance_expected/variance_standardized [n_genes] = the vst_data columns of :141; order[n_genes] =
  * gene ids (0-based) sorted by variance_standardized descending, stable (:152); the first n_features of
- * it are Features (:153).  n_features is clamped to n_genes (:134-137). */
+ * it are Features (:153).  n_features is clamped to n_genes (:134-137).  From 1024 genes on (and span >= 0.02) the whole
+ * finish -- sorts, Loess vertex fits, prediction, rank -- runs on the device (hvg_dev.cu, ~0.5 ms at 33k genes); smaller
+ * tables and CSC_HVG_HOST=1 take the host implementation of the same algorithm (hvg.cu). */
 csc_status csc_hvg_finish(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
                           int64_t n_features, double span, double* mean, double* variance,
                           double* variance_expected, double* variance_standardized, int64_t* order);
 
 /* The same for one process per GPU: called by EVERY rank of the context's communicator (csc_comm_init) with the
- * all-reduced table; the Loess vertex fits are dealt out over the ranks and their (value, slope) pairs all-reduced, so
- * every rank returns bit-identical outputs without N copies of the same host job competing for the host cores. */
+ * all-reduced table.  On the device path every rank runs the (deterministic) finish on its own copy and nothing is
+ * exchanged; on the host path the Loess vertex fits are dealt out over the ranks and their (value, slope) pairs
+ * all-reduced, so every rank returns bit-identical outputs without N copies of the same host job competing for the
+ * host cores. */
 csc_status csc_hvg_finish_collective(csc_ctx* ctx, const csc_vec* gene_stats, int64_t n_genes, int64_t n_cells_total,
                                      int64_t n_features, double span, double* mean, double* variance,
                                      double* variance_expected, double* variance_standardized, int64_t* order);

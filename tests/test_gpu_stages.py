@@ -236,6 +236,68 @@ def test_hvg_set_bit_exact(cs, oracle, ctx, medium_counts, nfeat):
     print(f"HVG boundary margin at rank {nfeat}: {margin:.3e}")
 
 
+def _tied_moment_table(n_genes, n_cells, seed):
+    """Exact moment tables (S1, S2) with heavily repeated means: low-count genes share their S1, so the q-th nearest
+    distance of a Loess vertex is attained by many points and the tie rule (lower gene index first) decides."""
+    rng = np.random.default_rng(seed)
+    s1 = rng.integers(3, 60, n_genes).astype(np.float64)
+    s1[rng.random(n_genes) < 0.2] = float(rng.integers(100, 5000))      # a fifth of the genes share ONE mean
+    big = rng.random(n_genes) < 0.3
+    s1[big] = rng.integers(60, 20000, int(big.sum())).astype(np.float64)
+    s2 = s1 + 2.0 * rng.integers(0, 40, n_genes) * (1.0 + np.floor(s1 / 50.0))
+    assert np.all((s2 - s1 * s1 / n_cells) > 0)
+    return s1, s2
+
+
+@pytest.mark.parametrize("n_genes,span", [(1024, 0.3), (6000, 0.3), (20011, 0.3), (6000, 0.05), (6000, 1.0)])
+def test_hvg_device_finish_matches_oracle_with_tied_means(cs, oracle, ctx, n_genes, span):
+    """hvg_dev.cu (>= 1024 genes): window selection by binary searches, tied rim by merge path, block-reduced QR."""
+    n_cells = 25000
+    s1, s2 = _tied_moment_table(n_genes, n_cells, 5 + n_genes)
+    st = ctx.vec_from(np.concatenate([s1, s2]))
+    got = ctx.hvg_finish(st, n_genes, n_cells, 2000, span)
+    want = oracle.hvg_from_moments(s1, s2, n_cells, 2000, span)
+    assert np.array_equal(got["mean"], want["mean"])
+    assert np.array_equal(got["variance"], want["variance"])
+    assert np.allclose(got["variance_expected"], want["variance_expected"], rtol=1e-9)
+    assert np.allclose(got["variance_standardized"], want["variance_standardized"], rtol=1e-9)
+    # equal (S1, S2) pairs give equal variance_standardized: the stable rank (ties by gene index) must agree wherever
+    # the oracle's neighbouring values are not within rounding of each other
+    vs = want["variance_standardized"]
+    o_w, o_g = want["order"], got["order"]
+    differ = np.nonzero(o_w != o_g)[0]
+    for r in differ:
+        assert abs(vs[o_w[r]] - vs[o_g[r]]) <= 1e-9 * abs(vs[o_w[r]]), (r, o_w[r], o_g[r])
+    print(f"{n_genes} genes span {span}: {differ.size} rank positions differ inside rounding ties")
+
+
+def test_hvg_device_and_host_finish_agree(cs, ctx, monkeypatch):
+    n_genes, n_cells = 12000, 40000
+    s1, s2 = _tied_moment_table(n_genes, n_cells, 77)
+    st = ctx.vec_from(np.concatenate([s1, s2]))
+    dev = ctx.hvg_finish(st, n_genes, n_cells, 2000, 0.3)
+    monkeypatch.setenv("CSC_HVG_HOST", "1")
+    host = ctx.hvg_finish(st, n_genes, n_cells, 2000, 0.3)
+    monkeypatch.delenv("CSC_HVG_HOST")
+    assert np.array_equal(dev["mean"], host["mean"]) and np.array_equal(dev["variance"], host["variance"])
+    assert np.allclose(dev["variance_expected"], host["variance_expected"], rtol=1e-11)
+    vs = host["variance_standardized"]
+    differ = np.nonzero(dev["order"] != host["order"])[0]
+    for r in differ:
+        assert abs(vs[dev["order"][r]] - vs[host["order"][r]]) <= 1e-11 * abs(vs[host["order"][r]])
+
+
+def test_hvg_device_finish_rejects_zero_variance_gene(cs, ctx):
+    n_genes, n_cells = 3000, 25000
+    s1, s2 = _tied_moment_table(n_genes, n_cells, 3)
+    s1[1234] = 7.0 * n_cells          # the same count in every cell: variance exactly 0
+    s2[1234] = 49.0 * n_cells
+    st = ctx.vec_from(np.concatenate([s1, s2]))
+    with pytest.raises(cs.CellScopesCudaError) as ei:
+        ctx.hvg_finish(st, n_genes, n_cells, 2000, 0.3)
+    assert ei.value.code == -1 and "gene 1234" in str(ei.value)
+
+
 def test_hvg_nfeatures_clamped(cs, ctx, small_counts):
     raw = ctx.sparse_from_scipy(small_counts)
     g, n = small_counts.shape
