@@ -18,6 +18,10 @@ published algorithm of the pinned version is restated and marked [3P]:
   Distances.jl 0.10.11                      (CosineDist)
   NearestNeighborDescent.jl 0.3.6           (replaced by EXACT kNN, see knn_exact)
 
+Anchors outside this repository (tests/test_oracle.py): the Loess local regression and the Hermite blending
+reproduce R's published loess values on `cars` wherever R's kd-tree and Loess.jl's share a vertex; PCA against
+numpy.linalg.svd / scikit-learn; the Mann-Whitney p-values against scipy.stats; the kNN against an fp64 brute force.
+
 All citations ``processing.jl:N`` are /root/reference/src/scrna/processing.jl,
 ``utils.jl:N`` are /root/reference/src/scrna/utils.jl.
 
@@ -217,25 +221,29 @@ def loess_fit(x, y, span=0.75, degree=2, cell=0.2, odd_median="middle", centred=
     val = np.empty(verts.size)
     slope = np.empty(verts.size)
     for vi, v in enumerate(verts):
-        d = np.abs(x - v)
-        order = np.argsort(d, kind="stable")[:q]
-        dq = d[order]
-        dmax = float(dq.max())
-        if dmax == 0.0:
-            dmax = 1.0
-        u = dq / dmax
-        w = np.sqrt((1.0 - u ** 3) ** 3)
-        xc = x[order] - v if centred else x[order]
-        us = np.stack([w, w * xc, w * xc * xc], axis=1)
-        vs = y[order] * w
-        coef = _pivoted_qr_solve3(us, vs)
-        if centred:
-            val[vi] = coef[0]
-            slope[vi] = coef[1]
-        else:
-            val[vi] = coef[0] + coef[1] * v + coef[2] * v * v
-            slope[vi] = coef[1] + 2.0 * coef[2] * v
+        val[vi], slope[vi] = loess_local_fit(x, y, v, q, centred)
     return verts, val, slope
+
+
+def loess_local_fit(x, y, v, q, centred=True):
+    """The local regression of loess_fit at ONE point v: (fitted value, derivative) from the q nearest points (ties:
+    lower index first), tricube weights, degree 2.  Separate so that it can be checked on its own against published
+    values of R's loess (same local fit, different kd-tree: tests/test_oracle.py)."""
+    d = np.abs(x - v)
+    order = np.argsort(d, kind="stable")[:q]
+    dq = d[order]
+    dmax = float(dq.max())
+    if dmax == 0.0:
+        dmax = 1.0
+    u = dq / dmax
+    w = np.sqrt((1.0 - u ** 3) ** 3)
+    xc = x[order] - v if centred else x[order]
+    us = np.stack([w, w * xc, w * xc * xc], axis=1)
+    vs = y[order] * w
+    coef = _pivoted_qr_solve3(us, vs)
+    if centred:
+        return coef[0], coef[1]
+    return coef[0] + coef[1] * v + coef[2] * v * v, coef[1] + 2.0 * coef[2] * v
 
 
 def loess_predict(model, z):
